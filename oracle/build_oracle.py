@@ -1,0 +1,77 @@
+"""Build the CPU oracle (TEST INFRASTRUCTURE) and, when /root/reference is present, oracle/_ref.
+
+    python oracle/build_oracle.py            # libs2a_oracle.so (+ _ref if the reference is mounted)
+
+* oracle/libs2a_oracle.so   <- oracle/s2a_oracle.c        (gcc, -ffp-contract=off)
+* oracle/_ref/libref_iou_*.so <- oracle/ref_shim_iou.cpp + the reference header, compiled where
+  it lies under /root/reference (g++ = CPU semantics, nvcc host pass = CUDA semantics).
+* oracle/_ref/<ext>/<ext>.so  <- the reference's own torch extensions (CPU builds, and CUDA
+  builds for sm_100a) compiled from the sources in /root/reference by torch's cpp_extension;
+  see build_ref_extensions().  Nothing from the reference is copied into the repo.
+
+The built files are git-ignored but travel to the GPU box with the gpurun snapshot.
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = "/root/reference"
+REF_OUT = os.path.join(HERE, "_ref")
+
+
+def _run(cmd):
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("command failed: %s\n%s" % (" ".join(cmd), r.stdout))
+    return r.stdout
+
+
+def _stale(out, srcs):
+    if not os.path.exists(out):
+        return True
+    t = os.path.getmtime(out)
+    return any(os.path.getmtime(s) > t for s in srcs if os.path.exists(s))
+
+
+def build_oracle(force=False):
+    src = os.path.join(HERE, "s2a_oracle.c")
+    out = os.path.join(HERE, "libs2a_oracle.so")
+    if force or _stale(out, [src]):
+        _run(["gcc", "-O2", "-std=c11", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math",
+              "-fvisibility=hidden", "-o", out, src, "-lm"])
+    return out
+
+
+def build_ref_shims(force=False):
+    """The reference header compiled in place, four ways: {5,6}-float boxes x {CPU,CUDA} semantics."""
+    if not os.path.isdir(REF):
+        return []
+    os.makedirs(REF_OUT, exist_ok=True)
+    shim = os.path.join(HERE, "ref_shim_iou.cpp")
+    outs = []
+    for tag, inc, ml in (("iou", "utils/box_iou_rotated/src", False),
+                         ("nms", "utils/nms_rotated/src", False),
+                         ("ml", "utils/ml_nms_rotated/src", True)):
+        hdr = os.path.join(REF, inc, "box_iou_rotated_utils.h")
+        for sem in ("cpu", "cudasem"):
+            out = os.path.join(REF_OUT, "libref_%s_%s.so" % (tag, sem))
+            outs.append(out)
+            if not (force or _stale(out, [shim, hdr])):
+                continue
+            defs = ["-DREF_SYM(n)=ref_%s_%s_##n" % (tag, sem)] + (["-DREF_ML"] if ml else [])
+            if sem == "cpu":
+                _run(["g++", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-I", os.path.join(REF, inc)]
+                     + defs + ["-o", out, shim])
+            else:
+                # nvcc's host pass defines __CUDACC__, which selects the header's device-side hull sort.
+                _run(["nvcc", "-O2", "-x", "cu", "-shared", "-Xcompiler", "-fPIC,-ffp-contract=off",
+                      "-gencode", "arch=compute_100a,code=sm_100a", "-I", os.path.join(REF, inc)]
+                     + defs + ["-o", out, shim])
+    return outs
+
+
+if __name__ == "__main__":
+    print(build_oracle(force="--force" in sys.argv))
+    for o in build_ref_shims(force="--force" in sys.argv):
+        print(o)

@@ -1,0 +1,234 @@
+"""numpy/ctypes front-end of the CPU oracle (oracle/s2a_oracle.c) and of oracle/_ref.
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs -- never by s2anet_b200/.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+_f32p = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
+_i64p = np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")
+_u8p = np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS")
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        path = os.path.join(HERE, "libs2a_oracle.so")
+        if not os.path.exists(path):
+            from . import build_oracle
+            build_oracle.build_oracle()
+        L = C.CDLL(path)
+        L.s2a_oracle_single_iou.restype = C.c_float
+        L.s2a_oracle_single_iou.argtypes = [_f32p, _f32p]
+        L.s2a_oracle_box_iou_rotated.restype = None
+        L.s2a_oracle_box_iou_rotated.argtypes = [_f32p, C.c_int64, _f32p, C.c_int64, _f32p]
+        L.s2a_oracle_nms_rotated.restype = C.c_int64
+        L.s2a_oracle_nms_rotated.argtypes = [_f32p, _f32p, C.c_void_p, C.c_int64, C.c_float, C.c_int, _i64p]
+        L.s2a_oracle_arf_forward.restype = None
+        L.s2a_oracle_arf_forward.argtypes = [_f32p, _u8p] + [C.c_int] * 6 + [_f32p]
+        L.s2a_oracle_arf_backward.restype = None
+        L.s2a_oracle_arf_backward.argtypes = [_f32p, _u8p] + [C.c_int] * 6 + [_f32p]
+        L.s2a_oracle_ri_pool.restype = None
+        L.s2a_oracle_ri_pool.argtypes = [_f32p] + [C.c_int] * 5 + [_f32p]
+        L.s2a_oracle_deform_conv_forward.restype = C.c_int
+        L.s2a_oracle_deform_conv_forward.argtypes = [_f32p, _f32p, _f32p, _f32p] + [C.c_int] * 16
+        L.s2a_oracle_alignconv_offset.restype = None
+        L.s2a_oracle_alignconv_offset.argtypes = [_f32p, C.c_int, C.c_int, C.c_float, _f32p]
+        L.s2a_oracle_alignconv_forward.restype = C.c_int
+        L.s2a_oracle_alignconv_forward.argtypes = [_f32p, _f32p, _f32p, _f32p] + [C.c_int] * 5 + [C.c_float]
+        L.s2a_oracle_conv2d.restype = None
+        L.s2a_oracle_conv2d.argtypes = [_f32p, _f32p, C.c_void_p, _f32p] + [C.c_int] * 9
+        L.s2a_oracle_orconv_forward.restype = None
+        L.s2a_oracle_orconv_forward.argtypes = [_f32p, _f32p, _u8p, C.c_void_p, _f32p, C.c_void_p] + [C.c_int] * 11
+        _lib = L
+    return _lib
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def single_iou(b1, b2):
+    return float(lib().s2a_oracle_single_iou(_f32(b1), _f32(b2)))
+
+
+def box_iou_rotated(boxes1, boxes2):
+    b1, b2 = _f32(boxes1).reshape(-1, 5), _f32(boxes2).reshape(-1, 5)
+    out = np.empty((b1.shape[0], b2.shape[0]), np.float32)
+    if out.size:
+        lib().s2a_oracle_box_iou_rotated(b1, b1.shape[0], b2, b2.shape[0], out)
+    return out
+
+
+def nms_rotated(dets, scores, thr, labels=None, ge=False):
+    """keep indices (int64, original order ids, descending score).  labels=None -> nms_rotated,
+    else ml_nms_rotated.  ge=True selects the reference CPU build's >= predicate."""
+    d, s = _f32(dets).reshape(-1, 5), _f32(scores).reshape(-1)
+    n = d.shape[0]
+    keep = np.empty(max(n, 1), np.int64)
+    lab = None
+    if labels is not None:
+        lab = _f32(labels).reshape(-1)
+    nk = lib().s2a_oracle_nms_rotated(d, s, None if lab is None else lab.ctypes.data, n, float(thr),
+                                      int(bool(ge)), keep)
+    return keep[:nk].copy()
+
+
+def multiclass_nms_rotated(bboxes, scores, score_thr=0.05, iou_thr=0.5, max_per_img=2000):
+    """utils/bbox_nms_rotated.py:5-64 restated on numpy: strict score threshold, row-major
+    (box, class) expansion, ml-NMS, optional top-max_per_img re-sort.
+    Returns (dets [k,6] = x,y,w,h,theta,score ; labels [k] float32)."""
+    b, s = _f32(bboxes).reshape(-1, 5), _f32(scores)
+    mask = s > np.float32(score_thr)
+    bi, ci = np.nonzero(mask)                      # row-major order == torch boolean-mask order
+    if bi.size == 0:
+        return np.zeros((0, 6), np.float32), np.zeros((0,), np.float32)
+    cb, cs, cl = b[bi], s[bi, ci], ci.astype(np.float32)
+    keep = nms_rotated(cb, cs, iou_thr, labels=cl)
+    cb, cs, cl = cb[keep], cs[keep], cl[keep]
+    if keep.size > max_per_img:
+        order = np.argsort(-cs, kind="stable")[:max_per_img]
+        cb, cs, cl = cb[order], cs[order], cl[order]
+    return np.concatenate([cb, cs[:, None]], 1), cl
+
+
+def arf_forward(w, indices):
+    w = _f32(w)
+    O, I, nOri, kH, kW = w.shape
+    idx = np.ascontiguousarray(indices, np.uint8)
+    nRot = idx.shape[-1]
+    out = np.zeros((O * nRot, I * nOri, kH, kW), np.float32)
+    lib().s2a_oracle_arf_forward(w, idx.reshape(-1), O, I, nOri, kH, kW, nRot, out)
+    return out
+
+
+def arf_backward(indices, gout, O, I):
+    idx = np.ascontiguousarray(indices, np.uint8)
+    nOri, kH, kW, nRot = idx.shape
+    g = _f32(gout)
+    out = np.zeros((O, I, nOri, kH, kW), np.float32)
+    lib().s2a_oracle_arf_backward(g, idx.reshape(-1), O, I, nOri, kH, kW, nRot, out)
+    return out
+
+
+def ri_pool(x, n_ori=8):
+    x = _f32(x)
+    B, Cc, H, W = x.shape
+    out = np.empty((B, Cc // n_ori, H, W), np.float32)
+    lib().s2a_oracle_ri_pool(x, B, Cc, H, W, n_ori, out)
+    return out
+
+
+def deform_conv_forward(x, offset, w, stride=(1, 1), padding=(0, 0), dilation=(1, 1), groups=1,
+                        deformable_groups=1, relu=False):
+    x, offset, w = _f32(x), _f32(offset), _f32(w)
+    B, Cc, H, W = x.shape
+    Co, _, kH, kW = w.shape
+    Ho = (H + 2 * padding[0] - (dilation[0] * (kH - 1) + 1)) // stride[0] + 1
+    Wo = (W + 2 * padding[1] - (dilation[1] * (kW - 1) + 1)) // stride[1] + 1
+    out = np.empty((B, Co, Ho, Wo), np.float32)
+    rc = lib().s2a_oracle_deform_conv_forward(x, offset, w, out, B, Cc, H, W, Co, kH, kW, stride[0], stride[1],
+                                              padding[0], padding[1], dilation[0], dilation[1], groups,
+                                              deformable_groups, int(relu))
+    if rc != 0:
+        raise ValueError("bad deform-conv geometry")
+    return out
+
+
+def alignconv_offset(anchors, H, W, stride):
+    a = _f32(anchors).reshape(-1, 5)
+    out = np.empty((18, H, W), np.float32)
+    lib().s2a_oracle_alignconv_offset(a, H, W, float(stride), out)
+    return out
+
+
+def alignconv_forward(x, anchors, w, stride):
+    x, anchors, w = _f32(x), _f32(anchors), _f32(w)
+    B, Cc, H, W = x.shape
+    Co = w.shape[0]
+    out = np.empty((B, Co, H, W), np.float32)
+    rc = lib().s2a_oracle_alignconv_forward(x, anchors, w, out, B, Cc, H, W, Co, float(stride))
+    if rc != 0:
+        raise ValueError("bad alignconv geometry")
+    return out
+
+
+def conv2d(x, w, bias=None, pad=1):
+    x, w = _f32(x), _f32(w)
+    B, Cc, H, W = x.shape
+    Co, _, kH, kW = w.shape
+    out = np.empty((B, Co, H + 2 * pad - kH + 1, W + 2 * pad - kW + 1), np.float32)
+    b = None if bias is None else _f32(bias)
+    lib().s2a_oracle_conv2d(x, w, None if b is None else b.ctypes.data, out, B, Cc, H, W, Co, kH, kW, pad, pad)
+    return out
+
+
+def orconv_forward(x, w, indices, bias=None, pad=1, pool_group=0):
+    x, w = _f32(x), _f32(w)
+    O, I, nOri, kH, kW = w.shape
+    idx = np.ascontiguousarray(indices, np.uint8)
+    nRot = idx.shape[-1]
+    B, _, H, W = x.shape
+    Ho, Wo = H + 2 * pad - kH + 1, W + 2 * pad - kW + 1
+    out = np.empty((B, O * nRot, Ho, Wo), np.float32)
+    pooled = np.empty((B, O * nRot // pool_group, Ho, Wo), np.float32) if pool_group else None
+    b = None if bias is None else _f32(bias)
+    lib().s2a_oracle_orconv_forward(x, w, idx.reshape(-1), None if b is None else b.ctypes.data, out,
+                                    None if pooled is None else pooled.ctypes.data, B, H, W, O, I, nOri, kH, kW,
+                                    nRot, pad, pool_group)
+    return (out, pooled) if pool_group else out
+
+
+def arf_indices(n_orientation=1, n_rotation=8, k=3):
+    """models/orn/modules/ORConv.py:41-75 (get_indices) restated: uint8 [nOri, k, k, nRot],
+    1-based destination entry for source tap l under rotation 45deg*r."""
+    import math
+    table = {
+        1: {a: (1,) for a in range(0, 360, 45)},
+        3: {0: (1, 2, 3, 4, 5, 6, 7, 8, 9), 45: (2, 3, 6, 1, 5, 9, 4, 7, 8), 90: (3, 6, 9, 2, 5, 8, 1, 4, 7),
+            135: (6, 9, 8, 3, 5, 7, 2, 1, 4), 180: (9, 8, 7, 6, 5, 4, 3, 2, 1), 225: (8, 7, 4, 9, 5, 1, 6, 3, 2),
+            270: (7, 4, 1, 8, 5, 2, 9, 6, 3), 315: (4, 1, 2, 7, 5, 3, 8, 9, 6)},
+    }
+    d_ori, d_rot = 360 / n_orientation, 360 / n_rotation
+    idx = np.zeros((n_orientation * k * k, n_rotation), np.uint8)
+    for i in range(n_orientation):
+        for j in range(k * k):
+            for r in range(n_rotation):
+                angle = d_rot * r
+                layer = (i + math.floor(angle / d_ori)) % n_orientation
+                idx[i * k * k + j, r] = int(layer * k * k + table[k][int(angle)][j])
+    return idx.reshape(n_orientation, k, k, n_rotation)
+
+
+# ---- oracle/_ref: the reference's own code compiled in place (see build_oracle.py) -------
+
+def ref_lib(tag, sem):
+    """tag in {iou, nms, ml}; sem in {cpu, cudasem}.  Returns (CDLL, prefix) or None if absent."""
+    path = os.path.join(HERE, "_ref", "libref_%s_%s.so" % (tag, sem))
+    if not os.path.exists(path):
+        return None
+    L = C.CDLL(path)
+    pre = "ref_%s_%s_" % (tag, sem)
+    f = getattr(L, pre + "single_iou")
+    f.restype, f.argtypes = C.c_float, [_f32p, _f32p]
+    g = getattr(L, pre + "pairwise")
+    g.restype, g.argtypes = None, [_f32p, C.c_int64, _f32p, C.c_int64, _f32p]
+    return L, pre
+
+
+def ref_pairwise(tag, sem, boxes1, boxes2):
+    r = ref_lib(tag, sem)
+    if r is None:
+        return None
+    L, pre = r
+    st = 6 if tag == "ml" else 5
+    b1, b2 = _f32(boxes1).reshape(-1, st), _f32(boxes2).reshape(-1, st)
+    out = np.empty((b1.shape[0], b2.shape[0]), np.float32)
+    getattr(L, pre + "pairwise")(b1, b1.shape[0], b2, b2.shape[0], out)
+    return out
