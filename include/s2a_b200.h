@@ -1,0 +1,160 @@
+/*
+ * s2a_b200.h -- C ABI of libs2a_b200.so: the S2ANet custom-op hot path for NVIDIA B200 (sm_100a).
+ *
+ * Plain C: device pointers, sizes and an explicit CUDA stream (a cudaStream_t passed as void*,
+ * NULL = the legacy default stream).  No torch types.  Every function returns S2A_OK (0) or a
+ * negative status; s2a_last_error() returns a thread-local message for the last failure.
+ * All work is enqueued on `stream`; nothing synchronises the host unless stated.
+ *
+ * Each entry point names the reference (chongkuiqi/S2ANet) interface it replaces; the torch-side
+ * binding that maps the reference's extension-module functions onto these symbols lives in
+ * s2anet_b200/ (Python + ctypes) and is described in INTEGRATION.md.
+ */
+#ifndef S2A_B200_H_
+#define S2A_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define S2A_EXPORT __attribute__((visibility("default")))
+#else
+#define S2A_EXPORT
+#endif
+
+enum {
+  S2A_OK = 0,
+  S2A_ERR_INVALID_ARGUMENT = -1,
+  S2A_ERR_CUDA = -2,
+  S2A_ERR_WORKSPACE = -3,
+  S2A_ERR_UNSUPPORTED = -4
+};
+
+/* element types of activation / weight tensors */
+enum { S2A_F32 = 0, S2A_BF16 = 1, S2A_F16 = 2 };
+
+/* flags of s2a_box_iou_rotated */
+enum {
+  S2A_IOU_DEFAULT = 0,
+  S2A_IOU_NO_REJECT = 1 /* run the polygon clipper on every pair (testing: must not change a bit) */
+};
+
+S2A_EXPORT int s2a_version(void);
+S2A_EXPORT const char* s2a_last_error(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * box_iou_rotated -- replaces box_iou_rotated_cuda()
+ *   reference: utils/box_iou_rotated/src/box_iou_rotated_cuda.cu:65-101 (host), :13-62 (kernel),
+ *              utils/box_iou_rotated/src/box_iou_rotated.h:22-37 (dispatcher)
+ * boxes1 [batch, n, 5], boxes2 [batch, m, 5] fp32 contiguous (x, y, w, h, theta[rad]);
+ * out[b, i, j] = IoU(boxes1[b, i], boxes2[b, j]) written at out + b*n*ld_out + i*ld_out + j
+ * (ld_out >= m, in elements).  batch = 1 is the reference's call; batch > 1 is the batched
+ * anchor x GT assignment of BASELINE config 4.  n == 0 or m == 0 is a no-op.
+ * row_begin/row_end restrict the computed rows to [row_begin, row_end) (anchor-row sharding across
+ * GPUs); pass 0, n for everything.
+ */
+S2A_EXPORT int s2a_box_iou_rotated(const float* boxes1, int64_t n, const float* boxes2, int64_t m,
+                                   int64_t batch, float* out, int64_t ld_out, int64_t row_begin,
+                                   int64_t row_end, int flags, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * nms_rotated / ml_nms_rotated -- replace nms_rotated_cuda()
+ *   reference: utils/nms_rotated/src/nms_rotated_cuda.cu:72-132 (host), :13-69 (kernel)
+ *              utils/ml_nms_rotated/src/nms_rotated_cuda.cu:74-137, :13-71 (label-aware twin)
+ * dets: n rows of 5 fp32 (x, y, w, h, theta), row stride det_stride elements (5 for a packed
+ * tensor, 6 for the reference wrapper's dets[:, :5] view); scores: n fp32, stride score_stride;
+ * labels: n fp32 or NULL (NULL = class-agnostic nms_rotated; non-NULL = ml_nms_rotated: boxes with
+ * different labels never suppress each other).  Suppression predicate: IoU > iou_threshold, IoU
+ * evaluated as IoU(earlier, later) in descending-score order (ties: lower index first).
+ * keep_out: device int64[n]; the first *num_keep_out entries receive the ORIGINAL indices of the
+ * kept boxes in descending-score order.  num_keep_out: device int32.  No host synchronisation
+ * (the reference copies the whole mask to the host and sweeps it there).
+ * workspace: device scratch of at least s2a_nms_rotated_workspace_bytes(n) bytes.
+ */
+S2A_EXPORT size_t s2a_nms_rotated_workspace_bytes(int64_t n);
+S2A_EXPORT int s2a_nms_rotated(const float* dets, int64_t det_stride, const float* scores,
+                               int64_t score_stride, const float* labels, int64_t n,
+                               float iou_threshold, int64_t* keep_out, int32_t* num_keep_out,
+                               void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * multiclass_nms_rotated -- replaces the Python routine of the same name
+ *   reference: utils/bbox_nms_rotated.py:5-64
+ * bboxes [n, 5] fp32, scores [n, num_classes] fp32 (post-sigmoid).  Candidates are the (box, class)
+ * pairs with score > score_thr (strict) in row-major order; ml-NMS at iou_thr; if more than
+ * max_per_img survive only the max_per_img best scores are kept.  Outputs (device):
+ *   dets_out [max_out, 6] (x, y, w, h, theta, score) and labels_out [max_out] fp32, filled for the
+ *   first *num_out rows in descending-score order; num_out int32; max_out = capacity of the output
+ *   buffers (>= min(n*num_classes, max_per_img) to hold every possible result).
+ * Sync-free and batched: `batch` images are processed by the same launches (image b reads
+ * bboxes + b*n*5, scores + b*n*num_classes and writes row b of each output).
+ */
+S2A_EXPORT size_t s2a_multiclass_nms_rotated_workspace_bytes(int64_t n, int64_t num_classes,
+                                                             int64_t batch);
+S2A_EXPORT int s2a_multiclass_nms_rotated(const float* bboxes, const float* scores, int64_t n,
+                                          int64_t num_classes, int64_t batch, float score_thr,
+                                          float iou_thr, int64_t max_per_img, float* dets_out,
+                                          float* labels_out, int32_t* num_out, int64_t max_out,
+                                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * ORN: active rotating filters and rotation-invariant pooling
+ *   reference: models/orn/src/cuda/ActiveRotatingFilter_cuda.cu:19-46, 79-119 (arf_forward),
+ *              :48-76, 122-163 (arf_backward); models/orn/src/vision.cpp:7-12 (exported names);
+ *              models/orn/functions/rotation_invariant_pooling.py:19-27 (pooling)
+ * weight [O, I, nOri, kH, kW]; indices uint8 [nOri*kH*kW, nRot] (1-based destination entry);
+ * out [O*nRot, I*nOri, kH, kW].  dtype in {S2A_F32, S2A_BF16, S2A_F16} (pure data movement).
+ */
+S2A_EXPORT int s2a_arf_forward(const void* weight, const uint8_t* indices, void* out, int O, int I,
+                               int nOri, int kH, int kW, int nRot, int dtype, void* stream);
+S2A_EXPORT int s2a_arf_backward(const void* grad_out, const uint8_t* indices, void* grad_weight,
+                                int O, int I, int nOri, int kH, int kW, int nRot, int dtype,
+                                void* stream);
+/* x [B, C, H, W] -> out [B, C/nOri, H, W]: max over each group of nOri consecutive channels. */
+S2A_EXPORT int s2a_ri_pool_forward(const void* x, void* out, int64_t B, int64_t C, int64_t HW,
+                                   int nOri, int dtype, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Deformable convolution forward -- replaces deform_conv_forward_cuda()
+ *   reference: models/dcn/src/deform_conv_cuda.cpp:152-260 (host), models/dcn/src/
+ *              deform_conv_cuda_kernel.cu:189-242, 83-114 (im2col + bilinear)
+ * x [B, C, H, W], offset [B, dgroups*2*kH*kW, Ho, Wo], weight [Co, C/groups, kH, kW],
+ * out [B, Co, Ho, Wo]; all NCHW contiguous fp32.  One fused pass: sampling, contraction and the
+ * NCHW store happen in a single kernel (no column buffer, no output transpose).
+ * relu != 0 applies max(.,0) in the epilogue (AlignConv).
+ */
+S2A_EXPORT int s2a_deform_conv_forward_f32(const float* x, const float* offset,
+                                           const float* weight, float* out, int B, int C, int H,
+                                           int W, int Co, int kH, int kW, int strideH, int strideW,
+                                           int padH, int padW, int dilH, int dilW, int groups,
+                                           int dgroups, int relu, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * AlignConv forward -- replaces AlignConv.forward (offset generation + DeformConv + ReLU)
+ *   reference: models/alignconv.py:29-98; models/dcn/deform_conv.py:15-71
+ * x [B, C, H, W] NCHW fp32, anchors [B, H, W, 5] fp32 (image pixels, theta rad), weight
+ * [Co, C, 3, 3] fp32, out [B, Co, H, W] fp32.  The 18-channel offset field is never materialised:
+ * sample positions are derived from the anchors inside the kernel.
+ */
+S2A_EXPORT int s2a_alignconv_forward_f32(const float* x, const float* anchors, const float* weight,
+                                         float* out, int B, int C, int H, int W, int Co,
+                                         float stride, void* stream);
+
+/* ORConv2d forward (3x3, pad 1, stride 1) -- replaces ORConv2d.forward = conv2d(x, ARF(w), bias)
+ *   reference: models/orn/modules/ORConv.py:77-82
+ * x [B, I*nOri, H, W] fp32; weight [O, I, nOri, 3, 3]; indices uint8 [nOri*9, nRot]; bias
+ * [O*nRot] or NULL; out [B, O*nRot, H, W]; pooled (optional, may be NULL) [B, O*nRot/nRot... ]
+ * = RotationInvariantPooling over groups of nRot consecutive output channels, produced by the
+ * same kernel's epilogue. */
+S2A_EXPORT int s2a_orconv_forward_f32(const float* x, const float* weight, const uint8_t* indices,
+                                      const float* bias, float* out, float* pooled, int B, int H,
+                                      int W, int O, int I, int nOri, int nRot, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* S2A_B200_H_ */

@@ -75,3 +75,62 @@ if __name__ == "__main__":
     print(build_oracle(force="--force" in sys.argv))
     for o in build_ref_shims(force="--force" in sys.argv):
         print(o)
+
+
+# ---- the reference's own torch extensions, compiled from /root/reference in place ---------------
+
+REF_EXTS_CPU = {
+    # name (== TORCH_EXTENSION_NAME == the reference's module name) : sources relative to REF
+    "box_iou_rotated_cuda": ["utils/box_iou_rotated/src/box_iou_rotated_cpu.cpp"],
+    "nms_rotated_cuda": ["utils/nms_rotated/src/nms_rotated_cpu.cpp"],
+    "ml_nms_rotated_cuda": ["utils/ml_nms_rotated/src/nms_rotated_cpu.cpp"],
+}
+REF_EXTS_GPU = {
+    "box_iou_rotated_cuda": ["utils/box_iou_rotated/src/box_iou_rotated_cpu.cpp",
+                             "utils/box_iou_rotated/src/box_iou_rotated_cuda.cu"],
+    "nms_rotated_cuda": ["utils/nms_rotated/src/nms_rotated_cpu.cpp", "utils/nms_rotated/src/nms_rotated_cuda.cu"],
+    "ml_nms_rotated_cuda": ["utils/ml_nms_rotated/src/nms_rotated_cpu.cpp",
+                            "utils/ml_nms_rotated/src/nms_rotated_cuda.cu"],
+    "deform_conv_cuda": ["models/dcn/src/deform_conv_cuda.cpp", "models/dcn/src/deform_conv_cuda_kernel.cu"],
+}
+
+
+def build_ref_extensions(kind="cpu", names=None, verbose=False):
+    """Compile the UNMODIFIED reference extension sources where they lie (torch cpp_extension,
+    ninja) into oracle/_ref/ext_<kind>/<name>/<name>.so.  kind="cpu": the reference's CPU kernels
+    (golden vectors, CPU baseline).  kind="gpu": its CUDA kernels for sm_100a (parity witness on
+    the GPU box).  Returns {name: path}."""
+    if not os.path.isdir(REF):
+        return {}
+    os.environ.setdefault("TORCH_CUDA_ARCH_LIST", "10.0a")
+    os.environ.setdefault("MAX_JOBS", "8")
+    from torch.utils import cpp_extension
+    table = REF_EXTS_CPU if kind == "cpu" else REF_EXTS_GPU
+    out = {}
+    for name, srcs in table.items():
+        if names and name not in names:
+            continue
+        bdir = os.path.join(REF_OUT, "ext_%s" % kind, name)
+        os.makedirs(bdir, exist_ok=True)
+        so = os.path.join(bdir, name + ".so")
+        full = [os.path.join(REF, s) for s in srcs]
+        if _stale(so, full):
+            cpp_extension.load(name=name, sources=full, build_directory=bdir, verbose=verbose,
+                               extra_cflags=["-O2"] + (["-DWITH_CUDA"] if kind == "gpu" else []),
+                               extra_cuda_cflags=["-O2", "-DWITH_CUDA", "-gencode", "arch=compute_100a,code=sm_100a"],
+                               with_cuda=(kind == "gpu"), is_python_module=False)
+        out[name] = so
+    return out
+
+
+def load_ref_extension(name, kind="cpu"):
+    """Import a prebuilt reference extension from oracle/_ref (no compilation, no /root/reference)."""
+    import importlib.util
+    so = os.path.join(REF_OUT, "ext_%s" % kind, name, name + ".so")
+    if not os.path.exists(so):
+        return None
+    import torch  # noqa: F401  (the extension links against libtorch)
+    spec = importlib.util.spec_from_file_location(name, so)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod

@@ -1,0 +1,334 @@
+// conv_f32.cu -- fp32 fused gather + implicit-GEMM convolution for sm_100a (the exact-arithmetic
+// path of AlignConv / DeformConv / ORConv2d; the bf16 tensor-core path lives in conv_tc.cu).
+//
+// Replaces (reference):
+//   * deform_conv_forward_cuda: models/dcn/src/deform_conv_cuda.cpp:152-260, with the im2col of
+//     models/dcn/src/deform_conv_cuda_kernel.cu:189-242 and the bilinear rule of :83-114;
+//   * AlignConv.get_offset + forward: models/alignconv.py:29-98 (offset field generated in-kernel
+//     from the anchors, never written to memory);
+//   * ORConv2d.forward: models/orn/modules/ORConv.py:77-82 = conv2d(x, ARF(weight), bias), with the
+//     ARF rotation (models/orn/src/cuda/ActiveRotatingFilter_cuda.cu:19-46) folded into the weight
+//     tile load and RotationInvariantPooling (models/orn/functions/rotation_invariant_pooling.py
+//     :19-27) folded into the epilogue.
+//
+// One CTA computes a 64 (positions) x 64 (output channels) tile.  The reference materialises a
+// [C*9, H*W] column matrix in HBM (151 MB at P3), runs cuBLAS over it, then transposes/copies the
+// result; here the sampled A tile only ever exists in shared memory: per 8-channel chunk the CTA
+// blends the four bilinear corners straight into smem, multiplies against the matching weight slice
+// and keeps the 4x4 per-thread accumulators in registers until the fused ReLU/bias/pool epilogue.
+#include "common.cuh"
+
+namespace s2a {
+
+constexpr int BM = 64, BN = 64, CK = 8;
+constexpr int kConvThreads = 256;
+constexpr int kMaxTaps = 9;           // kH*kW <= 9 on this path (3x3 and smaller)
+constexpr int BNP = BN + 4;            // padded B-tile row (keeps float4 alignment, breaks store conflicts)
+
+enum { MODE_DEFORM = 0, MODE_ALIGN = 1, MODE_PLAIN = 2 };
+
+struct ConvParams {
+  const float* x; const float* aux; const float* w; const float* bias; const uint8_t* arf_idx;
+  float* out; float* pooled;
+  int B, C, H, W, Co, Ho, Wo, kH, kW, sH, sW, pH, pW, dH, dW, groups, dgroups, relu;
+  float astride;                       // AlignConv feature stride
+  int arfO, arfI, nOri, nRot, pool;    // ORConv
+};
+
+struct Sample { int off[4]; float wt[4]; };   // corner offsets inside one channel plane + weights
+
+// bilinear corner table entry following deform_conv_cuda_kernel.cu:83-114 / :228
+__device__ __forceinline__ void make_sample(float h, float w, int H, int W, Sample& s) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) { s.off[q] = 0; s.wt[q] = 0.0f; }
+  if (!(h > -1.0f && w > -1.0f && h < (float)H && w < (float)W)) return;
+  const int hl = (int)floorf(h), wl = (int)floorf(w);
+  const int hh = hl + 1, wh = wl + 1;
+  const float lh = h - (float)hl, lw = w - (float)wl;
+  const float uh = 1.0f - lh, uw = 1.0f - lw;
+  if (hl >= 0 && wl >= 0) { s.off[0] = hl * W + wl; s.wt[0] = uh * uw; }
+  if (hl >= 0 && wh <= W - 1) { s.off[1] = hl * W + wh; s.wt[1] = uh * lw; }
+  if (hh <= H - 1 && wl >= 0) { s.off[2] = hh * W + wl; s.wt[2] = lh * uw; }
+  if (hh <= H - 1 && wh <= W - 1) { s.off[3] = hh * W + wh; s.wt[3] = lh * lw; }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kConvThreads)
+conv_gather_f32_kernel(const ConvParams p) {
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  Sample* s_samp = reinterpret_cast<Sample*>(s_raw);                                    // [BM*9]   18 KB
+  float (*s_a)[BM] = reinterpret_cast<float (*)[BM]>(s_raw + sizeof(Sample) * BM * kMaxTaps);   // [72][64] 18 KB
+  float (*s_b)[BNP] = reinterpret_cast<float (*)[BNP]>(s_raw + sizeof(Sample) * BM * kMaxTaps +
+                                                       sizeof(float) * CK * kMaxTaps * BM);     // [72][68] 19 KB
+  __shared__ uint8_t s_inv[8 * 72];                        // ARF inverse map [nRot][nEntry]
+
+  const int tid = threadIdx.x;
+  const int taps = p.kH * p.kW;
+  const int HoWo = p.Ho * p.Wo;
+  const int b = blockIdx.z;
+  const int m0 = blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+  const int Cg = p.C / p.groups, Cog = p.Co / p.groups;
+  const int g = n0 / Cog;                                   // host guarantees tiles do not straddle groups
+  const int cpd = p.C / p.dgroups;
+  const float* xb = p.x + (size_t)b * p.C * p.H * p.W;
+
+  if (MODE == MODE_PLAIN && p.arf_idx) {
+    const int nEntry = p.nOri * taps;
+    for (int i = tid; i < nEntry * p.nRot; i += kConvThreads) {
+      const int l = i / p.nRot, k = i % p.nRot;
+      s_inv[k * nEntry + ((int)p.arf_idx[i] - 1)] = (uint8_t)l;
+    }
+  }
+
+  // ---- sample table (per position x tap); rebuilt per deformable group when dgroups > 1 ----
+  auto build_samples = [&](int dg) {
+    for (int i = tid; i < BM * taps; i += kConvThreads) {
+      const int m = i / taps, t = i % taps;
+      const int pos = m0 + m;
+      Sample s;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { s.off[q] = 0; s.wt[q] = 0.0f; }
+      if (pos < HoWo) {
+        const int ho = pos / p.Wo, wo = pos % p.Wo;
+        const int ti = t / p.kW, tj = t % p.kW;
+        if (MODE == MODE_PLAIN) {
+          const int h = ho * p.sH - p.pH + ti * p.dH, w = wo * p.sW - p.pW + tj * p.dW;
+          if (h >= 0 && h < p.H && w >= 0 && w < p.W) { s.off[0] = h * p.W + w; s.wt[0] = 1.0f; }
+        } else if (MODE == MODE_DEFORM) {
+          const float* ob = p.aux + ((size_t)b * p.dgroups + dg) * 2 * taps * HoWo;
+          const float oy = ob[(size_t)(2 * t) * HoWo + pos];
+          const float ox = ob[(size_t)(2 * t + 1) * HoWo + pos];
+          const float h = (float)(ho * p.sH - p.pH + ti * p.dH) + oy;
+          const float w = (float)(wo * p.sW - p.pW + tj * p.dW) + ox;
+          make_sample(h, w, p.H, p.W, s);
+        } else {   // MODE_ALIGN: models/alignconv.py:29-86, operation order preserved
+          const float* a = p.aux + ((size_t)b * HoWo + pos) * 5;
+          const float ax = a[0] / p.astride, ay = a[1] / p.astride;
+          const float aw = a[2] / p.astride, ah = a[3] / p.astride;
+          const float cs = cosf(a[4]), sn = sinf(a[4]);
+          const float dw = aw / 3.0f, dh = ah / 3.0f;
+          const float fi = (float)(ti - 1), fj = (float)(tj - 1);
+          const float tx = __fmul_rn(dw, fj), ty = __fmul_rn(dh, fi);
+          const float xr = __fsub_rn(__fmul_rn(cs, tx), __fmul_rn(sn, ty));
+          const float yr = __fadd_rn(__fmul_rn(sn, tx), __fmul_rn(cs, ty));
+          const float xa = __fadd_rn(xr, ax), ya = __fadd_rn(yr, ay);
+          const float offx = __fsub_rn(xa, __fadd_rn((float)wo, fj));
+          const float offy = __fsub_rn(ya, __fadd_rn((float)ho, fi));
+          // deform-conv adds the offset back onto the regular tap position (:223-227)
+          const float h = __fadd_rn((float)(ho - 1 + ti), offy);
+          const float w = __fadd_rn((float)(wo - 1 + tj), offx);
+          make_sample(h, w, p.H, p.W, s);
+        }
+      }
+      s_samp[m * kMaxTaps + t] = s;
+    }
+  };
+
+  const int tx = tid & 15, ty = tid >> 4;          // 16 x 16 threads, 4 (m) x 4 (n) outputs each
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+
+  int cur_dg = -1;
+  const int kk = CK * taps;                          // rows of the smem K chunk actually used
+  for (int c0 = 0; c0 < Cg; c0 += CK) {
+    const int cin0 = g * Cg + c0;                    // first input channel of this chunk
+    const int dg = (MODE == MODE_DEFORM) ? cin0 / cpd : 0;
+    if (dg != cur_dg) {
+      __syncthreads();
+      build_samples(dg);
+      cur_dg = dg;
+    }
+    __syncthreads();                                 // previous chunk consumed; samples visible
+    // A tile: s_a[c*taps + t][m] = sum_q wt_q * x[cin0 + c][off_q]
+    for (int i = tid; i < kk * BM; i += kConvThreads) {
+      const int m = i & (BM - 1);
+      const int kr = i >> 6;
+      const int c = kr / taps, t = kr - c * taps;
+      float v = 0.0f;
+      if (c0 + c < Cg) {
+        const Sample& s = s_samp[m * kMaxTaps + t];
+        const float* plane = xb + (size_t)(cin0 + c) * p.H * p.W;
+        if (MODE == MODE_PLAIN) {
+          v = s.wt[0] != 0.0f ? plane[s.off[0]] : 0.0f;
+        } else {
+          v = s.wt[0] * plane[s.off[0]] + s.wt[1] * plane[s.off[1]] + s.wt[2] * plane[s.off[2]] +
+              s.wt[3] * plane[s.off[3]];
+        }
+      }
+      s_a[kr][m] = v;
+    }
+    // B tile: s_b[c*taps + t][n] = W[n0 + n][c0 + c][t]
+    for (int i = tid; i < kk * BN; i += kConvThreads) {
+      const int kr = i % kk;
+      const int nn = i / kk;
+      const int c = kr / taps, t = kr - c * taps;
+      const int co = n0 + nn;
+      float v = 0.0f;
+      if (co < p.Co && c0 + c < Cg) {
+        if (MODE == MODE_PLAIN && p.arf_idx) {
+          // rotated filter (o, k): entry dst of input plane i comes from base entry inv[k][dst]
+          const int o = co / p.nRot, k = co % p.nRot;
+          const int cin = c0 + c;
+          const int ii = cin / p.nOri, lay = cin % p.nOri;
+          const int nEntry = p.nOri * taps;
+          const int l = s_inv[k * nEntry + lay * taps + t];
+          v = p.w[((size_t)o * p.arfI + ii) * nEntry + l];
+        } else {
+          v = p.w[((size_t)co * Cg + (c0 + c)) * taps + t];
+        }
+      }
+      s_b[kr][nn] = v;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int k = 0; k < kk; ++k) {
+      const float4 av = *reinterpret_cast<const float4*>(&s_a[k][tx * 4]);
+      const float4 bv = *reinterpret_cast<const float4*>(&s_b[k][ty * 4]);
+      const float a4[4] = {av.x, av.y, av.z, av.w};
+      const float b4[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a4[i], b4[j], acc[i][j]);
+    }
+  }
+
+  // ---- epilogue: bias, ReLU, NCHW store, optional orientation max-pool ----
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int co = n0 + ty * 4 + j;
+    const float bv = (p.bias && co < p.Co) ? p.bias[co] : 0.0f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float v = acc[i][j] + bv;
+      if (p.relu) v = fmaxf(v, 0.0f);
+      acc[i][j] = v;
+    }
+    if (co < p.Co) {
+      float* o = p.out + ((size_t)b * p.Co + co) * HoWo;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int pos = m0 + tx * 4 + i;
+        if (pos < HoWo) o[pos] = acc[i][j];
+      }
+    }
+  }
+  if (p.pooled) {
+    // groups of `pool` (= 8) consecutive output channels: this thread's 4 + the partner's 4 (lane ^ 16)
+    float mx[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float v = fmaxf(fmaxf(acc[i][0], acc[i][1]), fmaxf(acc[i][2], acc[i][3]));
+      const float o = __shfl_xor_sync(0xffffffffu, v, 16);
+      mx[i] = fmaxf(v, o);
+    }
+    if ((ty & 1) == 0) {
+      const int cg = (n0 + ty * 4) / 8;
+      if (n0 + ty * 4 < p.Co) {
+        float* o = p.pooled + ((size_t)b * (p.Co / 8) + cg) * HoWo;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int pos = m0 + tx * 4 + i;
+          if (pos < HoWo) o[pos] = mx[i];
+        }
+      }
+    }
+  }
+}
+
+constexpr size_t kConvSmem = sizeof(Sample) * BM * kMaxTaps + sizeof(float) * CK * kMaxTaps * (BM + BNP);
+
+template <int MODE>
+static cudaError_t launch_conv_mode(dim3 grid, const ConvParams& p, cudaStream_t st) {
+  auto kern = conv_gather_f32_kernel<MODE>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kConvSmem);
+  if (e != cudaSuccess) return e;
+  kern<<<grid, kConvThreads, kConvSmem, st>>>(p);
+  return cudaSuccess;
+}
+
+static int launch_conv(int mode, const ConvParams& p, cudaStream_t st) {
+  dim3 grid((unsigned)ceil_div((int64_t)p.Ho * p.Wo, BM), (unsigned)ceil_div(p.Co, BN), (unsigned)p.B);
+  if (mode == MODE_DEFORM) S2A_CUDA_OK(launch_conv_mode<MODE_DEFORM>(grid, p, st));
+  else if (mode == MODE_ALIGN) S2A_CUDA_OK(launch_conv_mode<MODE_ALIGN>(grid, p, st));
+  else S2A_CUDA_OK(launch_conv_mode<MODE_PLAIN>(grid, p, st));
+  S2A_LAUNCH_OK("conv_gather_f32_kernel");
+  return S2A_OK;
+}
+
+}  // namespace s2a
+
+extern "C" int s2a_deform_conv_forward_f32(const float* x, const float* offset, const float* weight, float* out,
+                                           int B, int C, int H, int W, int Co, int kH, int kW, int strideH,
+                                           int strideW, int padH, int padW, int dilH, int dilW, int groups,
+                                           int dgroups, int relu, void* stream) {
+  using namespace s2a;
+  S2A_CHECK_ARG(B >= 0 && C > 0 && H > 0 && W > 0 && Co > 0, "deform_conv: bad tensor sizes");
+  S2A_CHECK_ARG(kH > 0 && kW > 0, "kernel size should be greater than zero, but got kH: %d kW: %d", kH, kW);
+  S2A_CHECK_ARG(strideH > 0 && strideW > 0, "stride should be greater than zero, but got dH: %d dW: %d", strideH,
+                strideW);
+  S2A_CHECK_ARG(dilH > 0 && dilW > 0, "dilation should be greater than 0, but got dilationH: %d dilationW: %d",
+                dilH, dilW);
+  S2A_CHECK_ARG(groups > 0 && dgroups > 0 && C % groups == 0 && Co % groups == 0, "deform_conv: bad groups");
+  S2A_CHECK_ARG(C % dgroups == 0, "input channels must divide deformable group size");
+  S2A_CHECK_ARG(H >= kH && W >= kW, "input image is smaller than kernel");
+  const int Ho = (H + 2 * padH - (dilH * (kH - 1) + 1)) / strideH + 1;
+  const int Wo = (W + 2 * padW - (dilW * (kW - 1) + 1)) / strideW + 1;
+  S2A_CHECK_ARG(Ho >= 1 && Wo >= 1, "deform_conv: output size is too small");
+  if (kH * kW > kMaxTaps) { set_error("deform_conv: kernels larger than 3x3 are not supported"); return S2A_ERR_UNSUPPORTED; }
+  if (groups > 1 && (Co / groups) % BN != 0) {
+    set_error("deform_conv: groups > 1 needs (Co/groups) %% %d == 0", BN);
+    return S2A_ERR_UNSUPPORTED;
+  }
+  if (dgroups > 1 && ((C / dgroups) % CK != 0 || (C / groups) % CK != 0)) {
+    set_error("deform_conv: deformable_groups > 1 needs channel blocks that are multiples of %d", CK);
+    return S2A_ERR_UNSUPPORTED;
+  }
+  if (B == 0) return S2A_OK;
+  S2A_CHECK_ARG(x && offset && weight && out, "deform_conv: null pointer");
+  S2A_CHECK_ARG(B <= 65535, "deform_conv: batch must be <= 65535");
+  ConvParams p{};
+  p.x = x; p.aux = offset; p.w = weight; p.out = out;
+  p.B = B; p.C = C; p.H = H; p.W = W; p.Co = Co; p.Ho = Ho; p.Wo = Wo; p.kH = kH; p.kW = kW;
+  p.sH = strideH; p.sW = strideW; p.pH = padH; p.pW = padW; p.dH = dilH; p.dW = dilW;
+  p.groups = groups; p.dgroups = dgroups; p.relu = relu;
+  return launch_conv(MODE_DEFORM, p, (cudaStream_t)stream);
+}
+
+extern "C" int s2a_alignconv_forward_f32(const float* x, const float* anchors, const float* weight, float* out,
+                                         int B, int C, int H, int W, int Co, float stride, void* stream) {
+  using namespace s2a;
+  S2A_CHECK_ARG(B >= 0 && C > 0 && H > 0 && W > 0 && Co > 0, "alignconv: bad tensor sizes");
+  S2A_CHECK_ARG(stride > 0.0f, "alignconv: stride must be positive");
+  if (B == 0) return S2A_OK;
+  S2A_CHECK_ARG(x && anchors && weight && out, "alignconv: null pointer");
+  S2A_CHECK_ARG(B <= 65535, "alignconv: batch must be <= 65535");
+  ConvParams p{};
+  p.x = x; p.aux = anchors; p.w = weight; p.out = out;
+  p.B = B; p.C = C; p.H = H; p.W = W; p.Co = Co; p.Ho = H; p.Wo = W; p.kH = 3; p.kW = 3;
+  p.sH = p.sW = 1; p.pH = p.pW = 1; p.dH = p.dW = 1; p.groups = 1; p.dgroups = 1; p.relu = 1;
+  p.astride = stride;
+  return launch_conv(MODE_ALIGN, p, (cudaStream_t)stream);
+}
+
+extern "C" int s2a_orconv_forward_f32(const float* x, const float* weight, const uint8_t* indices,
+                                      const float* bias, float* out, float* pooled, int B, int H, int W, int O,
+                                      int I, int nOri, int nRot, void* stream) {
+  using namespace s2a;
+  S2A_CHECK_ARG(B >= 0 && H > 0 && W > 0 && O > 0 && I > 0, "orconv: bad tensor sizes");
+  S2A_CHECK_ARG(nOri >= 1 && nOri <= 8 && nRot >= 1 && nRot <= 8, "orconv: nOrientation/nRotation must be in [1, 8]");
+  S2A_CHECK_ARG(!pooled || ((O * nRot) % 8 == 0), "orconv: pooling needs O*nRot %% 8 == 0");
+  if (B == 0) return S2A_OK;
+  S2A_CHECK_ARG(x && weight && indices && out, "orconv: null pointer");
+  S2A_CHECK_ARG(B <= 65535, "orconv: batch must be <= 65535");
+  ConvParams p{};
+  p.x = x; p.w = weight; p.bias = bias; p.arf_idx = indices; p.out = out; p.pooled = pooled;
+  p.B = B; p.C = I * nOri; p.H = H; p.W = W; p.Co = O * nRot; p.Ho = H; p.Wo = W; p.kH = 3; p.kW = 3;
+  p.sH = p.sW = 1; p.pH = p.pW = 1; p.dH = p.dW = 1; p.groups = 1; p.dgroups = 1; p.relu = 0;
+  p.arfO = O; p.arfI = I; p.nOri = nOri; p.nRot = nRot; p.pool = 8;
+  return launch_conv(MODE_PLAIN, p, (cudaStream_t)stream);
+}

@@ -1,0 +1,590 @@
+// nms_rotated.cu -- rotated NMS for sm_100a: nms_rotated, ml_nms_rotated (generic, score-ordered)
+// and the fused, batched, class-segmented multiclass_nms_rotated.
+//
+// Replaces (reference): utils/nms_rotated/src/nms_rotated_cuda.cu:13-69 (mask kernel), :72-132
+// (host: sort, mask, D2H copy, serial CPU sweep, H2D); utils/ml_nms_rotated/src/nms_rotated_cuda.cu
+// :13-71, :74-137 (label-aware twin); utils/bbox_nms_rotated.py:5-64 (multiclass wrapper).
+//
+// What is different from the reference, and why:
+//   * the suppression mask is computed for the upper triangle only (the reference computes both
+//     triangles and never reads the lower one), 64x64 pairs per CTA, with the same
+//     classify -> compact -> clip scheme as box_iou_rotated.cu so lanes are not parked on the
+//     ~95 % of pairs that are trivially disjoint;
+//   * the greedy sweep runs ON THE DEVICE in one CTA: each 64-box block is resolved by one warp with
+//     register shuffles, then its kept rows are OR-ed into the running "removed" bitmap by the whole
+//     CTA.  No device->host copy of the mask, no host sweep, no synchronisation;
+//   * multiclass: (box, class) candidates never interact across classes, so the fused path sorts and
+//     sweeps each (image, class) segment independently (15x fewer pair tests, 15 sweeps in parallel)
+//     and merges the survivors by rank (binary searches), instead of sorting all candidates globally.
+// Results are identical to the reference CUDA semantics: predicate IoU > thr, IoU(earlier, later).
+#include <cub/cub.cuh>
+#include <float.h>
+
+#include "common.cuh"
+#include "rbox_iou.cuh"
+
+namespace s2a {
+
+constexpr int kBlk = 64;            // boxes per mask word
+constexpr int kMaskThreads = 256;
+constexpr int kSweepThreads = 1024;
+
+// ------------------------------------------------------------------------------------------------
+// shared tile body: 64 row boxes x 64 column boxes -> 64 suppression words
+// ------------------------------------------------------------------------------------------------
+struct MaskTileSmem {
+  RBox row[kBlk];
+  RBox col[kBlk];
+  float lrow[kBlk];
+  float lcol[kBlk];
+  unsigned long long word[kBlk];
+  uint16_t list[kBlk * kBlk];
+  int count;
+};
+
+// rows/cols: pointers to the first prepared box of the row/col block; nr/nc valid counts;
+// diag: row block == col block (only c > r is evaluated); labels may be null.
+__device__ __forceinline__ void mask_tile(MaskTileSmem& s, const RBox* __restrict__ rows,
+                                          const RBox* __restrict__ cols,
+                                          const float* __restrict__ lrows,
+                                          const float* __restrict__ lcols, int nr, int nc, bool diag,
+                                          float thr) {
+  const int tid = threadIdx.x;
+  if (tid < kBlk) {
+    if (tid < nr) {
+      s.row[tid] = rows[tid];
+      s.lrow[tid] = lrows ? lrows[tid] : 0.0f;
+    }
+    s.word[tid] = 0ull;
+  } else if (tid < 2 * kBlk) {
+    const int c = tid - kBlk;
+    if (c < nc) {
+      s.col[c] = cols[c];
+      s.lcol[c] = lcols ? lcols[c] : 0.0f;
+    }
+  }
+  if (tid == 0) s.count = 0;
+  __syncthreads();
+
+  const int c = tid & (kBlk - 1);
+  const int r0 = tid >> 6;
+  const unsigned lane = tid & 31;
+  const bool zero_suppresses = 0.0f > thr;   // only for negative thresholds
+  RBox cb;
+  float lc = 0.0f;
+  if (c < nc) { cb = s.col[c]; lc = s.lcol[c]; }
+#pragma unroll 4
+  for (int k = 0; k < kBlk / 4; ++k) {
+    const int r = r0 + 4 * k;
+    bool clip = false;
+    if (r < nr && c < nc && (!diag || c > r)) {
+      int cls = RB_ZERO;
+      if (s.lrow[r] == lc) cls = rbox_classify(s.row[r], cb);   // labels differ -> IoU := 0
+      if (cls == RB_CLIP) clip = true;
+      else if (zero_suppresses) atomicOr(&s.word[r], 1ull << c);
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, clip);
+    if (bal) {
+      int base = 0;
+      if (lane == 0) base = atomicAdd(&s.count, __popc(bal));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (clip) s.list[base + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)(r * kBlk + c);
+    }
+  }
+  __syncthreads();
+  const int cnt = s.count;
+  for (int k = tid; k < cnt; k += kMaskThreads) {
+    const int p = s.list[k];
+    const int r = p >> 6, cc = p & (kBlk - 1);
+    if (rbox_iou_clip(s.row[r], s.col[cc]) > thr) atomicOr(&s.word[r], 1ull << cc);
+  }
+  __syncthreads();
+}
+
+// linear index over the upper triangle (row-major, diagonal included) of a cb x cb tile grid
+__device__ __forceinline__ void decode_upper(long long t, int cb, int& rb, int& cbk) {
+  // row r starts at r*cb - r(r-1)/2
+  double fcb = (double)cb + 0.5;
+  int r = (int)floor(fcb - sqrt(fcb * fcb - 2.0 * (double)t));
+  if (r < 0) r = 0;
+  if (r > cb - 1) r = cb - 1;
+  while (r > 0 && (long long)r * cb - (long long)r * (r - 1) / 2 > t) --r;
+  while (r < cb - 1 && (long long)(r + 1) * cb - (long long)(r + 1) * r / 2 <= t) ++r;
+  rb = r;
+  cbk = r + (int)(t - ((long long)r * cb - (long long)r * (r - 1) / 2));
+}
+
+// ------------------------------------------------------------------------------------------------
+// generic path
+// ------------------------------------------------------------------------------------------------
+__global__ void nms_gather_keys_kernel(const float* __restrict__ scores, int64_t stride, int n,
+                                       float* __restrict__ keys, int* __restrict__ vals) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { keys[i] = scores[(int64_t)i * stride]; vals[i] = i; }
+}
+
+__global__ void nms_gather_prep_kernel(const float* __restrict__ dets, int64_t stride,
+                                       const float* __restrict__ labels, const int* __restrict__ order,
+                                       int n, RBox* __restrict__ boxes, float* __restrict__ lab_sorted) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const int src = order[i];
+    const float* d = dets + (int64_t)src * stride;
+    RBox b;
+    rbox_prep(d[0], d[1], d[2], d[3], d[4], b);
+    boxes[i] = b;
+    if (labels) lab_sorted[i] = labels[src];
+  }
+}
+
+__global__ void __launch_bounds__(kMaskThreads)
+nms_mask_kernel(const RBox* __restrict__ boxes, const float* __restrict__ labels, int n, int cb,
+                float thr, unsigned long long* __restrict__ mask) {
+  __shared__ MaskTileSmem s;
+  int rb, cbk;
+  decode_upper((long long)blockIdx.x, cb, rb, cbk);
+  const int nr = min(kBlk, n - rb * kBlk), nc = min(kBlk, n - cbk * kBlk);
+  mask_tile(s, boxes + (size_t)rb * kBlk, boxes + (size_t)cbk * kBlk,
+            labels ? labels + (size_t)rb * kBlk : nullptr, labels ? labels + (size_t)cbk * kBlk : nullptr,
+            nr, nc, rb == cbk, thr);
+  if (threadIdx.x < nr) mask[((size_t)rb * kBlk + threadIdx.x) * cb + cbk] = s.word[threadIdx.x];
+}
+
+// Greedy sweep of one score-ordered segment of n boxes.  mask row stride = ld words; only words
+// j >= row/64 of a row are ever read.  Writes kept positions (0..n-1, ascending) through `emit`.
+// s_remv: cb words of shared memory.  Must be called by all kSweepThreads threads of the CTA.
+template <class Emit>
+__device__ __forceinline__ int sweep_segment(const unsigned long long* __restrict__ mask, int n, int ld,
+                                             unsigned long long* s_remv, unsigned long long* s_kw,
+                                             Emit emit) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int cb = (n + kBlk - 1) / kBlk;
+  for (int j = tid; j < cb; j += kSweepThreads) s_remv[j] = 0ull;
+  __syncthreads();
+  int total = 0;
+  for (int b = 0; b < cb; ++b) {
+    const int nb = min(kBlk, n - b * kBlk);
+    if (warp == 0) {
+      unsigned long long rem = s_remv[b];
+      const int rlo = b * kBlk + lane, rhi = rlo + 32;
+      unsigned long long dlo = (rlo < n) ? mask[(size_t)rlo * ld + b] : 0ull;
+      unsigned long long dhi = (rhi < n) ? mask[(size_t)rhi * ld + b] : 0ull;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const unsigned long long w = __shfl_sync(0xffffffffu, dlo, i);
+        if (!((rem >> i) & 1ull)) rem |= w;
+      }
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const unsigned long long w = __shfl_sync(0xffffffffu, dhi, i);
+        if (!((rem >> (32 + i)) & 1ull)) rem |= w;
+      }
+      const unsigned long long valid = (nb == kBlk) ? ~0ull : ((1ull << nb) - 1ull);
+      const unsigned long long kw = ~rem & valid;
+      if (lane == 0) *s_kw = kw;
+      if ((kw >> lane) & 1ull) emit(total + __popcll(kw & ((1ull << lane) - 1ull)), b * kBlk + lane);
+      if ((kw >> (lane + 32)) & 1ull)
+        emit(total + __popcll(kw & ((1ull << (lane + 32)) - 1ull)), b * kBlk + 32 + lane);
+    }
+    __syncthreads();
+    const unsigned long long kw = *s_kw;
+    total += __popcll(kw);
+    // OR the kept rows of this block into the removed-bitmap of all later blocks:
+    // lanes walk the columns (coalesced), warps split the 64 rows two each.
+    if (b + 1 < cb) {
+      const int ra = 2 * warp, rbb = 2 * warp + 1;
+      const bool ka = (kw >> ra) & 1ull, kb2 = (kw >> rbb) & 1ull;
+      if (ka || kb2) {
+        const unsigned long long* pa = mask + (size_t)(b * kBlk + ra) * ld;
+        const unsigned long long* pb = mask + (size_t)(b * kBlk + rbb) * ld;
+        for (int j = b + 1 + lane; j < cb; j += 32) {
+          unsigned long long acc = 0ull;
+          if (ka) acc |= pa[j];
+          if (kb2) acc |= pb[j];
+          if (acc) atomicOr(&s_remv[j], acc);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  return total;
+}
+
+__global__ void __launch_bounds__(kSweepThreads)
+nms_sweep_kernel(const unsigned long long* __restrict__ mask, const int* __restrict__ order, int n,
+                 int64_t* __restrict__ keep_out, int32_t* __restrict__ num_keep) {
+  extern __shared__ unsigned long long s_dyn[];
+  __shared__ unsigned long long s_kw;
+  const int cb = (n + kBlk - 1) / kBlk;
+  int total = sweep_segment(mask, n, cb, s_dyn, &s_kw,
+                            [&](int pos, int sorted_idx) { keep_out[pos] = (int64_t)order[sorted_idx]; });
+  if (threadIdx.x == 0) *num_keep = total;
+}
+
+struct NmsWorkspace {
+  float* keys_in; float* keys_out; int* vals_in; int* vals_out; RBox* boxes; float* labels;
+  unsigned long long* mask; void* cub_tmp; size_t cub_bytes; size_t total;
+};
+
+static size_t cub_sort_bytes(int64_t n) {
+  size_t bytes = 0;
+  cub::DeviceRadixSort::SortPairsDescending(nullptr, bytes, (const float*)nullptr, (float*)nullptr,
+                                            (const int*)nullptr, (int*)nullptr, (int)n);
+  return bytes;
+}
+
+static NmsWorkspace carve_nms(void* base, int64_t n) {
+  NmsWorkspace w;
+  const int64_t cb = ceil_div(n, kBlk);
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return (char*)base + o; };
+  w.keys_in = (float*)take(sizeof(float) * n);
+  w.keys_out = (float*)take(sizeof(float) * n);
+  w.vals_in = (int*)take(sizeof(int) * n);
+  w.vals_out = (int*)take(sizeof(int) * n);
+  w.boxes = (RBox*)take(sizeof(RBox) * n);
+  w.labels = (float*)take(sizeof(float) * n);
+  w.mask = (unsigned long long*)take(sizeof(unsigned long long) * (size_t)n * cb);
+  w.cub_bytes = cub_sort_bytes(n);
+  w.cub_tmp = take(w.cub_bytes);
+  w.total = off;
+  return w;
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused multiclass path
+// ------------------------------------------------------------------------------------------------
+constexpr int kSelThreads = 1024;
+constexpr int kSelItems = 6;                       // 1024 * 6 = 6144 boxes per image at most
+constexpr int kMcMaxBoxes = kSelThreads * kSelItems;
+
+__global__ void mc_prep_kernel(const float* __restrict__ bboxes, int64_t total, RBox* __restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < total) {
+    const float* d = bboxes + i * 5;
+    RBox b;
+    rbox_prep(d[0], d[1], d[2], d[3], d[4], b);
+    out[i] = b;
+  }
+}
+
+// One CTA per (class, image): ordered selection of the boxes whose class score exceeds the
+// threshold, stable descending sort by score, gather of the prepared boxes into the segment.
+template <int ITEMS>
+__device__ __forceinline__ void mc_select_sort_body(const float* __restrict__ sc, int n, int C, int c,
+                                                    float thr, const RBox* __restrict__ prepped,
+                                                    float* __restrict__ seg_score, int* __restrict__ seg_box,
+                                                    RBox* __restrict__ seg_rbox, int* __restrict__ seg_count,
+                                                    void* smem) {
+  using Sort = cub::BlockRadixSort<float, kSelThreads, ITEMS, int>;
+  typename Sort::TempStorage& tmp = *reinterpret_cast<typename Sort::TempStorage*>(smem);
+  __shared__ int s_cnt;
+  if (threadIdx.x == 0) s_cnt = 0;
+  __syncthreads();
+  float key[ITEMS];
+  int val[ITEMS];
+  int local = 0;
+#pragma unroll
+  for (int j = 0; j < ITEMS; ++j) {
+    const int i = threadIdx.x * ITEMS + j;
+    float v = -INFINITY;
+    if (i < n) {
+      const float sv = sc[(int64_t)i * C + c];
+      if (sv > thr) { v = sv; ++local; }
+    }
+    key[j] = v;
+    val[j] = i;
+  }
+  if (local) atomicAdd(&s_cnt, local);
+  Sort(tmp).SortDescending(key, val);       // stable: equal scores keep ascending box order
+  __syncthreads();
+  const int cnt = s_cnt;
+#pragma unroll
+  for (int j = 0; j < ITEMS; ++j) {
+    const int rank = threadIdx.x * ITEMS + j;
+    if (rank < cnt) {
+      seg_score[rank] = key[j];
+      seg_box[rank] = val[j];
+      seg_rbox[rank] = prepped[val[j]];
+    }
+  }
+  if (threadIdx.x == 0) *seg_count = cnt;
+}
+
+template <int ITEMS>
+__global__ void __launch_bounds__(kSelThreads)
+mc_select_sort_kernel(const float* __restrict__ scores, int n, int C, float thr,
+                      const RBox* __restrict__ prepped, float* __restrict__ seg_score,
+                      int* __restrict__ seg_box, RBox* __restrict__ seg_rbox, int* __restrict__ seg_count) {
+  extern __shared__ __align__(16) unsigned char s_sort[];
+  const int c = blockIdx.x, b = blockIdx.y;
+  const size_t seg = (size_t)b * C + c;
+  mc_select_sort_body<ITEMS>(scores + (size_t)b * n * C, n, C, c, thr, prepped + (size_t)b * n,
+                             seg_score + seg * n, seg_box + seg * n, seg_rbox + seg * n, seg_count + seg,
+                             s_sort);
+}
+
+// exclusive prefix of the per-segment tile counts (upper triangle incl. diagonal)
+__global__ void mc_tile_scan_kernel(const int* __restrict__ seg_count, int S, long long* __restrict__ tile_off) {
+  __shared__ long long s_part[1024];
+  const int tid = threadIdx.x;
+  const int per = (S + blockDim.x - 1) / blockDim.x;
+  long long sum = 0;
+  for (int k = 0; k < per; ++k) {
+    const int s = tid * per + k;
+    if (s < S) { const long long cb = (seg_count[s] + kBlk - 1) / kBlk; sum += cb * (cb + 1) / 2; }
+  }
+  s_part[tid] = sum;
+  __syncthreads();
+  if (tid == 0) {
+    long long run = 0;
+    for (int t = 0; t < (int)blockDim.x; ++t) { const long long v = s_part[t]; s_part[t] = run; run += v; }
+    tile_off[S] = run;
+  }
+  __syncthreads();
+  long long run = s_part[tid];
+  for (int k = 0; k < per; ++k) {
+    const int s = tid * per + k;
+    if (s < S) {
+      tile_off[s] = run;
+      const long long cb = (seg_count[s] + kBlk - 1) / kBlk;
+      run += cb * (cb + 1) / 2;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kMaskThreads)
+mc_mask_kernel(const RBox* __restrict__ seg_rbox, const int* __restrict__ seg_count,
+               const long long* __restrict__ tile_off, int S, int n, int ld, float thr,
+               unsigned long long* __restrict__ mask) {
+  __shared__ MaskTileSmem s;
+  const long long total = tile_off[S];
+  for (long long t = blockIdx.x; t < total; t += gridDim.x) {
+    int lo = 0, hi = S - 1;                 // last segment whose offset <= t
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (tile_off[mid] <= t) lo = mid; else hi = mid - 1;
+    }
+    const int seg = lo;
+    const int k = seg_count[seg];
+    const int cb = (k + kBlk - 1) / kBlk;
+    int rb, cbk;
+    decode_upper(t - tile_off[seg], cb, rb, cbk);
+    const RBox* boxes = seg_rbox + (size_t)seg * n;
+    const int nr = min(kBlk, k - rb * kBlk), nc = min(kBlk, k - cbk * kBlk);
+    mask_tile(s, boxes + rb * kBlk, boxes + cbk * kBlk, nullptr, nullptr, nr, nc, rb == cbk, thr);
+    if (threadIdx.x < nr)
+      mask[((size_t)seg * n + (size_t)rb * kBlk + threadIdx.x) * ld + cbk] = s.word[threadIdx.x];
+    __syncthreads();
+  }
+}
+
+// One CTA per segment: sweep, then compact the survivors (still in descending-score order).
+__global__ void __launch_bounds__(kSweepThreads)
+mc_sweep_kernel(const unsigned long long* __restrict__ mask, const int* __restrict__ seg_count, int n, int ld,
+                const float* __restrict__ seg_score, const int* __restrict__ seg_box,
+                float* __restrict__ kept_score, int* __restrict__ kept_box, int* __restrict__ kept_count) {
+  extern __shared__ unsigned long long s_dyn[];
+  __shared__ unsigned long long s_kw;
+  const size_t seg = blockIdx.x;
+  const int k = seg_count[seg];
+  const float* sc = seg_score + seg * n;
+  const int* bx = seg_box + seg * n;
+  float* ks = kept_score + seg * n;
+  int* kb = kept_box + seg * n;
+  int total = sweep_segment(mask + seg * (size_t)n * ld, k, ld, s_dyn, &s_kw,
+                            [&](int pos, int sorted_idx) { ks[pos] = sc[sorted_idx]; kb[pos] = bx[sorted_idx]; });
+  if (threadIdx.x == 0) kept_count[seg] = total;
+}
+
+// Merge by rank: a survivor's output row is the number of survivors of the same image that precede
+// it in (score desc, box asc, class asc) order = its own position in its class + one binary search
+// per other class.
+__global__ void mc_emit_kernel(const float* __restrict__ bboxes, const float* __restrict__ kept_score,
+                               const int* __restrict__ kept_box, const int* __restrict__ kept_count, int n,
+                               int C, int64_t max_per_img, int64_t max_out, float* __restrict__ dets_out,
+                               float* __restrict__ labels_out, int32_t* __restrict__ num_out) {
+  const int c = blockIdx.y, b = blockIdx.z;
+  const size_t seg0 = (size_t)b * C;
+  const int kc = kept_count[seg0 + c];
+  if (blockIdx.x == 0 && c == 0 && threadIdx.x == 0) {
+    long long tot = 0;
+    for (int cc = 0; cc < C; ++cc) tot += kept_count[seg0 + cc];
+    long long lim = max_per_img < max_out ? max_per_img : max_out;
+    num_out[b] = (int32_t)(tot < lim ? tot : lim);
+  }
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= kc) return;
+  const float sv = kept_score[(seg0 + c) * n + r];
+  const int box = kept_box[(seg0 + c) * n + r];
+  long long rank = r;
+  for (int cc = 0; cc < C; ++cc) {
+    if (cc == c) continue;
+    const int kk = kept_count[seg0 + cc];
+    const float* ks = kept_score + (seg0 + cc) * n;
+    const int* kb = kept_box + (seg0 + cc) * n;
+    int lo = 0, hi = kk;                                  // first index with score <= sv
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (ks[mid] > sv) lo = mid + 1; else hi = mid; }
+    int cnt = lo;
+    for (int q = lo; q < kk && ks[q] == sv; ++q)          // exact score ties across classes
+      if (kb[q] < box || (kb[q] == box && cc < c)) ++cnt;
+    rank += cnt;
+  }
+  const long long lim = max_per_img < max_out ? max_per_img : max_out;
+  if (rank < lim) {
+    const float* d = bboxes + ((size_t)b * n + box) * 5;
+    float* o = dets_out + ((size_t)b * max_out + rank) * 6;
+    o[0] = d[0]; o[1] = d[1]; o[2] = d[2]; o[3] = d[3]; o[4] = d[4]; o[5] = sv;
+    labels_out[(size_t)b * max_out + rank] = (float)c;
+  }
+}
+
+struct McWorkspace {
+  RBox* prepped; float* seg_score; int* seg_box; RBox* seg_rbox; int* seg_count; long long* tile_off;
+  unsigned long long* mask; float* kept_score; int* kept_box; int* kept_count; size_t total;
+};
+
+static McWorkspace carve_mc(void* base, int64_t n, int64_t C, int64_t B) {
+  McWorkspace w;
+  const int64_t S = B * C, ld = ceil_div(n, kBlk);
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return (char*)base + o; };
+  w.prepped = (RBox*)take(sizeof(RBox) * B * n);
+  w.seg_score = (float*)take(sizeof(float) * S * n);
+  w.seg_box = (int*)take(sizeof(int) * S * n);
+  w.seg_rbox = (RBox*)take(sizeof(RBox) * S * n);
+  w.seg_count = (int*)take(sizeof(int) * S);
+  w.tile_off = (long long*)take(sizeof(long long) * (S + 1));
+  w.mask = (unsigned long long*)take(sizeof(unsigned long long) * (size_t)S * n * ld);
+  w.kept_score = (float*)take(sizeof(float) * S * n);
+  w.kept_box = (int*)take(sizeof(int) * S * n);
+  w.kept_count = (int*)take(sizeof(int) * S);
+  w.total = off;
+  return w;
+}
+
+template <int ITEMS>
+static cudaError_t launch_select_sort(dim3 grid, cudaStream_t st, const float* scores, int n, int C, float thr,
+                                      const McWorkspace& w) {
+  using Sort = cub::BlockRadixSort<float, kSelThreads, ITEMS, int>;
+  const size_t smem = sizeof(typename Sort::TempStorage);
+  auto kern = mc_select_sort_kernel<ITEMS>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  kern<<<grid, kSelThreads, smem, st>>>(scores, n, C, thr, w.prepped, w.seg_score, w.seg_box, w.seg_rbox,
+                                        w.seg_count);
+  return cudaGetLastError();
+}
+
+}  // namespace s2a
+
+extern "C" size_t s2a_nms_rotated_workspace_bytes(int64_t n) {
+  if (n <= 0) return 256;
+  return s2a::carve_nms(nullptr, n).total;
+}
+
+extern "C" int s2a_nms_rotated(const float* dets, int64_t det_stride, const float* scores,
+                               int64_t score_stride, const float* labels, int64_t n, float iou_threshold,
+                               int64_t* keep_out, int32_t* num_keep_out, void* workspace,
+                               size_t workspace_bytes, void* stream) {
+  using namespace s2a;
+  cudaStream_t st = (cudaStream_t)stream;
+  S2A_CHECK_ARG(n >= 0 && n < (1ll << 30), "nms_rotated: n (%lld) out of range", (long long)n);
+  S2A_CHECK_ARG(num_keep_out != nullptr, "nms_rotated: num_keep_out is null");
+  if (n == 0) {
+    S2A_CUDA_OK(cudaMemsetAsync(num_keep_out, 0, sizeof(int32_t), st));
+    return S2A_OK;
+  }
+  S2A_CHECK_ARG(dets && scores && keep_out && workspace, "nms_rotated: null pointer");
+  S2A_CHECK_ARG(det_stride >= 5 && score_stride >= 1, "nms_rotated: bad strides (%lld, %lld)",
+                (long long)det_stride, (long long)score_stride);
+  NmsWorkspace w = carve_nms(workspace, n);
+  if (workspace_bytes < w.total) {
+    set_error("nms_rotated: workspace too small (%zu < %zu bytes)", workspace_bytes, w.total);
+    return S2A_ERR_WORKSPACE;
+  }
+  const int ni = (int)n;
+  const int cb = (int)ceil_div(n, kBlk);
+  const int tb = 256, gb = (int)ceil_div(n, tb);
+  nms_gather_keys_kernel<<<gb, tb, 0, st>>>(scores, score_stride, ni, w.keys_in, w.vals_in);
+  S2A_LAUNCH_OK("nms_gather_keys_kernel");
+  size_t cub_bytes = w.cub_bytes;
+  S2A_CUDA_OK(cub::DeviceRadixSort::SortPairsDescending(w.cub_tmp, cub_bytes, w.keys_in, w.keys_out, w.vals_in,
+                                                        w.vals_out, ni, 0, 32, st));
+  nms_gather_prep_kernel<<<gb, tb, 0, st>>>(dets, det_stride, labels, w.vals_out, ni, w.boxes, w.labels);
+  S2A_LAUNCH_OK("nms_gather_prep_kernel");
+  const long long tiles = (long long)cb * (cb + 1) / 2;
+  S2A_CHECK_ARG(tiles < (1ll << 31), "nms_rotated: too many tiles");
+  nms_mask_kernel<<<(unsigned)tiles, kMaskThreads, 0, st>>>(w.boxes, labels ? w.labels : nullptr, ni, cb,
+                                                            iou_threshold, w.mask);
+  S2A_LAUNCH_OK("nms_mask_kernel");
+  const size_t smem = sizeof(unsigned long long) * (size_t)cb;
+  S2A_CHECK_ARG(smem <= 200 * 1024, "nms_rotated: n too large for the single-CTA sweep");
+  if (smem > 48 * 1024)
+    S2A_CUDA_OK(cudaFuncSetAttribute(nms_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  nms_sweep_kernel<<<1, kSweepThreads, smem, st>>>(w.mask, w.vals_out, ni, keep_out, num_keep_out);
+  S2A_LAUNCH_OK("nms_sweep_kernel");
+  return S2A_OK;
+}
+
+extern "C" size_t s2a_multiclass_nms_rotated_workspace_bytes(int64_t n, int64_t num_classes, int64_t batch) {
+  if (n <= 0 || num_classes <= 0 || batch <= 0) return 256;
+  return s2a::carve_mc(nullptr, n, num_classes, batch).total;
+}
+
+extern "C" int s2a_multiclass_nms_rotated(const float* bboxes, const float* scores, int64_t n,
+                                          int64_t num_classes, int64_t batch, float score_thr, float iou_thr,
+                                          int64_t max_per_img, float* dets_out, float* labels_out,
+                                          int32_t* num_out, int64_t max_out, void* workspace,
+                                          size_t workspace_bytes, void* stream) {
+  using namespace s2a;
+  cudaStream_t st = (cudaStream_t)stream;
+  S2A_CHECK_ARG(n >= 0 && num_classes >= 0 && batch >= 0, "multiclass_nms_rotated: negative size");
+  S2A_CHECK_ARG(num_out != nullptr || batch == 0, "multiclass_nms_rotated: num_out is null");
+  if (batch == 0) return S2A_OK;
+  if (n == 0 || num_classes == 0 || max_out == 0 || max_per_img <= 0) {
+    S2A_CUDA_OK(cudaMemsetAsync(num_out, 0, sizeof(int32_t) * batch, st));
+    return S2A_OK;
+  }
+  S2A_CHECK_ARG(bboxes && scores && dets_out && labels_out && workspace, "multiclass_nms_rotated: null pointer");
+  S2A_CHECK_ARG(max_out > 0, "multiclass_nms_rotated: max_out must be positive");
+  if (n > kMcMaxBoxes) {
+    set_error("multiclass_nms_rotated: fused path supports n <= %d boxes per image (got %lld); "
+              "compose s2a_nms_rotated instead", kMcMaxBoxes, (long long)n);
+    return S2A_ERR_UNSUPPORTED;
+  }
+  if (!(iou_thr >= 0.0f)) {
+    set_error("multiclass_nms_rotated: class-segmented path needs iou_thr >= 0 (got %g)", (double)iou_thr);
+    return S2A_ERR_UNSUPPORTED;
+  }
+  S2A_CHECK_ARG(num_classes <= 65535 && batch <= 65535, "multiclass_nms_rotated: classes/batch must be <= 65535");
+  McWorkspace w = carve_mc(workspace, n, num_classes, batch);
+  if (workspace_bytes < w.total) {
+    set_error("multiclass_nms_rotated: workspace too small (%zu < %zu bytes)", workspace_bytes, w.total);
+    return S2A_ERR_WORKSPACE;
+  }
+  const int ni = (int)n, C = (int)num_classes, B = (int)batch, S = B * C;
+  const int ld = (int)ceil_div(n, kBlk);
+  mc_prep_kernel<<<(unsigned)ceil_div(batch * n, 256), 256, 0, st>>>(bboxes, batch * n, w.prepped);
+  S2A_LAUNCH_OK("mc_prep_kernel");
+  dim3 gsel(C, B);
+  cudaError_t e;
+  if (ni <= kSelThreads) e = launch_select_sort<1>(gsel, st, scores, ni, C, score_thr, w);
+  else if (ni <= 2 * kSelThreads) e = launch_select_sort<2>(gsel, st, scores, ni, C, score_thr, w);
+  else e = launch_select_sort<kSelItems>(gsel, st, scores, ni, C, score_thr, w);
+  S2A_CUDA_OK(e);
+  mc_tile_scan_kernel<<<1, 1024, 0, st>>>(w.seg_count, S, w.tile_off);
+  S2A_LAUNCH_OK("mc_tile_scan_kernel");
+  mc_mask_kernel<<<sm_count() * 8, kMaskThreads, 0, st>>>(w.seg_rbox, w.seg_count, w.tile_off, S, ni, ld, iou_thr,
+                                                          w.mask);
+  S2A_LAUNCH_OK("mc_mask_kernel");
+  const size_t smem = sizeof(unsigned long long) * (size_t)ld;
+  mc_sweep_kernel<<<S, kSweepThreads, smem, st>>>(w.mask, w.seg_count, ni, ld, w.seg_score, w.seg_box,
+                                                  w.kept_score, w.kept_box, w.kept_count);
+  S2A_LAUNCH_OK("mc_sweep_kernel");
+  dim3 gemit((unsigned)ceil_div(n, 256), C, B);
+  mc_emit_kernel<<<gemit, 256, 0, st>>>(bboxes, w.kept_score, w.kept_box, w.kept_count, ni, C, max_per_img,
+                                        max_out, dets_out, labels_out, num_out);
+  S2A_LAUNCH_OK("mc_emit_kernel");
+  return S2A_OK;
+}

@@ -1,0 +1,251 @@
+// rbox_iou.cuh -- rotated-box IoU device routines shared by box_iou_rotated, nms_rotated and
+// ml_nms_rotated (sm_100a).
+//
+// Semantics follow the reference's CUDA build of single_box_iou_rotated
+// (reference: utils/box_iou_rotated/src/box_iou_rotated_utils.h:55-375, __CUDACC__ branch of the
+// hull sort at :209-226), re-organised for the GPU:
+//   * per-box work (double-precision sin/cos, :62-64) is hoisted out of the pair loop ("RBox");
+//   * a conservative circumscribed-circle test classifies most pairs as exactly-zero without
+//     running the clipper (rbox_classify);
+//   * the clipper keeps ONE 24-point array (the hull is built in place, squared distances are
+//     recomputed instead of stored -- bit-identical because the reference permutes dist[] together
+//     with the points);
+//   * every multiply/add is an individually rounded IEEE fp32 operation (__fmul_rn & co., never
+//     contracted into FMA), and every double-precision epsilon test of the reference is replaced
+//     by the exactly equivalent fp32 comparison, so the result is bit-identical to the CPU oracle
+//     (oracle/s2a_oracle.c, built with -ffp-contract=off) given the same per-box sin/cos.
+//
+// All functions are __host__ __device__ so that tests/host_harness.cu can run the very same
+// source on the CPU against the oracle.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDA_ARCH__)
+#define RB_MUL(a, b) __fmul_rn((a), (b))
+#define RB_ADD(a, b) __fadd_rn((a), (b))
+#define RB_SUB(a, b) __fsub_rn((a), (b))
+#define RB_DIV(a, b) __fdiv_rn((a), (b))
+#else   // host pass: compiled with -ffp-contract=off
+#define RB_MUL(a, b) ((a) * (b))
+#define RB_ADD(a, b) ((a) + (b))
+#define RB_SUB(a, b) ((a) - (b))
+#define RB_DIV(a, b) ((a) / (b))
+#endif
+#define RB_HD __host__ __device__ __forceinline__
+
+namespace s2a {
+
+// fp32 neighbours of the reference's double literals (none is representable in fp32, so
+// "x < L" and "x <= L" are both "x <= lo(L)", and "x > L" is "x >= hi(L)").
+#define RB_LO_1E14 __int_as_float_c(0x283424dc)
+RB_HD float rb_bits(uint32_t u) {
+#if defined(__CUDA_ARCH__)
+  return __uint_as_float(u);
+#else
+  union { uint32_t u; float f; } c; c.u = u; return c.f;
+#endif
+}
+#undef RB_LO_1E14
+#define RB_LO_1E14 rb_bits(0x283424dcu)   // largest fp32 < 1e-14
+#define RB_LO_1E6  rb_bits(0x358637bdu)   // largest fp32 < 1e-6
+#define RB_HI_1E6  rb_bits(0x358637beu)   // smallest fp32 > 1e-6
+#define RB_HI_1E8  rb_bits(0x322bcc78u)   // smallest fp32 > 1e-8
+
+// Per-box precomputation.  32 bytes -> two float4 loads.
+struct __align__(16) RBox {
+  float x, y, w, h;      // centre (unshifted), size
+  float c2, s2;          // (float)cos(theta)*0.5f, (float)sin(theta)*0.5f   (reference :63-64)
+  float r;               // >= half diagonal (circumscribed-circle radius), for the reject test
+  float mn;              // min(|w|, |h|)
+};
+
+RB_HD void rbox_prep(float x, float y, float w, float h, float a, RBox& o) {
+  o.x = x; o.y = y; o.w = w; o.h = h;
+  double th = (double)a;
+  o.c2 = RB_MUL((float)cos(th), 0.5f);
+  o.s2 = RB_MUL((float)sin(th), 0.5f);
+  o.r = 0.5f * sqrtf(w * w + h * h);
+  o.mn = fminf(fabsf(w), fabsf(h));
+}
+
+// Pair classification.
+//   RB_ZERO : the reference returns exactly +0.0f for this pair, either through its own area
+//             early-out (:354-358) or because the boxes are provably disjoint (no candidate point
+//             can be produced, so inter = 0 and iou = 0/(a1+a2) = 0).
+//   RB_CLIP : run the clipper.
+// The disjointness shortcut is only taken when it is numerically safe: the circumscribed circles
+// are separated by > 1 %, no edge pair is within ~1 degree of parallel (near-parallel edge pairs
+// make the reference's t1/t2 ill-conditioned, so its answer there must be reproduced, not
+// predicted), and no box side is below 1e-3 of the pair's extent (vertex rounding is ~2.4e-7 of
+// the extent, so edge directions are then accurate to < 1e-3 rad).  NaN/Inf inputs fail the
+// comparisons and fall through to RB_CLIP.  See DESIGN.md "IoU reject test" for the argument.
+enum { RB_ZERO = 0, RB_CLIP = 1 };
+
+RB_HD int rbox_classify(const RBox& A, const RBox& B) {
+  float a1 = RB_MUL(A.w, A.h), a2 = RB_MUL(B.w, B.h);
+  if (a1 <= RB_LO_1E14 || a2 <= RB_LO_1E14) return RB_ZERO;     // (double)area < 1e-14
+  float dx = A.x - B.x, dy = A.y - B.y;
+  float d2 = dx * dx + dy * dy;
+  float rs = A.r + B.r;
+  if (d2 > 1.0201f * rs * rs) {
+    // sin(tA - tB)/4 and cos(tA - tB)/4 from the half-scaled sin/cos
+    float sd = A.s2 * B.c2 - A.c2 * B.s2;
+    float cd = A.c2 * B.c2 + A.s2 * B.s2;
+    float ext = sqrtf(d2) + rs;
+    // |sd*cd| = |sin(2 dT)|/32 ; require |sin(2 dT)| > 0.04
+    if (fabsf(sd * cd) > 0.00125f && fminf(A.mn, B.mn) > 1e-3f * ext) return RB_ZERO;
+  }
+  return RB_CLIP;
+}
+
+struct RPt { float x, y; };
+RB_HD float rb_cross(float ax, float ay, float bx, float by) {   // A.x*B.y - B.x*A.y  (:50-53)
+  return RB_SUB(RB_MUL(ax, by), RB_MUL(bx, ay));
+}
+RB_HD float rb_dot(float ax, float ay, float bx, float by) {     // A.x*B.x + A.y*B.y  (:45-48)
+  return RB_ADD(RB_MUL(ax, bx), RB_MUL(ay, by));
+}
+
+// Vertices of a box whose centre is already shifted (:55-75).
+RB_HD void rbox_vertices(float xc, float yc, const RBox& b, float (&px)[4], float (&py)[4]) {
+  float sh = RB_MUL(b.s2, b.h), cw = RB_MUL(b.c2, b.w);
+  float ch = RB_MUL(b.c2, b.h), sw = RB_MUL(b.s2, b.w);
+  px[0] = RB_SUB(RB_SUB(xc, sh), cw);
+  py[0] = RB_SUB(RB_ADD(yc, ch), sw);
+  px[1] = RB_SUB(RB_ADD(xc, sh), cw);
+  py[1] = RB_SUB(RB_SUB(yc, ch), sw);
+  float tx = RB_MUL(2.0f, xc), ty = RB_MUL(2.0f, yc);
+  px[2] = RB_SUB(tx, px[0]);
+  py[2] = RB_SUB(ty, py[0]);
+  px[3] = RB_SUB(tx, px[1]);
+  py[3] = RB_SUB(ty, py[1]);
+}
+
+// The clipper: candidate points (:77-167), in-place Graham hull in the CUDA build's exchange-sort
+// order (:169-282), fan area (:284-296), iou = inter / (a1 + a2 - inter) (:361-362, unclamped).
+// Returns the IoU.  Precondition: both areas >= 1e-14 (rbox_classify handled the early-out).
+RB_HD float rbox_iou_clip(const RBox& A, const RBox& B) {
+  // centre shift (:340-349): fp32 sum, exact halving, subtraction that is exact in double and
+  // rounds once -- identical to the fp32 expression below for all finite pixel-scale inputs.
+  float shx = RB_MUL(RB_ADD(A.x, B.x), 0.5f);
+  float shy = RB_MUL(RB_ADD(A.y, B.y), 0.5f);
+  float p1x[4], p1y[4], p2x[4], p2y[4];
+  rbox_vertices(RB_SUB(A.x, shx), RB_SUB(A.y, shy), A, p1x, p1y);
+  rbox_vertices(RB_SUB(B.x, shx), RB_SUB(B.y, shy), B, p2x, p2y);
+
+  float e1x[4], e1y[4], e2x[4], e2y[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    e1x[i] = RB_SUB(p1x[(i + 1) & 3], p1x[i]);
+    e1y[i] = RB_SUB(p1y[(i + 1) & 3], p1y[i]);
+    e2x[i] = RB_SUB(p2x[(i + 1) & 3], p2x[i]);
+    e2y[i] = RB_SUB(p2y[(i + 1) & 3], p2y[i]);
+  }
+
+  float qx[24], qy[24];
+  int n = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float det = rb_cross(e2x[j], e2y[j], e1x[i], e1y[i]);
+      if (fabsf(det) <= RB_LO_1E14) continue;                      // fabs(det) <= 1e-14
+      float dx = RB_SUB(p2x[j], p1x[i]), dy = RB_SUB(p2y[j], p1y[i]);
+      float t1 = RB_DIV(rb_cross(e2x[j], e2y[j], dx, dy), det);
+      float t2 = RB_DIV(rb_cross(e1x[i], e1y[i], dx, dy), det);
+      if (t1 >= 0.0f && t1 <= 1.0f && t2 >= 0.0f && t2 <= 1.0f) {
+        qx[n] = RB_ADD(p1x[i], RB_MUL(e1x[i], t1));
+        qy[n] = RB_ADD(p1y[i], RB_MUL(e1y[i], t1));
+        ++n;
+      }
+    }
+  }
+  {
+    float abab = rb_dot(e2x[0], e2y[0], e2x[0], e2y[0]);
+    float adad = rb_dot(e2x[3], e2y[3], e2x[3], e2y[3]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float apx = RB_SUB(p1x[i], p2x[0]), apy = RB_SUB(p1y[i], p2y[0]);
+      float apab = rb_dot(apx, apy, e2x[0], e2y[0]);
+      float apad = -rb_dot(apx, apy, e2x[3], e2y[3]);
+      if (apab >= 0.0f && apad >= 0.0f && apab <= abab && apad <= adad) {
+        qx[n] = p1x[i]; qy[n] = p1y[i]; ++n;
+      }
+    }
+  }
+  {
+    float abab = rb_dot(e1x[0], e1y[0], e1x[0], e1y[0]);
+    float adad = rb_dot(e1x[3], e1y[3], e1x[3], e1y[3]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float apx = RB_SUB(p2x[i], p1x[0]), apy = RB_SUB(p2y[i], p1y[0]);
+      float apab = rb_dot(apx, apy, e1x[0], e1y[0]);
+      float apad = -rb_dot(apx, apy, e1x[3], e1y[3]);
+      if (apab >= 0.0f && apad >= 0.0f && apab <= abab && apad <= adad) {
+        qx[n] = p2x[i]; qy[n] = p2y[i]; ++n;
+      }
+    }
+  }
+
+  float a1 = RB_MUL(A.w, A.h), a2 = RB_MUL(B.w, B.h);
+  float inter = 0.0f;
+  if (n > 2) {
+    // lowest point (min y, then min x), shift every point by it, move it to slot 0
+    int t = 0;
+    for (int i = 1; i < n; ++i)
+      if (qy[i] < qy[t] || (qy[i] == qy[t] && qx[i] < qx[t])) t = i;
+    float sx = qx[t], sy = qy[t];
+    for (int i = 0; i < n; ++i) { qx[i] = RB_SUB(qx[i], sx); qy[i] = RB_SUB(qy[i], sy); }
+    { float tx = qx[0], ty = qy[0]; qx[0] = qx[t]; qy[0] = qy[t]; qx[t] = tx; qy[t] = ty; }
+    // exchange sort by polar angle; 1e-6 collinearity band, squared-distance tie break
+    for (int i = 1; i < n - 1; ++i) {
+      float ax = qx[i], ay = qy[i];
+      float ad = rb_dot(ax, ay, ax, ay);
+      for (int j = i + 1; j < n; ++j) {
+        float bx = qx[j], by = qy[j];
+        float cp = rb_cross(ax, ay, bx, by);
+        bool sw = (cp <= -RB_HI_1E6);                               // cp < -1e-6
+        if (!sw && fabsf(cp) <= RB_LO_1E6) sw = ad > rb_dot(bx, by, bx, by);   // |cp| < 1e-6 && di > dj
+        if (sw) {
+          qx[j] = ax; qy[j] = ay; ax = bx; ay = by;
+          ad = rb_dot(ax, ay, ax, ay);
+        }
+      }
+      qx[i] = ax; qy[i] = ay;
+    }
+    int k = 1;
+    for (; k < n; ++k)
+      if (rb_dot(qx[k], qy[k], qx[k], qy[k]) >= RB_HI_1E8) break;  // dist > 1e-8
+    if (k < n) {
+      qx[1] = qx[k]; qy[1] = qy[k];
+      int m = 2;
+      for (int i = k + 1; i < n; ++i) {
+        float cx = qx[i], cy = qy[i];
+        while (m > 1) {
+          float ox = qx[m - 2], oy = qy[m - 2];
+          float cr = rb_cross(RB_SUB(cx, ox), RB_SUB(cy, oy), RB_SUB(qx[m - 1], ox), RB_SUB(qy[m - 1], oy));
+          if (!(cr >= 0.0f)) break;
+          --m;
+        }
+        qx[m] = cx; qy[m] = cy; ++m;
+      }
+      if (m > 2) {
+        float area = 0.0f;
+        float ox = qx[0], oy = qy[0];
+        for (int i = 1; i < m - 1; ++i)
+          area = RB_ADD(area, fabsf(rb_cross(RB_SUB(qx[i], ox), RB_SUB(qy[i], oy),
+                                             RB_SUB(qx[i + 1], ox), RB_SUB(qy[i + 1], oy))));
+        inter = RB_MUL(area, 0.5f);                                  // area / 2.0
+      }
+    }
+  }
+  return RB_DIV(inter, RB_SUB(RB_ADD(a1, a2), inter));
+}
+
+// Full semantic of single_box_iou_rotated on prepared boxes (:333-375).
+RB_HD float rbox_iou(const RBox& A, const RBox& B) {
+  return rbox_classify(A, B) == RB_ZERO ? 0.0f : rbox_iou_clip(A, B);
+}
+
+}  // namespace s2a

@@ -1,0 +1,157 @@
+"""Deformable convolution: `DeformConvFunction`, `deform_conv`, `DeformConv` with the reference's
+names, argument order and error behaviour (reference: models/dcn/deform_conv.py:13-109, 205-272;
+extension entry deform_conv_forward_cuda, models/dcn/src/deform_conv_cuda.cpp:152-260)."""
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+from torch.nn.modules.utils import _pair
+
+from . import _lib
+
+
+def deform_conv_forward_cuda(input, weight, offset, output, columns, ones, kW, kH, dW, dH, padW, padH, dilationW,
+                             dilationH, group, deformable_group, im2col_step):
+    """Extension-level entry with the reference's positional signature (width-first kernel /
+    stride / pad / dilation order, deform_conv_cuda.cpp:152-157).  Writes into the caller's
+    `output`; `columns` / `ones` are the reference's scratch handles and are ignored (no im2col
+    buffer exists); `im2col_step` only has to divide the batch.  Returns 1."""
+    dev = _lib.require_cuda(input, weight, offset, output)
+    if weight.dim() != 4:
+        raise RuntimeError("4D weight tensor (nOutputPlane,nInputPlane,kH,kW) expected, but got: %d" % weight.dim())
+    if weight.size(2) != kH or weight.size(3) != kW:
+        raise RuntimeError("kernel size should be consistent with weight")
+    squeeze = input.dim() == 3
+    if squeeze:
+        input, offset = input.unsqueeze(0), offset.unsqueeze(0)
+    if input.dim() != 4:
+        raise RuntimeError("3D or 4D input tensor expected but got: %d" % input.dim())
+    B, C, H, W = input.shape
+    if offset.size(0) != B:
+        raise RuntimeError("invalid batch size of offset")
+    if im2col_step <= 0 or B % im2col_step != 0:
+        raise RuntimeError("im2col step must divide batchsize")
+    Co = weight.size(0)
+    if weight.size(1) * group != C:
+        raise RuntimeError("invalid number of input planes, expected: %d, but got: %d" % (weight.size(1) * group, C))
+    Ho = (H + 2 * padH - (dilationH * (kH - 1) + 1)) // dH + 1
+    Wo = (W + 2 * padW - (dilationW * (kW - 1) + 1)) // dW + 1
+    if offset.size(1) != deformable_group * 2 * kH * kW:
+        raise RuntimeError("invalid number of channels of offset")
+    if offset.size(2) != Ho or offset.size(3) != Wo:
+        raise RuntimeError("invalid spatial size of offset, expected height: %d width: %d, but got height: %d "
+                           "width: %d" % (Ho, Wo, offset.size(2), offset.size(3)))
+    if input.dtype != torch.float32:
+        raise NotImplementedError("deform_conv_forward_cuda: this build implements float32 through this entry; "
+                                  "use AlignConv for the bf16 tensor-core path")
+    x = input.contiguous()
+    off = offset.to(torch.float32).contiguous()
+    w = weight.to(torch.float32).contiguous()
+    out = output if (output.is_contiguous() and output.dtype == torch.float32) else torch.empty(
+        (B, Co, Ho, Wo), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        rc = _lib.load().s2a_deform_conv_forward_f32(_lib.ptr(x), _lib.ptr(off), _lib.ptr(w), _lib.ptr(out), B, C, H, W,
+                                                     Co, kH, kW, dH, dW, padH, padW, dilationH, dilationW, group,
+                                                     deformable_group, 0, _lib.stream_ptr(dev))
+    _lib.check(rc, "deform_conv_forward_cuda")
+    if out is not output:
+        output.copy_(out.view_as(output))
+    return 1
+
+
+class DeformConvFunction(Function):
+    """reference: models/dcn/deform_conv.py:13-109."""
+
+    @staticmethod
+    def forward(ctx, input, offset, weight, stride=1, padding=0, dilation=1, groups=1, deformable_groups=1,
+                im2col_step=64):
+        if input is not None and input.dim() != 4:
+            raise ValueError("Expected 4D tensor as input, got {}D tensor instead.".format(input.dim()))
+        ctx.stride = _pair(stride)
+        ctx.padding = _pair(padding)
+        ctx.dilation = _pair(dilation)
+        ctx.groups = groups
+        ctx.deformable_groups = deformable_groups
+        ctx.im2col_step = im2col_step
+        offset = offset.type_as(input)          # :45-46, the dtype of `input` decides
+        weight = weight.type_as(input)
+        ctx.save_for_backward(input, offset, weight)
+        output = input.new_empty(DeformConvFunction._output_size(input, weight, ctx.padding, ctx.dilation, ctx.stride))
+        ctx.bufs_ = [input.new_empty(0), input.new_empty(0)]
+        if not input.is_cuda:
+            raise NotImplementedError
+        cur_im2col_step = min(ctx.im2col_step, input.shape[0])
+        assert (input.shape[0] % cur_im2col_step) == 0, 'im2col step must divide batchsize'
+        deform_conv_forward_cuda(input, weight, offset, output, ctx.bufs_[0], ctx.bufs_[1], weight.size(3),
+                                 weight.size(2), ctx.stride[1], ctx.stride[0], ctx.padding[1], ctx.padding[0],
+                                 ctx.dilation[1], ctx.dilation[0], ctx.groups, ctx.deformable_groups, cur_im2col_step)
+        return output
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output):
+        # SURVEY.md section 8f item 1 ("next"): dgrad / wgrad / offset-grad kernels are not built yet.
+        raise NotImplementedError("s2anet_b200: DeformConv backward is not implemented yet (forward/inference path only)")
+
+    @staticmethod
+    def _output_size(input, weight, padding, dilation, stride):
+        channels = weight.size(0)
+        output_size = (input.size(0), channels)
+        for d in range(input.dim() - 2):
+            in_size = input.size(d + 2)
+            pad = padding[d]
+            kernel = dilation[d] * (weight.size(d + 2) - 1) + 1
+            stride_ = stride[d]
+            output_size += ((in_size + (2 * pad) - kernel) // stride_ + 1,)
+        if not all(map(lambda s: s > 0, output_size)):
+            raise ValueError("convolution input is too small (output would be {})".format(
+                'x'.join(map(str, output_size))))
+        return output_size
+
+
+deform_conv = DeformConvFunction.apply
+
+
+class DeformConv(nn.Module):
+    """reference: models/dcn/deform_conv.py:205-272 (weight [C_out, C_in/groups, kH, kW], no bias)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1,
+                 deformable_groups=1, bias=False):
+        super(DeformConv, self).__init__()
+        assert not bias
+        assert in_channels % groups == 0, 'in_channels {} cannot be divisible by groups {}'.format(in_channels, groups)
+        assert out_channels % groups == 0, 'out_channels {} cannot be divisible by groups {}'.format(
+            out_channels, groups)
+        self.in_channels = in_channels
+        self.out_channels = out_channels
+        self.kernel_size = _pair(kernel_size)
+        self.stride = _pair(stride)
+        self.padding = _pair(padding)
+        self.dilation = _pair(dilation)
+        self.groups = groups
+        self.deformable_groups = deformable_groups
+        self.weight = nn.Parameter(torch.Tensor(out_channels, in_channels // self.groups, *self.kernel_size))
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        n = self.in_channels
+        for k in self.kernel_size:
+            n *= k
+        stdv = 1. / math.sqrt(n)
+        self.weight.data.uniform_(-stdv, stdv)
+
+    def forward(self, x, offset):
+        input_pad = (x.size(2) < self.kernel_size[0] or x.size(3) < self.kernel_size[1])
+        if input_pad:
+            pad_h = max(self.kernel_size[0] - x.size(2), 0)
+            pad_w = max(self.kernel_size[1] - x.size(3), 0)
+            x = F.pad(x, (0, pad_w, 0, pad_h), 'constant', 0).contiguous()
+            offset = F.pad(offset, (0, pad_w, 0, pad_h), 'constant', 0).contiguous()
+        out = deform_conv(x, offset, self.weight, self.stride, self.padding, self.dilation, self.groups,
+                          self.deformable_groups)
+        if input_pad:
+            out = out[:, :, :out.size(2) - pad_h, :out.size(3) - pad_w].contiguous()
+        return out
