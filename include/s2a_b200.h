@@ -154,6 +154,30 @@ S2A_EXPORT int s2a_orconv_forward_f32(const float* x, const float* weight, const
                                       const float* bias, float* out, float* pooled, int B, int H,
                                       int W, int O, int I, int nOri, int nRot, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Tensor-core (tcgen05) path: bf16 / fp16 activations in channels-last (NHWC) layout, fp32
+ * accumulation in TMEM.  Same reference interfaces as the _f32 entries above (AlignConv.forward,
+ * models/alignconv.py:88-98; ORConv2d.forward + RotationInvariantPooling, models/orn/modules/
+ * ORConv.py:77-82, models/orn/functions/rotation_invariant_pooling.py:19-27), for the half-precision
+ * inference path of val.py (:126, :196, :246).
+ *
+ * s2a_conv_pack_weight: [Co, C, 3, 3] weights (f32/bf16/f16) -> packed [Co][9*C] 16-bit in
+ * (64-channel block, tap, channel) K order.  With arf_indices != NULL the input is an ORConv bank
+ * [O, I, nOri, 3, 3] (Co = O*nRot, C = I*nOri) and the ARF rotation (ActiveRotatingFilter_cuda.cu
+ * :19-46) is applied while packing.  Needs C % 64 == 0.
+ * x [B, H, W, C], anchors [B, H, W, 5] fp32, out [B, H, W, Co], pooled [B, H, W, Co/8] (may be NULL),
+ * bias fp32 [Co] (may be NULL); dtype in {S2A_BF16, S2A_F16}; Co % 32 == 0, Co <= 256.
+ */
+S2A_EXPORT int s2a_conv_pack_weight(const void* weight, int in_dtype, const uint8_t* arf_indices,
+                                    void* packed, int out_dtype, int Co, int C, int nOri, int nRot,
+                                    void* stream);
+S2A_EXPORT int s2a_alignconv_forward_tc(const void* x, const float* anchors,
+                                        const void* packed_weight, void* out, int B, int C, int H,
+                                        int W, int Co, float stride, int dtype, void* stream);
+S2A_EXPORT int s2a_orconv_forward_tc(const void* x, const void* packed_weight, const float* bias,
+                                     void* out, void* pooled, int B, int C, int H, int W, int Co,
+                                     int dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

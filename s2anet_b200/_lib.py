@@ -33,6 +33,9 @@ PROTOTYPES = {
     "s2a_deform_conv_forward_f32": (_i32, [_vp, _vp, _vp, _vp] + [_i32] * 16 + [_vp]),
     "s2a_alignconv_forward_f32": (_i32, [_vp, _vp, _vp, _vp] + [_i32] * 5 + [_f32, _vp]),
     "s2a_orconv_forward_f32": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp] + [_i32] * 7 + [_vp]),
+    "s2a_conv_pack_weight": (_i32, [_vp, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "s2a_alignconv_forward_tc": (_i32, [_vp, _vp, _vp, _vp] + [_i32] * 5 + [_f32, _i32, _vp]),
+    "s2a_orconv_forward_tc": (_i32, [_vp, _vp, _vp, _vp, _vp] + [_i32] * 6 + [_vp]),
 }
 
 _lib = None

@@ -1,0 +1,571 @@
+// conv_tc.cu -- AlignConv and ORConv2d as a tcgen05 implicit GEMM for sm_100a (bf16 / fp16 in,
+// fp32 accumulate in TMEM).
+//
+// Replaces (reference): AlignConv.forward = get_offset + DeformConv + ReLU (models/alignconv.py:29-98,
+// models/dcn/src/deform_conv_cuda.cpp:152-260, deform_conv_cuda_kernel.cu:83-114, 189-242) and
+// ORConv2d.forward + RotationInvariantPooling (models/orn/modules/ORConv.py:77-82,
+// models/orn/src/cuda/ActiveRotatingFilter_cuda.cu:19-46, models/orn/functions/
+// rotation_invariant_pooling.py:19-27).
+//
+// GEMM view:  D[m, n] = sum_k A[m, k] * Wp[n, k]
+//   m : output position (a CTA owns an 8 x 16 spatial patch = 128 rows = one UMMA M)
+//   n : output channel (N = C_out <= 256, the whole channel dimension in one UMMA N)
+//   k : (64-channel block, tap, channel-in-block) -- 64-wide k-blocks, K' = 9*C_in
+//   A : never exists in global memory.  For AlignConv a[m, (cb,t,c)] is the bilinear sample of x at
+//       the position the m-th refined anchor assigns to tap t (alignconv.py:29-86 collapsed with
+//       deform_conv_cuda_kernel.cu:210-228); for ORConv it is the plain shifted pixel.
+//   Wp: weights pre-packed to [C_out][K'] 16-bit (ARF rotation folded into the packing for ORConv).
+//
+// Warp roles (192 threads): warps 0-3 produce A (gather 4 corners with 16-byte loads from the NHWC
+// feature map, blend in fp32, store 16-byte chunks into the 128B-swizzled K-major smem tile that
+// UMMA expects) and later run the epilogue (tcgen05.ld -> bias/ReLU/max-pool -> NHWC stores);
+// warp 4 streams the weight k-blocks with TMA (cp.async.bulk.tensor, SWIZZLE_128B); warp 5 owns
+// TMEM and issues tcgen05.mma (M=128, N=C_out, K=16, kind::f16) from one thread.  Stages are
+// recycled through full/empty mbarriers; tcgen05.commit releases a stage when its MMAs retire.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include <algorithm>
+#include <type_traits>
+
+#include "common.cuh"
+
+namespace s2a {
+
+constexpr int TC_M = 128;                 // rows per CTA tile (8 x 16 patch)
+constexpr int TC_PH = 8, TC_PW = 16;
+constexpr int TC_KB = 64;                 // k-block (elements) = 128 bytes of 16-bit data
+constexpr int TC_STAGES = 3;
+constexpr int TC_A_BYTES = TC_M * TC_KB * 2;          // 16 KB
+constexpr int TC_B_BYTES_MAX = 256 * TC_KB * 2;       // 32 KB
+constexpr int TC_THREADS = 192;
+constexpr int TC_TMEM_COLS = 256;
+constexpr uint32_t kSpinLimit = 1u << 26;            // watchdog: trap instead of hanging the GPU
+
+enum { TC_ALIGN = 0, TC_PLAIN = 1 };
+
+struct __align__(4) TapSample { short y0, x0; float ly, lx; };   // 12 bytes; y0 == -32768 -> nothing sampled
+
+struct TcParams {
+  const void* x;          // [B, H, W, C] 16-bit (channels_last)
+  const float* anchors;   // [B, H, W, 5] (TC_ALIGN)
+  const float* bias;      // [Co] fp32 or null
+  void* out;              // [B, H, W, Co] 16-bit
+  void* pooled;           // [B, H, W, Co/8] 16-bit or null
+  int B, C, H, W, Co;
+  int tiles_x, tiles_y;   // patches per image
+  float stride;
+  int relu;
+};
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > kSpinLimit) {
+      printf("s2a conv_tc: mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+      "l"((uint64_t)map), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
+// start address >> 4 | LBO (unused for swizzled K-major, 1) << 16 | SBO (8 rows * 128 B = 1024 B) >> 4
+// << 32 | version 1 << 46 | layout SWIZZLE_128B (2) << 61.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
+         (2ull << 61);
+}
+
+// 16-bit element helpers
+template <typename T> struct Half2Of;
+template <> struct Half2Of<__nv_bfloat16> { using type = __nv_bfloat162; };
+template <> struct Half2Of<__half> { using type = __half2; };
+__device__ __forceinline__ float2 to_f2(__nv_bfloat162 v) { return __bfloat1622float2(v); }
+__device__ __forceinline__ float2 to_f2(__half2 v) { return __half22float2(v); }
+template <typename T> __device__ __forceinline__ typename Half2Of<T>::type from_f2(float a, float b);
+template <> __device__ __forceinline__ __nv_bfloat162 from_f2<__nv_bfloat16>(float a, float b) {
+  return __floats2bfloat162_rn(a, b);
+}
+template <> __device__ __forceinline__ __half2 from_f2<__half>(float a, float b) { return __floats2half2_rn(a, b); }
+
+__device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+
+template <typename T>
+__device__ __forceinline__ void blend_acc(float (&acc)[8], const uint4& v, float w) {
+  using H2 = typename Half2Of<T>::type;
+  const H2* h = reinterpret_cast<const H2*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = to_f2(h[i]);
+    acc[2 * i] = fmaf(w, f.x, acc[2 * i]);
+    acc[2 * i + 1] = fmaf(w, f.y, acc[2 * i + 1]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------------------------
+template <int MODE, typename T>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B operands need 1024-byte aligned tiles: align the dynamic window by hand
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  // carve: A stages | B stages | sample table | barriers
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + TC_STAGES * TC_A_BYTES;
+  TapSample* s_tab = reinterpret_cast<TapSample*>(sB + TC_STAGES * TC_B_BYTES_MAX);
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s_tab) + sizeof(TapSample) * TC_M * 9);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 2 * TC_STAGES + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t bar_full = smem_u32(s_bar), bar_empty = smem_u32(s_bar + TC_STAGES),
+                 bar_acc = smem_u32(s_bar + 2 * TC_STAGES);
+
+  // tile -> (image, patch)
+  int tile = blockIdx.x;
+  const int tpi = p.tiles_x * p.tiles_y;
+  const int b = tile / tpi;
+  tile -= b * tpi;
+  const int ty0 = (tile / p.tiles_x) * TC_PH, tx0 = (tile % p.tiles_x) * TC_PW;
+  const int ncb = p.C / TC_KB;
+  const int nkb = ncb * 9;
+  const uint32_t b_bytes = (uint32_t)p.Co * TC_KB * 2;
+
+  if (tid == 0) {
+    for (int s = 0; s < TC_STAGES; ++s) {
+      mbar_init(bar_full + 8 * s, 128 + 1);     // 128 producer threads + the TMA thread's expect_tx arrive
+      mbar_init(bar_empty + 8 * s, 1);          // one tcgen05.commit
+    }
+    mbar_init(bar_acc, 1);
+    fence_barrier_init();
+  }
+  if (warp == 5) tmem_alloc(smem_u32(s_tmem), TC_TMEM_COLS);
+
+  if (warp < 4 && MODE == TC_ALIGN) {
+    // sample table: (row, tap) -> top-left pixel + fractional weights.
+    // Position formula: models/alignconv.py:29-86 with the offset added back as the deformable
+    // im2col does (deform_conv_cuda_kernel.cu:223-227), same operation order as csrc/conv_f32.cu.
+    for (int e = tid; e < TC_M * 9; e += 128) {
+      const int r = e / 9, t = e - 9 * r;
+      const int y = ty0 + r / TC_PW, x = tx0 + r % TC_PW;
+      TapSample s;
+      s.y0 = -32768; s.x0 = 0; s.ly = 0.0f; s.lx = 0.0f;
+      if (y < p.H && x < p.W) {
+        const float* a = p.anchors + ((size_t)(b * p.H + y) * p.W + x) * 5;
+        const float ax = a[0] / p.stride, ay = a[1] / p.stride, aw = a[2] / p.stride, ah = a[3] / p.stride;
+        const float cs = cosf(a[4]), sn = sinf(a[4]);
+        const float dw = aw / 3.0f, dh = ah / 3.0f;
+        const int ti = t / 3, tj = t - 3 * ti;
+        const float fi = (float)(ti - 1), fj = (float)(tj - 1);
+        const float txx = __fmul_rn(dw, fj), tyy = __fmul_rn(dh, fi);
+        const float xr = __fsub_rn(__fmul_rn(cs, txx), __fmul_rn(sn, tyy));
+        const float yr = __fadd_rn(__fmul_rn(sn, txx), __fmul_rn(cs, tyy));
+        const float xa = __fadd_rn(xr, ax), ya = __fadd_rn(yr, ay);
+        const float offx = __fsub_rn(xa, __fadd_rn((float)x, fj));
+        const float offy = __fsub_rn(ya, __fadd_rn((float)y, fi));
+        const float h = __fadd_rn((float)(y - 1 + ti), offy);
+        const float w = __fadd_rn((float)(x - 1 + tj), offx);
+        if (h > -1.0f && w > -1.0f && h < (float)p.H && w < (float)p.W) {
+          const float hf = floorf(h), wf = floorf(w);
+          s.y0 = (short)(int)hf; s.x0 = (short)(int)wf;
+          s.ly = h - hf; s.lx = w - wf;
+        }
+      }
+      s_tab[e] = s;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+
+  if (warp < 4) {
+    // ===================== A producers =====================
+    const int chunk = tid & 7;                 // 16-byte chunk (8 channels) inside the 128-byte row
+    const int rsub = tid >> 3;                 // 0..15
+    const uint8_t* xb = reinterpret_cast<const uint8_t*>(p.x) + (size_t)b * p.H * p.W * p.C * 2;
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % TC_STAGES;
+      const uint32_t ph = (uint32_t)(kb / TC_STAGES) & 1u;
+      const int cb = kb / 9, tap = kb - 9 * cb;
+      mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+      uint8_t* a_stage = sA + s * TC_A_BYTES;
+      const size_t coff = ((size_t)cb * TC_KB + chunk * 8) * 2;      // byte offset of this chunk inside a pixel
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint4 v[4][4];
+        float wt[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = (half * 4 + i) * 16 + rsub;
+          int y0, x0;
+          float ly, lx;
+          bool any;
+          if (MODE == TC_ALIGN) {
+            const TapSample sm = s_tab[r * 9 + tap];
+            y0 = sm.y0; x0 = sm.x0; ly = sm.ly; lx = sm.lx;
+            any = sm.y0 != -32768;
+          } else {
+            const int y = ty0 + r / TC_PW, x = tx0 + r % TC_PW;
+            y0 = y - 1 + tap / 3; x0 = x - 1 + tap % 3; ly = 0.0f; lx = 0.0f;
+            any = (y < p.H && x < p.W);
+          }
+          const float hy = 1.0f - ly, hx = 1.0f - lx;
+          const bool t_ok = any && y0 >= 0 && y0 < p.H, b_ok = any && y0 + 1 >= 0 && y0 + 1 <= p.H - 1;
+          const bool l_ok = x0 >= 0 && x0 < p.W, r_ok = x0 + 1 >= 0 && x0 + 1 <= p.W - 1;
+          wt[i][0] = (t_ok && l_ok) ? hy * hx : 0.0f;
+          wt[i][1] = (t_ok && r_ok) ? hy * lx : 0.0f;
+          wt[i][2] = (b_ok && l_ok) ? ly * hx : 0.0f;
+          wt[i][3] = (b_ok && r_ok) ? ly * lx : 0.0f;
+          const int yt = min(max(y0, 0), p.H - 1), yb = min(max(y0 + 1, 0), p.H - 1);
+          const int xl = min(max(x0, 0), p.W - 1), xr = min(max(x0 + 1, 0), p.W - 1);
+          const size_t rowt = (size_t)yt * p.W, rowb = (size_t)yb * p.W;
+          if (MODE == TC_ALIGN) {
+            v[i][0] = ldg_nc_v4(xb + (rowt + xl) * p.C * 2 + coff);
+            v[i][1] = ldg_nc_v4(xb + (rowt + xr) * p.C * 2 + coff);
+            v[i][2] = ldg_nc_v4(xb + (rowb + xl) * p.C * 2 + coff);
+            v[i][3] = ldg_nc_v4(xb + (rowb + xr) * p.C * 2 + coff);
+          } else {
+            v[i][0] = ldg_nc_v4(xb + (rowt + xl) * p.C * 2 + coff);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = (half * 4 + i) * 16 + rsub;
+          uint4 o;
+          if (MODE == TC_ALIGN) {
+            float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            blend_acc<T>(acc, v[i][0], wt[i][0]);
+            blend_acc<T>(acc, v[i][1], wt[i][1]);
+            blend_acc<T>(acc, v[i][2], wt[i][2]);
+            blend_acc<T>(acc, v[i][3], wt[i][3]);
+            using H2 = typename Half2Of<T>::type;
+            H2* oh = reinterpret_cast<H2*>(&o);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) oh[q] = from_f2<T>(acc[2 * q], acc[2 * q + 1]);
+          } else {
+            o = (wt[i][0] != 0.0f) ? v[i][0] : make_uint4(0u, 0u, 0u, 0u);
+          }
+          // K-major SWIZZLE_128B: 16-byte chunk c of row r lives at chunk position c ^ (r & 7)
+          *reinterpret_cast<uint4*>(a_stage + r * 128 + ((chunk ^ (r & 7)) << 4)) = o;
+        }
+      }
+      fence_proxy_async_smem();          // generic-proxy stores -> visible to the tensor core (async proxy)
+      mbar_arrive(bar_full + 8 * s);
+    }
+
+    // ===================== epilogue =====================
+    mbar_wait(bar_acc, 0);
+    tc_fence_after();
+    const int r = warp * 32 + lane;
+    const int y = ty0 + r / TC_PW, x = tx0 + r % TC_PW;
+    const bool valid = (y < p.H && x < p.W);
+    const size_t pos = (size_t)(b * p.H + y) * p.W + x;
+    using H2 = typename Half2Of<T>::type;
+    for (int c0 = 0; c0 < p.Co; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+      float f[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        float t = __uint_as_float(v[i]);
+        if (p.bias) t += __ldg(p.bias + c0 + i);
+        if (p.relu) t = fmaxf(t, 0.0f);
+        f[i] = t;
+      }
+      if (valid) {
+        uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(p.out) + (pos * p.Co + c0) * 2);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 o;
+          H2* oh = reinterpret_cast<H2*>(&o);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) oh[j] = from_f2<T>(f[q * 8 + 2 * j], f[q * 8 + 2 * j + 1]);
+          dst[q] = o;
+        }
+        if (p.pooled) {
+          float m[4];
+#pragma unroll
+          for (int gidx = 0; gidx < 4; ++gidx) {
+            float mv = f[gidx * 8];
+#pragma unroll
+            for (int j = 1; j < 8; ++j) mv = fmaxf(mv, f[gidx * 8 + j]);
+            m[gidx] = mv;
+          }
+          uint2 o;
+          H2* oh = reinterpret_cast<H2*>(&o);
+          oh[0] = from_f2<T>(m[0], m[1]);
+          oh[1] = from_f2<T>(m[2], m[3]);
+          *reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(p.pooled) + (pos * (p.Co / 8) + c0 / 8) * 2) = o;
+        }
+      }
+    }
+    tc_fence_before();
+  } else if (warp == 4) {
+    // ===================== weight k-blocks by TMA =====================
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % TC_STAGES;
+        const uint32_t ph = (uint32_t)(kb / TC_STAGES) & 1u;
+        mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+        mbar_arrive_expect_tx(bar_full + 8 * s, b_bytes);
+        tma_load_2d(smem_u32(sB + s * TC_B_BYTES_MAX), &tmap_w, kb * TC_KB, 0, bar_full + 8 * s);
+      }
+    }
+  } else {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 (1<<4), A/B format (bf16=1, f16=0)
+      // at bits 7 / 10, K-major A and B, N>>3 at bit 17, M>>4 at bit 24
+      const uint32_t fmt = (sizeof(T) == 2 && std::is_same<T, __nv_bfloat16>::value) ? 1u : 0u;
+      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.Co >> 3) << 17) |
+                             ((uint32_t)(TC_M >> 4) << 24);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % TC_STAGES;
+        const uint32_t ph = (uint32_t)(kb / TC_STAGES) & 1u;
+        mbar_wait(bar_full + 8 * s, ph);
+        tc_fence_after();
+        const uint64_t adesc = umma_desc_sw128(smem_u32(sA + s * TC_A_BYTES));
+        const uint64_t bdesc = umma_desc_sw128(smem_u32(sB + s * TC_B_BYTES_MAX));
+#pragma unroll
+        for (int k = 0; k < TC_KB / 16; ++k)      // +32 bytes (>>4 = 2) per K=16 step inside the swizzle atom
+          umma_f16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+        umma_commit(bar_empty + 8 * s);           // stage reusable once these MMAs have read it
+      }
+      umma_commit(bar_acc);                       // accumulator complete
+    }
+  }
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TC_TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight packing: [Co][C][3][3] (any of f32/bf16/f16) -> [Co][(cb, tap, c64)] 16-bit, optionally
+// through the ARF map (ORConv: w [O, I, nOri, 3, 3], indices [nOri*9, nRot])
+// ---------------------------------------------------------------------------------------------
+template <typename TIn, typename TOut>
+__global__ void pack_weight_kernel(const TIn* __restrict__ w, const uint8_t* __restrict__ arf_idx, TOut* __restrict__ wp,
+                                   int Co, int C, int nOri, int nRot, int arfI) {
+  __shared__ uint8_t s_inv[8 * 72];
+  const int nEntry = nOri * 9;
+  if (arf_idx) {
+    for (int i = threadIdx.x; i < nEntry * nRot; i += blockDim.x) {
+      const int l = i / nRot, k = i % nRot;
+      s_inv[k * nEntry + ((int)arf_idx[i] - 1)] = (uint8_t)l;
+    }
+    __syncthreads();
+  }
+  const int64_t total = (int64_t)Co * C * 9;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    // destination order: n, cb, tap, c
+    const int c = (int)(e % 64);
+    int64_t r = e / 64;
+    const int tap = (int)(r % 9);
+    r /= 9;
+    const int cb = (int)(r % (C / 64));
+    const int n = (int)(r / (C / 64));
+    const int cin = cb * 64 + c;
+    float v;
+    if (arf_idx) {
+      const int o = n / nRot, k = n % nRot;
+      const int ii = cin / nOri, lay = cin % nOri;
+      const int l = s_inv[k * nEntry + lay * 9 + tap];
+      v = (float)w[((int64_t)o * arfI + ii) * nEntry + l];
+    } else {
+      v = (float)w[((int64_t)n * C + cin) * 9 + tap];
+    }
+    wp[e] = (TOut)v;
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)ptr;
+  }
+  return fn;
+}
+
+constexpr size_t kTcSmemBytes = 1024 /*alignment slack*/ + (size_t)TC_STAGES * (TC_A_BYTES + TC_B_BYTES_MAX) +
+                                sizeof(TapSample) * TC_M * 9 + 8 * (2 * TC_STAGES + 1) + 16;
+
+template <int MODE, typename T>
+static int launch_tc(const CUtensorMap& tmap, const TcParams& p, cudaStream_t st) {
+  auto kern = conv_tc_kernel<MODE, T>;
+  S2A_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
+  const int tiles = p.B * p.tiles_x * p.tiles_y;
+  kern<<<tiles, TC_THREADS, kTcSmemBytes, st>>>(tmap, p);
+  S2A_LAUNCH_OK("conv_tc_kernel");
+  return S2A_OK;
+}
+
+static int conv_tc_common(int mode, const void* x, const float* anchors, const void* wp, const float* bias, void* out,
+                          void* pooled, int B, int C, int H, int W, int Co, float stride, int relu, int dtype,
+                          cudaStream_t st) {
+  S2A_CHECK_ARG(B >= 0 && C > 0 && H > 0 && W > 0 && Co > 0, "conv_tc: bad tensor sizes");
+  S2A_CHECK_ARG(dtype == S2A_BF16 || dtype == S2A_F16, "conv_tc: dtype must be bf16 or f16");
+  if (C % 64 != 0 || Co % 32 != 0 || Co > 256) {
+    set_error("conv_tc: needs C %% 64 == 0 and C_out a multiple of 32 up to 256 (got C=%d, C_out=%d)", C, Co);
+    return S2A_ERR_UNSUPPORTED;
+  }
+  S2A_CHECK_ARG(H < 32768 && W < 32768, "conv_tc: feature map too large");
+  if (B == 0) return S2A_OK;
+  S2A_CHECK_ARG(x && wp && out && (mode == TC_PLAIN || anchors), "conv_tc: null pointer");
+  S2A_CHECK_ARG(!pooled || Co % 8 == 0, "conv_tc: pooling needs C_out %% 8 == 0");
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) { set_error("conv_tc: cuTensorMapEncodeTiled is not available from the driver"); return S2A_ERR_CUDA; }
+  CUtensorMap tmap;
+  const cuuint64_t gdim[2] = {(cuuint64_t)C * 9, (cuuint64_t)Co};
+  const cuuint64_t gstr[1] = {(cuuint64_t)C * 9 * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)TC_KB, (cuuint32_t)Co};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult cr = enc(&tmap, dtype == S2A_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
+                    const_cast<void*>(wp), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) { set_error("conv_tc: cuTensorMapEncodeTiled failed (%d)", (int)cr); return S2A_ERR_CUDA; }
+  TcParams p{};
+  p.x = x; p.anchors = anchors; p.bias = bias; p.out = out; p.pooled = pooled;
+  p.B = B; p.C = C; p.H = H; p.W = W; p.Co = Co;
+  p.tiles_x = (W + TC_PW - 1) / TC_PW; p.tiles_y = (H + TC_PH - 1) / TC_PH;
+  p.stride = stride; p.relu = relu;
+  if (mode == TC_ALIGN) {
+    return dtype == S2A_BF16 ? launch_tc<TC_ALIGN, __nv_bfloat16>(tmap, p, st) : launch_tc<TC_ALIGN, __half>(tmap, p, st);
+  }
+  return dtype == S2A_BF16 ? launch_tc<TC_PLAIN, __nv_bfloat16>(tmap, p, st) : launch_tc<TC_PLAIN, __half>(tmap, p, st);
+}
+
+template <typename TIn>
+static int pack_dispatch(const void* w, const uint8_t* idx, void* wp, int Co, int C, int nOri, int nRot, int arfI,
+                         int out_dtype, cudaStream_t st) {
+  const int64_t total = (int64_t)Co * C * 9;
+  const int blocks = (int)std::min<int64_t>(ceil_div(total, 256), (int64_t)sm_count() * 8);
+  if (out_dtype == S2A_BF16)
+    pack_weight_kernel<TIn, __nv_bfloat16><<<blocks, 256, 0, st>>>((const TIn*)w, idx, (__nv_bfloat16*)wp, Co, C, nOri, nRot, arfI);
+  else
+    pack_weight_kernel<TIn, __half><<<blocks, 256, 0, st>>>((const TIn*)w, idx, (__half*)wp, Co, C, nOri, nRot, arfI);
+  S2A_LAUNCH_OK("pack_weight_kernel");
+  return S2A_OK;
+}
+
+}  // namespace s2a
+
+extern "C" int s2a_conv_pack_weight(const void* weight, int in_dtype, const uint8_t* arf_indices, void* packed,
+                                    int out_dtype, int Co, int C, int nOri, int nRot, void* stream) {
+  using namespace s2a;
+  S2A_CHECK_ARG(Co > 0 && C > 0 && C % 64 == 0, "conv_pack_weight: C must be a positive multiple of 64");
+  S2A_CHECK_ARG(out_dtype == S2A_BF16 || out_dtype == S2A_F16, "conv_pack_weight: packed dtype must be bf16 or f16");
+  S2A_CHECK_ARG(weight && packed, "conv_pack_weight: null pointer");
+  int arfI = 0;
+  if (arf_indices) {
+    S2A_CHECK_ARG(nOri >= 1 && nOri <= 8 && nRot >= 1 && nRot <= 8 && C % nOri == 0 && Co % nRot == 0,
+                  "conv_pack_weight: bad ARF configuration");
+    arfI = C / nOri;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (in_dtype) {
+    case S2A_F32: return pack_dispatch<float>(weight, arf_indices, packed, Co, C, nOri, nRot, arfI, out_dtype, st);
+    case S2A_BF16: return pack_dispatch<__nv_bfloat16>(weight, arf_indices, packed, Co, C, nOri, nRot, arfI, out_dtype, st);
+    case S2A_F16: return pack_dispatch<__half>(weight, arf_indices, packed, Co, C, nOri, nRot, arfI, out_dtype, st);
+  }
+  set_error("conv_pack_weight: unknown input dtype %d", in_dtype);
+  return S2A_ERR_INVALID_ARGUMENT;
+}
+
+extern "C" int s2a_alignconv_forward_tc(const void* x, const float* anchors, const void* packed_weight, void* out, int B,
+                                        int C, int H, int W, int Co, float stride, int dtype, void* stream) {
+  using namespace s2a;
+  S2A_CHECK_ARG(stride > 0.0f, "alignconv_tc: stride must be positive");
+  return conv_tc_common(TC_ALIGN, x, anchors, packed_weight, nullptr, out, nullptr, B, C, H, W, Co, stride, 1, dtype,
+                        (cudaStream_t)stream);
+}
+
+extern "C" int s2a_orconv_forward_tc(const void* x, const void* packed_weight, const float* bias, void* out, void* pooled,
+                                     int B, int C, int H, int W, int Co, int dtype, void* stream) {
+  using namespace s2a;
+  return conv_tc_common(TC_PLAIN, x, nullptr, packed_weight, bias, out, pooled, B, C, H, W, Co, 1.0f, 0, dtype,
+                        (cudaStream_t)stream);
+}

@@ -1,0 +1,99 @@
+"""GPU parity tests (-m gpu) for the tcgen05 (bf16 / fp16) AlignConv and ORConv2d kernels.
+
+Reference for these floating-point kernels = this repo's fp32 kernels (themselves checked against
+the oracle / torchvision / the reference CUDA op in test_gpu_conv.py) fed with the SAME 16-bit
+rounded inputs and weights, so the only differences are (a) the blended A operand is rounded to
+16 bits before the MMA and (b) summation order.  Stated tolerance (north_star "bf16/fp32 tolerance,
+max-abs and relative error stated"):  bf16: max-abs <= 2e-2 * max|ref|, relative L2 <= 5e-3;
+fp16: max-abs <= 4e-3 * max|ref|, relative L2 <= 1e-3.
+"""
+import numpy as np
+import pytest
+import torch
+
+from s2anet_b200 import synth
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+TOL = {torch.bfloat16: (2e-2, 5e-3), torch.float16: (4e-3, 1e-3)}
+
+
+def check(y, ref, dtype):
+    y, ref = y.float(), ref.float()
+    mx = float(ref.abs().max()) + 1e-12
+    err = float((y - ref).abs().max())
+    rel = float((y - ref).norm() / (ref.norm() + 1e-12))
+    amax, arel = TOL[dtype]
+    assert err <= amax * mx and rel <= arel, "max-abs %g (ref max %g), rel-L2 %g" % (err, mx, rel)
+    return err / mx, rel
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("B,C,H,W,Co,stride", [(1, 64, 8, 16, 32, 8), (2, 128, 13, 21, 256, 16), (1, 256, 8, 8, 256, 128),
+                                               (3, 64, 5, 3, 64, 64)])
+def test_alignconv_tc_vs_fp32(dtype, B, C, H, W, Co, stride):
+    from s2anet_b200.alignconv import alignconv_forward
+    g = torch.Generator().manual_seed(C + H + W)
+    x = torch.randn(B, C, H, W, generator=g).to(DEV).to(dtype)
+    w = (torch.randn(Co, C, 3, 3, generator=g) * 0.05).to(DEV).to(dtype)
+    anc = torch.from_numpy(synth.refined_anchors(B, H, W, stride, seed=H)).to(DEV)
+    y = alignconv_forward(x.contiguous(memory_format=torch.channels_last), anc, w, stride)
+    assert y.dtype == dtype and y.is_contiguous(memory_format=torch.channels_last)
+    ref = alignconv_forward(x.float(), anc, w.float(), stride)
+    check(y, ref, dtype)
+    # NCHW-contiguous input is accepted too (converted once)
+    y2 = alignconv_forward(x.contiguous(), anc, w, stride)
+    assert torch.equal(y, y2)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("B,I,H,W,O", [(1, 64, 8, 16, 4), (2, 256, 11, 19, 32), (1, 128, 3, 5, 8)])
+def test_orconv_tc_vs_fp32(dtype, B, I, H, W, O):
+    from s2anet_b200.orn import ORConv2d, orconv_forward
+    m = ORConv2d(I, O, 3, padding=1, arf_config=(1, 8)).to(DEV)
+    g = torch.Generator().manual_seed(I + H)
+    with torch.no_grad():
+        m.weight.copy_((torch.randn(m.weight.shape, generator=g) * 0.05).to(dtype).float())
+        m.bias.copy_(torch.randn(O * 8, generator=g) * 0.1)
+    x = torch.randn(B, I, H, W, generator=g).to(DEV).to(dtype)
+    y, yp = orconv_forward(x, m.weight.to(dtype), m.indices, m.bias, with_pool=True)
+    ref, refp = orconv_forward(x.float(), m.weight, m.indices, m.bias, with_pool=True)
+    check(y, ref, dtype)
+    check(yp, refp, dtype)
+    # fused pooling == pooling of the rounded output
+    assert torch.equal(yp, y.view(B, O, 8, H, W).max(dim=2)[0])
+
+
+def test_p3_full_size_tc_and_head_chain():
+    """BASELINE config 2 shape in bf16: AlignConv -> ORConv2d(+pool) chained in channels_last."""
+    from s2anet_b200.alignconv import AlignConv
+    from s2anet_b200.orn import ORConv2d, RotationInvariantPooling
+    dt = torch.bfloat16
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(1, 256, 128, 128, generator=g).to(DEV)
+    anc = torch.from_numpy(synth.refined_anchors(1, 128, 128, 8, seed=1)).to(DEV)
+    ac = AlignConv(256, 256).to(DEV)
+    ac.init_weights()
+    oc = ORConv2d(256, 32, 3, padding=1, arf_config=(1, 8)).to(DEV)
+    torch.nn.init.normal_(oc.weight, 0, 0.01)
+    oc.fuse_pool = True
+    pool = RotationInvariantPooling(256, 8)
+    with torch.no_grad():
+        ac16, oc16 = ac.to(dt), oc.to(dt)
+        xa = x.to(dt).contiguous(memory_format=torch.channels_last)
+        ya = ac16(xa, anc, 8)
+        yo = oc16(ya)
+        yp = pool(yo)
+    assert tuple(ya.shape) == (1, 256, 128, 128) and tuple(yo.shape) == (1, 256, 128, 128) and tuple(yp.shape) == (1, 32, 128, 128)
+    # references in fp32 from the same 16-bit weights
+    ac32 = AlignConv(256, 256).to(DEV)
+    oc32 = ORConv2d(256, 32, 3, padding=1, arf_config=(1, 8)).to(DEV)
+    with torch.no_grad():
+        ac32.deform_conv.weight.copy_(ac16.deform_conv.weight.float())
+        oc32.weight.copy_(oc16.weight.float())
+        oc32.bias.copy_(oc16.bias.float())
+        ra = ac32(x.to(dt).float(), anc, 8)
+        check(ya, ra, dt)
+        ro = oc32(ya.float())
+        check(yo, ro, dt)
+    assert torch.equal(yp, yo.view(1, 32, 8, 128, 128).max(dim=2)[0])
