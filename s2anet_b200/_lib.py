@@ -57,7 +57,18 @@ def load():
     return _lib
 
 
+# kernels of THIS library launched by one successful C call (library sorts inside are not counted)
+KERNELS_PER_CALL = {
+    "box_iou_rotated": 1, "box_iou_rotated_batched": 1, "nms_rotated": 4, "multiclass_nms_rotated": 6,
+    "arf_forward": 1, "arf_backward": 1, "ri_pool": 1, "deform_conv_forward_cuda": 1, "alignconv_forward": 1,
+    "orconv_forward": 1, "conv_pack_weight": 1, "alignconv_forward_tc": 1, "orconv_forward_tc": 1,
+}
+launches = 0          # running count, read by bench.py for "gpu_launches"
+
+
 def check(rc, what):
+    global launches
+    launches += KERNELS_PER_CALL.get(what, 0)
     if rc != 0:
         msg = load().s2a_last_error().decode("utf-8", "replace")
         raise RuntimeError("%s failed (status %d): %s" % (what, rc, msg))
