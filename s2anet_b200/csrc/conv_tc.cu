@@ -36,10 +36,14 @@ namespace s2a {
 constexpr int TC_M = 128;                 // rows per CTA tile (8 x 16 patch)
 constexpr int TC_PH = 8, TC_PW = 16;
 constexpr int TC_KB = 64;                 // k-block (elements) = 128 bytes of 16-bit data
-constexpr int TC_STAGES = 3;
+constexpr int TC_GROUPS = 3;               // producer groups of 4 warps; group g fills k-blocks g, g+G, ...
+constexpr int TC_SA = 4;                   // A stages (16 KB each) -- one per in-flight producer group + 1
+constexpr int TC_SB = 3;                   // B stages (32 KB each), filled by TMA
 constexpr int TC_A_BYTES = TC_M * TC_KB * 2;          // 16 KB
 constexpr int TC_B_BYTES_MAX = 256 * TC_KB * 2;       // 32 KB
-constexpr int TC_THREADS = 192;
+constexpr int TC_PROD_THREADS = TC_GROUPS * 128;
+constexpr int TC_THREADS = TC_PROD_THREADS + 64;      // + TMA warp + MMA warp
+constexpr int TC_NBAR = 2 * TC_SA + 2 * TC_SB + 1;
 constexpr int TC_TMEM_COLS = 256;
 constexpr uint32_t kSpinLimit = 1u << 26;            // watchdog: trap instead of hanging the GPU
 
@@ -185,14 +189,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams p) {
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   // carve: A stages | B stages | sample table | barriers
   uint8_t* sA = smem;
-  uint8_t* sB = smem + TC_STAGES * TC_A_BYTES;
-  TapSample* s_tab = reinterpret_cast<TapSample*>(sB + TC_STAGES * TC_B_BYTES_MAX);
+  uint8_t* sB = smem + TC_SA * TC_A_BYTES;
+  TapSample* s_tab = reinterpret_cast<TapSample*>(sB + TC_SB * TC_B_BYTES_MAX);
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s_tab) + sizeof(TapSample) * TC_M * 9);
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 2 * TC_STAGES + 1);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + TC_NBAR);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t bar_full = smem_u32(s_bar), bar_empty = smem_u32(s_bar + TC_STAGES),
-                 bar_acc = smem_u32(s_bar + 2 * TC_STAGES);
+  const uint32_t bar_full_a = smem_u32(s_bar), bar_empty_a = smem_u32(s_bar + TC_SA),
+                 bar_full_b = smem_u32(s_bar + 2 * TC_SA), bar_empty_b = smem_u32(s_bar + 2 * TC_SA + TC_SB),
+                 bar_acc = smem_u32(s_bar + 2 * TC_SA + 2 * TC_SB);
+  constexpr int kTmaWarp = TC_PROD_THREADS / 32, kMmaWarp = kTmaWarp + 1;
 
   // tile -> (image, patch)
   int tile = blockIdx.x;
@@ -205,20 +211,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams p) {
   const uint32_t b_bytes = (uint32_t)p.Co * TC_KB * 2;
 
   if (tid == 0) {
-    for (int s = 0; s < TC_STAGES; ++s) {
-      mbar_init(bar_full + 8 * s, 128 + 1);     // 128 producer threads + the TMA thread's expect_tx arrive
-      mbar_init(bar_empty + 8 * s, 1);          // one tcgen05.commit
+    for (int s = 0; s < TC_SA; ++s) {
+      mbar_init(bar_full_a + 8 * s, 128);       // the 128 threads of the producer group that owns the k-block
+      mbar_init(bar_empty_a + 8 * s, 1);        // one tcgen05.commit
+    }
+    for (int s = 0; s < TC_SB; ++s) {
+      mbar_init(bar_full_b + 8 * s, 1);         // the TMA thread's expect_tx arrive (+ the transaction bytes)
+      mbar_init(bar_empty_b + 8 * s, 1);
     }
     mbar_init(bar_acc, 1);
     fence_barrier_init();
   }
-  if (warp == 5) tmem_alloc(smem_u32(s_tmem), TC_TMEM_COLS);
+  if (warp == kMmaWarp) tmem_alloc(smem_u32(s_tmem), TC_TMEM_COLS);
 
-  if (warp < 4 && MODE == TC_ALIGN) {
+  if (warp < kTmaWarp && MODE == TC_ALIGN) {
     // sample table: (row, tap) -> top-left pixel + fractional weights.
     // Position formula: models/alignconv.py:29-86 with the offset added back as the deformable
     // im2col does (deform_conv_cuda_kernel.cu:223-227), same operation order as csrc/conv_f32.cu.
-    for (int e = tid; e < TC_M * 9; e += 128) {
+    for (int e = tid; e < TC_M * 9; e += TC_PROD_THREADS) {
       const int r = e / 9, t = e - 9 * r;
       const int y = ty0 + r / TC_PW, x = tx0 + r % TC_PW;
       TapSample s;
@@ -252,16 +262,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams p) {
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
 
-  if (warp < 4) {
+  if (warp < kTmaWarp) {
     // ===================== A producers =====================
-    const int chunk = tid & 7;                 // 16-byte chunk (8 channels) inside the 128-byte row
-    const int rsub = tid >> 3;                 // 0..15
+    const int group = warp >> 2;               // producer group: owns k-blocks group, group + G, ...
+    const int gt = tid & 127;                  // thread index inside the group
+    const int chunk = gt & 7;                  // 16-byte chunk (8 channels) inside the 128-byte row
+    const int rsub = gt >> 3;                  // 0..15
     const uint8_t* xb = reinterpret_cast<const uint8_t*>(p.x) + (size_t)b * p.H * p.W * p.C * 2;
-    for (int kb = 0; kb < nkb; ++kb) {
-      const int s = kb % TC_STAGES;
-      const uint32_t ph = (uint32_t)(kb / TC_STAGES) & 1u;
+    for (int kb = group; kb < nkb; kb += TC_GROUPS) {
+      const int s = kb % TC_SA;
+      const uint32_t ph = (uint32_t)(kb / TC_SA) & 1u;
       const int cb = kb / 9, tap = kb - 9 * cb;
-      mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+      mbar_wait(bar_empty_a + 8 * s, ph ^ 1u);
       uint8_t* a_stage = sA + s * TC_A_BYTES;
       const size_t coff = ((size_t)cb * TC_KB + chunk * 8) * 2;      // byte offset of this chunk inside a pixel
 #pragma unroll
@@ -324,20 +336,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams p) {
         }
       }
       fence_proxy_async_smem();          // generic-proxy stores -> visible to the tensor core (async proxy)
-      mbar_arrive(bar_full + 8 * s);
+      mbar_arrive(bar_full_a + 8 * s);
     }
 
     // ===================== epilogue =====================
     mbar_wait(bar_acc, 0);
     tc_fence_after();
-    const int r = warp * 32 + lane;
+    const int quad = warp & 3;                 // TMEM lane quadrant this warp may read
+    const int r = quad * 32 + lane;
     const int y = ty0 + r / TC_PW, x = tx0 + r % TC_PW;
     const bool valid = (y < p.H && x < p.W);
     const size_t pos = (size_t)(b * p.H + y) * p.W + x;
     using H2 = typename Half2Of<T>::type;
-    for (int c0 = 0; c0 < p.Co; c0 += 32) {
+    for (int c0 = group * 32; c0 < p.Co; c0 += 32 * TC_GROUPS) {   // 32-column chunks round-robin over the groups
       uint32_t v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+      tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, v);
       float f[32];
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
@@ -374,15 +387,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams p) {
       }
     }
     tc_fence_before();
-  } else if (warp == 4) {
+  } else if (warp == kTmaWarp) {
     // ===================== weight k-blocks by TMA =====================
     if (lane == 0) {
       for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % TC_STAGES;
-        const uint32_t ph = (uint32_t)(kb / TC_STAGES) & 1u;
-        mbar_wait(bar_empty + 8 * s, ph ^ 1u);
-        mbar_arrive_expect_tx(bar_full + 8 * s, b_bytes);
-        tma_load_2d(smem_u32(sB + s * TC_B_BYTES_MAX), &tmap_w, kb * TC_KB, 0, bar_full + 8 * s);
+        const int s = kb % TC_SB;
+        const uint32_t ph = (uint32_t)(kb / TC_SB) & 1u;
+        mbar_wait(bar_empty_b + 8 * s, ph ^ 1u);
+        mbar_arrive_expect_tx(bar_full_b + 8 * s, b_bytes);
+        tma_load_2d(smem_u32(sB + s * TC_B_BYTES_MAX), &tmap_w, kb * TC_KB, 0, bar_full_b + 8 * s);
       }
     }
   } else {
@@ -394,22 +407,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams p) {
       const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.Co >> 3) << 17) |
                              ((uint32_t)(TC_M >> 4) << 24);
       for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % TC_STAGES;
-        const uint32_t ph = (uint32_t)(kb / TC_STAGES) & 1u;
-        mbar_wait(bar_full + 8 * s, ph);
+        const int sa = kb % TC_SA, sb = kb % TC_SB;
+        mbar_wait(bar_full_a + 8 * sa, (uint32_t)(kb / TC_SA) & 1u);
+        mbar_wait(bar_full_b + 8 * sb, (uint32_t)(kb / TC_SB) & 1u);
         tc_fence_after();
-        const uint64_t adesc = umma_desc_sw128(smem_u32(sA + s * TC_A_BYTES));
-        const uint64_t bdesc = umma_desc_sw128(smem_u32(sB + s * TC_B_BYTES_MAX));
+        const uint64_t adesc = umma_desc_sw128(smem_u32(sA + sa * TC_A_BYTES));
+        const uint64_t bdesc = umma_desc_sw128(smem_u32(sB + sb * TC_B_BYTES_MAX));
 #pragma unroll
         for (int k = 0; k < TC_KB / 16; ++k)      // +32 bytes (>>4 = 2) per K=16 step inside the swizzle atom
           umma_f16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-        umma_commit(bar_empty + 8 * s);           // stage reusable once these MMAs have read it
+        umma_commit(bar_empty_a + 8 * sa);        // stages reusable once these MMAs have read them
+        umma_commit(bar_empty_b + 8 * sb);
       }
       umma_commit(bar_acc);                       // accumulator complete
     }
   }
   __syncthreads();
-  if (warp == 5) {
+  if (warp == kMmaWarp) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TC_TMEM_COLS);
   }
@@ -470,8 +484,8 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-constexpr size_t kTcSmemBytes = 1024 /*alignment slack*/ + (size_t)TC_STAGES * (TC_A_BYTES + TC_B_BYTES_MAX) +
-                                sizeof(TapSample) * TC_M * 9 + 8 * (2 * TC_STAGES + 1) + 16;
+constexpr size_t kTcSmemBytes = 1024 /*alignment slack*/ + (size_t)TC_SA * TC_A_BYTES + (size_t)TC_SB * TC_B_BYTES_MAX +
+                                sizeof(TapSample) * TC_M * 9 + 8 * TC_NBAR + 16;
 
 template <int MODE, typename T>
 static int launch_tc(const CUtensorMap& tmap, const TcParams& p, cudaStream_t st) {

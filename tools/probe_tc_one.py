@@ -1,0 +1,21 @@
+"""One AlignConv + one ORConv tcgen05 launch at batch 8 P3 (for ncu --set full)."""
+import os, sys
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from s2anet_b200 import synth
+from s2anet_b200.alignconv import alignconv_forward
+from s2anet_b200.orn import orconv_forward
+from oracle import oracle as O
+dev = "cuda:0"
+B, s, H = 8, 8, 128
+dt = torch.bfloat16
+x = torch.randn(B, 256, H, H, device=dev).to(dt).contiguous(memory_format=torch.channels_last)
+anc = torch.from_numpy(synth.refined_anchors(B, H, H, s, 1)).to(dev)
+w = (torch.randn(256, 256, 3, 3, device=dev) * 0.01).to(dt)
+wo = (torch.randn(32, 256, 1, 3, 3, device=dev) * 0.01).to(dt)
+idx = torch.from_numpy(O.arf_indices(1, 8, 3)).to(dev)
+for _ in range(3):
+    y = alignconv_forward(x, anc, w, s)
+    z = orconv_forward(y, wo, idx, None, with_pool=True)
+torch.cuda.synchronize()
+print("ok", float(y.float().abs().mean()), float(z[0].float().abs().mean()))
