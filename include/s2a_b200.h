@@ -177,6 +177,18 @@ S2A_EXPORT int s2a_alignconv_forward_tc(const void* x, const float* anchors,
 S2A_EXPORT int s2a_orconv_forward_tc(const void* x, const void* packed_weight, const float* bias,
                                      void* out, void* pooled, int B, int C, int H, int W, int Co,
                                      int dtype, void* stream);
+/* Multi-level forms: all FPN levels of a batch in ONE persistent launch (the reference loops over
+ * levels in Python, models/head.py:265).  Arrays have nlevels (<= 8) entries; every level shares
+ * B, C, Co, the packed weights (and bias); xs[l] is [B, Hs[l], Ws[l], C] etc. */
+S2A_EXPORT int s2a_alignconv_forward_tc_multi(int nlevels, const void* const* xs,
+                                              const float* const* anchors, const void* packed_weight,
+                                              void* const* outs, const int* Hs, const int* Ws,
+                                              const float* strides, int B, int C, int Co, int dtype,
+                                              void* stream);
+S2A_EXPORT int s2a_orconv_forward_tc_multi(int nlevels, const void* const* xs,
+                                           const void* packed_weight, const float* bias,
+                                           void* const* outs, void* const* pooleds, const int* Hs,
+                                           const int* Ws, int B, int C, int Co, int dtype, void* stream);
 
 #ifdef __cplusplus
 }

@@ -80,3 +80,56 @@ def orconv_forward_tc(x, weight, indices, bias, with_pool=False):
                                                B, C, H, W, Co, _lib.dtype_code(xc), _lib.stream_ptr(dev))
     _lib.check(rc, "orconv_forward_tc")
     return (out, pooled) if with_pool else out
+
+
+def _ptr_array(tensors):
+    import ctypes as C
+    return (C.c_void_p * len(tensors))(*[None if t is None else t.data_ptr() for t in tensors])
+
+
+def _int_array(vals):
+    import ctypes as C
+    return (C.c_int * len(vals))(*[int(v) for v in vals])
+
+
+def alignconv_forward_tc_multi(xs, anchors, weight, strides):
+    """All FPN levels in one persistent launch: xs[l] [B,C,H_l,W_l] (16-bit), anchors[l] [B,H_l,W_l,5]."""
+    import ctypes as C
+    dev = _lib.require_cuda(*xs, *anchors, weight)
+    B, Cc = xs[0].shape[:2]
+    Co = weight.size(0)
+    xc = [_nhwc(x) for x in xs]
+    an = [a.to(torch.float32).contiguous() for a in anchors]
+    wp = pack_weight(weight, xs[0].dtype)
+    outs = [torch.empty((B, Co, x.size(2), x.size(3)), dtype=x.dtype, device=dev, memory_format=torch.channels_last)
+            for x in xs]
+    st = (C.c_float * len(xs))(*[float(s) for s in strides])
+    with torch.cuda.device(dev):
+        rc = _lib.load().s2a_alignconv_forward_tc_multi(len(xs), _ptr_array(xc), _ptr_array(an), _lib.ptr(wp),
+                                                        _ptr_array(outs), _int_array([x.size(2) for x in xs]),
+                                                        _int_array([x.size(3) for x in xs]), st, B, Cc, Co,
+                                                        _lib.dtype_code(xc[0]), _lib.stream_ptr(dev))
+    _lib.check(rc, "alignconv_forward_tc_multi")
+    return outs
+
+
+def orconv_forward_tc_multi(xs, weight, indices, bias, with_pool=False):
+    dev = _lib.require_cuda(*xs, weight, indices, bias)
+    B, Cc = xs[0].shape[:2]
+    O, I, nOri = weight.shape[:3]
+    nRot = indices.size(3)
+    Co = O * nRot
+    xc = [_nhwc(x) for x in xs]
+    wp = pack_weight(weight, xs[0].dtype, indices)
+    b = None if bias is None else bias.detach().to(torch.float32).contiguous()
+    outs = [torch.empty((B, Co, x.size(2), x.size(3)), dtype=x.dtype, device=dev, memory_format=torch.channels_last)
+            for x in xs]
+    pooled = [torch.empty((B, Co // 8, x.size(2), x.size(3)), dtype=x.dtype, device=dev,
+                          memory_format=torch.channels_last) for x in xs] if with_pool else [None] * len(xs)
+    with torch.cuda.device(dev):
+        rc = _lib.load().s2a_orconv_forward_tc_multi(len(xs), _ptr_array(xc), _lib.ptr(wp), _lib.ptr(b), _ptr_array(outs),
+                                                     _ptr_array(pooled), _int_array([x.size(2) for x in xs]),
+                                                     _int_array([x.size(3) for x in xs]), B, Cc, Co,
+                                                     _lib.dtype_code(xc[0]), _lib.stream_ptr(dev))
+    _lib.check(rc, "orconv_forward_tc_multi")
+    return (outs, pooled) if with_pool else outs

@@ -27,41 +27,77 @@
 #include <cuda_fp16.h>
 
 #include <algorithm>
+#include <cstdlib>
+#include <cstring>
 #include <type_traits>
 
 #include "common.cuh"
 
 namespace s2a {
 
-constexpr int TC_M = 128;                 // rows per CTA tile (8 x 16 patch)
+constexpr int TC_M = 128;                 // rows per tile (8 x 16 patch) = one UMMA M
 constexpr int TC_PH = 8, TC_PW = 16;
 constexpr int TC_KB = 64;                 // k-block (elements) = 128 bytes of 16-bit data
 constexpr int TC_GROUPS = 3;               // producer groups of 4 warps; group g fills k-blocks g, g+G, ...
-constexpr int TC_SA = 4;                   // A stages (16 KB each) -- one per in-flight producer group + 1
+constexpr int TC_SA = 4;                   // A stages (16 KB each)
 constexpr int TC_SB = 3;                   // B stages (32 KB each), filled by TMA
 constexpr int TC_A_BYTES = TC_M * TC_KB * 2;          // 16 KB
 constexpr int TC_B_BYTES_MAX = 256 * TC_KB * 2;       // 32 KB
 constexpr int TC_PROD_THREADS = TC_GROUPS * 128;
-constexpr int TC_THREADS = TC_PROD_THREADS + 64;      // + TMA warp + MMA warp
-constexpr int TC_NBAR = 2 * TC_SA + 2 * TC_SB + 1;
-constexpr int TC_TMEM_COLS = 256;
+constexpr int TC_EPI_THREADS = 128;                   // 4 epilogue warps, one per TMEM lane quadrant
+constexpr int TC_THREADS = TC_PROD_THREADS + 64 + TC_EPI_THREADS;   // producers | TMA warp | MMA warp | epilogue
+constexpr int TC_ACC_STAGES = 2;                      // double-buffered accumulator: 2 x 256 TMEM columns
+constexpr int TC_TMEM_COLS = 512;
+constexpr int TC_NBAR = 2 * TC_SA + 2 * TC_SB + 2 * TC_ACC_STAGES + 2;
+constexpr int TC_MAX_LEVELS = 8;
 constexpr uint32_t kSpinLimit = 1u << 26;            // watchdog: trap instead of hanging the GPU
 
 enum { TC_ALIGN = 0, TC_PLAIN = 1 };
 
 struct __align__(4) TapSample { short y0, x0; float ly, lx; };   // 12 bytes; y0 == -32768 -> nothing sampled
 
-struct TcParams {
+struct TcLevel {
   const void* x;          // [B, H, W, C] 16-bit (channels_last)
   const float* anchors;   // [B, H, W, 5] (TC_ALIGN)
-  const float* bias;      // [Co] fp32 or null
   void* out;              // [B, H, W, Co] 16-bit
   void* pooled;           // [B, H, W, Co/8] 16-bit or null
-  int B, C, H, W, Co;
-  int tiles_x, tiles_y;   // patches per image
+  int H, W, tiles_x, tiles_y;
+  int tile_begin;         // first global tile index of this level
   float stride;
-  int relu;
 };
+
+struct TcParams {
+  TcLevel lv[TC_MAX_LEVELS];
+  const float* bias;      // [Co] fp32 or null
+  int nlevels, total_tiles;
+  int B, C, Co;
+  int relu;
+  int debug;              // timing experiments only (S2A_TC_DEBUG): 1 = no weight TMA after warm-up, 2 = no gather loads
+};
+
+struct TileCoord { int lvl, b, ty0, tx0; };
+
+// TMA descriptors: the packed weights, and (TC_PLAIN only) one 4-D NHWC map per level
+struct TcMaps {
+  CUtensorMap w;
+  CUtensorMap x[TC_MAX_LEVELS];
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int tile) {
+  int l = 0;
+#pragma unroll 1
+  while (l + 1 < p.nlevels && tile >= p.lv[l + 1].tile_begin) ++l;
+  const TcLevel& L = p.lv[l];
+  int t = tile - L.tile_begin;
+  const int tpi = L.tiles_x * L.tiles_y;
+  TileCoord c;
+  c.lvl = l;
+  c.b = t / tpi;
+  t -= c.b * tpi;
+  c.ty0 = (t / L.tiles_x) * TC_PH;
+  c.tx0 = (t % L.tiles_x) * TC_PW;
+  return c;
+}
 
 // ---------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -107,6 +143,13 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
       "l"((uint64_t)map), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3,
+                                            uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(dst),
+      "l"((uint64_t)map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
       : "memory");
 }
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
@@ -166,262 +209,337 @@ __device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
   return r;
 }
 
+// Packed 16-bit bilinear blend of one 16-byte chunk (8 channels): o = w0*v0 + w1*v1 + w2*v2 + w3*v3 with
+// HMUL2/HFMA2 on bf16x2 / f16x2 pairs.  The reference's half-precision path evaluates the same
+// expression in scalar_t = half (deformable_im2col_bilinear, deform_conv_cuda_kernel.cu:110-113), and
+// the value is rounded to 16 bits for the tensor core either way; doing the four-term sum in packed
+// 16-bit math quarters the producer warps' instruction count, which is what bounds this kernel.
 template <typename T>
-__device__ __forceinline__ void blend_acc(float (&acc)[8], const uint4& v, float w) {
+__device__ __forceinline__ uint4 blend4(const uint4& v0, const uint4& v1, const uint4& v2, const uint4& v3,
+                                        const float (&w)[4]) {
   using H2 = typename Half2Of<T>::type;
-  const H2* h = reinterpret_cast<const H2*>(&v);
+  const H2 w0 = from_f2<T>(w[0], w[0]), w1 = from_f2<T>(w[1], w[1]), w2 = from_f2<T>(w[2], w[2]),
+           w3 = from_f2<T>(w[3], w[3]);
+  const H2* a = reinterpret_cast<const H2*>(&v0);
+  const H2* b = reinterpret_cast<const H2*>(&v1);
+  const H2* c = reinterpret_cast<const H2*>(&v2);
+  const H2* d = reinterpret_cast<const H2*>(&v3);
+  uint4 o;
+  H2* oh = reinterpret_cast<H2*>(&o);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const float2 f = to_f2(h[i]);
-    acc[2 * i] = fmaf(w, f.x, acc[2 * i]);
-    acc[2 * i + 1] = fmaf(w, f.y, acc[2 * i + 1]);
+    H2 t = __hmul2(w0, a[i]);
+    t = __hfma2(w1, b[i], t);
+    t = __hfma2(w2, c[i], t);
+    t = __hfma2(w3, d[i], t);
+    oh[i] = t;
   }
+  return o;
 }
 
 // ---------------------------------------------------------------------------------------------
-// the kernel
+// the kernel: persistent, one CTA per SM, tiles of all levels handed out round-robin
 // ---------------------------------------------------------------------------------------------
+// sample table of one tile: (row, tap) -> top-left pixel + fractional weights.  Position formula:
+// models/alignconv.py:29-86 with the offset added back as the deformable im2col does
+// (deform_conv_cuda_kernel.cu:223-227); same operation order as csrc/conv_f32.cu.
+__device__ __forceinline__ void build_tap_table(const TcParams& p, const TileCoord& tc, TapSample* tab, int t0, int nt) {
+  const TcLevel& L = p.lv[tc.lvl];
+  for (int e = t0; e < TC_M * 9; e += nt) {
+    const int r = e / 9, t = e - 9 * r;
+    const int y = tc.ty0 + r / TC_PW, x = tc.tx0 + r % TC_PW;
+    TapSample s;
+    s.y0 = -32768; s.x0 = 0; s.ly = 0.0f; s.lx = 0.0f;
+    if (y < L.H && x < L.W) {
+      const float* a = L.anchors + ((size_t)(tc.b * L.H + y) * L.W + x) * 5;
+      const float ax = a[0] / L.stride, ay = a[1] / L.stride, aw = a[2] / L.stride, ah = a[3] / L.stride;
+      const float cs = cosf(a[4]), sn = sinf(a[4]);
+      const float dw = aw / 3.0f, dh = ah / 3.0f;
+      const int ti = t / 3, tj = t - 3 * ti;
+      const float fi = (float)(ti - 1), fj = (float)(tj - 1);
+      const float txx = __fmul_rn(dw, fj), tyy = __fmul_rn(dh, fi);
+      const float xr = __fsub_rn(__fmul_rn(cs, txx), __fmul_rn(sn, tyy));
+      const float yr = __fadd_rn(__fmul_rn(sn, txx), __fmul_rn(cs, tyy));
+      const float xa = __fadd_rn(xr, ax), ya = __fadd_rn(yr, ay);
+      const float offx = __fsub_rn(xa, __fadd_rn((float)x, fj));
+      const float offy = __fsub_rn(ya, __fadd_rn((float)y, fi));
+      const float h = __fadd_rn((float)(y - 1 + ti), offy);
+      const float w = __fadd_rn((float)(x - 1 + tj), offx);
+      if (h > -1.0f && w > -1.0f && h < (float)L.H && w < (float)L.W) {
+        const float hf = floorf(h), wf = floorf(w);
+        s.y0 = (short)(int)hf; s.x0 = (short)(int)wf;
+        s.ly = h - hf; s.lx = w - wf;
+      }
+    }
+    tab[e] = s;
+  }
+}
+
 template <int MODE, typename T>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const TcParams p) {
+conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B operands need 1024-byte aligned tiles: align the dynamic window by hand
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  // carve: A stages | B stages | sample table | barriers
+  // carve: A stages | B stages | 2 sample tables | barriers | tmem pointer
   uint8_t* sA = smem;
   uint8_t* sB = smem + TC_SA * TC_A_BYTES;
   TapSample* s_tab = reinterpret_cast<TapSample*>(sB + TC_SB * TC_B_BYTES_MAX);
-  uint64_t* s_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s_tab) + sizeof(TapSample) * TC_M * 9);
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s_tab) + 2 * sizeof(TapSample) * TC_M * 9);
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + TC_NBAR);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t bar_full_a = smem_u32(s_bar), bar_empty_a = smem_u32(s_bar + TC_SA),
-                 bar_full_b = smem_u32(s_bar + 2 * TC_SA), bar_empty_b = smem_u32(s_bar + 2 * TC_SA + TC_SB),
-                 bar_acc = smem_u32(s_bar + 2 * TC_SA + 2 * TC_SB);
-  constexpr int kTmaWarp = TC_PROD_THREADS / 32, kMmaWarp = kTmaWarp + 1;
+  const uint32_t bar_full_a = smem_u32(s_bar), bar_empty_a = bar_full_a + 8 * TC_SA,
+                 bar_full_b = bar_empty_a + 8 * TC_SA, bar_empty_b = bar_full_b + 8 * TC_SB,
+                 bar_acc_full = bar_empty_b + 8 * TC_SB, bar_acc_empty = bar_acc_full + 8 * TC_ACC_STAGES,
+                 bar_tab_full = bar_acc_empty + 8 * TC_ACC_STAGES;       // 2 barriers
+  constexpr int kTmaWarp = TC_PROD_THREADS / 32, kMmaWarp = kTmaWarp + 1, kEpiWarp0 = kTmaWarp + 2;
 
-  // tile -> (image, patch)
-  int tile = blockIdx.x;
-  const int tpi = p.tiles_x * p.tiles_y;
-  const int b = tile / tpi;
-  tile -= b * tpi;
-  const int ty0 = (tile / p.tiles_x) * TC_PH, tx0 = (tile % p.tiles_x) * TC_PW;
   const int ncb = p.C / TC_KB;
   const int nkb = ncb * 9;
   const uint32_t b_bytes = (uint32_t)p.Co * TC_KB * 2;
+  const int first_tile = blockIdx.x, tile_step = gridDim.x;
 
   if (tid == 0) {
     for (int s = 0; s < TC_SA; ++s) {
-      mbar_init(bar_full_a + 8 * s, 128);       // the 128 threads of the producer group that owns the k-block
+      // ALIGN: the 128 threads of the producer group that owns the k-block; PLAIN: the TMA thread's expect_tx
+      mbar_init(bar_full_a + 8 * s, MODE == TC_ALIGN ? 128 : 1);
       mbar_init(bar_empty_a + 8 * s, 1);        // one tcgen05.commit
     }
     for (int s = 0; s < TC_SB; ++s) {
       mbar_init(bar_full_b + 8 * s, 1);         // the TMA thread's expect_tx arrive (+ the transaction bytes)
       mbar_init(bar_empty_b + 8 * s, 1);
     }
-    mbar_init(bar_acc, 1);
+    for (int s = 0; s < TC_ACC_STAGES; ++s) {
+      mbar_init(bar_acc_full + 8 * s, 1);       // tcgen05.commit after the last k-block of a tile
+      mbar_init(bar_acc_empty + 8 * s, TC_EPI_THREADS);
+      mbar_init(bar_tab_full + 8 * s, TC_EPI_THREADS);
+    }
     fence_barrier_init();
   }
   if (warp == kMmaWarp) tmem_alloc(smem_u32(s_tmem), TC_TMEM_COLS);
-
-  if (warp < kTmaWarp && MODE == TC_ALIGN) {
-    // sample table: (row, tap) -> top-left pixel + fractional weights.
-    // Position formula: models/alignconv.py:29-86 with the offset added back as the deformable
-    // im2col does (deform_conv_cuda_kernel.cu:223-227), same operation order as csrc/conv_f32.cu.
-    for (int e = tid; e < TC_M * 9; e += TC_PROD_THREADS) {
-      const int r = e / 9, t = e - 9 * r;
-      const int y = ty0 + r / TC_PW, x = tx0 + r % TC_PW;
-      TapSample s;
-      s.y0 = -32768; s.x0 = 0; s.ly = 0.0f; s.lx = 0.0f;
-      if (y < p.H && x < p.W) {
-        const float* a = p.anchors + ((size_t)(b * p.H + y) * p.W + x) * 5;
-        const float ax = a[0] / p.stride, ay = a[1] / p.stride, aw = a[2] / p.stride, ah = a[3] / p.stride;
-        const float cs = cosf(a[4]), sn = sinf(a[4]);
-        const float dw = aw / 3.0f, dh = ah / 3.0f;
-        const int ti = t / 3, tj = t - 3 * ti;
-        const float fi = (float)(ti - 1), fj = (float)(tj - 1);
-        const float txx = __fmul_rn(dw, fj), tyy = __fmul_rn(dh, fi);
-        const float xr = __fsub_rn(__fmul_rn(cs, txx), __fmul_rn(sn, tyy));
-        const float yr = __fadd_rn(__fmul_rn(sn, txx), __fmul_rn(cs, tyy));
-        const float xa = __fadd_rn(xr, ax), ya = __fadd_rn(yr, ay);
-        const float offx = __fsub_rn(xa, __fadd_rn((float)x, fj));
-        const float offy = __fsub_rn(ya, __fadd_rn((float)y, fi));
-        const float h = __fadd_rn((float)(y - 1 + ti), offy);
-        const float w = __fadd_rn((float)(x - 1 + tj), offx);
-        if (h > -1.0f && w > -1.0f && h < (float)p.H && w < (float)p.W) {
-          const float hf = floorf(h), wf = floorf(w);
-          s.y0 = (short)(int)hf; s.x0 = (short)(int)wf;
-          s.ly = h - hf; s.lx = w - wf;
-        }
-      }
-      s_tab[e] = s;
-    }
-  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
 
   if (warp < kTmaWarp) {
-    // ===================== A producers =====================
-    const int group = warp >> 2;               // producer group: owns k-blocks group, group + G, ...
+    // ===================== A producers (AlignConv: bilinear gather through the LSU) =====================
+    // In TC_PLAIN mode (ORConv2d) the A tile is a shifted patch of the NHWC map, which TMA fetches
+    // directly (zero-filled outside the map), so these warps have nothing to do.
+    const int group = warp >> 2;               // producer group: owns global k-blocks group, group + G, ...
     const int gt = tid & 127;                  // thread index inside the group
     const int chunk = gt & 7;                  // 16-byte chunk (8 channels) inside the 128-byte row
     const int rsub = gt >> 3;                  // 0..15
-    const uint8_t* xb = reinterpret_cast<const uint8_t*>(p.x) + (size_t)b * p.H * p.W * p.C * 2;
-    for (int kb = group; kb < nkb; kb += TC_GROUPS) {
-      const int s = kb % TC_SA;
-      const uint32_t ph = (uint32_t)(kb / TC_SA) & 1u;
-      const int cb = kb / 9, tap = kb - 9 * cb;
-      mbar_wait(bar_empty_a + 8 * s, ph ^ 1u);
-      uint8_t* a_stage = sA + s * TC_A_BYTES;
-      const size_t coff = ((size_t)cb * TC_KB + chunk * 8) * 2;      // byte offset of this chunk inside a pixel
+    long long gkb_base = 0;                    // global k-block index of this tile's k-block 0
+    int it = 0;
+    for (int tile = first_tile; MODE == TC_ALIGN && tile < p.total_tiles; tile += tile_step, ++it, gkb_base += nkb) {
+      const TileCoord tc = decode_tile(p, tile);
+      const TcLevel& L = p.lv[tc.lvl];
+      const int H = L.H, W = L.W;
+      const uint8_t* xb = reinterpret_cast<const uint8_t*>(L.x) + (size_t)tc.b * H * W * p.C * 2;
+      const TapSample* tab = s_tab + (it & 1) * (TC_M * 9);
+      if (MODE == TC_ALIGN) mbar_wait(bar_tab_full + 8 * (it & 1), (uint32_t)(it >> 1) & 1u);
+      // first k-block of this tile that belongs to this group
+      int kb = (int)((group - (gkb_base % TC_GROUPS) + TC_GROUPS) % TC_GROUPS);
+      for (; kb < nkb; kb += TC_GROUPS) {
+        const long long gkb = gkb_base + kb;
+        const int s = (int)(gkb % TC_SA);
+        const uint32_t ph = (uint32_t)(gkb / TC_SA) & 1u;
+        const int cb = kb / 9, tap = kb - 9 * cb;
+        mbar_wait(bar_empty_a + 8 * s, ph ^ 1u);
+        uint8_t* a_stage = sA + s * TC_A_BYTES;
+        if (p.debug & 2) { fence_proxy_async_smem(); mbar_arrive(bar_full_a + 8 * s); continue; }
+        const size_t coff = ((size_t)cb * TC_KB + chunk * 8) * 2;      // byte offset of this chunk inside a pixel
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        uint4 v[4][4];
-        float wt[4][4];
+        for (int half = 0; half < 2; ++half) {
+          uint4 v[4][4];
+          float wt[4][4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int r = (half * 4 + i) * 16 + rsub;
-          int y0, x0;
-          float ly, lx;
-          bool any;
-          if (MODE == TC_ALIGN) {
-            const TapSample sm = s_tab[r * 9 + tap];
-            y0 = sm.y0; x0 = sm.x0; ly = sm.ly; lx = sm.lx;
-            any = sm.y0 != -32768;
-          } else {
-            const int y = ty0 + r / TC_PW, x = tx0 + r % TC_PW;
-            y0 = y - 1 + tap / 3; x0 = x - 1 + tap % 3; ly = 0.0f; lx = 0.0f;
-            any = (y < p.H && x < p.W);
+          for (int i = 0; i < 4; ++i) {
+            const int r = (half * 4 + i) * 16 + rsub;
+            int y0, x0;
+            float ly, lx;
+            bool any;
+            if (MODE == TC_ALIGN) {
+              const TapSample sm = tab[r * 9 + tap];
+              y0 = sm.y0; x0 = sm.x0; ly = sm.ly; lx = sm.lx;
+              any = sm.y0 != -32768;
+            } else {
+              const int y = tc.ty0 + r / TC_PW, x = tc.tx0 + r % TC_PW;
+              y0 = y - 1 + tap / 3; x0 = x - 1 + tap % 3; ly = 0.0f; lx = 0.0f;
+              any = (y < H && x < W);
+            }
+            const float hy = 1.0f - ly, hx = 1.0f - lx;
+            const bool t_ok = any && y0 >= 0 && y0 < H, b_ok = any && y0 + 1 >= 0 && y0 + 1 <= H - 1;
+            const bool l_ok = x0 >= 0 && x0 < W, r_ok = x0 + 1 >= 0 && x0 + 1 <= W - 1;
+            wt[i][0] = (t_ok && l_ok) ? hy * hx : 0.0f;
+            wt[i][1] = (t_ok && r_ok) ? hy * lx : 0.0f;
+            wt[i][2] = (b_ok && l_ok) ? ly * hx : 0.0f;
+            wt[i][3] = (b_ok && r_ok) ? ly * lx : 0.0f;
+            const int yt = min(max(y0, 0), H - 1), yb = min(max(y0 + 1, 0), H - 1);
+            const int xl = min(max(x0, 0), W - 1), xr = min(max(x0 + 1, 0), W - 1);
+            const size_t rowt = (size_t)yt * W, rowb = (size_t)yb * W;
+            if (MODE == TC_ALIGN) {
+              v[i][0] = ldg_nc_v4(xb + (rowt + xl) * p.C * 2 + coff);
+              v[i][1] = ldg_nc_v4(xb + (rowt + xr) * p.C * 2 + coff);
+              v[i][2] = ldg_nc_v4(xb + (rowb + xl) * p.C * 2 + coff);
+              v[i][3] = ldg_nc_v4(xb + (rowb + xr) * p.C * 2 + coff);
+            } else {
+              v[i][0] = ldg_nc_v4(xb + (rowt + xl) * p.C * 2 + coff);
+            }
           }
-          const float hy = 1.0f - ly, hx = 1.0f - lx;
-          const bool t_ok = any && y0 >= 0 && y0 < p.H, b_ok = any && y0 + 1 >= 0 && y0 + 1 <= p.H - 1;
-          const bool l_ok = x0 >= 0 && x0 < p.W, r_ok = x0 + 1 >= 0 && x0 + 1 <= p.W - 1;
-          wt[i][0] = (t_ok && l_ok) ? hy * hx : 0.0f;
-          wt[i][1] = (t_ok && r_ok) ? hy * lx : 0.0f;
-          wt[i][2] = (b_ok && l_ok) ? ly * hx : 0.0f;
-          wt[i][3] = (b_ok && r_ok) ? ly * lx : 0.0f;
-          const int yt = min(max(y0, 0), p.H - 1), yb = min(max(y0 + 1, 0), p.H - 1);
-          const int xl = min(max(x0, 0), p.W - 1), xr = min(max(x0 + 1, 0), p.W - 1);
-          const size_t rowt = (size_t)yt * p.W, rowb = (size_t)yb * p.W;
-          if (MODE == TC_ALIGN) {
-            v[i][0] = ldg_nc_v4(xb + (rowt + xl) * p.C * 2 + coff);
-            v[i][1] = ldg_nc_v4(xb + (rowt + xr) * p.C * 2 + coff);
-            v[i][2] = ldg_nc_v4(xb + (rowb + xl) * p.C * 2 + coff);
-            v[i][3] = ldg_nc_v4(xb + (rowb + xr) * p.C * 2 + coff);
-          } else {
-            v[i][0] = ldg_nc_v4(xb + (rowt + xl) * p.C * 2 + coff);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int r = (half * 4 + i) * 16 + rsub;
+            uint4 o;
+            if (MODE == TC_ALIGN) {
+              o = blend4<T>(v[i][0], v[i][1], v[i][2], v[i][3], wt[i]);
+            } else {
+              o = (wt[i][0] != 0.0f) ? v[i][0] : make_uint4(0u, 0u, 0u, 0u);
+            }
+            // K-major SWIZZLE_128B: 16-byte chunk c of row r lives at chunk position c ^ (r & 7)
+            *reinterpret_cast<uint4*>(a_stage + r * 128 + ((chunk ^ (r & 7)) << 4)) = o;
           }
         }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int r = (half * 4 + i) * 16 + rsub;
-          uint4 o;
-          if (MODE == TC_ALIGN) {
-            float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            blend_acc<T>(acc, v[i][0], wt[i][0]);
-            blend_acc<T>(acc, v[i][1], wt[i][1]);
-            blend_acc<T>(acc, v[i][2], wt[i][2]);
-            blend_acc<T>(acc, v[i][3], wt[i][3]);
-            using H2 = typename Half2Of<T>::type;
-            H2* oh = reinterpret_cast<H2*>(&o);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) oh[q] = from_f2<T>(acc[2 * q], acc[2 * q + 1]);
-          } else {
-            o = (wt[i][0] != 0.0f) ? v[i][0] : make_uint4(0u, 0u, 0u, 0u);
-          }
-          // K-major SWIZZLE_128B: 16-byte chunk c of row r lives at chunk position c ^ (r & 7)
-          *reinterpret_cast<uint4*>(a_stage + r * 128 + ((chunk ^ (r & 7)) << 4)) = o;
-        }
-      }
-      fence_proxy_async_smem();          // generic-proxy stores -> visible to the tensor core (async proxy)
-      mbar_arrive(bar_full_a + 8 * s);
-    }
-
-    // ===================== epilogue =====================
-    mbar_wait(bar_acc, 0);
-    tc_fence_after();
-    const int quad = warp & 3;                 // TMEM lane quadrant this warp may read
-    const int r = quad * 32 + lane;
-    const int y = ty0 + r / TC_PW, x = tx0 + r % TC_PW;
-    const bool valid = (y < p.H && x < p.W);
-    const size_t pos = (size_t)(b * p.H + y) * p.W + x;
-    using H2 = typename Half2Of<T>::type;
-    for (int c0 = group * 32; c0 < p.Co; c0 += 32 * TC_GROUPS) {   // 32-column chunks round-robin over the groups
-      uint32_t v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, v);
-      float f[32];
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        float t = __uint_as_float(v[i]);
-        if (p.bias) t += __ldg(p.bias + c0 + i);
-        if (p.relu) t = fmaxf(t, 0.0f);
-        f[i] = t;
-      }
-      if (valid) {
-        uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(p.out) + (pos * p.Co + c0) * 2);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint4 o;
-          H2* oh = reinterpret_cast<H2*>(&o);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) oh[j] = from_f2<T>(f[q * 8 + 2 * j], f[q * 8 + 2 * j + 1]);
-          dst[q] = o;
-        }
-        if (p.pooled) {
-          float m[4];
-#pragma unroll
-          for (int gidx = 0; gidx < 4; ++gidx) {
-            float mv = f[gidx * 8];
-#pragma unroll
-            for (int j = 1; j < 8; ++j) mv = fmaxf(mv, f[gidx * 8 + j]);
-            m[gidx] = mv;
-          }
-          uint2 o;
-          H2* oh = reinterpret_cast<H2*>(&o);
-          oh[0] = from_f2<T>(m[0], m[1]);
-          oh[1] = from_f2<T>(m[2], m[3]);
-          *reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(p.pooled) + (pos * (p.Co / 8) + c0 / 8) * 2) = o;
-        }
+        fence_proxy_async_smem();          // generic-proxy stores -> visible to the tensor core (async proxy)
+        mbar_arrive(bar_full_a + 8 * s);
       }
     }
-    tc_fence_before();
   } else if (warp == kTmaWarp) {
     // ===================== weight k-blocks by TMA =====================
     if (lane == 0) {
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % TC_SB;
-        const uint32_t ph = (uint32_t)(kb / TC_SB) & 1u;
-        mbar_wait(bar_empty_b + 8 * s, ph ^ 1u);
-        mbar_arrive_expect_tx(bar_full_b + 8 * s, b_bytes);
-        tma_load_2d(smem_u32(sB + s * TC_B_BYTES_MAX), &tmap_w, kb * TC_KB, 0, bar_full_b + 8 * s);
+      long long gkb = 0;
+      for (int tile = first_tile; tile < p.total_tiles; tile += tile_step) {
+        const TileCoord tc = decode_tile(p, tile);
+        for (int kb = 0; kb < nkb; ++kb, ++gkb) {
+          if (MODE == TC_PLAIN) {
+            // A tile = the 8 x 16 patch shifted by the tap, 64 channels: one 4-D box {64, 16, 8, 1}
+            const int sa = (int)(gkb % TC_SA);
+            const int cb = kb / 9, tap = kb - 9 * cb;
+            mbar_wait(bar_empty_a + 8 * sa, ((uint32_t)(gkb / TC_SA) & 1u) ^ 1u);
+            mbar_arrive_expect_tx(bar_full_a + 8 * sa, TC_A_BYTES);
+            tma_load_4d(smem_u32(sA + sa * TC_A_BYTES), &maps.x[tc.lvl], cb * TC_KB, tc.tx0 - 1 + tap % 3,
+                        tc.ty0 - 1 + tap / 3, tc.b, bar_full_a + 8 * sa);
+          }
+          const int s = (int)(gkb % TC_SB);
+          const uint32_t ph = (uint32_t)(gkb / TC_SB) & 1u;
+          mbar_wait(bar_empty_b + 8 * s, ph ^ 1u);
+          if ((p.debug & 1) && gkb >= TC_SB) { mbar_arrive(bar_full_b + 8 * s); continue; }
+          mbar_arrive_expect_tx(bar_full_b + 8 * s, b_bytes);
+          tma_load_2d(smem_u32(sB + s * TC_B_BYTES_MAX), &maps.w, kb * TC_KB, 0, bar_full_b + 8 * s);
+        }
       }
     }
-  } else {
+  } else if (warp == kMmaWarp) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 (1<<4), A/B format (bf16=1, f16=0)
       // at bits 7 / 10, K-major A and B, N>>3 at bit 17, M>>4 at bit 24
-      const uint32_t fmt = (sizeof(T) == 2 && std::is_same<T, __nv_bfloat16>::value) ? 1u : 0u;
+      const uint32_t fmt = std::is_same<T, __nv_bfloat16>::value ? 1u : 0u;
       const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.Co >> 3) << 17) |
                              ((uint32_t)(TC_M >> 4) << 24);
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int sa = kb % TC_SA, sb = kb % TC_SB;
-        mbar_wait(bar_full_a + 8 * sa, (uint32_t)(kb / TC_SA) & 1u);
-        mbar_wait(bar_full_b + 8 * sb, (uint32_t)(kb / TC_SB) & 1u);
+      long long gkb = 0;
+      int it = 0;
+      for (int tile = first_tile; tile < p.total_tiles; tile += tile_step, ++it) {
+        const int as = it & 1;
+        mbar_wait(bar_acc_empty + 8 * as, ((uint32_t)(it >> 1) & 1u) ^ 1u);     // epilogue drained this accumulator
         tc_fence_after();
-        const uint64_t adesc = umma_desc_sw128(smem_u32(sA + sa * TC_A_BYTES));
-        const uint64_t bdesc = umma_desc_sw128(smem_u32(sB + sb * TC_B_BYTES_MAX));
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * 256);
+        for (int kb = 0; kb < nkb; ++kb, ++gkb) {
+          const int sa = (int)(gkb % TC_SA), sb = (int)(gkb % TC_SB);
+          mbar_wait(bar_full_a + 8 * sa, (uint32_t)(gkb / TC_SA) & 1u);
+          mbar_wait(bar_full_b + 8 * sb, (uint32_t)(gkb / TC_SB) & 1u);
+          tc_fence_after();
+          const uint64_t adesc = umma_desc_sw128(smem_u32(sA + sa * TC_A_BYTES));
+          const uint64_t bdesc = umma_desc_sw128(smem_u32(sB + sb * TC_B_BYTES_MAX));
 #pragma unroll
-        for (int k = 0; k < TC_KB / 16; ++k)      // +32 bytes (>>4 = 2) per K=16 step inside the swizzle atom
-          umma_f16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-        umma_commit(bar_empty_a + 8 * sa);        // stages reusable once these MMAs have read them
-        umma_commit(bar_empty_b + 8 * sb);
+          for (int k = 0; k < TC_KB / 16; ++k)      // +32 bytes (>>4 = 2) per K=16 step inside the swizzle atom
+            umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit(bar_empty_a + 8 * sa);        // stages reusable once these MMAs have read them
+          umma_commit(bar_empty_b + 8 * sb);
+        }
+        umma_commit(bar_acc_full + 8 * as);         // accumulator of this tile complete
       }
-      umma_commit(bar_acc);                       // accumulator complete
+    }
+  } else {
+    // ===================== epilogue warps (also build the sample tables) =====================
+    const int et = tid - kEpiWarp0 * 32;          // 0..127
+    const int quad = warp & 3;                    // TMEM lane quadrant this warp may read (warp id % 4)
+    using H2 = typename Half2Of<T>::type;
+    if (MODE == TC_ALIGN) {
+      // tables of the first two tiles
+      for (int j = 0; j < 2; ++j) {
+        const int tile = first_tile + j * tile_step;
+        if (tile < p.total_tiles) {
+          build_tap_table(p, decode_tile(p, tile), s_tab + j * (TC_M * 9), et, TC_EPI_THREADS);
+          mbar_arrive(bar_tab_full + 8 * j);
+        }
+      }
+    }
+    int it = 0;
+    for (int tile = first_tile; tile < p.total_tiles; tile += tile_step, ++it) {
+      const int as = it & 1;
+      const TileCoord tc = decode_tile(p, tile);
+      const TcLevel& L = p.lv[tc.lvl];
+      mbar_wait(bar_acc_full + 8 * as, (uint32_t)(it >> 1) & 1u);
+      tc_fence_after();
+      const int r = quad * 32 + lane;
+      const int y = tc.ty0 + r / TC_PW, x = tc.tx0 + r % TC_PW;
+      const bool valid = (y < L.H && x < L.W);
+      const size_t pos = (size_t)(tc.b * L.H + y) * L.W + x;
+      for (int c0 = 0; c0 < p.Co; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * 256 + c0), v);
+        float f[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float t = __uint_as_float(v[i]);
+          if (p.bias) t += __ldg(p.bias + c0 + i);
+          if (p.relu) t = fmaxf(t, 0.0f);
+          f[i] = t;
+        }
+        if (valid) {
+          uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(L.out) + (pos * p.Co + c0) * 2);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint4 o;
+            H2* oh = reinterpret_cast<H2*>(&o);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) oh[j] = from_f2<T>(f[q * 8 + 2 * j], f[q * 8 + 2 * j + 1]);
+            dst[q] = o;
+          }
+          if (L.pooled) {
+            float m[4];
+#pragma unroll
+            for (int gidx = 0; gidx < 4; ++gidx) {
+              float mv = f[gidx * 8];
+#pragma unroll
+              for (int j = 1; j < 8; ++j) mv = fmaxf(mv, f[gidx * 8 + j]);
+              m[gidx] = mv;
+            }
+            uint2 o;
+            H2* oh = reinterpret_cast<H2*>(&o);
+            oh[0] = from_f2<T>(m[0], m[1]);
+            oh[1] = from_f2<T>(m[2], m[3]);
+            *reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(L.pooled) + (pos * (p.Co / 8) + c0 / 8) * 2) = o;
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(bar_acc_empty + 8 * as);          // accumulator may be overwritten by tile it + 2
+      if (MODE == TC_ALIGN) {
+        // every A k-block of tile `it` has been produced (its MMAs completed), so table (it & 1) is free:
+        // build the table of tile it + 2 into it
+        const int nxt = tile + 2 * tile_step;
+        if (nxt < p.total_tiles) {
+          build_tap_table(p, decode_tile(p, nxt), s_tab + as * (TC_M * 9), et, TC_EPI_THREADS);
+          mbar_arrive(bar_tab_full + 8 * as);
+        }
+      }
     }
   }
+  tc_fence_before();
   __syncthreads();
   if (warp == kMmaWarp) {
     tc_fence_after();
@@ -485,47 +603,73 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 constexpr size_t kTcSmemBytes = 1024 /*alignment slack*/ + (size_t)TC_SA * TC_A_BYTES + (size_t)TC_SB * TC_B_BYTES_MAX +
-                                sizeof(TapSample) * TC_M * 9 + 8 * TC_NBAR + 16;
+                                2 * sizeof(TapSample) * TC_M * 9 + 8 * TC_NBAR + 16;
 
 template <int MODE, typename T>
-static int launch_tc(const CUtensorMap& tmap, const TcParams& p, cudaStream_t st) {
+static int launch_tc(const TcMaps& tmap, const TcParams& p, cudaStream_t st) {
   auto kern = conv_tc_kernel<MODE, T>;
   S2A_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
-  const int tiles = p.B * p.tiles_x * p.tiles_y;
-  kern<<<tiles, TC_THREADS, kTcSmemBytes, st>>>(tmap, p);
+  const int grid = std::min(p.total_tiles, sm_count());      // persistent: at most one CTA per SM
+  kern<<<grid, TC_THREADS, kTcSmemBytes, st>>>(tmap, p);
   S2A_LAUNCH_OK("conv_tc_kernel");
   return S2A_OK;
 }
 
-static int conv_tc_common(int mode, const void* x, const float* anchors, const void* wp, const float* bias, void* out,
-                          void* pooled, int B, int C, int H, int W, int Co, float stride, int relu, int dtype,
-                          cudaStream_t st) {
-  S2A_CHECK_ARG(B >= 0 && C > 0 && H > 0 && W > 0 && Co > 0, "conv_tc: bad tensor sizes");
+static int conv_tc_common(int mode, int nlevels, const void* const* xs, const float* const* anchors, const void* wp,
+                          const float* bias, void* const* outs, void* const* pooleds, const int* Hs, const int* Ws,
+                          const float* strides, int B, int C, int Co, int relu, int dtype, cudaStream_t st) {
+  S2A_CHECK_ARG(nlevels >= 1 && nlevels <= TC_MAX_LEVELS, "conv_tc: 1..%d levels per launch", TC_MAX_LEVELS);
+  S2A_CHECK_ARG(B >= 0 && C > 0 && Co > 0, "conv_tc: bad tensor sizes");
   S2A_CHECK_ARG(dtype == S2A_BF16 || dtype == S2A_F16, "conv_tc: dtype must be bf16 or f16");
   if (C % 64 != 0 || Co % 32 != 0 || Co > 256) {
     set_error("conv_tc: needs C %% 64 == 0 and C_out a multiple of 32 up to 256 (got C=%d, C_out=%d)", C, Co);
     return S2A_ERR_UNSUPPORTED;
   }
-  S2A_CHECK_ARG(H < 32768 && W < 32768, "conv_tc: feature map too large");
   if (B == 0) return S2A_OK;
-  S2A_CHECK_ARG(x && wp && out && (mode == TC_PLAIN || anchors), "conv_tc: null pointer");
-  S2A_CHECK_ARG(!pooled || Co % 8 == 0, "conv_tc: pooling needs C_out %% 8 == 0");
+  S2A_CHECK_ARG(xs && wp && outs && Hs && Ws, "conv_tc: null pointer");
+  TcParams p{};
+  long long tiles = 0;
+  for (int l = 0; l < nlevels; ++l) {
+    S2A_CHECK_ARG(Hs[l] > 0 && Ws[l] > 0 && Hs[l] < 32768 && Ws[l] < 32768, "conv_tc: bad feature map size");
+    S2A_CHECK_ARG(xs[l] && outs[l] && (mode == TC_PLAIN || (anchors && anchors[l])), "conv_tc: null level pointer");
+    TcLevel& L = p.lv[l];
+    L.x = xs[l]; L.anchors = anchors ? anchors[l] : nullptr; L.out = outs[l]; L.pooled = pooleds ? pooleds[l] : nullptr;
+    L.H = Hs[l]; L.W = Ws[l];
+    L.tiles_x = (Ws[l] + TC_PW - 1) / TC_PW; L.tiles_y = (Hs[l] + TC_PH - 1) / TC_PH;
+    L.tile_begin = (int)tiles;
+    L.stride = strides ? strides[l] : 1.0f;
+    S2A_CHECK_ARG(mode == TC_PLAIN || L.stride > 0.0f, "alignconv_tc: stride must be positive");
+    tiles += (long long)B * L.tiles_x * L.tiles_y;
+  }
+  S2A_CHECK_ARG(tiles < (1ll << 31), "conv_tc: too many tiles");
+  S2A_CHECK_ARG(!(pooleds && pooleds[0]) || Co % 8 == 0, "conv_tc: pooling needs C_out %% 8 == 0");
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) { set_error("conv_tc: cuTensorMapEncodeTiled is not available from the driver"); return S2A_ERR_CUDA; }
-  CUtensorMap tmap;
+  TcMaps tmap;
+  memset(&tmap, 0, sizeof(tmap));
+  const CUtensorMapDataType tdt = dtype == S2A_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  if (mode == TC_PLAIN) {
+    for (int l = 0; l < nlevels; ++l) {
+      const cuuint64_t xd[4] = {(cuuint64_t)C, (cuuint64_t)Ws[l], (cuuint64_t)Hs[l], (cuuint64_t)B};
+      const cuuint64_t xs_[3] = {(cuuint64_t)C * 2, (cuuint64_t)Ws[l] * C * 2, (cuuint64_t)Hs[l] * Ws[l] * C * 2};
+      const cuuint32_t xb[4] = {(cuuint32_t)TC_KB, (cuuint32_t)TC_PW, (cuuint32_t)TC_PH, 1};
+      const cuuint32_t xe[4] = {1, 1, 1, 1};
+      CUresult xr = enc(&tmap.x[l], tdt, 4, const_cast<void*>(xs[l]), xd, xs_, xb, xe, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (xr != CUDA_SUCCESS) { set_error("conv_tc: cuTensorMapEncodeTiled (x, level %d) failed (%d)", l, (int)xr); return S2A_ERR_CUDA; }
+    }
+  }
   const cuuint64_t gdim[2] = {(cuuint64_t)C * 9, (cuuint64_t)Co};
   const cuuint64_t gstr[1] = {(cuuint64_t)C * 9 * 2};
   const cuuint32_t box[2] = {(cuuint32_t)TC_KB, (cuuint32_t)Co};
   const cuuint32_t estr[2] = {1, 1};
-  CUresult cr = enc(&tmap, dtype == S2A_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
+  CUresult cr = enc(&tmap.w, tdt, 2,
                     const_cast<void*>(wp), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (cr != CUDA_SUCCESS) { set_error("conv_tc: cuTensorMapEncodeTiled failed (%d)", (int)cr); return S2A_ERR_CUDA; }
-  TcParams p{};
-  p.x = x; p.anchors = anchors; p.bias = bias; p.out = out; p.pooled = pooled;
-  p.B = B; p.C = C; p.H = H; p.W = W; p.Co = Co;
-  p.tiles_x = (W + TC_PW - 1) / TC_PW; p.tiles_y = (H + TC_PH - 1) / TC_PH;
-  p.stride = stride; p.relu = relu;
+  p.bias = bias; p.nlevels = nlevels; p.total_tiles = (int)tiles;
+  p.B = B; p.C = C; p.Co = Co; p.relu = relu;
+  { const char* e = getenv("S2A_TC_DEBUG"); p.debug = e ? atoi(e) : 0; }
   if (mode == TC_ALIGN) {
     return dtype == S2A_BF16 ? launch_tc<TC_ALIGN, __nv_bfloat16>(tmap, p, st) : launch_tc<TC_ALIGN, __half>(tmap, p, st);
   }
@@ -572,14 +716,31 @@ extern "C" int s2a_conv_pack_weight(const void* weight, int in_dtype, const uint
 extern "C" int s2a_alignconv_forward_tc(const void* x, const float* anchors, const void* packed_weight, void* out, int B,
                                         int C, int H, int W, int Co, float stride, int dtype, void* stream) {
   using namespace s2a;
-  S2A_CHECK_ARG(stride > 0.0f, "alignconv_tc: stride must be positive");
-  return conv_tc_common(TC_ALIGN, x, anchors, packed_weight, nullptr, out, nullptr, B, C, H, W, Co, stride, 1, dtype,
-                        (cudaStream_t)stream);
+  S2A_CHECK_ARG(H > 0 && W > 0, "alignconv_tc: bad feature map size");
+  return conv_tc_common(TC_ALIGN, 1, &x, &anchors, packed_weight, nullptr, &out, nullptr, &H, &W, &stride, B, C, Co, 1,
+                        dtype, (cudaStream_t)stream);
 }
 
 extern "C" int s2a_orconv_forward_tc(const void* x, const void* packed_weight, const float* bias, void* out, void* pooled,
                                      int B, int C, int H, int W, int Co, int dtype, void* stream) {
   using namespace s2a;
-  return conv_tc_common(TC_PLAIN, x, nullptr, packed_weight, bias, out, pooled, B, C, H, W, Co, 1.0f, 0, dtype,
+  S2A_CHECK_ARG(H > 0 && W > 0, "orconv_tc: bad feature map size");
+  return conv_tc_common(TC_PLAIN, 1, &x, nullptr, packed_weight, bias, &out, &pooled, &H, &W, nullptr, B, C, Co, 0, dtype,
                         (cudaStream_t)stream);
+}
+
+extern "C" int s2a_alignconv_forward_tc_multi(int nlevels, const void* const* xs, const float* const* anchors,
+                                              const void* packed_weight, void* const* outs, const int* Hs, const int* Ws,
+                                              const float* strides, int B, int C, int Co, int dtype, void* stream) {
+  using namespace s2a;
+  return conv_tc_common(TC_ALIGN, nlevels, xs, anchors, packed_weight, nullptr, outs, nullptr, Hs, Ws, strides, B, C, Co,
+                        1, dtype, (cudaStream_t)stream);
+}
+
+extern "C" int s2a_orconv_forward_tc_multi(int nlevels, const void* const* xs, const void* packed_weight,
+                                           const float* bias, void* const* outs, void* const* pooleds, const int* Hs,
+                                           const int* Ws, int B, int C, int Co, int dtype, void* stream) {
+  using namespace s2a;
+  return conv_tc_common(TC_PLAIN, nlevels, xs, nullptr, packed_weight, bias, outs, pooleds, Hs, Ws, nullptr, B, C, Co, 0,
+                        dtype, (cudaStream_t)stream);
 }

@@ -97,3 +97,25 @@ def test_p3_full_size_tc_and_head_chain():
         ro = oc32(ya.float())
         check(yo, ro, dt)
     assert torch.equal(yp, yo.view(1, 32, 8, 128, 128).max(dim=2)[0])
+
+
+def test_multi_level_launch_equals_per_level():
+    """Five FPN levels of a batch in one persistent launch == five single-level launches, bit for bit."""
+    from s2anet_b200.conv_tc import alignconv_forward_tc, alignconv_forward_tc_multi, orconv_forward_tc, orconv_forward_tc_multi
+    from s2anet_b200.orn import ORConv2d
+    dt = torch.bfloat16
+    B, C = 3, 128
+    g = torch.Generator().manual_seed(7)
+    strides = (8, 16, 32, 64, 128)
+    sizes = ((40, 24), (20, 12), (10, 6), (5, 3), (3, 2))
+    xs = [torch.randn(B, C, h, w, generator=g).to(DEV).to(dt).contiguous(memory_format=torch.channels_last) for h, w in sizes]
+    ancs = [torch.from_numpy(synth.refined_anchors(B, h, w, s, seed=h)).to(DEV) for (h, w), s in zip(sizes, strides)]
+    w = (torch.randn(256, C, 3, 3, generator=g) * 0.05).to(DEV).to(dt)
+    multi = alignconv_forward_tc_multi(xs, ancs, w, strides)
+    for x, a, s, y in zip(xs, ancs, strides, multi):
+        assert torch.equal(y, alignconv_forward_tc(x, a, w, s))
+    m = ORConv2d(C, 32, 3, padding=1, arf_config=(1, 8)).to(DEV).to(dt)
+    outs, pooled = orconv_forward_tc_multi(xs, m.weight, m.indices, m.bias, with_pool=True)
+    for x, y, yp in zip(xs, outs, pooled):
+        r, rp = orconv_forward_tc(x, m.weight, m.indices, m.bias, with_pool=True)
+        assert torch.equal(y, r) and torch.equal(yp, rp)
