@@ -54,7 +54,12 @@ constexpr uint32_t kSpinLimit = 1u << 26;            // watchdog: trap instead o
 
 enum { TC_ALIGN = 0, TC_PLAIN = 1 };
 
-struct __align__(4) TapSample { short y0, x0; float ly, lx; };   // 12 bytes; y0 == -32768 -> nothing sampled
+// One (row, tap) gather recipe, 12 bytes: byte offset of the (clamped) top-left corner pixel inside the
+// image (a multiple of 16, so the two low bits carry "right corner is one pixel further" / "bottom
+// corners are one row further"), and the four bilinear weights already rounded to the 16-bit type.
+// Corners that fall outside the map keep a valid (clamped) address and get weight 0, which is the
+// reference's rule (deform_conv_cuda_kernel.cu:97-108, :228).
+struct __align__(4) TapSample { uint32_t base; uint32_t w01; uint32_t w23; };
 
 struct TcLevel {
   const void* x;          // [B, H, W, C] 16-bit (channels_last)
@@ -203,6 +208,22 @@ template <> __device__ __forceinline__ __nv_bfloat162 from_f2<__nv_bfloat16>(flo
 }
 template <> __device__ __forceinline__ __half2 from_f2<__half>(float a, float b) { return __floats2half2_rn(a, b); }
 
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
+// Pull the 128-byte lines (one 64-channel block per pixel) of the halo region around a tile into L1 a
+// whole channel block ahead of their use: rows [ty0-4, ty0+12), cols [tx0-4, tx0+20) = 384 pixels,
+// one per producer thread.  The gather's L1 hit rate is what bounds AlignConv (each 16-load batch
+// waits for its slowest load), and the first tap of every channel block used to miss on every line.
+constexpr int TC_HALO = 4;
+constexpr int TC_PF_W = TC_PW + 2 * TC_HALO, TC_PF_H = TC_PH + 2 * TC_HALO;     // 24 x 16
+__device__ __forceinline__ void prefetch_halo(const TcParams& p, const TileCoord& tc, int cb, int idx) {
+  if (idx >= TC_PF_W * TC_PF_H) return;
+  const TcLevel& L = p.lv[tc.lvl];
+  const int y = tc.ty0 - TC_HALO + idx / TC_PF_W, x = tc.tx0 - TC_HALO + idx % TC_PF_W;
+  if (y < 0 || y >= L.H || x < 0 || x >= L.W) return;
+  prefetch_l1(reinterpret_cast<const uint8_t*>(L.x) + (((size_t)(tc.b * L.H + y) * L.W + x) * p.C + (size_t)cb * TC_KB) * 2);
+}
+
 __device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
   uint4 r;
   asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
@@ -215,11 +236,14 @@ __device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
 // the value is rounded to 16 bits for the tensor core either way; doing the four-term sum in packed
 // 16-bit math quarters the producer warps' instruction count, which is what bounds this kernel.
 template <typename T>
-__device__ __forceinline__ uint4 blend4(const uint4& v0, const uint4& v1, const uint4& v2, const uint4& v3,
-                                        const float (&w)[4]) {
+__device__ __forceinline__ uint4 blend4(const uint4& v0, const uint4& v1, const uint4& v2, const uint4& v3, uint32_t w01,
+                                        uint32_t w23) {
   using H2 = typename Half2Of<T>::type;
-  const H2 w0 = from_f2<T>(w[0], w[0]), w1 = from_f2<T>(w[1], w[1]), w2 = from_f2<T>(w[2], w[2]),
-           w3 = from_f2<T>(w[3], w[3]);
+  // broadcast each 16-bit weight to both halves of a pair
+  const uint32_t u0 = __byte_perm(w01, 0, 0x1010), u1 = __byte_perm(w01, 0, 0x3232);
+  const uint32_t u2 = __byte_perm(w23, 0, 0x1010), u3 = __byte_perm(w23, 0, 0x3232);
+  const H2 w0 = *reinterpret_cast<const H2*>(&u0), w1 = *reinterpret_cast<const H2*>(&u1),
+           w2 = *reinterpret_cast<const H2*>(&u2), w3 = *reinterpret_cast<const H2*>(&u3);
   const H2* a = reinterpret_cast<const H2*>(&v0);
   const H2* b = reinterpret_cast<const H2*>(&v1);
   const H2* c = reinterpret_cast<const H2*>(&v2);
@@ -243,15 +267,17 @@ __device__ __forceinline__ uint4 blend4(const uint4& v0, const uint4& v1, const 
 // sample table of one tile: (row, tap) -> top-left pixel + fractional weights.  Position formula:
 // models/alignconv.py:29-86 with the offset added back as the deformable im2col does
 // (deform_conv_cuda_kernel.cu:223-227); same operation order as csrc/conv_f32.cu.
+template <typename T>
 __device__ __forceinline__ void build_tap_table(const TcParams& p, const TileCoord& tc, TapSample* tab, int t0, int nt) {
   const TcLevel& L = p.lv[tc.lvl];
+  const int H = L.H, W = L.W;
   for (int e = t0; e < TC_M * 9; e += nt) {
     const int r = e / 9, t = e - 9 * r;
     const int y = tc.ty0 + r / TC_PW, x = tc.tx0 + r % TC_PW;
     TapSample s;
-    s.y0 = -32768; s.x0 = 0; s.ly = 0.0f; s.lx = 0.0f;
-    if (y < L.H && x < L.W) {
-      const float* a = L.anchors + ((size_t)(tc.b * L.H + y) * L.W + x) * 5;
+    s.base = 0u; s.w01 = 0u; s.w23 = 0u;
+    if (y < H && x < W) {
+      const float* a = L.anchors + ((size_t)(tc.b * H + y) * W + x) * 5;
       const float ax = a[0] / L.stride, ay = a[1] / L.stride, aw = a[2] / L.stride, ah = a[3] / L.stride;
       const float cs = cosf(a[4]), sn = sinf(a[4]);
       const float dw = aw / 3.0f, dh = ah / 3.0f;
@@ -265,10 +291,18 @@ __device__ __forceinline__ void build_tap_table(const TcParams& p, const TileCoo
       const float offy = __fsub_rn(ya, __fadd_rn((float)y, fi));
       const float h = __fadd_rn((float)(y - 1 + ti), offy);
       const float w = __fadd_rn((float)(x - 1 + tj), offx);
-      if (h > -1.0f && w > -1.0f && h < (float)L.H && w < (float)L.W) {
+      if (h > -1.0f && w > -1.0f && h < (float)H && w < (float)W) {
         const float hf = floorf(h), wf = floorf(w);
-        s.y0 = (short)(int)hf; s.x0 = (short)(int)wf;
-        s.ly = h - hf; s.lx = w - wf;
+        const int y0 = (int)hf, x0 = (int)wf;
+        const float ly = h - hf, lx = w - wf, hy = 1.0f - ly, hx = 1.0f - lx;
+        const bool t_ok = y0 >= 0, b_ok = y0 + 1 <= H - 1, l_ok = x0 >= 0, r_ok = x0 + 1 <= W - 1;
+        const int yt = max(y0, 0), yb = min(y0 + 1, H - 1), xl = max(x0, 0), xrr = min(x0 + 1, W - 1);
+        using H2 = typename Half2Of<T>::type;
+        const H2 p01 = from_f2<T>((t_ok && l_ok) ? hy * hx : 0.0f, (t_ok && r_ok) ? hy * lx : 0.0f);
+        const H2 p23 = from_f2<T>((b_ok && l_ok) ? ly * hx : 0.0f, (b_ok && r_ok) ? ly * lx : 0.0f);
+        s.w01 = *reinterpret_cast<const uint32_t*>(&p01);
+        s.w23 = *reinterpret_cast<const uint32_t*>(&p23);
+        s.base = (uint32_t)(((size_t)yt * W + xl) * p.C * 2) | (xrr > xl ? 1u : 0u) | (yb > yt ? 2u : 0u);
       }
     }
     tab[e] = s;
@@ -337,6 +371,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       const TileCoord tc = decode_tile(p, tile);
       const TcLevel& L = p.lv[tc.lvl];
       const int H = L.H, W = L.W;
+      const uint32_t pix_stride = (uint32_t)p.C * 2u, row_stride = (uint32_t)W * pix_stride;
       const uint8_t* xb = reinterpret_cast<const uint8_t*>(L.x) + (size_t)tc.b * H * W * p.C * 2;
       const TapSample* tab = s_tab + (it & 1) * (TC_M * 9);
       if (MODE == TC_ALIGN) mbar_wait(bar_tab_full + 8 * (it & 1), (uint32_t)(it >> 1) & 1u);
@@ -347,60 +382,38 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         const int s = (int)(gkb % TC_SA);
         const uint32_t ph = (uint32_t)(gkb / TC_SA) & 1u;
         const int cb = kb / 9, tap = kb - 9 * cb;
+        if (tap < TC_GROUPS && !(p.debug & 4)) {
+          // this group's first k-block of channel block cb: prefetch its third of the halo of the NEXT
+          // channel block (or of the next tile's first one) -- 9 k-blocks ahead of the loads that need it
+          if (cb + 1 < ncb) prefetch_halo(p, tc, cb + 1, group * 128 + gt);
+          else if (tile + tile_step < p.total_tiles) prefetch_halo(p, decode_tile(p, tile + tile_step), 0, group * 128 + gt);
+        }
         mbar_wait(bar_empty_a + 8 * s, ph ^ 1u);
         uint8_t* a_stage = sA + s * TC_A_BYTES;
         if (p.debug & 2) { fence_proxy_async_smem(); mbar_arrive(bar_full_a + 8 * s); continue; }
-        const size_t coff = ((size_t)cb * TC_KB + chunk * 8) * 2;      // byte offset of this chunk inside a pixel
+        // 128-byte row r = j*16 + rsub of the stage; chunk position swizzled by (r & 7) == (rsub & 7)
+        uint8_t* a_dst = a_stage + rsub * 128 + ((chunk ^ (rsub & 7)) << 4);
+        const uint8_t* src = xb + ((size_t)cb * TC_KB + chunk * 8) * 2;   // this thread's 16 bytes inside a pixel
+        const TapSample* trow = tab + rsub * 9 + tap;
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           uint4 v[4][4];
-          float wt[4][4];
+          uint32_t w01[4], w23[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const int r = (half * 4 + i) * 16 + rsub;
-            int y0, x0;
-            float ly, lx;
-            bool any;
-            if (MODE == TC_ALIGN) {
-              const TapSample sm = tab[r * 9 + tap];
-              y0 = sm.y0; x0 = sm.x0; ly = sm.ly; lx = sm.lx;
-              any = sm.y0 != -32768;
-            } else {
-              const int y = tc.ty0 + r / TC_PW, x = tc.tx0 + r % TC_PW;
-              y0 = y - 1 + tap / 3; x0 = x - 1 + tap % 3; ly = 0.0f; lx = 0.0f;
-              any = (y < H && x < W);
-            }
-            const float hy = 1.0f - ly, hx = 1.0f - lx;
-            const bool t_ok = any && y0 >= 0 && y0 < H, b_ok = any && y0 + 1 >= 0 && y0 + 1 <= H - 1;
-            const bool l_ok = x0 >= 0 && x0 < W, r_ok = x0 + 1 >= 0 && x0 + 1 <= W - 1;
-            wt[i][0] = (t_ok && l_ok) ? hy * hx : 0.0f;
-            wt[i][1] = (t_ok && r_ok) ? hy * lx : 0.0f;
-            wt[i][2] = (b_ok && l_ok) ? ly * hx : 0.0f;
-            wt[i][3] = (b_ok && r_ok) ? ly * lx : 0.0f;
-            const int yt = min(max(y0, 0), H - 1), yb = min(max(y0 + 1, 0), H - 1);
-            const int xl = min(max(x0, 0), W - 1), xr = min(max(x0 + 1, 0), W - 1);
-            const size_t rowt = (size_t)yt * W, rowb = (size_t)yb * W;
-            if (MODE == TC_ALIGN) {
-              v[i][0] = ldg_nc_v4(xb + (rowt + xl) * p.C * 2 + coff);
-              v[i][1] = ldg_nc_v4(xb + (rowt + xr) * p.C * 2 + coff);
-              v[i][2] = ldg_nc_v4(xb + (rowb + xl) * p.C * 2 + coff);
-              v[i][3] = ldg_nc_v4(xb + (rowb + xr) * p.C * 2 + coff);
-            } else {
-              v[i][0] = ldg_nc_v4(xb + (rowt + xl) * p.C * 2 + coff);
-            }
+            const TapSample sm = trow[(half * 4 + i) * 16 * 9];
+            w01[i] = sm.w01; w23[i] = sm.w23;
+            const uint8_t* q = src + (sm.base & ~3u);
+            const uint32_t dx = (sm.base & 1u) ? pix_stride : 0u, dy = (sm.base & 2u) ? row_stride : 0u;
+            v[i][0] = ldg_nc_v4(q);
+            v[i][1] = ldg_nc_v4(q + dx);
+            v[i][2] = ldg_nc_v4(q + dy);
+            v[i][3] = ldg_nc_v4(q + dy + dx);
           }
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int r = (half * 4 + i) * 16 + rsub;
-            uint4 o;
-            if (MODE == TC_ALIGN) {
-              o = blend4<T>(v[i][0], v[i][1], v[i][2], v[i][3], wt[i]);
-            } else {
-              o = (wt[i][0] != 0.0f) ? v[i][0] : make_uint4(0u, 0u, 0u, 0u);
-            }
-            // K-major SWIZZLE_128B: 16-byte chunk c of row r lives at chunk position c ^ (r & 7)
-            *reinterpret_cast<uint4*>(a_stage + r * 128 + ((chunk ^ (r & 7)) << 4)) = o;
-          }
+          for (int i = 0; i < 4; ++i)
+            *reinterpret_cast<uint4*>(a_dst + (half * 4 + i) * 2048) =
+                blend4<T>(v[i][0], v[i][1], v[i][2], v[i][3], w01[i], w23[i]);
         }
         fence_proxy_async_smem();          // generic-proxy stores -> visible to the tensor core (async proxy)
         mbar_arrive(bar_full_a + 8 * s);
@@ -472,7 +485,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       for (int j = 0; j < 2; ++j) {
         const int tile = first_tile + j * tile_step;
         if (tile < p.total_tiles) {
-          build_tap_table(p, decode_tile(p, tile), s_tab + j * (TC_M * 9), et, TC_EPI_THREADS);
+          build_tap_table<T>(p, decode_tile(p, tile), s_tab + j * (TC_M * 9), et, TC_EPI_THREADS);
           mbar_arrive(bar_tab_full + 8 * j);
         }
       }
@@ -533,7 +546,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         // build the table of tile it + 2 into it
         const int nxt = tile + 2 * tile_step;
         if (nxt < p.total_tiles) {
-          build_tap_table(p, decode_tile(p, nxt), s_tab + as * (TC_M * 9), et, TC_EPI_THREADS);
+          build_tap_table<T>(p, decode_tile(p, nxt), s_tab + as * (TC_M * 9), et, TC_EPI_THREADS);
           mbar_arrive(bar_tab_full + 8 * as);
         }
       }
@@ -631,6 +644,7 @@ static int conv_tc_common(int mode, int nlevels, const void* const* xs, const fl
   long long tiles = 0;
   for (int l = 0; l < nlevels; ++l) {
     S2A_CHECK_ARG(Hs[l] > 0 && Ws[l] > 0 && Hs[l] < 32768 && Ws[l] < 32768, "conv_tc: bad feature map size");
+    S2A_CHECK_ARG((long long)Hs[l] * Ws[l] * C * 2 < (1ll << 32), "conv_tc: one image of a level must be < 4 GiB");
     S2A_CHECK_ARG(xs[l] && outs[l] && (mode == TC_PLAIN || (anchors && anchors[l])), "conv_tc: null level pointer");
     TcLevel& L = p.lv[l];
     L.x = xs[l]; L.anchors = anchors ? anchors[l] : nullptr; L.out = outs[l]; L.pooled = pooleds ? pooleds[l] : nullptr;
