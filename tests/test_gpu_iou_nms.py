@@ -231,7 +231,12 @@ def _ref_gpu(name):
 def test_against_reference_cuda_kernels_on_this_gpu(oracle):
     """The reference's own CUDA extensions (unmodified sources, compiled for sm_100a in the
     authoring container) run beside ours: IoU within 1e-5; keep lists identical except for pairs
-    whose IoU lies within 1e-6 of the threshold (listed)."""
+    whose IoU lies within 1e-6 of the threshold (listed).
+
+    Known, documented exception: nvcc contracts the reference's parallel-edge
+    determinant into an FMA, so for a box paired with an IDENTICAL box its binary returns ~1/3
+    instead of 1.0.  Every pair that differs by more than 1e-5 must be such a duplicate pair, and for
+    those this library must hold the float64-correct value (1.0)."""
     iou_ref = _ref_gpu("box_iou_rotated_cuda")
     nms_ref = _ref_gpu("nms_rotated_cuda")
     ml_ref = _ref_gpu("ml_nms_rotated_cuda")
@@ -240,8 +245,12 @@ def test_against_reference_cuda_kernels_on_this_gpu(oracle):
     b, s, l = synth.clustered_boxes(seed=0)
     tb, ts, tl = (torch.from_numpy(x).to(DEV) for x in (b, s, l))
     mine, ref = box_iou_rotated(tb, tb), iou_ref.box_iou_rotated(tb, tb)
-    err = float((mine - ref).abs().max())
-    assert err <= 1e-5, err
+    bad = ((mine - ref).abs() > 1e-5).nonzero().cpu().numpy()
+    print("pairs differing from the reference CUDA binary by > 1e-5:", bad.tolist())
+    for i, j in bad:
+        assert np.array_equal(b[i], b[j]), "non-duplicate pair (%d, %d) differs from the reference kernel" % (i, j)
+        assert abs(float(mine[i, j]) - 1.0) <= 1e-5
+    assert len(bad) <= 20
     for thr in (0.3, 0.5):
         near = ((ref - thr).abs() < 1e-6).nonzero().cpu().numpy()
         k1, k2 = nms_rotated_op(tb, ts, thr), nms_ref.nms_rotated(tb, ts, thr)
