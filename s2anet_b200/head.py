@@ -152,22 +152,58 @@ class S2ANetHead(nn.Module):
         return a
 
     # ---- forward ------------------------------------------------------------------------------
+    @staticmethod
+    def _tower(seq, x):
+        """A conv+ReLU tower.  Stock PyTorch either way: on CUDA the fused cuDNN conv+bias+ReLU op is
+        used (one kernel per layer instead of conv, bias-add and clamp)."""
+        for block in seq:
+            conv = block[0]
+            if x.is_cuda and not torch.is_grad_enabled() and hasattr(torch, "cudnn_convolution_relu"):
+                x = torch.cudnn_convolution_relu(x, conv.weight, conv.bias, conv.stride, conv.padding, conv.dilation,
+                                                 conv.groups)
+            else:
+                x = torch.relu(conv(x))
+        return x
+
     def forward_single(self, x, stride):
         """models/head.py:296-348."""
-        fam_bbox_pred = self.fam_reg_head(self.fam_reg_ls(x))
-        fam_cls_pred = self.fam_cls_head(self.fam_cls_ls(x))
+        fam_cls_pred, fam_bbox_pred, init_anchors, refine = self._fam(x, stride)
+        or_feat = self.or_conv(self.align_conv(x, refine, stride))
+        odm_cls_feat = self.or_pool(or_feat) if self.with_orconv else or_feat
+        odm_cls_pred, odm_bbox_pred = self._odm(or_feat, odm_cls_feat)
+        return fam_cls_pred, fam_bbox_pred, odm_cls_pred, odm_bbox_pred, init_anchors, refine
+
+    def _fam(self, x, stride):
+        fam_bbox_pred = self.fam_reg_head(self._tower(self.fam_reg_ls, x))
+        fam_cls_pred = self.fam_cls_head(self._tower(self.fam_cls_ls, x))
         B, _, H, W = fam_bbox_pred.shape
         init_anchors = self.grid_anchors(H, W, stride, x.device)
         deltas = fam_bbox_pred.detach().permute(0, 2, 3, 1).reshape(B, H * W, 5)
         refine = rboxes_decode(init_anchors[None], deltas, wh_ratio_clip=1e-6).reshape(B, H, W, 5)   # head.py:27-52
-        or_feat = self.or_conv(self.align_conv(x, refine, stride))
-        odm_cls_feat = self.or_pool(or_feat) if self.with_orconv else or_feat
-        odm_cls_pred = self.odm_cls_head(self.odm_cls_ls(odm_cls_feat))
-        odm_bbox_pred = self.odm_reg_head(self.odm_reg_ls(or_feat))
-        return fam_cls_pred, fam_bbox_pred, odm_cls_pred, odm_bbox_pred, init_anchors, refine
+        return fam_cls_pred, fam_bbox_pred, init_anchors, refine
+
+    def _odm(self, or_feat, odm_cls_feat):
+        odm_cls_pred = self.odm_cls_head(self._tower(self.odm_cls_ls, odm_cls_feat))
+        odm_bbox_pred = self.odm_reg_head(self._tower(self.odm_reg_ls, or_feat))
+        return odm_cls_pred, odm_bbox_pred
 
     def forward_levels(self, feats):
-        return [self.forward_single(x, s) for x, s in zip(feats, self.featmap_strides)]
+        """All levels.  In 16-bit mode AlignConv and ORConv2d each run as ONE persistent multi-level
+        launch (the reference loops over levels in Python, head.py:265)."""
+        x0 = feats[0]
+        if not (x0.is_cuda and x0.dtype in (torch.bfloat16, torch.float16) and self.with_orconv):
+            return [self.forward_single(x, s) for x, s in zip(feats, self.featmap_strides)]
+        from . import conv_tc
+        fam = [self._fam(x, s) for x, s in zip(feats, self.featmap_strides)]
+        aligned = conv_tc.alignconv_forward_tc_multi(list(feats), [f[3] for f in fam], self.align_conv.deform_conv.weight,
+                                                     self.featmap_strides)
+        or_feats, pooled = conv_tc.orconv_forward_tc_multi(aligned, self.or_conv.weight, self.or_conv.indices,
+                                                           self.or_conv.bias, with_pool=True)
+        outs = []
+        for (fam_cls, fam_reg, init, refine), of, pf in zip(fam, or_feats, pooled):
+            odm_cls, odm_reg = self._odm(of, pf)
+            outs.append((fam_cls, fam_reg, odm_cls, odm_reg, init, refine))
+        return outs
 
     @torch.no_grad()
     def select_and_decode(self, outs):
