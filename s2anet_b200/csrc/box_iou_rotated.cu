@@ -3,75 +3,73 @@
 // Replaces box_iou_rotated_cuda (reference: utils/box_iou_rotated/src/box_iou_rotated_cuda.cu
 // :13-62 kernel, :65-101 host).  The reference gives one thread one pair and runs the full polygon
 // clipper (2x24-point local arrays, double-precision sin/cos per pair) for every pair.  Here a CTA
-// owns a 64x64 tile of the IoU matrix and works in three phases:
-//   1. prepare: the 64 row boxes and 64 column boxes are loaded with coalesced reads and their
+// owns a 64x256 tile of the IoU matrix and works in three phases:
+//   1. prepare: the 64 row boxes and 256 column boxes are loaded with coalesced reads and their
 //      sin/cos evaluated ONCE per box (not once per pair) into shared memory;
 //   2. classify: every pair runs the cheap, conservative disjointness test (rbox_classify); pairs
-//      proven to have IoU == 0 are finished, the rest are appended to a per-CTA work list with a
-//      warp ballot + one shared atomic per warp;
-//   3. clip: the work list is processed densely (no idle lanes for the ~94 % rejected pairs), then
-//      the tile is written with fully coalesced 128-byte rows.
+//      proven to have IoU == 0 are stored at once (a warp writes 128 contiguous bytes of a row), the
+//      rest are appended to a per-CTA work list with a warp ballot + one shared atomic per warp;
+//   3. clip: the work list is processed densely (no idle lanes for the ~97 % rejected pairs) and
+//      each result stored to its element.
 // HBM traffic is the algorithmic minimum (4 B per pair out, 20 B per box in per tile).
 #include "common.cuh"
 #include "rbox_iou.cuh"
 
 namespace s2a {
 
-constexpr int kTile = 64;
+constexpr int kTileR = 64;             // rows (boxes1) per CTA tile
+constexpr int kTileC = 256;            // columns (boxes2) per CTA tile
 constexpr int kIouThreads = 256;
 
 __global__ void __launch_bounds__(kIouThreads)
 box_iou_rotated_kernel(const float* __restrict__ boxes1, int64_t n, const float* __restrict__ boxes2,
                        int64_t m, float* __restrict__ out, int64_t ld_out, int64_t row_begin,
                        int64_t row_end, int flags) {
-  __shared__ RBox s_row[kTile];
-  __shared__ RBox s_col[kTile];
-  __shared__ float s_raw[2 * kTile * 5];
-  __shared__ float s_tile[kTile * kTile];
-  __shared__ uint16_t s_list[kTile * kTile];
+  __shared__ RBox s_row[kTileR];
+  __shared__ RBox s_col[kTileC];
+  __shared__ __align__(16) uint16_t s_list[kTileR * kTileC];   // 64 x 256 pairs: 14-bit pair ids
+  float* s_raw = reinterpret_cast<float*>(s_list);             // raw boxes live here only until they are prepared
   __shared__ int s_count;
 
   const int tid = threadIdx.x;
   const int64_t b = blockIdx.z;
-  const int64_t row0 = row_begin + (int64_t)blockIdx.x * kTile;
-  const int64_t col0 = (int64_t)blockIdx.y * kTile;
-  const int nr = (int)min((int64_t)kTile, row_end - row0);
-  const int nc = (int)min((int64_t)kTile, m - col0);
+  const int64_t row0 = row_begin + (int64_t)blockIdx.x * kTileR;
+  const int64_t col0 = (int64_t)blockIdx.y * kTileC;
+  const int nr = (int)min((int64_t)kTileR, row_end - row0);
+  const int nc = (int)min((int64_t)kTileC, m - col0);
   const float* g1 = boxes1 + (b * n + row0) * 5;
   const float* g2 = boxes2 + (b * m + col0) * 5;
 
   // phase 1: coalesced raw loads, then one thread per box does the double-precision sin/cos
   for (int i = tid; i < nr * 5; i += kIouThreads) s_raw[i] = g1[i];
-  for (int i = tid; i < nc * 5; i += kIouThreads) s_raw[kTile * 5 + i] = g2[i];
+  for (int i = tid; i < nc * 5; i += kIouThreads) s_raw[kTileR * 5 + i] = g2[i];
   if (tid == 0) s_count = 0;
   __syncthreads();
-  if (tid < kTile) {
-    if (tid < nr) {
-      const float* r = s_raw + tid * 5;
-      rbox_prep(r[0], r[1], r[2], r[3], r[4], s_row[tid]);
-    }
-  } else if (tid < 2 * kTile) {
-    int c = tid - kTile;
-    if (c < nc) {
-      const float* r = s_raw + kTile * 5 + c * 5;
-      rbox_prep(r[0], r[1], r[2], r[3], r[4], s_col[c]);
+  for (int i = tid; i < nr + nc; i += kIouThreads) {
+    if (i < nr) {
+      const float* r = s_raw + i * 5;
+      rbox_prep(r[0], r[1], r[2], r[3], r[4], s_row[i]);
+    } else {
+      const float* r = s_raw + kTileR * 5 + (i - nr) * 5;
+      rbox_prep(r[0], r[1], r[2], r[3], r[4], s_col[i - nr]);
     }
   }
   __syncthreads();
 
-  // phase 2: classify.  A warp covers 32 consecutive columns of one row: the row box is a
-  // shared-memory broadcast, the column box lives in registers for all 16 rows of this thread.
-  const int c = tid & (kTile - 1);
-  const int r0 = tid >> 6;
+  // phase 2: classify.  Thread t owns column t of the tile (its box stays in registers) and walks
+  // the 64 rows (row box = shared-memory broadcast).  Pairs proven to be exactly zero are stored
+  // right away -- a warp writes 32 consecutive floats of one output row -- the others go to the
+  // work list (warp ballot + one shared atomic per warp).
   const unsigned lane = tid & 31;
-  RBox cb;
-  if (c < nc) cb = s_col[c];
   const bool no_reject = (flags & S2A_IOU_NO_REJECT) != 0;
-#pragma unroll 4
-  for (int k = 0; k < kTile / 4; ++k) {
-    const int r = r0 + 4 * k;
+  float* o = out + (b * n + row0) * ld_out + col0;
+  RBox cb;
+  const bool col_ok = tid < nc;
+  if (col_ok) cb = s_col[tid];
+#pragma unroll 2
+  for (int r = 0; r < nr; ++r) {
     bool clip = false;
-    if (r < nr && c < nc) {
+    if (col_ok) {
       const RBox rb = s_row[r];
       int cls;
       if (no_reject) {
@@ -80,7 +78,7 @@ box_iou_rotated_kernel(const float* __restrict__ boxes1, int64_t n, const float*
       } else {
         cls = rbox_classify(rb, cb);
       }
-      if (cls == RB_ZERO) s_tile[r * kTile + c] = 0.0f;
+      if (cls == RB_ZERO) o[(int64_t)r * ld_out + tid] = 0.0f;
       else clip = true;
     }
     const unsigned bal = __ballot_sync(0xffffffffu, clip);
@@ -88,24 +86,17 @@ box_iou_rotated_kernel(const float* __restrict__ boxes1, int64_t n, const float*
       int base = 0;
       if (lane == 0) base = atomicAdd(&s_count, __popc(bal));
       base = __shfl_sync(0xffffffffu, base, 0);
-      if (clip) s_list[base + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)(r * kTile + c);
+      if (clip) s_list[base + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)(r * kTileC + tid);
     }
   }
   __syncthreads();
 
-  // phase 3: dense clipping of the surviving pairs
+  // phase 3: dense clipping of the surviving pairs (typically < 3 % of the tile)
   const int cnt = s_count;
   for (int k = tid; k < cnt; k += kIouThreads) {
     const int p = s_list[k];
-    s_tile[p] = rbox_iou_clip(s_row[p >> 6], s_col[p & (kTile - 1)]);
-  }
-  __syncthreads();
-
-  // coalesced tile store: each warp writes 32 consecutive floats of one output row
-  float* o = out + (b * n + row0) * ld_out + col0;
-  for (int idx = tid; idx < kTile * kTile; idx += kIouThreads) {
-    const int r = idx >> 6, cc = idx & (kTile - 1);
-    if (r < nr && cc < nc) o[(int64_t)r * ld_out + cc] = s_tile[idx];
+    const int r = p >> 8, c = p & (kTileC - 1);
+    o[(int64_t)r * ld_out + c] = rbox_iou_clip(s_row[r], s_col[c]);
   }
 }
 
@@ -123,9 +114,9 @@ extern "C" int s2a_box_iou_rotated(const float* boxes1, int64_t n, const float* 
   if (row_end == row_begin || m == 0 || batch == 0) return S2A_OK;
   S2A_CHECK_ARG(boxes1 && boxes2 && out, "box_iou_rotated: null pointer");
   S2A_CHECK_ARG(ld_out >= m, "box_iou_rotated: ld_out (%lld) < m (%lld)", (long long)ld_out, (long long)m);
-  S2A_CHECK_ARG(batch <= 65535 && ceil_div(m, kTile) <= 65535,
-                "box_iou_rotated: batch and ceil(m/64) must be <= 65535");
-  dim3 grid((unsigned)ceil_div(row_end - row_begin, kTile), (unsigned)ceil_div(m, kTile), (unsigned)batch);
+  S2A_CHECK_ARG(batch <= 65535 && ceil_div(m, kTileC) <= 65535,
+                "box_iou_rotated: batch and ceil(m/256) must be <= 65535");
+  dim3 grid((unsigned)ceil_div(row_end - row_begin, kTileR), (unsigned)ceil_div(m, kTileC), (unsigned)batch);
   box_iou_rotated_kernel<<<grid, kIouThreads, 0, (cudaStream_t)stream>>>(boxes1, n, boxes2, m, out, ld_out,
                                                                          row_begin, row_end, flags);
   S2A_LAUNCH_OK("box_iou_rotated_kernel");

@@ -74,27 +74,52 @@ RB_HD void rbox_prep(float x, float y, float w, float h, float a, RBox& o) {
 //             early-out (:354-358) or because the boxes are provably disjoint (no candidate point
 //             can be produced, so inter = 0 and iou = 0/(a1+a2) = 0).
 //   RB_CLIP : run the clipper.
-// The disjointness shortcut is only taken when it is numerically safe: the circumscribed circles
-// are separated by > 1 %, no edge pair is within ~1 degree of parallel (near-parallel edge pairs
-// make the reference's t1/t2 ill-conditioned, so its answer there must be reproduced, not
-// predicted), and no box side is below 1e-3 of the pair's extent (vertex rounding is ~2.4e-7 of
-// the extent, so edge directions are then accurate to < 1e-3 rad).  NaN/Inf inputs fail the
-// comparisons and fall through to RB_CLIP.  See DESIGN.md "IoU reject test" for the argument.
+// Disjointness is established by a circumscribed-circle test (1 % margin) and, for the pairs that
+// fail it, a separating-axis test over the four edge normals (margin 4e-3 of the pair's extent).
+// The shortcut is only TAKEN when it is numerically safe to predict the reference's answer:
+//   * no box side below 2e-3 of the extent (vertex rounding is ~2.4e-7 of the extent, so edge
+//     directions are then accurate to ~1e-4 rad), and
+//   * either no edge pair within ~0.6 degrees of parallel (|sin 2dT| > 0.02: every edge-pair
+//     determinant is well conditioned), or -- for near-parallel / near-perpendicular boxes -- every
+//     pair of parallel edges is at least 0.1 extent apart perpendicular to itself, which forces the
+//     reference's |t1|, |t2| far above 1 whatever the noisy determinant is.  Near-parallel AND
+//     near-collinear edges (boxes shifted along a shared edge line) are where the reference's t1/t2
+//     are ill-conditioned; its answer there is reproduced by the clipper, never predicted.
+// NaN/Inf inputs fail the comparisons and fall through to RB_CLIP.  See DESIGN.md "IoU reject test".
 enum { RB_ZERO = 0, RB_CLIP = 1 };
 
 RB_HD int rbox_classify(const RBox& A, const RBox& B) {
   float a1 = RB_MUL(A.w, A.h), a2 = RB_MUL(B.w, B.h);
   if (a1 <= RB_LO_1E14 || a2 <= RB_LO_1E14) return RB_ZERO;     // (double)area < 1e-14
-  float dx = A.x - B.x, dy = A.y - B.y;
-  float d2 = dx * dx + dy * dy;
-  float rs = A.r + B.r;
-  if (d2 > 1.0201f * rs * rs) {
-    // sin(tA - tB)/4 and cos(tA - tB)/4 from the half-scaled sin/cos
-    float sd = A.s2 * B.c2 - A.c2 * B.s2;
-    float cd = A.c2 * B.c2 + A.s2 * B.s2;
-    float ext = sqrtf(d2) + rs;
-    // |sd*cd| = |sin(2 dT)|/32 ; require |sin(2 dT)| > 0.04
-    if (fabsf(sd * cd) > 0.00125f && fminf(A.mn, B.mn) > 1e-3f * ext) return RB_ZERO;
+  const float dx = B.x - A.x, dy = B.y - A.y;
+  const float d2 = dx * dx + dy * dy;
+  const float rs = A.r + B.r;
+  const float ext = sqrtf(d2) + rs;
+  // sin(tB - tA)/4 and cos(tB - tA)/4 from the half-scaled sin/cos
+  const float sd = B.s2 * A.c2 - B.c2 * A.s2;
+  const float cd = A.c2 * B.c2 + A.s2 * B.s2;
+  const float S = 4.0f * fabsf(sd), C = 4.0f * fabsf(cd);
+  const float wA = fabsf(A.w), hA = fabsf(A.h), wB = fabsf(B.w), hB = fabsf(B.h);
+  // centre offset in A's frame and in B's frame
+  const float duA = 2.0f * (dx * A.c2 + dy * A.s2), dvA = 2.0f * (dy * A.c2 - dx * A.s2);
+  bool sep = d2 > 1.0201f * rs * rs;
+  if (!sep) {
+    const float mg = 4e-3f * ext;
+    const float duB = 2.0f * (dx * B.c2 + dy * B.s2), dvB = 2.0f * (dy * B.c2 - dx * B.s2);
+    sep = (fabsf(duA) > 0.5f * (wA + wB * C + hB * S) + mg) || (fabsf(dvA) > 0.5f * (hA + wB * S + hB * C) + mg) ||
+          (fabsf(duB) > 0.5f * (wB + wA * C + hA * S) + mg) || (fabsf(dvB) > 0.5f * (hB + wA * S + hA * C) + mg);
+  }
+  if (sep && fminf(A.mn, B.mn) > 2e-3f * ext) {
+    // |sd*cd| = |sin(2 dT)|/32
+    if (fabsf(sd * cd) > 0.000625f) return RB_ZERO;
+    // near-parallel (C >= S) or near-perpendicular: B's half extents along A's axes
+    const float bu = 0.5f * (C >= S ? wB : hB), bv = 0.5f * (C >= S ? hB : wB);
+    const float au = 0.5f * wA, av = 0.5f * hA, g = 0.1f * ext;
+    const float gv = fminf(fminf(fabsf(dvA + bv - av), fabsf(dvA + bv + av)),
+                           fminf(fabsf(dvA - bv - av), fabsf(dvA - bv + av)));
+    const float gu = fminf(fminf(fabsf(duA + bu - au), fabsf(duA + bu + au)),
+                           fminf(fabsf(duA - bu - au), fabsf(duA - bu + au)));
+    if (gv > g && gu > g) return RB_ZERO;
   }
   return RB_CLIP;
 }
@@ -152,8 +177,17 @@ RB_HD float rbox_iou_clip(const RBox& A, const RBox& B) {
       float det = rb_cross(e2x[j], e2y[j], e1x[i], e1y[i]);
       if (fabsf(det) <= RB_LO_1E14) continue;                      // fabs(det) <= 1e-14
       float dx = RB_SUB(p2x[j], p1x[i]), dy = RB_SUB(p2y[j], p1y[i]);
-      float t1 = RB_DIV(rb_cross(e2x[j], e2y[j], dx, dy), det);
-      float t2 = RB_DIV(rb_cross(e1x[i], e1y[i], dx, dy), det);
+      const float n1 = rb_cross(e2x[j], e2y[j], dx, dy), n2 = rb_cross(e1x[i], e1y[i], dx, dy);
+      // Exact pre-test: a quotient whose magnitude clearly exceeds 1, or that is clearly negative,
+      // cannot pass "0 <= t <= 1" after IEEE division either (the 1e-4 / 1e-30 margins dwarf the
+      // half-ulp of the division and exclude the underflow-to-(-0) case), so the two divisions are
+      // skipped for the ~3 of 4 edge pairs that are nowhere near crossing.  NaNs fail every
+      // comparison here and take the exact path.
+      const float ad = fabsf(det), lim = 1.0001f * ad, tiny = 1e-30f * ad;
+      if (fabsf(n1) > lim || fabsf(n2) > lim) continue;
+      if (((n1 < 0.0f) != (det < 0.0f) && fabsf(n1) > tiny) || ((n2 < 0.0f) != (det < 0.0f) && fabsf(n2) > tiny)) continue;
+      float t1 = RB_DIV(n1, det);
+      float t2 = RB_DIV(n2, det);
       if (t1 >= 0.0f && t1 <= 1.0f && t2 >= 0.0f && t2 <= 1.0f) {
         qx[n] = RB_ADD(p1x[i], RB_MUL(e1x[i], t1));
         qy[n] = RB_ADD(p1y[i], RB_MUL(e1y[i], t1));
