@@ -346,6 +346,41 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * B * args.steps / float(te.item())
 
+    # ---- second headline metric: rotated IoU pairs/s on BASELINE configs[3]
+    # (21,824 anchors x 500 GTs x 64 images; anchor rows sharded over the ranks, no collective needed
+    # for the assignment-aware form: every rank keeps its row block)
+    from s2anet_b200 import synth
+    from s2anet_b200.box_iou_rotated import box_iou_rotated_batched
+    import numpy as np
+    IB, IM = 64, 500
+    an = torch.from_numpy(synth.all_level_anchors(IB, 3)).to(dev)
+    gt = torch.from_numpy(np.stack([synth.dota_like_gt(IM, 100 + i) for i in range(IB)])).to(dev)
+    rb, re = sdist.shard_rows(an.size(1), rank, world)
+    iou_out = torch.empty((IB, an.size(1), IM), dtype=torch.float32, device=dev)      # 2.8 GB, rows [rb, re) written
+    for _ in range(3):
+        box_iou_rotated_batched(an, gt, rb, re, out=iou_out)
+    sync_all()
+    i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 5
+    i0.record()
+    for _ in range(reps):
+        box_iou_rotated_batched(an, gt, rb, re, out=iou_out)
+    i1.record()
+    sync_all()
+    ti = torch.tensor([i0.elapsed_time(i1) / reps], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ti, op=dist.ReduceOp.MAX)
+    iou_ms = float(ti.item())
+    pairs = IB * an.size(1) * IM
+    iou_bytes = 4.0 * pairs + 20.0 * IB * (an.size(1) + IM)
+    peaks0 = load_peaks()
+    iou_metric = {"metric": "rotated IoU pairs/s", "value": pairs / (iou_ms / 1e3), "unit": "pairs/s", "ms": iou_ms,
+                  "config": "21,824 anchors x 500 GTs x 64 images (BASELINE configs[3]), anchor rows sharded over %d GPU(s)" % world,
+                  "roofline": {"bound": "hbm", "achieved": iou_bytes / (iou_ms / 1e3) / 1e9 / world, "peak": peaks0["hbm"],
+                               "unit": "GB/s", "frac": iou_bytes / (iou_ms / 1e3) / 1e9 / world / peaks0["hbm"],
+                               "note": "algorithmic bytes 4*N*M + 20*(N+M) per image; per-GPU figure"}}
+    del iou_out, an, gt
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -360,9 +395,10 @@ def main():
         outs = head.forward_levels(feat_sets[0])
         refines = [o[5] for o in outs]
         del outs
-        def align_all():
-            for x, a, s in zip(feat_sets[0], refines, STRIDES):
-                alignconv_forward(x, a, w, s)
+        from s2anet_b200.conv_tc import alignconv_forward_tc_multi
+
+        def align_all():                 # what the step runs: ONE persistent launch over the five levels
+            alignconv_forward_tc_multi(feat_sets[0], refines, w, STRIDES)
         for _ in range(3):
             align_all()
         torch.cuda.synchronize()
@@ -393,6 +429,7 @@ def main():
                 "alignconv_share_of_step": t_align / (ms / 1e3 / args.steps)}
 
     cpu = None
+    line_iou = iou_metric
     if not args.no_cpu_baseline and world == 1:
         torch.set_num_threads(os.cpu_count() or 1)
         cpu_head = build_head(torch, None, torch.float32, seed=0)
@@ -417,7 +454,7 @@ def main():
                    "l2": "two rotating feature sets (2 x %.0f MB) plus >1 GB of activations per step: working set > 126 MB L2"
                          % (h2d_bytes / 1e6)},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes},
-        "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+        "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "iou": line_iou,
     }
     print(json.dumps(line))
     if world > 1:

@@ -6,11 +6,13 @@
 // owns a 64x256 tile of the IoU matrix and works in three phases:
 //   1. prepare: the 64 row boxes and 256 column boxes are loaded with coalesced reads and their
 //      sin/cos evaluated ONCE per box (not once per pair) into shared memory;
-//   2. classify: every pair runs the cheap, conservative disjointness test (rbox_classify); pairs
+//   2. fast classify: every pair runs a branch-free ~25-flop test (rbox_classify_fast); the ~93 %
 //      proven to have IoU == 0 are stored at once (a warp writes 128 contiguous bytes of a row), the
 //      rest are appended to a per-CTA work list with a warp ballot + one shared atomic per warp;
-//   3. clip: the work list is processed densely (no idle lanes for the ~97 % rejected pairs) and
-//      each result stored to its element.
+//   3. full classify of the listed pairs (separating axes, collinearity guard), compacting in place;
+//   4. clip: the ~3 % survivors are clipped densely and each result stored to its element.
+// Splitting 2/3/4 matters because the longer tests would otherwise run for almost every warp with
+// one or two active lanes (ncu, round 1: 69 % of issued instructions were that divergent tail).
 // HBM traffic is the algorithmic minimum (4 B per pair out, 20 B per box in per tile).
 #include "common.cuh"
 #include "rbox_iou.cuh"
@@ -56,42 +58,71 @@ box_iou_rotated_kernel(const float* __restrict__ boxes1, int64_t n, const float*
   }
   __syncthreads();
 
-  // phase 2: classify.  Thread t owns column t of the tile (its box stays in registers) and walks
-  // the 64 rows (row box = shared-memory broadcast).  Pairs proven to be exactly zero are stored
-  // right away -- a warp writes 32 consecutive floats of one output row -- the others go to the
-  // work list (warp ballot + one shared atomic per warp).
+  // phase 2: fast classification of every pair.  Thread t owns column t of the tile (its box stays
+  // in registers) and walks the 64 rows (row box = shared-memory broadcast).  ~93 % of the pairs are
+  // proven zero by the branch-free fast test and stored right away -- a warp writes 32 consecutive
+  // floats of one output row; the others are appended to the work list (warp ballot + one shared
+  // atomic per warp), so the longer tests below never run with mostly idle lanes.
   const unsigned lane = tid & 31;
   const bool no_reject = (flags & S2A_IOU_NO_REJECT) != 0;
   float* o = out + (b * n + row0) * ld_out + col0;
   RBox cb;
   const bool col_ok = tid < nc;
   if (col_ok) cb = s_col[tid];
-#pragma unroll 2
+#pragma unroll 4
   for (int r = 0; r < nr; ++r) {
-    bool clip = false;
+    bool maybe = false;
     if (col_ok) {
-      const RBox rb = s_row[r];
+      if (!no_reject && rbox_classify_fast(s_row[r], cb) == RB_ZERO) o[(int64_t)r * ld_out + tid] = 0.0f;
+      else maybe = true;
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, maybe);
+    if (bal) {
+      int base = 0;
+      if (lane == 0) base = atomicAdd(&s_count, __popc(bal));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (maybe) s_list[base + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)(r * kTileC + tid);
+    }
+  }
+  __syncthreads();
+
+  // phase 3: full classification (area early-out, separating axes, collinearity guard) of the listed
+  // pairs, compacting the survivors in place: round q reads entries [256q, 256q+256) and, after a
+  // barrier, appends at positions below the number of entries processed so far.
+  const int cnt_maybe = s_count;
+  __syncthreads();
+  if (tid == 0) s_count = 0;
+  __syncthreads();
+  for (int k0 = 0; k0 < cnt_maybe; k0 += kIouThreads) {
+    const int k = k0 + tid;
+    bool clip = false;
+    int p = 0;
+    if (k < cnt_maybe) {
+      p = s_list[k];
+      const RBox& rb = s_row[p >> 8];
+      const RBox& cc = s_col[p & (kTileC - 1)];
       int cls;
       if (no_reject) {
-        float a1 = RB_MUL(rb.w, rb.h), a2 = RB_MUL(cb.w, cb.h);
+        float a1 = RB_MUL(rb.w, rb.h), a2 = RB_MUL(cc.w, cc.h);
         cls = (a1 <= RB_LO_1E14 || a2 <= RB_LO_1E14) ? RB_ZERO : RB_CLIP;
       } else {
-        cls = rbox_classify(rb, cb);
+        cls = rbox_classify(rb, cc);
       }
-      if (cls == RB_ZERO) o[(int64_t)r * ld_out + tid] = 0.0f;
+      if (cls == RB_ZERO) o[(int64_t)(p >> 8) * ld_out + (p & (kTileC - 1))] = 0.0f;
       else clip = true;
     }
+    __syncthreads();                       // every entry of this round has been read
     const unsigned bal = __ballot_sync(0xffffffffu, clip);
     if (bal) {
       int base = 0;
       if (lane == 0) base = atomicAdd(&s_count, __popc(bal));
       base = __shfl_sync(0xffffffffu, base, 0);
-      if (clip) s_list[base + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)(r * kTileC + tid);
+      if (clip) s_list[base + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)p;
     }
   }
   __syncthreads();
 
-  // phase 3: dense clipping of the surviving pairs (typically < 3 % of the tile)
+  // phase 4: dense clipping of the survivors (typically < 3 % of the tile)
   const int cnt = s_count;
   for (int k = tid; k < cnt; k += kIouThreads) {
     const int p = s_list[k];

@@ -79,8 +79,8 @@ __device__ __forceinline__ void mask_tile(MaskTileSmem& s, const RBox* __restric
     bool clip = false;
     if (r < nr && c < nc && (!diag || c > r)) {
       int cls = RB_ZERO;
-      if (s.lrow[r] == lc) cls = rbox_classify(s.row[r], cb);   // labels differ -> IoU := 0
-      if (cls == RB_CLIP) clip = true;
+      if (s.lrow[r] == lc) cls = rbox_classify_fast(s.row[r], cb);   // labels differ -> IoU := 0
+      if (cls != RB_ZERO) clip = true;                               // listed: full classify + clip below
       else if (zero_suppresses) atomicOr(&s.word[r], 1ull << c);
     }
     const unsigned bal = __ballot_sync(0xffffffffu, clip);
@@ -96,7 +96,7 @@ __device__ __forceinline__ void mask_tile(MaskTileSmem& s, const RBox* __restric
   for (int k = tid; k < cnt; k += kMaskThreads) {
     const int p = s.list[k];
     const int r = p >> 6, cc = p & (kBlk - 1);
-    if (rbox_iou_clip(s.row[r], s.col[cc]) > thr) atomicOr(&s.word[r], 1ull << cc);
+    if (rbox_iou(s.row[r], s.col[cc]) > thr) atomicOr(&s.word[r], 1ull << cc);
   }
   __syncthreads();
 }

@@ -86,7 +86,22 @@ RB_HD void rbox_prep(float x, float y, float w, float h, float a, RBox& o) {
 //     near-collinear edges (boxes shifted along a shared edge line) are where the reference's t1/t2
 //     are ill-conditioned; its answer there is reproduced by the clipper, never predicted.
 // NaN/Inf inputs fail the comparisons and fall through to RB_CLIP.  See DESIGN.md "IoU reject test".
-enum { RB_ZERO = 0, RB_CLIP = 1 };
+
+// Stage 1 (every pair, ~25 flops, no divergence): the common case "circles clearly apart, edges clearly
+// not parallel, no sliver" -> exactly zero.  Everything else is RB_MAYBE and goes to stage 2.
+// `ext` over-estimates the pair's extent with the L1 norm (conservative: margins only grow).
+enum { RB_ZERO = 0, RB_CLIP = 1, RB_MAYBE = 2 };
+
+RB_HD int rbox_classify_fast(const RBox& A, const RBox& B) {
+  const float dx = B.x - A.x, dy = B.y - A.y;
+  const float rs = A.r + B.r;
+  const float sd = B.s2 * A.c2 - B.c2 * A.s2;        // sin(tB - tA)/4
+  const float cd = A.c2 * B.c2 + A.s2 * B.s2;        // cos(tB - tA)/4
+  const float ext = fabsf(dx) + fabsf(dy) + rs;
+  const bool ok = (dx * dx + dy * dy > 1.0201f * rs * rs) && (fabsf(sd * cd) > 0.000625f) &&
+                  (fminf(A.mn, B.mn) > 2e-3f * ext);
+  return ok ? RB_ZERO : RB_MAYBE;
+}
 
 RB_HD int rbox_classify(const RBox& A, const RBox& B) {
   float a1 = RB_MUL(A.w, A.h), a2 = RB_MUL(B.w, B.h);
@@ -94,7 +109,7 @@ RB_HD int rbox_classify(const RBox& A, const RBox& B) {
   const float dx = B.x - A.x, dy = B.y - A.y;
   const float d2 = dx * dx + dy * dy;
   const float rs = A.r + B.r;
-  const float ext = sqrtf(d2) + rs;
+  const float ext = fabsf(dx) + fabsf(dy) + rs;
   // sin(tB - tA)/4 and cos(tB - tA)/4 from the half-scaled sin/cos
   const float sd = B.s2 * A.c2 - B.c2 * A.s2;
   const float cd = A.c2 * B.c2 + A.s2 * B.s2;
