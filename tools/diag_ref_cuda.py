@@ -134,3 +134,16 @@ import torchvision
 off = torch.zeros(1, 18, 128, 128, device=dev); outb = torch.empty(1, 256, 128, 128, device=dev)
 ms = timeit(lambda: dc.deform_conv_forward_cuda(x, w, off, outb, x.new_empty(0), x.new_empty(0), 3, 3, 1, 1, 1, 1, 1, 1, 1, 1, 1))
 print("reference deform_conv_cuda fp32 P3: %.3f ms" % ms)
+
+xh, wh, offh = x.half(), w.half(), off.half(); outh = torch.empty(1, 256, 128, 128, device=dev, dtype=torch.half)
+ms = timeit(lambda: dc.deform_conv_forward_cuda(xh, wh, offh, outh, xh.new_empty(0), xh.new_empty(0), 3, 3, 1, 1, 1, 1, 1, 1, 1, 1, 1))
+print("reference deform_conv_cuda fp16 P3 B=1: %.3f ms" % ms)
+x8 = torch.randn(8, 256, 128, 128, device=dev).half(); off8 = torch.zeros(8, 18, 128, 128, device=dev).half(); out8 = torch.empty(8, 256, 128, 128, device=dev, dtype=torch.half)
+ms = timeit(lambda: dc.deform_conv_forward_cuda(x8, wh, off8, out8, xh.new_empty(0), xh.new_empty(0), 3, 3, 1, 1, 1, 1, 1, 1, 1, 1, 8))
+print("reference deform_conv_cuda fp16 P3 B=8: %.3f ms" % ms)
+xcl = x8.contiguous(memory_format=torch.channels_last); a8 = torch.from_numpy(synth.refined_anchors(8, 128, 128, 8, 1)).to(dev)
+ms = timeit(lambda: alignconv_forward(xcl, a8, wh, 8))
+print("s2a alignconv fp16 P3 B=8 (incl. offset generation): %.3f ms" % ms)
+import torch.nn.functional as F
+ms = timeit(lambda: F.conv2d(xcl, w.half().contiguous(memory_format=torch.channels_last), padding=1))
+print("cuDNN conv fp16 P3 B=8: %.3f ms" % ms)
