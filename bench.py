@@ -42,6 +42,18 @@ def load_peaks():
     return {"bf16_burst": 1590.0, "bf16_sustained": 1400.0, "hbm": 6650.0, "source": "fallback (B200_PROFILING.md)"}
 
 
+def load_traffic(batch):
+    """DRAM bytes per launch of the roofline kernel from the committed `ncu --set full` capture
+    (profiles/roofline_traffic.json; captured at batch 8, the default): read + write, or None."""
+    path = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if batch != 8 or not os.path.exists(path):
+        return None
+    with open(path) as f:
+        t = json.load(f).get("conv_tc_kernel<ALIGN,bf16>")
+    return None if not t else {"dram_bytes": t["dram_bytes_read"] + t["dram_bytes_write"],
+                               "algorithmic_bytes": t["algorithmic_bytes"], "source": t["source"]}
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
 
@@ -424,7 +436,7 @@ def main():
         ach = flops_p3 / t_p3 / 1e12
         roof = {"bound": "tensor", "kernel": "conv_tc_kernel<ALIGN,bf16> (AlignConv, P3 level of the batch, one launch)",
                 "achieved": ach, "peak": peaks["bf16_burst"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_burst"],
-                "peak_source": peaks["source"] + " bf16_tflops (burst: kernel timed alone)", "traffic": None,
+                "peak_source": peaks["source"] + " bf16_tflops (burst: kernel timed alone)", "traffic": load_traffic(B),
                 "all_levels_tflops": ALIGN_FLOPS_PER_IMAGE * B / t_align / 1e12,
                 "alignconv_share_of_step": t_align / (ms / 1e3 / args.steps)}
 
