@@ -190,6 +190,41 @@ S2A_EXPORT int s2a_orconv_forward_tc_multi(int nlevels, const void* const* xs,
                                            void* const* outs, void* const* pooleds, const int* Hs,
                                            const int* Ws, int B, int C, int Co, int dtype, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Box decode stages of the head, one launch over all FPN levels and images.
+ *
+ * s2a_fam_decode -- replaces fam_bbox_decode + gen_grid_anchors
+ *   reference: models/head.py:27-52 (fam_bbox_decode, wh_ratio_clip=1e-6), models/anchors.py:75-126
+ *              (one square anchor per location: centre s*i + (s-1)/2, w = h = anchor_scale*s,
+ *              theta = anchor_angle), models/boxes.py:82-162 (delta2bbox_rotated), utils/general.py:925-930.
+ * deltas[l]: fam_bbox_pred of level l, logical shape [B, 5, H, W] with element strides
+ * delta_strides[4*l .. 4*l+3] (NCHW or channels_last), dtype in {S2A_F32, S2A_BF16, S2A_F16};
+ * refined[l]: [B, H, W, 5] fp32 contiguous (x, y, w, h, theta) = the rotated anchors AlignConv consumes.
+ *
+ * s2a_select_decode -- replaces get_bboxes_single_img up to the NMS call
+ *   reference: models/head.py:684-717: sigmoid, per-level top-`topk` by best class score (only on
+ *              levels with more than `topk` locations), gather, concatenation over levels, final
+ *              delta2bbox_rotated with wh_ratio_clip (default 16/1000, models/boxes.py:226).
+ * cls[l] [B, C, H, W] logits and reg[l] [B, 5, H, W] deltas (strided, dtype as above), anchors[l]
+ * [B, H*W, 5] fp32 (the refined anchors).  Outputs: bboxes_out [B, n_total, 5] fp32, scores_out
+ * [B, n_total, C] fp32 (post-sigmoid, rounded through the input dtype like the reference's half
+ * tensors), n_total = sum_l min(H*W, topk); index_out (optional, may be NULL) [B, n_total] int32 =
+ * location y*W + x of each candidate inside its level.  Candidates of a top-k level are ordered by
+ * descending best score, ties by ascending location (torch.topk leaves ties unspecified).
+ */
+S2A_EXPORT int s2a_fam_decode(int nlevels, const void* const* deltas, const int64_t* delta_strides,
+                              float* const* refined, const int* Hs, const int* Ws,
+                              const float* strides, int B, float anchor_scale, float anchor_angle,
+                              double wh_ratio_clip, int dtype, void* stream);
+S2A_EXPORT size_t s2a_select_decode_workspace_bytes(int nlevels, const int* Hs, const int* Ws, int B);
+S2A_EXPORT int s2a_select_decode(int nlevels, const void* const* cls, const int64_t* cls_strides,
+                                 const void* const* reg, const int64_t* reg_strides,
+                                 const float* const* anchors, const int* Hs, const int* Ws, int B,
+                                 int num_classes, int topk, double wh_ratio_clip, int dtype,
+                                 float* bboxes_out, float* scores_out, int32_t* index_out,
+                                 int64_t n_total, void* workspace, size_t workspace_bytes,
+                                 void* stream);
+
 #ifdef __cplusplus
 }
 #endif

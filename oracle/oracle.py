@@ -232,3 +232,87 @@ def ref_pairwise(tag, sem, boxes1, boxes2):
     out = np.empty((b1.shape[0], b2.shape[0]), np.float32)
     getattr(L, pre + "pairwise")(b1, b1.shape[0], b2, b2.shape[0], out)
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# box decode stages (numpy restatement; fp32 step by step like the reference's elementwise torch ops)
+# ------------------------------------------------------------------------------------------------
+def norm_angle(a):
+    """utils/general.py:925-930: (a - (-pi/4)) % pi + (-pi/4) in fp32 (Python/torch remainder sign rule)."""
+    a = _f32(a)
+    lo = np.float32(-np.pi / 4)
+    return (np.mod(a - lo, np.float32(np.pi)) + lo).astype(np.float32)
+
+
+def delta2bbox_rotated(anchors, deltas, wh_ratio_clip=16 / 1000):
+    """models/boxes.py:82-162 (is_encode_relative=True).  anchors [...,5] fp32; deltas [...,5] float32 or
+    float16 -- a float16 input keeps the reference's half-precision steps (clamp, exp and pi*dangle are
+    evaluated on the half tensor) before meeting the fp32 anchors."""
+    anchors = _f32(anchors)
+    dt = np.float16 if deltas.dtype == np.float16 else np.float32
+    d = np.asarray(deltas, dtype=dt)
+    lim = dt(abs(np.log(wh_ratio_clip)))                       # torch.clamp converts its bounds to the tensor dtype
+    dx, dy = d[..., 0].astype(np.float32), d[..., 1].astype(np.float32)
+    dw = np.clip(d[..., 2], -lim, lim)
+    dh = np.clip(d[..., 3], -lim, lim)
+    with np.errstate(over="ignore"):               # fp16 exp overflows to inf at the 1e-6 clip, as in torch
+        ew = np.exp(dw.astype(np.float32)).astype(dt).astype(np.float32)
+        eh = np.exp(dh.astype(np.float32)).astype(dt).astype(np.float32)
+    pda = (d[..., 4].astype(np.float32) * np.float32(np.pi)).astype(dt).astype(np.float32)
+    rx, ry, rw, rh, ra = (anchors[..., i] for i in range(5))
+    cosa, sina = np.cos(ra), np.sin(ra)
+    gx = dx * rw * cosa - dy * rh * sina + rx
+    gy = dx * rw * sina + dy * rh * cosa + ry
+    gw = rw * ew
+    gh = rh * eh
+    ga = norm_angle(pda + ra)
+    return np.stack([gx, gy, gw, gh, ga], axis=-1).astype(np.float32)
+
+
+def grid_anchors(H, W, stride, scale=4.0, angle=0.0):
+    """models/anchors.py:75-126 for one square anchor per location -> [H, W, 5] fp32."""
+    s = np.float32(stride)
+    xs = np.arange(W, dtype=np.float32) * s + np.float32(0.5) * (s - np.float32(1))
+    ys = np.arange(H, dtype=np.float32) * s + np.float32(0.5) * (s - np.float32(1))
+    a = np.zeros((H, W, 5), np.float32)
+    a[..., 0] = xs[None, :]
+    a[..., 1] = ys[:, None]
+    a[..., 2] = a[..., 3] = s * np.float32(scale)
+    a[..., 4] = np.float32(angle)
+    return a
+
+
+def fam_decode(fam_bbox_pred, stride, scale=4.0, angle=0.0, wh_ratio_clip=1e-6):
+    """models/head.py:27-52: fam_bbox_pred [B,5,H,W] -> refined anchors [B,H,W,5]."""
+    B, _, H, W = fam_bbox_pred.shape
+    d = np.transpose(fam_bbox_pred, (0, 2, 3, 1))
+    return delta2bbox_rotated(grid_anchors(H, W, stride, scale, angle)[None], d, wh_ratio_clip)
+
+
+def sigmoid_in(x):
+    dt = np.float16 if x.dtype == np.float16 else np.float32
+    xf = np.asarray(x, np.float32)
+    return (np.float32(1) / (np.float32(1) + np.exp(-xf))).astype(dt)
+
+
+def select_decode(cls_preds, bbox_preds, anchors, topk=2000, wh_ratio_clip=16 / 1000):
+    """models/head.py:684-717 for a batch: per level sigmoid, top-k by best class score (descending,
+    ties by ascending location), gather; concatenate levels; decode.  Returns (bboxes [B,n,5] fp32,
+    scores [B,n,C] fp32, index [B,n] int32)."""
+    B = cls_preds[0].shape[0]
+    out_b, out_s, out_i = [], [], []
+    for b in range(B):
+        sl, dl, al, il = [], [], [], []
+        for cls, reg, anc in zip(cls_preds, bbox_preds, anchors):
+            C, H, W = cls.shape[1:]
+            sc = sigmoid_in(np.transpose(cls[b], (1, 2, 0)).reshape(H * W, C))
+            de = np.transpose(reg[b], (1, 2, 0)).reshape(H * W, 5)
+            an = _f32(anc[b]).reshape(H * W, 5)
+            idx = np.arange(H * W)
+            if topk > 0 and H * W > topk:
+                best = sc.max(axis=1).astype(np.float32)
+                idx = np.lexsort((idx, -best))[:topk]
+            sl.append(sc[idx].astype(np.float32)); dl.append(de[idx]); al.append(an[idx]); il.append(idx.astype(np.int32))
+        out_b.append(delta2bbox_rotated(np.concatenate(al), np.concatenate(dl), wh_ratio_clip))
+        out_s.append(np.concatenate(sl)); out_i.append(np.concatenate(il))
+    return np.stack(out_b), np.stack(out_s), np.stack(out_i)

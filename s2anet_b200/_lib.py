@@ -15,7 +15,7 @@ S2A_F32, S2A_BF16, S2A_F16 = 0, 1, 2
 S2A_IOU_NO_REJECT = 1
 _DTYPES = {torch.float32: S2A_F32, torch.bfloat16: S2A_BF16, torch.float16: S2A_F16}
 
-_vp, _i64, _i32, _f32, _sz = C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_size_t
+_vp, _i64, _i32, _f32, _f64, _sz = C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_double, C.c_size_t
 
 # name -> (restype, argtypes); must list every symbol include/s2a_b200.h declares
 PROTOTYPES = {
@@ -38,6 +38,10 @@ PROTOTYPES = {
     "s2a_orconv_forward_tc": (_i32, [_vp, _vp, _vp, _vp, _vp] + [_i32] * 6 + [_vp]),
     "s2a_alignconv_forward_tc_multi": (_i32, [_i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp] + [_i32] * 4 + [_vp]),
     "s2a_orconv_forward_tc_multi": (_i32, [_i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp] + [_i32] * 4 + [_vp]),
+    "s2a_fam_decode": (_i32, [_i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _f32, _f32, _f64, _i32, _vp]),
+    "s2a_select_decode_workspace_bytes": (_sz, [_i32, _vp, _vp, _i32]),
+    "s2a_select_decode": (_i32, [_i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _f64, _i32, _vp, _vp, _vp,
+                                 _i64, _vp, _sz, _vp]),
 }
 
 _lib = None
@@ -64,7 +68,7 @@ KERNELS_PER_CALL = {
     "box_iou_rotated": 1, "box_iou_rotated_batched": 1, "nms_rotated": 4, "multiclass_nms_rotated": 6,
     "arf_forward": 1, "arf_backward": 1, "ri_pool": 1, "deform_conv_forward_cuda": 1, "alignconv_forward": 1,
     "orconv_forward": 1, "conv_pack_weight": 1, "alignconv_forward_tc": 1, "orconv_forward_tc": 1,
-    "alignconv_forward_tc_multi": 1, "orconv_forward_tc_multi": 1,
+    "alignconv_forward_tc_multi": 1, "orconv_forward_tc_multi": 1, "fam_decode": 1, "select_decode": 1,
 }
 launches = 0          # running count, read by bench.py for "gpu_launches"
 

@@ -1,0 +1,358 @@
+// decode.cu -- the two box-decode stages that sit either side of AlignConv/ORConv in the S2ANet head,
+// each as ONE launch over all FPN levels and all images of the batch.
+//
+// Replaces (reference):
+//   * fam_bbox_decode + gen_grid_anchors: models/head.py:27-52, models/anchors.py:75-126 --
+//     `s2a_fam_decode` turns fam_bbox_pred [B,5,H,W] into the refined rotated anchors [B,H,W,5]
+//     (the grid anchor is analytic: centre s*i + (s-1)/2, w = h = scale*s, theta = angle).
+//   * get_bboxes_single_img up to (not including) the NMS: models/head.py:684-717 -- sigmoid,
+//     per-level top-k by best class score, gather, concatenation over levels, final
+//     delta2bbox_rotated; `s2a_select_decode` does all of it for the whole batch.
+// Arithmetic: models/boxes.py:82-162 (delta2bbox_rotated) and utils/general.py:925-930 (norm_angle),
+// operation by operation with individually rounded fp32 operations and the same dtype promotion as
+// PyTorch applies in the reference's half-precision validation: anchors are
+// fp32, deltas are T; clamp / exp / pi*dangle are evaluated in T (rounded to T), everything that
+// touches an anchor value is fp32.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include <cub/block/block_radix_sort.cuh>
+
+#include "common.cuh"
+
+namespace s2a {
+
+constexpr int DEC_MAX_LEVELS = 8;
+constexpr int DEC_THREADS = 1024;
+
+template <typename T> __device__ __forceinline__ float ld_as_float(const T* p);
+template <> __device__ __forceinline__ float ld_as_float<float>(const float* p) { return __ldg(p); }
+template <> __device__ __forceinline__ float ld_as_float<__nv_bfloat16>(const __nv_bfloat16* p) {
+  return __bfloat162float(*p);
+}
+template <> __device__ __forceinline__ float ld_as_float<__half>(const __half* p) { return __half2float(*p); }
+
+// round a float through T (what storing a T tensor element does)
+template <typename T> __device__ __forceinline__ float round_through(float v);
+template <> __device__ __forceinline__ float round_through<float>(float v) { return v; }
+template <> __device__ __forceinline__ float round_through<__nv_bfloat16>(float v) {
+  return __bfloat162float(__float2bfloat16_rn(v));
+}
+template <> __device__ __forceinline__ float round_through<__half>(float v) { return __half2float(__float2half_rn(v)); }
+
+// torch.sigmoid on a T tensor: T(1 / (1 + exp(-float(x)))) (ATen UnarySpecialOpsKernel)
+template <typename T> __device__ __forceinline__ float sigmoid_t(float x) {
+  return round_through<T>(__fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x))));
+}
+
+// models/boxes.py:82-162 with is_encode_relative=True; a = (x, y, w, h, theta) fp32, d = deltas already
+// widened from T.  lim = max_ratio rounded to T (torch.clamp converts its bounds to the tensor dtype).
+template <typename T>
+__device__ __forceinline__ void delta2bbox_rotated(const float a[5], float dx, float dy, float dw, float dh, float da,
+                                                   float lim, float out[5]) {
+  dw = dw < -lim ? -lim : (dw > lim ? lim : dw);          // NaN stays NaN, like torch.clamp
+  dh = dh < -lim ? -lim : (dh > lim ? lim : dh);
+  const float cosa = cosf(a[4]), sina = sinf(a[4]);
+  const float dxw = __fmul_rn(dx, a[2]), dyh = __fmul_rn(dy, a[3]);
+  out[0] = __fadd_rn(__fsub_rn(__fmul_rn(dxw, cosa), __fmul_rn(dyh, sina)), a[0]);      // boxes.py:148
+  out[1] = __fadd_rn(__fadd_rn(__fmul_rn(dxw, sina), __fmul_rn(dyh, cosa)), a[1]);      // boxes.py:149
+  out[2] = __fmul_rn(a[2], round_through<T>(expf(dw)));                                 // boxes.py:155
+  out[3] = __fmul_rn(a[3], round_through<T>(expf(dh)));
+  const float kPi = 3.14159274101257324f, kQuarterPi = 0.785398185253143311f;           // float(np.pi), float(np.pi / 4)
+  const float ga = __fadd_rn(round_through<T>(__fmul_rn(da, kPi)), a[4]);               // boxes.py:159
+  // norm_angle (utils/general.py:925-930): (ga + pi/4) % pi - pi/4 with Python's sign convention
+  float m = fmodf(__fadd_rn(ga, kQuarterPi), kPi);
+  if (m != 0.0f && m < 0.0f) m = __fadd_rn(m, kPi);
+  out[4] = __fsub_rn(m, kQuarterPi);
+}
+
+// ------------------------------------------------------------------------------------------------
+// FAM decode
+// ------------------------------------------------------------------------------------------------
+struct FamLevel {
+  const void* deltas;     // [B, 5, H, W], element strides s[4]
+  float* out;             // [B, H, W, 5] fp32 contiguous
+  long long s[4];
+  int H, W;
+  long long begin;        // first global position index of this level (positions = B*H*W per level)
+  float stride;
+};
+struct FamParams {
+  FamLevel lv[DEC_MAX_LEVELS];
+  int nlevels, B;
+  long long total;
+  float scale, angle, lim;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) fam_decode_kernel(const __grid_constant__ FamParams p) {
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < p.total; g += (long long)gridDim.x * blockDim.x) {
+    int l = 0;
+    while (l + 1 < p.nlevels && g >= p.lv[l + 1].begin) ++l;
+    const FamLevel& L = p.lv[l];
+    long long r = g - L.begin;
+    const int x = (int)(r % L.W);
+    r /= L.W;
+    const int y = (int)(r % L.H);
+    const int b = (int)(r / L.H);
+    // models/anchors.py:94-95: centre = index * stride + 0.5 * (stride - 1); base size = scale * stride
+    const float half = __fmul_rn(0.5f, __fsub_rn(L.stride, 1.0f));
+    const float a[5] = {__fadd_rn(__fmul_rn((float)x, L.stride), half), __fadd_rn(__fmul_rn((float)y, L.stride), half),
+                        __fmul_rn(L.stride, p.scale), __fmul_rn(L.stride, p.scale), p.angle};
+    const T* d = reinterpret_cast<const T*>(L.deltas) + b * L.s[0] + y * L.s[2] + x * L.s[3];
+    float o[5];
+    delta2bbox_rotated<T>(a, ld_as_float(d), ld_as_float(d + L.s[1]), ld_as_float(d + 2 * L.s[1]),
+                          ld_as_float(d + 3 * L.s[1]), ld_as_float(d + 4 * L.s[1]), p.lim, o);
+    float* dst = L.out + (((long long)b * L.H + y) * L.W + x) * 5;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) dst[i] = o[i];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// select (per-level top-k) + decode
+// ------------------------------------------------------------------------------------------------
+struct SelLevel {
+  const void* cls;        // [B, C, H, W] logits, element strides cs[4]
+  const void* reg;        // [B, 5, H, W] deltas, element strides rs[4]
+  const float* anchors;   // [B, H*W, 5] fp32 contiguous
+  long long cs[4], rs[4];
+  int H, W, n, k;         // n = H*W, k = min(n, topk)
+  int out_off;            // first row of this level in the concatenated candidate list
+  long long key_off;      // offset of this level inside one image's key scratch
+};
+struct SelParams {
+  SelLevel lv[DEC_MAX_LEVELS];
+  int nlevels, B, C, n_total;
+  long long keys_per_image;
+  uint32_t* keys;         // workspace [B][keys_per_image]
+  float* bboxes;          // [B, n_total, 5]
+  float* scores;          // [B, n_total, C]
+  int32_t* index_out;     // optional [B, n_total]: position (y*W + x) of every candidate inside its level
+  float lim;
+};
+
+__device__ __forceinline__ unsigned long long composite_key(uint32_t key, int i) {
+  return ((unsigned long long)key << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)i);
+}
+
+template <typename T, int ITEMS>
+__global__ void __launch_bounds__(DEC_THREADS) select_decode_kernel(const __grid_constant__ SelParams p) {
+  using Sort = cub::BlockRadixSort<unsigned long long, DEC_THREADS, ITEMS>;
+  extern __shared__ __align__(16) uint8_t dsm[];
+  typename Sort::TempStorage& sort_tmp = *reinterpret_cast<typename Sort::TempStorage*>(dsm);
+  __shared__ unsigned long long s_sel[DEC_THREADS * ITEMS];
+  __shared__ unsigned int s_hist[256];
+  __shared__ unsigned long long s_prefix;
+  __shared__ int s_remaining, s_done, s_count;
+
+  const SelLevel& L = p.lv[blockIdx.x];
+  const int b = blockIdx.y, tid = threadIdx.x;
+  const int n = L.n, k = L.k, C = p.C;
+  const T* cls = reinterpret_cast<const T*>(L.cls) + b * L.cs[0];
+  const T* reg = reinterpret_cast<const T*>(L.reg) + b * L.rs[0];
+  const bool select = n > k;
+
+  if (select) {
+    // ---- keys: best class score of every location (models/head.py:700-701) -------------------
+    uint32_t* keys = p.keys + (long long)b * p.keys_per_image + L.key_off;
+    for (int i = tid; i < n; i += DEC_THREADS) {
+      const int y = i / L.W, x = i - y * L.W;
+      const T* q = cls + y * L.cs[2] + x * L.cs[3];
+      float m = -INFINITY;
+      for (int c = 0; c < C; ++c) m = fmaxf(m, ld_as_float(q + c * L.cs[1]));
+      // sigmoid is monotone, so max_c sigmoid(x_c) == sigmoid(max_c x_c) bit for bit; scores are >= 0,
+      // so their bit patterns order like unsigned integers
+      keys[i] = __float_as_uint(sigmoid_t<T>(m));
+    }
+    if (tid == 0) { s_prefix = 0ull; s_remaining = k; s_done = 0; s_count = 0; }
+    __syncthreads();
+    // ---- radix select of the k-th largest composite (score, lower index first): exact top-k with a
+    // defined tie rule (torch.topk leaves ties unspecified) --------------------------------------
+    for (int shift = 56; shift >= 0; shift -= 8) {
+      for (int i = tid; i < 256; i += DEC_THREADS) s_hist[i] = 0u;
+      __syncthreads();
+      const unsigned long long prefix = s_prefix;
+      for (int i = tid; i < n; i += DEC_THREADS) {
+        const unsigned long long c = composite_key(keys[i], i);
+        if (shift == 56 || (c >> (shift + 8)) == (prefix >> (shift + 8))) atomicAdd(&s_hist[(c >> shift) & 255u], 1u);
+      }
+      __syncthreads();
+      if (tid < 32) {
+        // lane owns bins [8*lane, 8*lane+8); suffix sums from the top bin downwards
+        unsigned int loc[8], sum = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { loc[j] = s_hist[tid * 8 + j]; sum += loc[j]; }
+        unsigned int incl = sum;              // inclusive suffix scan over lanes
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const unsigned int v = __shfl_down_sync(0xffffffffu, incl, o);
+          if (tid + o < 32) incl += v;
+        }
+        const unsigned int above = incl - sum;   // elements in the bins of higher lanes
+        const unsigned int rem = (unsigned int)s_remaining;
+        if (above < rem && incl >= rem) {     // the crossing bin is in this lane
+          unsigned int cum = above;
+          for (int j = 7; j >= 0; --j) {
+            if (cum + loc[j] >= rem) {
+              s_prefix = prefix | ((unsigned long long)(tid * 8 + j) << shift);
+              s_remaining = (int)(rem - cum);
+              if (loc[j] == rem - cum) s_done = 1;      // the whole bin is selected: threshold found
+              break;
+            }
+            cum += loc[j];
+          }
+        }
+      }
+      __syncthreads();
+      if (s_done) break;
+    }
+    const unsigned long long thr = s_prefix;
+    // ---- collect the k selected composites and sort them (descending score, ascending index) ----
+    for (int i = tid; i < DEC_THREADS * ITEMS; i += DEC_THREADS) s_sel[i] = 0ull;
+    __syncthreads();
+    for (int i = tid; i < n; i += DEC_THREADS) {
+      const unsigned long long c = composite_key(keys[i], i);
+      if (c >= thr) {
+        const int pos = atomicAdd(&s_count, 1);
+        if (pos < DEC_THREADS * ITEMS) s_sel[pos] = c;
+      }
+    }
+    __syncthreads();
+    unsigned long long items[ITEMS];
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) items[j] = s_sel[tid * ITEMS + j];
+    __syncthreads();
+    Sort(sort_tmp).SortDescending(items);
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) s_sel[tid * ITEMS + j] = items[j];
+    __syncthreads();
+  }
+
+  // ---- gather + sigmoid + final decode (models/head.py:703-717) ---------------------------------
+  for (int j = tid; j < k; j += DEC_THREADS) {
+    const int i = select ? (int)(0xFFFFFFFFu - (uint32_t)(s_sel[j] & 0xFFFFFFFFull)) : j;
+    const int y = i / L.W, x = i - y * L.W;
+    const long long row = (long long)b * p.n_total + L.out_off + j;
+    const T* q = cls + y * L.cs[2] + x * L.cs[3];
+    float* so = p.scores + row * C;
+    for (int c = 0; c < C; ++c) so[c] = sigmoid_t<T>(ld_as_float(q + c * L.cs[1]));
+    const T* d = reg + y * L.rs[2] + x * L.rs[3];
+    const float* ap = L.anchors + ((long long)b * n + i) * 5;
+    const float a[5] = {__ldg(ap), __ldg(ap + 1), __ldg(ap + 2), __ldg(ap + 3), __ldg(ap + 4)};
+    float o[5];
+    delta2bbox_rotated<T>(a, ld_as_float(d), ld_as_float(d + L.rs[1]), ld_as_float(d + 2 * L.rs[1]),
+                          ld_as_float(d + 3 * L.rs[1]), ld_as_float(d + 4 * L.rs[1]), p.lim, o);
+    float* bo = p.bboxes + row * 5;
+#pragma unroll
+    for (int e = 0; e < 5; ++e) bo[e] = o[e];
+    if (p.index_out) p.index_out[row] = i;
+  }
+}
+
+template <typename T> static float limit_in(float max_ratio);
+template <> float limit_in<__nv_bfloat16>(float m) { return __bfloat162float(__float2bfloat16_rn(m)); }
+template <> float limit_in<__half>(float m) { return __half2float(__float2half_rn(m)); }
+
+static float clamp_limit(double wh_ratio_clip, int dtype) {
+  const float m = (float)fabs(log(wh_ratio_clip));           // boxes.py:115: np.abs(np.log(wh_ratio_clip))
+  return dtype == S2A_BF16 ? limit_in<__nv_bfloat16>(m) : dtype == S2A_F16 ? limit_in<__half>(m) : m;
+}
+
+template <typename T, int ITEMS>
+static int launch_select(const SelParams& p, cudaStream_t st) {
+  using Sort = cub::BlockRadixSort<unsigned long long, DEC_THREADS, ITEMS>;
+  auto kern = select_decode_kernel<T, ITEMS>;
+  const size_t smem = sizeof(typename Sort::TempStorage);
+  S2A_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<dim3(p.nlevels, p.B), DEC_THREADS, smem, st>>>(p);
+  S2A_LAUNCH_OK("select_decode_kernel");
+  return S2A_OK;
+}
+
+template <typename T>
+static int launch_select_items(const SelParams& p, int kmax, cudaStream_t st) {
+  if (kmax <= 2 * DEC_THREADS) return launch_select<T, 2>(p, st);
+  return launch_select<T, 4>(p, st);
+}
+
+}  // namespace s2a
+
+extern "C" int s2a_fam_decode(int nlevels, const void* const* deltas, const int64_t* delta_strides, float* const* refined,
+                              const int* Hs, const int* Ws, const float* strides, int B, float anchor_scale,
+                              float anchor_angle, double wh_ratio_clip, int dtype, void* stream) {
+  using namespace s2a;
+  S2A_CHECK_ARG(nlevels >= 1 && nlevels <= DEC_MAX_LEVELS, "fam_decode: 1..%d levels per call", DEC_MAX_LEVELS);
+  S2A_CHECK_ARG(B >= 0 && wh_ratio_clip > 0.0, "fam_decode: bad batch size or wh_ratio_clip");
+  S2A_CHECK_ARG(dtype == S2A_F32 || dtype == S2A_BF16 || dtype == S2A_F16, "fam_decode: unknown dtype %d", dtype);
+  if (B == 0) return S2A_OK;
+  S2A_CHECK_ARG(deltas && delta_strides && refined && Hs && Ws && strides, "fam_decode: null pointer");
+  FamParams p{};
+  long long total = 0;
+  for (int l = 0; l < nlevels; ++l) {
+    S2A_CHECK_ARG(Hs[l] > 0 && Ws[l] > 0 && deltas[l] && refined[l] && strides[l] > 0.0f, "fam_decode: bad level %d", l);
+    FamLevel& L = p.lv[l];
+    L.deltas = deltas[l]; L.out = refined[l]; L.H = Hs[l]; L.W = Ws[l]; L.begin = total; L.stride = strides[l];
+    for (int i = 0; i < 4; ++i) L.s[i] = delta_strides[4 * l + i];
+    total += (long long)B * Hs[l] * Ws[l];
+  }
+  p.nlevels = nlevels; p.B = B; p.total = total; p.scale = anchor_scale; p.angle = anchor_angle;
+  p.lim = clamp_limit(wh_ratio_clip, dtype);
+  const int blocks = (int)std::min<long long>(ceil_div(total, 256), (long long)sm_count() * 8);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == S2A_F32) fam_decode_kernel<float><<<blocks, 256, 0, st>>>(p);
+  else if (dtype == S2A_BF16) fam_decode_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(p);
+  else fam_decode_kernel<__half><<<blocks, 256, 0, st>>>(p);
+  S2A_LAUNCH_OK("fam_decode_kernel");
+  return S2A_OK;
+}
+
+extern "C" size_t s2a_select_decode_workspace_bytes(int nlevels, const int* Hs, const int* Ws, int B) {
+  size_t keys = 0;
+  for (int l = 0; l < nlevels; ++l) keys += (size_t)Hs[l] * Ws[l];
+  return keys * sizeof(uint32_t) * (size_t)(B > 0 ? B : 0) + 256;
+}
+
+extern "C" int s2a_select_decode(int nlevels, const void* const* cls, const int64_t* cls_strides, const void* const* reg,
+                                 const int64_t* reg_strides, const float* const* anchors, const int* Hs, const int* Ws,
+                                 int B, int num_classes, int topk, double wh_ratio_clip, int dtype, float* bboxes_out,
+                                 float* scores_out, int32_t* index_out, int64_t n_total, void* workspace,
+                                 size_t workspace_bytes, void* stream) {
+  using namespace s2a;
+  S2A_CHECK_ARG(nlevels >= 1 && nlevels <= DEC_MAX_LEVELS, "select_decode: 1..%d levels per call", DEC_MAX_LEVELS);
+  S2A_CHECK_ARG(B >= 0 && num_classes > 0 && wh_ratio_clip > 0.0, "select_decode: bad sizes");
+  S2A_CHECK_ARG(dtype == S2A_F32 || dtype == S2A_BF16 || dtype == S2A_F16, "select_decode: unknown dtype %d", dtype);
+  if (B == 0) return S2A_OK;
+  S2A_CHECK_ARG(cls && cls_strides && reg && reg_strides && anchors && Hs && Ws && bboxes_out && scores_out,
+                "select_decode: null pointer");
+  SelParams p{};
+  long long keys = 0;
+  int off = 0, kmax = 0;
+  for (int l = 0; l < nlevels; ++l) {
+    S2A_CHECK_ARG(Hs[l] > 0 && Ws[l] > 0 && (long long)Hs[l] * Ws[l] < (1ll << 31) && cls[l] && reg[l] && anchors[l],
+                  "select_decode: bad level %d", l);
+    SelLevel& L = p.lv[l];
+    L.cls = cls[l]; L.reg = reg[l]; L.anchors = anchors[l]; L.H = Hs[l]; L.W = Ws[l]; L.n = Hs[l] * Ws[l];
+    L.k = (topk > 0 && L.n > topk) ? topk : L.n;          // models/head.py:699: only levels with more than topk locations
+    for (int i = 0; i < 4; ++i) { L.cs[i] = cls_strides[4 * l + i]; L.rs[i] = reg_strides[4 * l + i]; }
+    L.out_off = off; L.key_off = keys;
+    off += L.k; keys += L.n;
+    if (L.n > L.k) kmax = std::max(kmax, L.k);
+  }
+  S2A_CHECK_ARG(n_total == off, "select_decode: n_total must be sum_l min(H*W, topk) = %d (got %lld)", off, (long long)n_total);
+  if (kmax > 4 * DEC_THREADS) {
+    set_error("select_decode: topk up to %d is supported (got %d)", 4 * DEC_THREADS, kmax);
+    return S2A_ERR_UNSUPPORTED;
+  }
+  if (workspace_bytes < s2a_select_decode_workspace_bytes(nlevels, Hs, Ws, B) || !workspace) {
+    set_error("select_decode: workspace too small");
+    return S2A_ERR_WORKSPACE;
+  }
+  p.nlevels = nlevels; p.B = B; p.C = num_classes; p.n_total = off; p.keys_per_image = keys;
+  p.keys = reinterpret_cast<uint32_t*>(workspace); p.bboxes = bboxes_out; p.scores = scores_out; p.index_out = index_out;
+  p.lim = clamp_limit(wh_ratio_clip, dtype);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == S2A_F32) return launch_select_items<float>(p, kmax, st);
+  if (dtype == S2A_BF16) return launch_select_items<__nv_bfloat16>(p, kmax, st);
+  return launch_select_items<__half>(p, kmax, st);
+}

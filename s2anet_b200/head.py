@@ -19,34 +19,16 @@ import math
 import torch
 import torch.nn as nn
 
+from . import decode
 from .alignconv import AlignConv
+from .decode import norm_angle, rboxes_decode_torch  # noqa: F401
 from .nms_rotated import multiclass_nms_rotated_batched
 from .orn import ORConv2d, RotationInvariantPooling
 
 
-def norm_angle(angle):
-    """utils/general.py:925-930: wrap into [-pi/4, 3pi/4)."""
-    lo = -math.pi / 4
-    return torch.remainder(angle - lo, math.pi) + lo
-
-
 def rboxes_decode(anchors, deltas, wh_ratio_clip=16 / 1000):
-    """models/boxes.py:82-162 (delta2bbox_rotated, is_encode_relative=True).  anchors [...,5],
-    deltas [...,5] (broadcastable); computed in fp32 like the reference's promoted arithmetic."""
-    anchors = anchors.float()
-    deltas = deltas.float()
-    dx, dy, dw, dh, da = deltas.unbind(-1)
-    max_ratio = abs(math.log(wh_ratio_clip))
-    dw = dw.clamp(min=-max_ratio, max=max_ratio)
-    dh = dh.clamp(min=-max_ratio, max=max_ratio)
-    rx, ry, rw, rh, ra = anchors.unbind(-1)
-    cosa, sina = torch.cos(ra), torch.sin(ra)
-    gx = dx * rw * cosa - dy * rh * sina + rx
-    gy = dx * rw * sina + dy * rh * cosa + ry
-    gw = rw * dw.exp()
-    gh = rh * dh.exp()
-    ga = norm_angle(math.pi * da + ra)
-    return torch.stack([gx, gy, gw, gh, ga], dim=-1)
+    """models/boxes.py:82-162 in PyTorch (the reference's own formulation; CPU reference arm and tests)."""
+    return rboxes_decode_torch(anchors, deltas, wh_ratio_clip)
 
 
 class S2ANetHead(nn.Module):
@@ -173,13 +155,20 @@ class S2ANetHead(nn.Module):
         odm_cls_pred, odm_bbox_pred = self._odm(or_feat, odm_cls_feat)
         return fam_cls_pred, fam_bbox_pred, odm_cls_pred, odm_bbox_pred, init_anchors, refine
 
-    def _fam(self, x, stride):
+    def _fam_preds(self, x):
         fam_bbox_pred = self.fam_reg_head(self._tower(self.fam_reg_ls, x))
         fam_cls_pred = self.fam_cls_head(self._tower(self.fam_cls_ls, x))
+        return fam_cls_pred, fam_bbox_pred
+
+    def _fam(self, x, stride):
+        fam_cls_pred, fam_bbox_pred = self._fam_preds(x)
         B, _, H, W = fam_bbox_pred.shape
         init_anchors = self.grid_anchors(H, W, stride, x.device)
-        deltas = fam_bbox_pred.detach().permute(0, 2, 3, 1).reshape(B, H * W, 5)
-        refine = rboxes_decode(init_anchors[None], deltas, wh_ratio_clip=1e-6).reshape(B, H, W, 5)   # head.py:27-52
+        if x.is_cuda:       # fused grid-anchor generation + decode (models/head.py:27-52, models/anchors.py:75-126)
+            refine = decode.fam_decode([fam_bbox_pred], [stride], self.anchor_scale, self.anchor_angle, 1e-6)[0]
+        else:
+            deltas = fam_bbox_pred.detach().permute(0, 2, 3, 1).reshape(B, H * W, 5)
+            refine = rboxes_decode(init_anchors[None], deltas, wh_ratio_clip=1e-6).reshape(B, H, W, 5)
         return fam_cls_pred, fam_bbox_pred, init_anchors, refine
 
     def _odm(self, or_feat, odm_cls_feat):
@@ -194,8 +183,11 @@ class S2ANetHead(nn.Module):
         if not (x0.is_cuda and x0.dtype in (torch.bfloat16, torch.float16) and self.with_orconv):
             return [self.forward_single(x, s) for x, s in zip(feats, self.featmap_strides)]
         from . import conv_tc
-        fam = [self._fam(x, s) for x, s in zip(feats, self.featmap_strides)]
-        aligned = conv_tc.alignconv_forward_tc_multi(list(feats), [f[3] for f in fam], self.align_conv.deform_conv.weight,
+        preds = [self._fam_preds(x) for x in feats]
+        refines = decode.fam_decode([pr[1] for pr in preds], self.featmap_strides, self.anchor_scale, self.anchor_angle, 1e-6)
+        fam = [(pr[0], pr[1], self.grid_anchors(x.size(2), x.size(3), s, x.device), rf)
+               for pr, rf, x, s in zip(preds, refines, feats, self.featmap_strides)]
+        aligned = conv_tc.alignconv_forward_tc_multi(list(feats), refines, self.align_conv.deform_conv.weight,
                                                      self.featmap_strides)
         or_feats, pooled = conv_tc.orconv_forward_tc_multi(aligned, self.or_conv.weight, self.or_conv.indices,
                                                            self.or_conv.bias, with_pool=True)
@@ -209,6 +201,9 @@ class S2ANetHead(nn.Module):
     def select_and_decode(self, outs):
         """models/head.py:684-717 batched over images: sigmoid, per-level top-k by best class score,
         concatenation, final decode.  Returns (bboxes [B,n,5] fp32, scores [B,n,C] fp32)."""
+        if outs[0][2].is_cuda:      # one fused launch: sigmoid + per-level top-k + gather + decode
+            return decode.select_decode([o[2] for o in outs], [o[3] for o in outs], [o[5] for o in outs],
+                                        self.max_before_nms_per_level)
         scores_l, deltas_l, anchors_l = [], [], []
         k = self.max_before_nms_per_level
         for (_, _, cls, reg, _, refine) in outs:
