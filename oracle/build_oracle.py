@@ -123,14 +123,28 @@ def build_ref_extensions(kind="cpu", names=None, verbose=False):
     return out
 
 
+_LOADED = {}
+
+
 def load_ref_extension(name, kind="cpu"):
-    """Import a prebuilt reference extension from oracle/_ref (no compilation, no /root/reference)."""
+    """Import a prebuilt reference extension from oracle/_ref (no compilation, no /root/reference).
+
+    The CPU-only and the CUDA build of one extension export the same (weak, inline) C++ dispatcher symbols;
+    whichever is loaded first wins the dynamic symbol resolution for both.  The CUDA build's dispatcher
+    serves CPU tensors too, the CPU build's does not ("Not compiled with GPU support"), so on a machine with
+    a GPU the CUDA build is always loaded first."""
     import importlib.util
+    key = (name, kind)
+    if key in _LOADED:
+        return _LOADED[key]
     so = os.path.join(REF_OUT, "ext_%s" % kind, name, name + ".so")
     if not os.path.exists(so):
         return None
     import torch  # noqa: F401  (the extension links against libtorch)
+    if kind == "cpu" and torch.cuda.is_available():
+        load_ref_extension(name, "gpu")
     spec = importlib.util.spec_from_file_location(name, so)
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
+    _LOADED[key] = mod
     return mod

@@ -16,12 +16,14 @@
 //       deform_conv_cuda_kernel.cu:210-228); for ORConv it is the plain shifted pixel.
 //   Wp: weights pre-packed to [C_out][K'] 16-bit (ARF rotation folded into the packing for ORConv).
 //
-// Warp roles (192 threads): warps 0-3 produce A (gather 4 corners with 16-byte loads from the NHWC
-// feature map, blend in fp32, store 16-byte chunks into the 128B-swizzled K-major smem tile that
-// UMMA expects) and later run the epilogue (tcgen05.ld -> bias/ReLU/max-pool -> NHWC stores);
-// warp 4 streams the weight k-blocks with TMA (cp.async.bulk.tensor, SWIZZLE_128B); warp 5 owns
-// TMEM and issues tcgen05.mma (M=128, N=C_out, K=16, kind::f16) from one thread.  Stages are
-// recycled through full/empty mbarriers; tcgen05.commit releases a stage when its MMAs retire.
+// Warp roles (576 threads, persistent CTA pairs): warps 0-11 are three producer groups that build AlignConv's
+// A tiles (per (row, tap) recipe -> 4 corner loads of 16 bytes from the NHWC map -> packed 16-bit blend -> 16-byte
+// store into the 128B-swizzled K-major stage); warp 12 is the TMA warp (weight k-blocks, and for ORConv the A
+// tile as one 4-D box); warp 13 allocates TMEM and one of its threads issues tcgen05.mma.cta_group::2
+// (M = 256 across the pair, N = C_out, K = 16, kind::f16); warps 14-17 are the epilogue (tcgen05.ld -> bias /
+// ReLU / 8-way orientation max -> staging -> TMA store) and build the gather recipes two tiles ahead.  Stages
+// are recycled through full/empty mbarriers; tcgen05.commit (multicast to both CTAs) releases a stage when its
+// MMAs retire; two 256-column TMEM accumulators let the epilogue of one tile overlap the next main loop.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -39,27 +41,40 @@ constexpr int TC_M = 128;                 // rows per tile (8 x 16 patch) = one 
 constexpr int TC_PH = 8, TC_PW = 16;
 constexpr int TC_KB = 64;                 // k-block (elements) = 128 bytes of 16-bit data
 constexpr int TC_GROUPS = 3;               // producer groups of 4 warps; group g fills k-blocks g, g+G, ...
-constexpr int TC_SA = 4;                   // A stages (16 KB each)
-constexpr int TC_SB = 3;                   // B stages (32 KB each), filled by TMA
+constexpr int TC_OUT_CH = 32;              // channels per epilogue TMA store (64-byte rows, SWIZZLE_64B)
+constexpr int TC_OUT_BYTES = TC_M * TC_OUT_CH * 2;    // 8 KB, double-buffered
 constexpr int TC_A_BYTES = TC_M * TC_KB * 2;          // 16 KB
-constexpr int TC_B_BYTES_MAX = 256 * TC_KB * 2;       // 32 KB
+
+enum { TC_ALIGN = 0, TC_PLAIN = 1 };
+
+// Per-mode pipeline shape.
+//  * ORConv2d (TC_PLAIN) is fed entirely by TMA and bound by the tensor pipe: a CTA PAIR (cta_group::2, one
+//    TPC) shares every weight k-block -- each CTA stages half of the C_out rows -- and A + B of a k-block
+//    travel through one ring of 6 stages with one full/empty barrier pair per stage.
+//  * AlignConv (TC_ALIGN) is bound by the bilinear gather (LSU wavefronts, L1 hit rate).  Shared memory must
+//    stay under the 196 KB carve-out so that ~60 KB of L1 remain for the gather (ncu: 90 % L1 hits at 60 KB,
+//    75 % at 28 KB; measured 0.284 ms at 28 KB vs 0.235 ms at 60 KB).  CTA pairs are used here too because a
+//    half-width weight stage (16 KB) is what makes room for 5 A stages + 3 B stages + the sample tables;
+//    A and B keep separate rings (the producers' ring is the deeper one).
+template <int MODE> struct TcCfg;
+template <> struct TcCfg<TC_ALIGN> { static constexpr int CG = 2, SA = 5, SB = 3; static constexpr bool UNIFIED = false; };
+template <> struct TcCfg<TC_PLAIN> { static constexpr int CG = 2, SA = 6, SB = 6; static constexpr bool UNIFIED = true; };
+constexpr int TC_MAX_STAGES = 8;
 constexpr int TC_PROD_THREADS = TC_GROUPS * 128;
 constexpr int TC_EPI_THREADS = 128;                   // 4 epilogue warps, one per TMEM lane quadrant
 constexpr int TC_THREADS = TC_PROD_THREADS + 64 + TC_EPI_THREADS;   // producers | TMA warp | MMA warp | epilogue
 constexpr int TC_ACC_STAGES = 2;                      // double-buffered accumulator: 2 x 256 TMEM columns
 constexpr int TC_TMEM_COLS = 512;
-constexpr int TC_NBAR = 2 * TC_SA + 2 * TC_SB + 2 * TC_ACC_STAGES + 2;
+constexpr int TC_NBAR = 4 * TC_MAX_STAGES + 2 * TC_ACC_STAGES + 2;
 constexpr int TC_MAX_LEVELS = 8;
 constexpr uint32_t kSpinLimit = 1u << 26;            // watchdog: trap instead of hanging the GPU
 
-enum { TC_ALIGN = 0, TC_PLAIN = 1 };
-
-// One (row, tap) gather recipe, 12 bytes: byte offset of the (clamped) top-left corner pixel inside the
-// image (a multiple of 16, so the two low bits carry "right corner is one pixel further" / "bottom
-// corners are one row further"), and the four bilinear weights already rounded to the 16-bit type.
-// Corners that fall outside the map keep a valid (clamped) address and get weight 0, which is the
-// reference's rule (deform_conv_cuda_kernel.cu:97-108, :228).
-struct __align__(4) TapSample { uint32_t base; uint32_t w01; uint32_t w23; };
+// One (row, tap) gather recipe, 16 bytes (one LDS.128): byte offset of the (clamped) top-left corner pixel
+// inside the image (a multiple of 16, so the two low bits carry "right corner is one pixel further" /
+// "bottom corners are one row further"), and the four bilinear weights already rounded to the 16-bit
+// type.  Corners that fall outside the map keep a valid (clamped) address and get weight 0, which is
+// the reference's rule (deform_conv_cuda_kernel.cu:97-108, :228).
+struct __align__(16) TapSample { uint32_t base; uint32_t w01; uint32_t w23; uint32_t pad; };
 
 struct TcLevel {
   const void* x;          // [B, H, W, C] 16-bit (channels_last)
@@ -85,7 +100,8 @@ struct TileCoord { int lvl, b, ty0, tx0; };
 // TMA descriptors: the packed weights, and (TC_PLAIN only) one 4-D NHWC map per level
 struct TcMaps {
   CUtensorMap w;
-  CUtensorMap x[TC_MAX_LEVELS];
+  CUtensorMap x[TC_MAX_LEVELS];   // TC_PLAIN: A tiles are loaded from these
+  CUtensorMap y[TC_MAX_LEVELS];   // outputs: the epilogue stores 8 x 16 x 32-channel boxes through these
 };
 
 __device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int tile) {
@@ -130,6 +146,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// non-blocking probe of a phase (mbarrier.test_wait never suspends the thread)
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
@@ -144,35 +172,113 @@ __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.p
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
-      "l"((uint64_t)map), "r"(c0), "r"(c1), "r"(bar)
-      : "memory");
+// cluster helpers (CTA pair)
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
 }
+__device__ __forceinline__ uint32_t cluster_id_x() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_count_x() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `addr` (a shared::cta address of this CTA) inside CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+// arrive on an mbarrier that may live in the peer CTA (shared::cluster address)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+
+// TMA loads.  `bar` is a shared::cluster address: with cta_group::2 the completion may be signalled on
+// the leader CTA's barrier while the data lands in this CTA's shared memory.
+template <int CG>
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  if (CG == 2)
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::
+            "r"(dst), "l"((uint64_t)map), "r"(c0), "r"(c1), "r"(bar)
+        : "memory");
+  else
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+                 "l"((uint64_t)map), "r"(c0), "r"(c1), "r"(bar)
+                 : "memory");
+}
+template <int CG>
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3,
                                             uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(dst),
-      "l"((uint64_t)map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
-      : "memory");
+  if (CG == 2)
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], "
+        "[%6];" ::"r"(dst), "l"((uint64_t)map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
+        : "memory");
+  else
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(dst),
+        "l"((uint64_t)map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
+        : "memory");
 }
-__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+// TMA store of a 4-D box from shared memory (bulk async-group completion)
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"((uint64_t)map),
+               "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_THREADS) : "memory"); }
+
+// TMEM allocation; for a CTA pair one warp of EACH CTA executes it (both get the same base)
+template <int CG> __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+  if (CG == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  } else {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
 }
+template <int CG> __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  if (CG == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+  else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// D[tmem, (128*CG) x N] (+)= A[smem, 128 rows per CTA] * B[smem, N/CG rows per CTA]; issued by the leader CTA only
+template <int CG>
 __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
-      : "memory");
+  if (CG == 2)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+        : "memory");
+  else
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+        : "memory");
 }
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+// arrive (once the MMAs issued so far have completed) on the barrier at the same offset in every CTA of the group
+template <int CG> __device__ __forceinline__ void umma_commit(uint32_t bar) {
+  if (CG == 2)
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"((uint16_t)3)
+                 : "memory");
+  else
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
@@ -275,7 +381,7 @@ __device__ __forceinline__ void build_tap_table(const TcParams& p, const TileCoo
     const int r = e / 9, t = e - 9 * r;
     const int y = tc.ty0 + r / TC_PW, x = tc.tx0 + r % TC_PW;
     TapSample s;
-    s.base = 0u; s.w01 = 0u; s.w23 = 0u;
+    s.base = 0u; s.w01 = 0u; s.w23 = 0u; s.pad = 0u;
     if (y < H && x < W) {
       const float* a = L.anchors + ((size_t)(tc.b * H + y) * W + x) * 5;
       const float ax = a[0] / L.stride, ay = a[1] / L.stride, aw = a[2] / L.stride, ah = a[3] / L.stride;
@@ -309,53 +415,92 @@ __device__ __forceinline__ void build_tap_table(const TcParams& p, const TileCoo
   }
 }
 
+// Work assignment: the launch is a grid of CTA groups (clusters of CG CTAs; CG = 2 is a CTA pair = one TPC).
+// Group q owns the tiles CG*q .. CG*q + CG - 1: each CTA produces its own 128-row A tile and stages its own
+// 1/CG of the weight k-block (C_out/CG rows); the leader CTA (rank 0) issues ONE tcgen05.mma per K=16 step
+// for the whole group (M = 128*CG, N = C_out), and each CTA drains its own 128 accumulator lanes.  When the
+// number of tiles is not a multiple of CG the last group's spare CTA runs a "ghost" copy of the last tile
+// and stores nothing.
 template <int MODE, typename T>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcParams p) {
+  using Cfg = TcCfg<MODE>;
+  constexpr int CG = Cfg::CG, SA = Cfg::SA, SB = Cfg::SB;
+  constexpr bool UNI = Cfg::UNIFIED;                   // B shares A's stage index and barriers
+  static_assert(!UNI || SA == SB, "a unified ring needs equally many A and B stages");
+  static_assert(TC_GROUPS < SA && SA <= TC_MAX_STAGES && SB <= TC_MAX_STAGES, "stage rings");
+  constexpr int B_STAGE_BYTES = (256 / CG) * TC_KB * 2;
   extern __shared__ uint8_t smem_raw[];
-  // SWIZZLE_128B operands need 1024-byte aligned tiles: align the dynamic window by hand
+  // SWIZZLE_128B operands need 1024-byte aligned tiles: align the dynamic window by hand (the offset is
+  // the same in both CTAs of a pair, which the paired MMA and the multicast commits rely on)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  // carve: A stages | B stages | 2 sample tables | barriers | tmem pointer
+  // carve: A stages | B stages | 2 output staging buffers (PLAIN) or 2 sample tables (ALIGN) | barriers | tmem pointer.
+  // In ALIGN mode the epilogue of a tile stages its output in that tile's own sample table, which is dead by
+  // then (every A k-block of the tile has been produced) and is rebuilt for tile + 2 right after the stores.
   uint8_t* sA = smem;
-  uint8_t* sB = smem + TC_SA * TC_A_BYTES;
-  TapSample* s_tab = reinterpret_cast<TapSample*>(sB + TC_SB * TC_B_BYTES_MAX);
-  uint64_t* s_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s_tab) + 2 * sizeof(TapSample) * TC_M * 9);
+  uint8_t* sB = sA + SA * TC_A_BYTES;
+  uint8_t* s_out_plain = sB + SB * B_STAGE_BYTES;
+  TapSample* s_tab = reinterpret_cast<TapSample*>(s_out_plain);
+  static_assert(sizeof(TapSample) * TC_M * 9 >= 2 * TC_OUT_BYTES && (sizeof(TapSample) * TC_M * 9) % 512 == 0, "staging aliases a table");
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_out_plain + (MODE == TC_ALIGN ? 2 * sizeof(TapSample) * TC_M * 9
+                                                                                    : (size_t)2 * TC_OUT_BYTES));
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + TC_NBAR);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t bar_full_a = smem_u32(s_bar), bar_empty_a = bar_full_a + 8 * TC_SA,
-                 bar_full_b = bar_empty_a + 8 * TC_SA, bar_empty_b = bar_full_b + 8 * TC_SB,
-                 bar_acc_full = bar_empty_b + 8 * TC_SB, bar_acc_empty = bar_acc_full + 8 * TC_ACC_STAGES,
+  const uint32_t bar_full_a = smem_u32(s_bar), bar_empty_a = bar_full_a + 8 * TC_MAX_STAGES,
+                 bar_full_b = bar_empty_a + 8 * TC_MAX_STAGES, bar_empty_b = bar_full_b + 8 * TC_MAX_STAGES,
+                 bar_acc_full = bar_empty_b + 8 * TC_MAX_STAGES, bar_acc_empty = bar_acc_full + 8 * TC_ACC_STAGES,
                  bar_tab_full = bar_acc_empty + 8 * TC_ACC_STAGES;       // 2 barriers
   constexpr int kTmaWarp = TC_PROD_THREADS / 32, kMmaWarp = kTmaWarp + 1, kEpiWarp0 = kTmaWarp + 2;
 
+  const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;     // 0 = leader (issues the MMAs, owns the "full" barriers)
+  const bool leader = cta_rank == 0;
+  // "full" barriers and the accumulator-empty barrier live in the leader CTA; everybody signals them there
+  const uint32_t ld_full_a = CG == 2 ? map_to_cta(bar_full_a, 0) : bar_full_a,
+                 ld_full_b = UNI ? ld_full_a : (CG == 2 ? map_to_cta(bar_full_b, 0) : bar_full_b),
+                 ld_acc_empty = CG == 2 ? map_to_cta(bar_acc_empty, 0) : bar_acc_empty;
+
   const int ncb = p.C / TC_KB;
   const int nkb = ncb * 9;
-  const uint32_t b_bytes = (uint32_t)p.Co * TC_KB * 2;
-  const int first_tile = blockIdx.x, tile_step = gridDim.x;
+  const int co_part = p.Co / CG;                     // weight rows (output channels) staged by this CTA
+  const uint32_t b_bytes_group = (uint32_t)p.Co * TC_KB * 2;
+  const int ngroups = (p.total_tiles + CG - 1) / CG;
+  const int first_q = CG == 2 ? (int)cluster_id_x() : (int)blockIdx.x;
+  const int q_step = CG == 2 ? (int)cluster_count_x() : (int)gridDim.x;
+  // tile of this CTA in group q; ghost = duplicate of the last tile, nothing stored
+#define S2A_TILE_OF(q) min((q) * CG + (int)cta_rank, p.total_tiles - 1)
+#define S2A_IS_GHOST(q) ((q) * CG + (int)cta_rank >= p.total_tiles)
 
   if (tid == 0) {
-    for (int s = 0; s < TC_SA; ++s) {
-      // ALIGN: the 128 threads of the producer group that owns the k-block; PLAIN: the TMA thread's expect_tx
-      mbar_init(bar_full_a + 8 * s, MODE == TC_ALIGN ? 128 : 1);
-      mbar_init(bar_empty_a + 8 * s, 1);        // one tcgen05.commit
+    for (int s = 0; s < SA; ++s) {
+      // full_a: ALIGN -- one elected arrive per producer warp of the owning group, from every CTA of the group;
+      //         PLAIN -- the leader TMA thread's expect_tx arrive (+ the TMA bytes of A and B from every CTA)
+      mbar_init(bar_full_a + 8 * s, MODE == TC_ALIGN ? 4 * CG : 1);
+      mbar_init(bar_empty_a + 8 * s, 1);        // one (multicast) tcgen05.commit
     }
-    for (int s = 0; s < TC_SB; ++s) {
-      mbar_init(bar_full_b + 8 * s, 1);         // the TMA thread's expect_tx arrive (+ the transaction bytes)
+    for (int s = 0; s < SB && !UNI; ++s) {
+      mbar_init(bar_full_b + 8 * s, 1);         // the leader TMA thread's expect_tx arrive (+ bytes)
       mbar_init(bar_empty_b + 8 * s, 1);
     }
     for (int s = 0; s < TC_ACC_STAGES; ++s) {
-      mbar_init(bar_acc_full + 8 * s, 1);       // tcgen05.commit after the last k-block of a tile
-      mbar_init(bar_acc_empty + 8 * s, TC_EPI_THREADS);
+      mbar_init(bar_acc_full + 8 * s, 1);       // tcgen05.commit after the last k-block of a tile group
+      mbar_init(bar_acc_empty + 8 * s, CG * TC_EPI_THREADS);
       mbar_init(bar_tab_full + 8 * s, TC_EPI_THREADS);
     }
     fence_barrier_init();
   }
-  if (warp == kMmaWarp) tmem_alloc(smem_u32(s_tmem), TC_TMEM_COLS);
+  if (warp == kMmaWarp) tmem_alloc<CG>(smem_u32(s_tmem), TC_TMEM_COLS);
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all();              // barriers of both CTAs initialised before anybody signals them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
+  long long dbg_c0 = 0;
+  unsigned long long dbg_t0 = 0;
+  if ((p.debug & 8) && blockIdx.x == 0) {
+    dbg_c0 = clock64();
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t0));
+  }
 
   if (warp < kTmaWarp) {
     // ===================== A producers (AlignConv: bilinear gather through the LSU) =====================
@@ -365,114 +510,187 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     const int gt = tid & 127;                  // thread index inside the group
     const int chunk = gt & 7;                  // 16-byte chunk (8 channels) inside the 128-byte row
     const int rsub = gt >> 3;                  // 0..15
-    long long gkb_base = 0;                    // global k-block index of this tile's k-block 0
+    // Group g produces the global k-blocks g, g + G, g + 2G, ... (the sequence runs on across tiles).  Stage
+    // index and phase bit advance incrementally: no 64-bit div/mod on these latency-critical paths.
+    int kb = group;                            // k-block inside the current tile
+    int s = group % SA;                        // A stage of that k-block
+    uint32_t ph = (uint32_t)(group / SA) & 1u;
     int it = 0;
-    for (int tile = first_tile; MODE == TC_ALIGN && tile < p.total_tiles; tile += tile_step, ++it, gkb_base += nkb) {
+    for (int q = first_q; MODE == TC_ALIGN && q < ngroups; q += q_step, ++it) {
+      const int tile = S2A_TILE_OF(q);
       const TileCoord tc = decode_tile(p, tile);
       const TcLevel& L = p.lv[tc.lvl];
       const int H = L.H, W = L.W;
       const uint32_t pix_stride = (uint32_t)p.C * 2u, row_stride = (uint32_t)W * pix_stride;
       const uint8_t* xb = reinterpret_cast<const uint8_t*>(L.x) + (size_t)tc.b * H * W * p.C * 2;
       const TapSample* tab = s_tab + (it & 1) * (TC_M * 9);
-      if (MODE == TC_ALIGN) mbar_wait(bar_tab_full + 8 * (it & 1), (uint32_t)(it >> 1) & 1u);
-      // first k-block of this tile that belongs to this group
-      int kb = (int)((group - (gkb_base % TC_GROUPS) + TC_GROUPS) % TC_GROUPS);
-      for (; kb < nkb; kb += TC_GROUPS) {
-        const long long gkb = gkb_base + kb;
-        const int s = (int)(gkb % TC_SA);
-        const uint32_t ph = (uint32_t)(gkb / TC_SA) & 1u;
-        const int cb = kb / 9, tap = kb - 9 * cb;
+      mbar_wait(bar_tab_full + 8 * (it & 1), (uint32_t)(it >> 1) & 1u);
+      int cb = kb / 9, tap = kb - 9 * cb;
+      for (; kb < nkb; kb += TC_GROUPS, tap += TC_GROUPS, s += TC_GROUPS) {
+        if (tap >= 9) { tap -= 9; ++cb; }
+        if (s >= SA) { s -= SA; ph ^= 1u; }
         if (tap < TC_GROUPS && !(p.debug & 4)) {
           // this group's first k-block of channel block cb: prefetch its third of the halo of the NEXT
           // channel block (or of the next tile's first one) -- 9 k-blocks ahead of the loads that need it
           if (cb + 1 < ncb) prefetch_halo(p, tc, cb + 1, group * 128 + gt);
-          else if (tile + tile_step < p.total_tiles) prefetch_halo(p, decode_tile(p, tile + tile_step), 0, group * 128 + gt);
+          else if (q + q_step < ngroups) prefetch_halo(p, decode_tile(p, S2A_TILE_OF(q + q_step)), 0, group * 128 + gt);
         }
         mbar_wait(bar_empty_a + 8 * s, ph ^ 1u);
         uint8_t* a_stage = sA + s * TC_A_BYTES;
-        if (p.debug & 2) { fence_proxy_async_smem(); mbar_arrive(bar_full_a + 8 * s); continue; }
-        // 128-byte row r = j*16 + rsub of the stage; chunk position swizzled by (r & 7) == (rsub & 7)
-        uint8_t* a_dst = a_stage + rsub * 128 + ((chunk ^ (rsub & 7)) << 4);
-        const uint8_t* src = xb + ((size_t)cb * TC_KB + chunk * 8) * 2;   // this thread's 16 bytes inside a pixel
-        const TapSample* trow = tab + rsub * 9 + tap;
+        if (!(p.debug & 2)) {
+          // 128-byte row r = j*16 + rsub of the stage; chunk position swizzled by (r & 7) == (rsub & 7)
+          uint8_t* a_dst = a_stage + rsub * 128 + ((chunk ^ (rsub & 7)) << 4);
+          const uint8_t* src = xb + ((size_t)cb * TC_KB + chunk * 8) * 2;   // this thread's 16 bytes inside a pixel
+          const TapSample* trow = tab + rsub * 9 + tap;
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          uint4 v[4][4];
-          uint32_t w01[4], w23[4];
+          for (int half = 0; half < 2; ++half) {
+            uint4 v[4][4];
+            uint32_t w01[4], w23[4];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const TapSample sm = trow[(half * 4 + i) * 16 * 9];
-            w01[i] = sm.w01; w23[i] = sm.w23;
-            const uint8_t* q = src + (sm.base & ~3u);
-            const uint32_t dx = (sm.base & 1u) ? pix_stride : 0u, dy = (sm.base & 2u) ? row_stride : 0u;
-            v[i][0] = ldg_nc_v4(q);
-            v[i][1] = ldg_nc_v4(q + dx);
-            v[i][2] = ldg_nc_v4(q + dy);
-            v[i][3] = ldg_nc_v4(q + dy + dx);
+            for (int i = 0; i < 4; ++i) {
+              const uint4 sm = *reinterpret_cast<const uint4*>(trow + (half * 4 + i) * 16 * 9);   // one LDS.128
+              w01[i] = sm.y; w23[i] = sm.z;
+              const uint8_t* q0 = src + (sm.x & ~3u);
+              const uint32_t dx = (sm.x & 1u) ? pix_stride : 0u, dy = (sm.x & 2u) ? row_stride : 0u;
+              v[i][0] = ldg_nc_v4(q0);
+              v[i][1] = ldg_nc_v4(q0 + dx);
+              v[i][2] = ldg_nc_v4(q0 + dy);
+              v[i][3] = ldg_nc_v4(q0 + dy + dx);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              *reinterpret_cast<uint4*>(a_dst + (half * 4 + i) * 2048) =
+                  blend4<T>(v[i][0], v[i][1], v[i][2], v[i][3], w01[i], w23[i]);
           }
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            *reinterpret_cast<uint4*>(a_dst + (half * 4 + i) * 2048) =
-                blend4<T>(v[i][0], v[i][1], v[i][2], v[i][3], w01[i], w23[i]);
         }
         fence_proxy_async_smem();          // generic-proxy stores -> visible to the tensor core (async proxy)
-        mbar_arrive(bar_full_a + 8 * s);
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(ld_full_a + 8 * s);     // on the leader CTA's barrier
       }
+      kb -= nkb;                           // first k-block of this group in the next tile
     }
   } else if (warp == kTmaWarp) {
-    // ===================== weight k-blocks by TMA =====================
+    // ===================== TMA: this CTA's C_out/CG weight rows (and, PLAIN, its A tile) =====================
     if (lane == 0) {
-      long long gkb = 0;
-      for (int tile = first_tile; tile < p.total_tiles; tile += tile_step) {
-        const TileCoord tc = decode_tile(p, tile);
-        for (int kb = 0; kb < nkb; ++kb, ++gkb) {
-          if (MODE == TC_PLAIN) {
-            // A tile = the 8 x 16 patch shifted by the tap, 64 channels: one 4-D box {64, 16, 8, 1}
-            const int sa = (int)(gkb % TC_SA);
-            const int cb = kb / 9, tap = kb - 9 * cb;
-            mbar_wait(bar_empty_a + 8 * sa, ((uint32_t)(gkb / TC_SA) & 1u) ^ 1u);
-            mbar_arrive_expect_tx(bar_full_a + 8 * sa, TC_A_BYTES);
-            tma_load_4d(smem_u32(sA + sa * TC_A_BYTES), &maps.x[tc.lvl], cb * TC_KB, tc.tx0 - 1 + tap % 3,
-                        tc.ty0 - 1 + tap / 3, tc.b, bar_full_a + 8 * sa);
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;                   // phase bits of the stage rings
+      bool warm = false;
+      for (int q = first_q; q < ngroups; q += q_step) {
+        const TileCoord tc = decode_tile(p, S2A_TILE_OF(q));
+        int cb = 0, tap = 0;
+        for (int kb = 0; kb < nkb; ++kb) {
+          if (UNI) {
+            // one ring: A tile (TC_PLAIN: the 8 x 16 patch shifted by the tap, 64 channels = one 4-D box
+            // {64, 16, 8, 1}, zero-filled outside the map) and the weight k-block complete the same barrier
+            mbar_wait(bar_empty_a + 8 * sa, pa ^ 1u);
+            if ((p.debug & 1) && warm) {
+              if (leader) mbar_arrive(bar_full_a + 8 * sa);
+            } else {
+              if (leader) mbar_arrive_expect_tx(bar_full_a + 8 * sa, b_bytes_group + CG * TC_A_BYTES);
+              const int ti = tap / 3;
+              tma_load_4d<CG>(smem_u32(sA + sa * TC_A_BYTES), &maps.x[tc.lvl], cb * TC_KB, tc.tx0 - 1 + (tap - 3 * ti),
+                              tc.ty0 - 1 + ti, tc.b, ld_full_a + 8 * sa);
+              tma_load_2d<CG>(smem_u32(sB + sa * B_STAGE_BYTES), &maps.w, kb * TC_KB, (int)cta_rank * co_part, ld_full_a + 8 * sa);
+            }
+            if (++sa == SA) { sa = 0; pa ^= 1u; }
+          } else {
+            mbar_wait(bar_empty_b + 8 * sb, pb ^ 1u);
+            if ((p.debug & 1) && warm) {
+              if (leader) mbar_arrive(bar_full_b + 8 * sb);
+            } else {
+              if (leader) mbar_arrive_expect_tx(bar_full_b + 8 * sb, b_bytes_group);
+              tma_load_2d<CG>(smem_u32(sB + sb * B_STAGE_BYTES), &maps.w, kb * TC_KB, (int)cta_rank * co_part, ld_full_b + 8 * sb);
+            }
+            if (++sb == SB) { sb = 0; pb ^= 1u; }
           }
-          const int s = (int)(gkb % TC_SB);
-          const uint32_t ph = (uint32_t)(gkb / TC_SB) & 1u;
-          mbar_wait(bar_empty_b + 8 * s, ph ^ 1u);
-          if ((p.debug & 1) && gkb >= TC_SB) { mbar_arrive(bar_full_b + 8 * s); continue; }
-          mbar_arrive_expect_tx(bar_full_b + 8 * s, b_bytes);
-          tma_load_2d(smem_u32(sB + s * TC_B_BYTES_MAX), &maps.w, kb * TC_KB, 0, bar_full_b + 8 * s);
+          if (++tap == 9) { tap = 0; ++cb; }
         }
+        warm = true;
       }
     }
   } else if (warp == kMmaWarp) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (lane == 0 && leader) {
       // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 (1<<4), A/B format (bf16=1, f16=0)
-      // at bits 7 / 10, K-major A and B, N>>3 at bit 17, M>>4 at bit 24
+      // at bits 7 / 10, K-major A and B, N>>3 at bit 17, M>>4 at bit 24 (M = 128 per CTA of the group)
       const uint32_t fmt = std::is_same<T, __nv_bfloat16>::value ? 1u : 0u;
       const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.Co >> 3) << 17) |
-                             ((uint32_t)(TC_M >> 4) << 24);
-      long long gkb = 0;
-      int it = 0;
-      for (int tile = first_tile; tile < p.total_tiles; tile += tile_step, ++it) {
+                             ((uint32_t)((TC_M * CG) >> 4) << 24);
+      // tcgen05.mma issue blocks this thread while the tensor pipe is busy (measured: no deep issue queue),
+      // so everything else this thread does per k-block must overlap with MMAs that are already queued:
+      // the wait for the NEXT stage (and, at a tile boundary, for the next accumulator) sits between the
+      // second and the third MMA of the current k-block.  tools/umma_bench2.cu: 634 -> 528 cycles per
+      // k-block (ideal 512) for exactly this change.
+      int sa = 0, sb = 0, it = 0;
+      uint32_t pa = 0, pb = 0;
+      long long tl[10];
+      mbar_wait(bar_acc_empty, 1u);
+      mbar_wait(bar_full_a, 0u);
+      if (!UNI) mbar_wait(bar_full_b, 0u);
+      tc_fence_after();
+      for (int q = first_q; q < ngroups; q += q_step, ++it) {
         const int as = it & 1;
-        mbar_wait(bar_acc_empty + 8 * as, ((uint32_t)(it >> 1) & 1u) ^ 1u);     // epilogue drained this accumulator
-        tc_fence_after();
+        if ((p.debug & 8) && it < 9) tl[it] = clock64();
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * 256);
-        for (int kb = 0; kb < nkb; ++kb, ++gkb) {
-          const int sa = (int)(gkb % TC_SA), sb = (int)(gkb % TC_SB);
-          mbar_wait(bar_full_a + 8 * sa, (uint32_t)(gkb / TC_SA) & 1u);
-          mbar_wait(bar_full_b + 8 * sb, (uint32_t)(gkb / TC_SB) & 1u);
-          tc_fence_after();
+        const bool last_tile = q + q_step >= ngroups;
+        for (int kb = 0; kb < nkb; ++kb) {
           const uint64_t adesc = umma_desc_sw128(smem_u32(sA + sa * TC_A_BYTES));
-          const uint64_t bdesc = umma_desc_sw128(smem_u32(sB + sb * TC_B_BYTES_MAX));
-#pragma unroll
-          for (int k = 0; k < TC_KB / 16; ++k)      // +32 bytes (>>4 = 2) per K=16 step inside the swizzle atom
-            umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-          umma_commit(bar_empty_a + 8 * sa);        // stages reusable once these MMAs have read them
-          umma_commit(bar_empty_b + 8 * sb);
+          const uint64_t bdesc = umma_desc_sw128(smem_u32(sB + (UNI ? sa : sb) * B_STAGE_BYTES));
+          // +32 bytes (>>4 = 2) per K=16 step inside the swizzle atom
+          umma_f16<CG>(d_tmem, adesc, bdesc, idesc, kb != 0 ? 1u : 0u);
+          umma_f16<CG>(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
+          int nsa = sa + 1, nsb = sb + 1;
+          uint32_t npa = pa, npb = pb;
+          if (nsa == SA) { nsa = 0; npa ^= 1u; }
+          if (nsb == SB) { nsb = 0; npb ^= 1u; }
+          if (MODE == TC_PLAIN) {
+            // tensor-bound: the next stage is (nearly) always there; wait for it in the shadow of the two MMAs
+            // just queued (and, at a tile boundary, for the next accumulator to be drained)
+            if (kb + 1 < nkb) {
+              mbar_wait(bar_full_a + 8 * nsa, npa);
+              if (!UNI) mbar_wait(bar_full_b + 8 * nsb, npb);
+              tc_fence_after();
+            } else if (!last_tile) {
+              mbar_wait(bar_acc_empty + 8 * (as ^ 1), ((uint32_t)((it + 1) >> 1) & 1u) ^ 1u);
+              mbar_wait(bar_full_a + 8 * nsa, npa);
+              if (!UNI) mbar_wait(bar_full_b + 8 * nsb, npb);
+              tc_fence_after();
+            }
+            umma_f16<CG>(d_tmem, adesc + 4, bdesc + 4, idesc, 1u);
+            umma_f16<CG>(d_tmem, adesc + 6, bdesc + 6, idesc, 1u);
+            umma_commit<CG>(bar_empty_a + 8 * sa);  // stage (of every CTA of the group) reusable once these MMAs have read it
+            if (!UNI) umma_commit<CG>(bar_empty_b + 8 * sb);
+            if (kb + 1 == nkb) umma_commit<CG>(bar_acc_full + 8 * as);   // accumulators of this tile group complete
+          } else {
+            // producer-bound (AlignConv): the next stage is usually NOT ready yet.  Probe without blocking; if
+            // it is not there, release this k-block's stage FIRST -- blocking here with two MMAs unissued would
+            // hold the stage until the next one is full and cost the producers one stage of their ring.
+            const bool more = kb + 1 < nkb || !last_tile;
+            const bool new_acc = kb + 1 == nkb;
+            const uint32_t acc_bar = bar_acc_empty + 8 * (as ^ 1), acc_par = ((uint32_t)((it + 1) >> 1) & 1u) ^ 1u;
+            const bool ready = more && mbar_test(bar_full_a + 8 * nsa, npa) && (UNI || mbar_test(bar_full_b + 8 * nsb, npb)) &&
+                               (!new_acc || mbar_test(acc_bar, acc_par));
+            if (ready) tc_fence_after();
+            umma_f16<CG>(d_tmem, adesc + 4, bdesc + 4, idesc, 1u);
+            umma_f16<CG>(d_tmem, adesc + 6, bdesc + 6, idesc, 1u);
+            umma_commit<CG>(bar_empty_a + 8 * sa);
+            if (!UNI) umma_commit<CG>(bar_empty_b + 8 * sb);
+            if (new_acc) umma_commit<CG>(bar_acc_full + 8 * as);
+            if (more && !ready) {
+              if (new_acc) mbar_wait(acc_bar, acc_par);
+              mbar_wait(bar_full_a + 8 * nsa, npa);
+              if (!UNI) mbar_wait(bar_full_b + 8 * nsb, npb);
+              tc_fence_after();
+            }
+          }
+          sa = nsa; pa = npa; sb = nsb; pb = npb;
         }
-        umma_commit(bar_acc_full + 8 * as);         // accumulator of this tile complete
+      }
+      if ((p.debug & 8) && blockIdx.x == 0) {
+        tl[min(it, 9)] = clock64();
+        printf("s2a conv_tc MMA thread: start +%lld;", tl[0] - dbg_c0);
+        for (int i = 0; i < min(it, 9); ++i) printf(" tile%d %lld", i, tl[i + 1] - tl[i]);
+        printf("\n");
       }
     }
   } else {
@@ -483,80 +701,93 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     if (MODE == TC_ALIGN) {
       // tables of the first two tiles
       for (int j = 0; j < 2; ++j) {
-        const int tile = first_tile + j * tile_step;
-        if (tile < p.total_tiles) {
-          build_tap_table<T>(p, decode_tile(p, tile), s_tab + j * (TC_M * 9), et, TC_EPI_THREADS);
+        const int q = first_q + j * q_step;
+        if (q < ngroups) {
+          build_tap_table<T>(p, decode_tile(p, S2A_TILE_OF(q)), s_tab + j * (TC_M * 9), et, TC_EPI_THREADS);
           mbar_arrive(bar_tab_full + 8 * j);
         }
       }
     }
     int it = 0;
-    for (int tile = first_tile; tile < p.total_tiles; tile += tile_step, ++it) {
+    for (int q = first_q; q < ngroups; q += q_step, ++it) {
       const int as = it & 1;
-      const TileCoord tc = decode_tile(p, tile);
+      const bool ghost = S2A_IS_GHOST(q);
+      const TileCoord tc = decode_tile(p, S2A_TILE_OF(q));
       const TcLevel& L = p.lv[tc.lvl];
       mbar_wait(bar_acc_full + 8 * as, (uint32_t)(it >> 1) & 1u);
       tc_fence_after();
+      uint8_t* s_out = MODE == TC_ALIGN ? reinterpret_cast<uint8_t*>(s_tab + as * (TC_M * 9)) : s_out_plain;
       const int r = quad * 32 + lane;
       const int y = tc.ty0 + r / TC_PW, x = tc.tx0 + r % TC_PW;
-      const bool valid = (y < L.H && x < L.W);
+      const bool valid = (y < L.H && x < L.W) && !ghost;
       const size_t pos = (size_t)(tc.b * L.H + y) * L.W + x;
-      for (int c0 = 0; c0 < p.Co; c0 += 32) {
+      // 32 channels at a time: TMEM -> registers -> bias / ReLU / 8-way orientation max -> 16-bit -> a 64-byte row
+      // of the staging buffer (SWIZZLE_64B, conflict-free) -> one TMA store of the 8 x 16 x 32-channel box.  The
+      // stores never touch the LSU global path the gather lives on, and partial tiles are clipped by TMA.
+      for (int c0 = 0, ci = 0; c0 < p.Co && !(p.debug & 32); c0 += TC_OUT_CH, ++ci) {
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * 256 + c0), v);
-        float f[32];
+        uint32_t pk[16];
+        float m[4];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float t = __uint_as_float(v[i]);
-          if (p.bias) t += __ldg(p.bias + c0 + i);
-          if (p.relu) t = fmaxf(t, 0.0f);
-          f[i] = t;
+        for (int i = 0; i < 32; i += 2) {
+          float t0 = __uint_as_float(v[i]), t1 = __uint_as_float(v[i + 1]);
+          if (p.bias) { t0 += __ldg(p.bias + c0 + i); t1 += __ldg(p.bias + c0 + i + 1); }
+          if (p.relu) { t0 = fmaxf(t0, 0.0f); t1 = fmaxf(t1, 0.0f); }
+          const H2 h = from_f2<T>(t0, t1);
+          pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&h);
+          const float mx = fmaxf(t0, t1);
+          m[i >> 3] = (i & 7) == 0 ? mx : fmaxf(m[i >> 3], mx);
         }
-        if (valid) {
-          uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(L.out) + (pos * p.Co + c0) * 2);
+        if (et == 0) tma_store_wait_read();        // the store issued one iteration ago has left its buffer ...
+        uint8_t* row = s_out + (ci & 1) * TC_OUT_BYTES + r * (TC_OUT_CH * 2);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            uint4 o;
-            H2* oh = reinterpret_cast<H2*>(&o);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) oh[j] = from_f2<T>(f[q * 8 + 2 * j], f[q * 8 + 2 * j + 1]);
-            dst[q] = o;
-          }
-          if (L.pooled) {
-            float m[4];
-#pragma unroll
-            for (int gidx = 0; gidx < 4; ++gidx) {
-              float mv = f[gidx * 8];
-#pragma unroll
-              for (int j = 1; j < 8; ++j) mv = fmaxf(mv, f[gidx * 8 + j]);
-              m[gidx] = mv;
-            }
-            uint2 o;
-            H2* oh = reinterpret_cast<H2*>(&o);
-            oh[0] = from_f2<T>(m[0], m[1]);
-            oh[1] = from_f2<T>(m[2], m[3]);
-            *reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(L.pooled) + (pos * (p.Co / 8) + c0 / 8) * 2) = o;
-          }
+        for (int j = 0; j < 4; ++j)
+          *reinterpret_cast<uint4*>(row + ((j ^ ((r >> 1) & 3)) << 4)) =
+              make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+        fence_proxy_async_smem();
+        epi_bar_sync();                            // ... and, after this barrier, everybody knows it
+        if (et == 0 && !ghost && !(p.debug & 64))
+          tma_store_4d(&maps.y[tc.lvl], smem_u32(s_out + (ci & 1) * TC_OUT_BYTES), c0, tc.tx0, tc.ty0, tc.b);
+        if (valid && L.pooled) {
+          uint2 o;
+          H2* oh = reinterpret_cast<H2*>(&o);
+          oh[0] = from_f2<T>(m[0], m[1]);
+          oh[1] = from_f2<T>(m[2], m[3]);
+          *reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(L.pooled) + (pos * (p.Co / 8) + c0 / 8) * 2) = o;
         }
       }
       tc_fence_before();
-      mbar_arrive(bar_acc_empty + 8 * as);          // accumulator may be overwritten by tile it + 2
+      mbar_arrive_cluster(ld_acc_empty + 8 * as);    // accumulator may be overwritten by tile group it + 2
       if (MODE == TC_ALIGN) {
         // every A k-block of tile `it` has been produced (its MMAs completed), so table (it & 1) is free:
         // build the table of tile it + 2 into it
-        const int nxt = tile + 2 * tile_step;
-        if (nxt < p.total_tiles) {
-          build_tap_table<T>(p, decode_tile(p, nxt), s_tab + as * (TC_M * 9), et, TC_EPI_THREADS);
+        const int nxt = q + 2 * q_step;
+        if (nxt < ngroups) {
+          if (et == 0) tma_store_wait_read();      // the last output box has left the buffer
+          epi_bar_sync();
+          build_tap_table<T>(p, decode_tile(p, S2A_TILE_OF(nxt)), s_tab + as * (TC_M * 9), et, TC_EPI_THREADS);
           mbar_arrive(bar_tab_full + 8 * as);
         }
       }
     }
   }
+#undef S2A_TILE_OF
+#undef S2A_IS_GHOST
+  if (tid == kEpiWarp0 * 32) tma_store_wait_all();     // this thread issued every output store of the CTA
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all();   // no CTA may exit (or free TMEM) while its partner can still signal / read it
+  else __syncthreads();
+  if ((p.debug & 8) && blockIdx.x == 0 && tid == 0) {
+    unsigned long long t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    const long long c1 = clock64();
+    printf("s2a conv_tc clock probe: %lld cycles in %llu ns = %.0f MHz\n", c1 - dbg_c0, t1 - dbg_t0,
+           (double)(c1 - dbg_c0) * 1e3 / (double)(t1 - dbg_t0));
+  }
   if (warp == kMmaWarp) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TC_TMEM_COLS);
+    tmem_dealloc<CG>(tmem_base, TC_TMEM_COLS);
   }
 }
 
@@ -615,15 +846,37 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-constexpr size_t kTcSmemBytes = 1024 /*alignment slack*/ + (size_t)TC_SA * TC_A_BYTES + (size_t)TC_SB * TC_B_BYTES_MAX +
-                                2 * sizeof(TapSample) * TC_M * 9 + 8 * TC_NBAR + 16;
+template <int MODE>
+constexpr size_t tc_smem_bytes() {
+  using Cfg = TcCfg<MODE>;
+  return 1024 /*alignment slack*/ + (size_t)Cfg::SA * TC_A_BYTES + (size_t)Cfg::SB * ((256 / Cfg::CG) * TC_KB * 2) +
+         (MODE == TC_ALIGN ? 2 * sizeof(TapSample) * TC_M * 9 : (size_t)2 * TC_OUT_BYTES) + 8 * TC_NBAR + 16;
+}
 
 template <int MODE, typename T>
 static int launch_tc(const TcMaps& tmap, const TcParams& p, cudaStream_t st) {
+  constexpr int CG = TcCfg<MODE>::CG;
   auto kern = conv_tc_kernel<MODE, T>;
-  S2A_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
-  const int grid = std::min(p.total_tiles, sm_count());      // persistent: at most one CTA per SM
-  kern<<<grid, TC_THREADS, kTcSmemBytes, st>>>(tmap, p);
+  constexpr size_t smem = tc_smem_bytes<MODE>();
+  static_assert(smem <= 227 * 1024, "shared memory budget");
+  static_assert(MODE != TC_ALIGN || smem <= 195 * 1024, "AlignConv must fit the 196 KB carve-out (L1 for the gather)");
+  S2A_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // persistent: at most one CTA per SM, launched as clusters of CG CTAs (CG = 2: a CTA pair = one TPC)
+  const int ngroups = (p.total_tiles + CG - 1) / CG;
+  const int nclusters = std::max(1, std::min(ngroups, sm_count() / CG));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(nclusters * CG));
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  S2A_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tmap, p));
   S2A_LAUNCH_OK("conv_tc_kernel");
   return S2A_OK;
 }
@@ -673,9 +926,19 @@ static int conv_tc_common(int mode, int nlevels, const void* const* xs, const fl
       if (xr != CUDA_SUCCESS) { set_error("conv_tc: cuTensorMapEncodeTiled (x, level %d) failed (%d)", l, (int)xr); return S2A_ERR_CUDA; }
     }
   }
+  for (int l = 0; l < nlevels; ++l) {
+    const cuuint64_t yd[4] = {(cuuint64_t)Co, (cuuint64_t)Ws[l], (cuuint64_t)Hs[l], (cuuint64_t)B};
+    const cuuint64_t ys_[3] = {(cuuint64_t)Co * 2, (cuuint64_t)Ws[l] * Co * 2, (cuuint64_t)Hs[l] * Ws[l] * Co * 2};
+    const cuuint32_t yb[4] = {(cuuint32_t)TC_OUT_CH, (cuuint32_t)TC_PW, (cuuint32_t)TC_PH, 1};
+    const cuuint32_t ye[4] = {1, 1, 1, 1};
+    CUresult yr = enc(&tmap.y[l], tdt, 4, outs[l], yd, ys_, yb, ye, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (yr != CUDA_SUCCESS) { set_error("conv_tc: cuTensorMapEncodeTiled (out, level %d) failed (%d)", l, (int)yr); return S2A_ERR_CUDA; }
+  }
   const cuuint64_t gdim[2] = {(cuuint64_t)C * 9, (cuuint64_t)Co};
   const cuuint64_t gstr[1] = {(cuuint64_t)C * 9 * 2};
-  const cuuint32_t box[2] = {(cuuint32_t)TC_KB, (cuuint32_t)Co};
+  const int cg = mode == TC_PLAIN ? TcCfg<TC_PLAIN>::CG : TcCfg<TC_ALIGN>::CG;
+  const cuuint32_t box[2] = {(cuuint32_t)TC_KB, (cuuint32_t)(Co / cg)};   // each CTA of a group stages 1/CG of the rows
   const cuuint32_t estr[2] = {1, 1};
   CUresult cr = enc(&tmap.w, tdt, 2,
                     const_cast<void*>(wp), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
