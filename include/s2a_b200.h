@@ -190,6 +190,22 @@ S2A_EXPORT int s2a_orconv_forward_tc_multi(int nlevels, const void* const* xs,
                                            void* const* outs, void* const* pooleds, const int* Hs,
                                            const int* Ws, int B, int C, int Co, int dtype, void* stream);
 
+/* Stock convolution layers of the head on the same tcgen05 kernel (context, SURVEY 8 "callers": the FAM / ODM
+ * towers and prediction convs of S2ANetHead.forward_single, models/head.py:296-348, are nn.Conv2d (+ReLU) in the
+ * reference; routing them through conv_tc_kernel<PLAIN> removes the cuDNN launches between the custom ops).
+ * Square kernels of size 1 or 3, stride 1, padding ks/2, dilation 1, groups 1.
+ * s2a_conv2d_pack_weight: [Co, C, ks, ks] (f32/bf16/f16) -> packed [Co_pad][ks*ks*Cp] 16-bit with
+ * Co_pad = round_up(Co, 32), Cp = round_up(C, 64) (zero padded).
+ * s2a_conv2d_forward_tc_multi: xs[l] [B, H_l, W_l, C] (C % 8 == 0), outs[l] [B, H_l, W_l, Co_pad], bias fp32
+ * [Co_pad] or NULL, relu != 0 applies max(., 0); one persistent launch for all levels. */
+S2A_EXPORT int s2a_conv2d_pack_weight(const void* weight, int in_dtype, void* packed, int out_dtype,
+                                      int Co, int C, int ks, void* stream);
+S2A_EXPORT int s2a_conv2d_forward_tc_multi(int nlevels, const void* const* xs,
+                                           const void* packed_weight, const float* bias,
+                                           void* const* outs, const int* Hs, const int* Ws, int B,
+                                           int C, int Co_pad, int ks, int relu, int dtype,
+                                           void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Box decode stages of the head, one launch over all FPN levels and images.
  *

@@ -133,3 +133,54 @@ def orconv_forward_tc_multi(xs, weight, indices, bias, with_pool=False):
                                                      _lib.dtype_code(xc[0]), _lib.stream_ptr(dev))
     _lib.check(rc, "orconv_forward_tc_multi")
     return (outs, pooled) if with_pool else outs
+
+
+def pack_conv2d_weight(weight, bias, dtype):
+    """Pack (and cache) a stock [Co,C,ks,ks] conv weight (+ fp32 bias padded to Co_pad) for conv2d_forward_tc_multi."""
+    key = (weight.data_ptr(), weight._version, dtype, weight.device, "conv2d",
+           None if bias is None else (bias.data_ptr(), bias._version))
+    hit = _PACK_CACHE.get(key)
+    if hit is not None:
+        return hit
+    dev = weight.device
+    w = weight.detach().contiguous()
+    Co, C, ks, ks2 = w.shape
+    if ks != ks2 or ks not in (1, 3):
+        raise ValueError("conv2d_forward_tc: square kernels of size 1 or 3 only")
+    Co_pad, Cp = (Co + 31) // 32 * 32, (C + 63) // 64 * 64
+    packed = torch.empty((Co_pad, ks * ks * Cp), dtype=dtype, device=dev)
+    with torch.cuda.device(dev):
+        rc = _lib.load().s2a_conv2d_pack_weight(_lib.ptr(w), _lib.dtype_code(w), _lib.ptr(packed), _lib.dtype_code(packed),
+                                                Co, C, ks, _lib.stream_ptr(dev))
+    _lib.check(rc, "conv2d_pack_weight")
+    b = None
+    if bias is not None:
+        b = torch.zeros((Co_pad,), dtype=torch.float32, device=dev)
+        b[:Co] = bias.detach().float()
+    if len(_PACK_CACHE) > 64:
+        _PACK_CACHE.clear()
+    _PACK_CACHE[key] = (packed, b, Co_pad, ks)
+    return _PACK_CACHE[key]
+
+
+def conv2d_forward_tc_multi(xs, weight, bias=None, relu=False):
+    """nn.Conv2d(C, Co, ks, stride 1, padding ks//2) (+ReLU) on all FPN levels in one persistent tcgen05 launch.
+    xs[l] [B,C,H_l,W_l] bf16/fp16 -> [B,Co,H_l,W_l] channels_last views (of a Co_pad-channel buffer when Co % 32)."""
+    dev = _lib.require_cuda(*xs, weight, bias)
+    B, C = xs[0].shape[:2]
+    if weight.size(1) != C:
+        raise ValueError("conv2d_forward_tc: input has %d channels, weight expects %d" % (C, weight.size(1)))
+    if C % 8:
+        raise ValueError("conv2d_forward_tc: C must be a multiple of 8")
+    packed, b, Co_pad, ks = pack_conv2d_weight(weight, bias, xs[0].dtype)
+    xc = [_nhwc(x) for x in xs]
+    outs = [torch.empty((B, Co_pad, x.size(2), x.size(3)), dtype=x.dtype, device=dev, memory_format=torch.channels_last)
+            for x in xs]
+    with torch.cuda.device(dev):
+        rc = _lib.load().s2a_conv2d_forward_tc_multi(len(xs), _ptr_array(xc), _lib.ptr(packed), _lib.ptr(b), _ptr_array(outs),
+                                                     _int_array([x.size(2) for x in xs]), _int_array([x.size(3) for x in xs]),
+                                                     B, C, Co_pad, ks, 1 if relu else 0, _lib.dtype_code(xc[0]),
+                                                     _lib.stream_ptr(dev))
+    _lib.check(rc, "conv2d_forward_tc_multi")
+    Co = weight.size(0)
+    return outs if Co == Co_pad else [o[:, :Co] for o in outs]

@@ -91,6 +91,7 @@ struct TcParams {
   const float* bias;      // [Co] fp32 or null
   int nlevels, total_tiles;
   int B, C, Co;
+  int ks;                 // TC_PLAIN: square kernel size, 1 or 3 (pad ks/2, stride 1); TC_ALIGN: 3
   int relu;
   int debug;              // timing experiments only (S2A_TC_DEBUG): 1 = no weight TMA after warm-up, 2 = no gather loads
 };
@@ -460,8 +461,9 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                  ld_full_b = UNI ? ld_full_a : (CG == 2 ? map_to_cta(bar_full_b, 0) : bar_full_b),
                  ld_acc_empty = CG == 2 ? map_to_cta(bar_acc_empty, 0) : bar_acc_empty;
 
-  const int ncb = p.C / TC_KB;
-  const int nkb = ncb * 9;
+  const int ncb = (p.C + TC_KB - 1) / TC_KB;         // 64-channel blocks (TC_PLAIN: a partial block is zero-filled by TMA)
+  const int ntap = p.ks * p.ks;
+  const int nkb = ncb * ntap;
   const int co_part = p.Co / CG;                     // weight rows (output channels) staged by this CTA
   const uint32_t b_bytes_group = (uint32_t)p.Co * TC_KB * 2;
   const int ngroups = (p.total_tiles + CG - 1) / CG;
@@ -587,9 +589,9 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
               if (leader) mbar_arrive(bar_full_a + 8 * sa);
             } else {
               if (leader) mbar_arrive_expect_tx(bar_full_a + 8 * sa, b_bytes_group + CG * TC_A_BYTES);
-              const int ti = tap / 3;
-              tma_load_4d<CG>(smem_u32(sA + sa * TC_A_BYTES), &maps.x[tc.lvl], cb * TC_KB, tc.tx0 - 1 + (tap - 3 * ti),
-                              tc.ty0 - 1 + ti, tc.b, ld_full_a + 8 * sa);
+              const int ti = tap / p.ks, half = p.ks >> 1;
+              tma_load_4d<CG>(smem_u32(sA + sa * TC_A_BYTES), &maps.x[tc.lvl], cb * TC_KB, tc.tx0 - half + (tap - p.ks * ti),
+                              tc.ty0 - half + ti, tc.b, ld_full_a + 8 * sa);
               tma_load_2d<CG>(smem_u32(sB + sa * B_STAGE_BYTES), &maps.w, kb * TC_KB, (int)cta_rank * co_part, ld_full_a + 8 * sa);
             }
             if (++sa == SA) { sa = 0; pa ^= 1u; }
@@ -603,7 +605,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
             }
             if (++sb == SB) { sb = 0; pb ^= 1u; }
           }
-          if (++tap == 9) { tap = 0; ++cb; }
+          if (++tap == ntap) { tap = 0; ++cb; }
         }
         warm = true;
       }
@@ -830,6 +832,25 @@ __global__ void pack_weight_kernel(const TIn* __restrict__ w, const uint8_t* __r
   }
 }
 
+// plain conv weights [Co][C][ks][ks] -> [Co_pad][(cb, tap, c64)] with C padded to a multiple of 64 and Co to
+// Co_pad (zero rows / zero channels), for the stock conv layers of the head routed through conv_tc_kernel<PLAIN>
+template <typename TIn, typename TOut>
+__global__ void pack_conv2d_kernel(const TIn* __restrict__ w, TOut* __restrict__ wp, int Co, int Co_pad, int C, int ncb,
+                                   int ntap) {
+  const int64_t total = (int64_t)Co_pad * ncb * ntap * 64;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(e % 64);
+    int64_t r = e / 64;
+    const int tap = (int)(r % ntap);
+    r /= ntap;
+    const int cb = (int)(r % ncb);
+    const int n = (int)(r / ncb);
+    const int cin = cb * 64 + c;
+    const float v = (n < Co && cin < C) ? (float)w[((int64_t)n * C + cin) * ntap + tap] : 0.0f;
+    wp[e] = (TOut)v;
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -883,14 +904,17 @@ static int launch_tc(const TcMaps& tmap, const TcParams& p, cudaStream_t st) {
 
 static int conv_tc_common(int mode, int nlevels, const void* const* xs, const float* const* anchors, const void* wp,
                           const float* bias, void* const* outs, void* const* pooleds, const int* Hs, const int* Ws,
-                          const float* strides, int B, int C, int Co, int relu, int dtype, cudaStream_t st) {
+                          const float* strides, int B, int C, int Co, int relu, int dtype, cudaStream_t st, int ks = 3) {
   S2A_CHECK_ARG(nlevels >= 1 && nlevels <= TC_MAX_LEVELS, "conv_tc: 1..%d levels per launch", TC_MAX_LEVELS);
   S2A_CHECK_ARG(B >= 0 && C > 0 && Co > 0, "conv_tc: bad tensor sizes");
   S2A_CHECK_ARG(dtype == S2A_BF16 || dtype == S2A_F16, "conv_tc: dtype must be bf16 or f16");
-  if (C % 64 != 0 || Co % 32 != 0 || Co > 256) {
-    set_error("conv_tc: needs C %% 64 == 0 and C_out a multiple of 32 up to 256 (got C=%d, C_out=%d)", C, Co);
+  S2A_CHECK_ARG(ks == 3 || (ks == 1 && mode == TC_PLAIN), "conv_tc: kernel size must be 3 (or 1 for the plain conv)");
+  if ((mode == TC_ALIGN ? C % 64 != 0 : C % 8 != 0) || Co % 32 != 0 || Co > 256) {
+    set_error("conv_tc: needs C %% 64 == 0 (plain conv: C %% 8 == 0) and C_out a multiple of 32 up to 256 (got C=%d, C_out=%d)",
+              C, Co);
     return S2A_ERR_UNSUPPORTED;
   }
+  const int Kp = ((C + TC_KB - 1) / TC_KB) * TC_KB * ks * ks;      // packed K' (C padded to 64-channel blocks)
   if (B == 0) return S2A_OK;
   S2A_CHECK_ARG(xs && wp && outs && Hs && Ws, "conv_tc: null pointer");
   TcParams p{};
@@ -935,8 +959,8 @@ static int conv_tc_common(int mode, int nlevels, const void* const* xs, const fl
                       CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (yr != CUDA_SUCCESS) { set_error("conv_tc: cuTensorMapEncodeTiled (out, level %d) failed (%d)", l, (int)yr); return S2A_ERR_CUDA; }
   }
-  const cuuint64_t gdim[2] = {(cuuint64_t)C * 9, (cuuint64_t)Co};
-  const cuuint64_t gstr[1] = {(cuuint64_t)C * 9 * 2};
+  const cuuint64_t gdim[2] = {(cuuint64_t)Kp, (cuuint64_t)Co};
+  const cuuint64_t gstr[1] = {(cuuint64_t)Kp * 2};
   const int cg = mode == TC_PLAIN ? TcCfg<TC_PLAIN>::CG : TcCfg<TC_ALIGN>::CG;
   const cuuint32_t box[2] = {(cuuint32_t)TC_KB, (cuuint32_t)(Co / cg)};   // each CTA of a group stages 1/CG of the rows
   const cuuint32_t estr[2] = {1, 1};
@@ -945,7 +969,7 @@ static int conv_tc_common(int mode, int nlevels, const void* const* xs, const fl
                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (cr != CUDA_SUCCESS) { set_error("conv_tc: cuTensorMapEncodeTiled failed (%d)", (int)cr); return S2A_ERR_CUDA; }
   p.bias = bias; p.nlevels = nlevels; p.total_tiles = (int)tiles;
-  p.B = B; p.C = C; p.Co = Co; p.relu = relu;
+  p.B = B; p.C = C; p.Co = Co; p.relu = relu; p.ks = ks;
   { const char* e = getenv("S2A_TC_DEBUG"); p.debug = e ? atoi(e) : 0; }
   if (mode == TC_ALIGN) {
     return dtype == S2A_BF16 ? launch_tc<TC_ALIGN, __nv_bfloat16>(tmap, p, st) : launch_tc<TC_ALIGN, __half>(tmap, p, st);
@@ -1020,4 +1044,38 @@ extern "C" int s2a_orconv_forward_tc_multi(int nlevels, const void* const* xs, c
   using namespace s2a;
   return conv_tc_common(TC_PLAIN, nlevels, xs, nullptr, packed_weight, bias, outs, pooleds, Hs, Ws, nullptr, B, C, Co, 0,
                         dtype, (cudaStream_t)stream);
+}
+
+extern "C" int s2a_conv2d_pack_weight(const void* weight, int in_dtype, void* packed, int out_dtype, int Co, int C, int ks,
+                                      void* stream) {
+  using namespace s2a;
+  S2A_CHECK_ARG(Co > 0 && C > 0 && (ks == 1 || ks == 3), "conv2d_pack_weight: bad sizes (kernel size 1 or 3)");
+  S2A_CHECK_ARG(out_dtype == S2A_BF16 || out_dtype == S2A_F16, "conv2d_pack_weight: packed dtype must be bf16 or f16");
+  S2A_CHECK_ARG(weight && packed, "conv2d_pack_weight: null pointer");
+  const int ncb = (C + TC_KB - 1) / TC_KB, ntap = ks * ks, Co_pad = (Co + 31) / 32 * 32;
+  const int64_t total = (int64_t)Co_pad * ncb * ntap * 64;
+  const int blocks = (int)std::min<int64_t>(ceil_div(total, 256), (int64_t)sm_count() * 8);
+  cudaStream_t st = (cudaStream_t)stream;
+#define S2A_PACK2D(TIN)                                                                                                     \
+  if (out_dtype == S2A_BF16)                                                                                                \
+    pack_conv2d_kernel<TIN, __nv_bfloat16><<<blocks, 256, 0, st>>>((const TIN*)weight, (__nv_bfloat16*)packed, Co, Co_pad, C, ncb, ntap); \
+  else                                                                                                                      \
+    pack_conv2d_kernel<TIN, __half><<<blocks, 256, 0, st>>>((const TIN*)weight, (__half*)packed, Co, Co_pad, C, ncb, ntap);
+  switch (in_dtype) {
+    case S2A_F32: S2A_PACK2D(float) break;
+    case S2A_BF16: S2A_PACK2D(__nv_bfloat16) break;
+    case S2A_F16: S2A_PACK2D(__half) break;
+    default: set_error("conv2d_pack_weight: unknown input dtype %d", in_dtype); return S2A_ERR_INVALID_ARGUMENT;
+  }
+#undef S2A_PACK2D
+  S2A_LAUNCH_OK("pack_conv2d_kernel");
+  return S2A_OK;
+}
+
+extern "C" int s2a_conv2d_forward_tc_multi(int nlevels, const void* const* xs, const void* packed_weight, const float* bias,
+                                           void* const* outs, const int* Hs, const int* Ws, int B, int C, int Co_pad, int ks,
+                                           int relu, int dtype, void* stream) {
+  using namespace s2a;
+  return conv_tc_common(TC_PLAIN, nlevels, xs, nullptr, packed_weight, bias, outs, nullptr, Hs, Ws, nullptr, B, C, Co_pad, relu,
+                        dtype, (cudaStream_t)stream, ks);
 }

@@ -177,25 +177,35 @@ class S2ANetHead(nn.Module):
         return odm_cls_pred, odm_bbox_pred
 
     def forward_levels(self, feats):
-        """All levels.  In 16-bit mode AlignConv and ORConv2d each run as ONE persistent multi-level
-        launch (the reference loops over levels in Python, head.py:265)."""
+        """All levels.  In 16-bit mode every layer -- the stock conv towers and prediction convs as well as
+        AlignConv and ORConv2d -- runs as ONE persistent multi-level tcgen05 launch (the reference loops over
+        levels in Python, head.py:265, and its convs are cuDNN calls)."""
         x0 = feats[0]
         if not (x0.is_cuda and x0.dtype in (torch.bfloat16, torch.float16) and self.with_orconv):
             return [self.forward_single(x, s) for x, s in zip(feats, self.featmap_strides)]
         from . import conv_tc
-        preds = [self._fam_preds(x) for x in feats]
-        refines = decode.fam_decode([pr[1] for pr in preds], self.featmap_strides, self.anchor_scale, self.anchor_angle, 1e-6)
-        fam = [(pr[0], pr[1], self.grid_anchors(x.size(2), x.size(3), s, x.device), rf)
-               for pr, rf, x, s in zip(preds, refines, feats, self.featmap_strides)]
-        aligned = conv_tc.alignconv_forward_tc_multi(list(feats), refines, self.align_conv.deform_conv.weight,
+
+        def conv(xs, m, relu=False):
+            return conv_tc.conv2d_forward_tc_multi(xs, m.weight, m.bias, relu=relu)
+
+        def tower(seq, xs):
+            for block in seq:                       # nn.Sequential(Conv2d, ReLU): one launch per layer for all levels
+                xs = conv(xs, block[0], relu=True)
+            return xs
+
+        feats = list(feats)
+        fam_reg = conv(tower(self.fam_reg_ls, feats), self.fam_reg_head)
+        fam_cls = conv(tower(self.fam_cls_ls, feats), self.fam_cls_head)
+        refines = decode.fam_decode(fam_reg, self.featmap_strides, self.anchor_scale, self.anchor_angle, 1e-6)
+        aligned = conv_tc.alignconv_forward_tc_multi(feats, refines, self.align_conv.deform_conv.weight,
                                                      self.featmap_strides)
         or_feats, pooled = conv_tc.orconv_forward_tc_multi(aligned, self.or_conv.weight, self.or_conv.indices,
                                                            self.or_conv.bias, with_pool=True)
-        outs = []
-        for (fam_cls, fam_reg, init, refine), of, pf in zip(fam, or_feats, pooled):
-            odm_cls, odm_reg = self._odm(of, pf)
-            outs.append((fam_cls, fam_reg, odm_cls, odm_reg, init, refine))
-        return outs
+        odm_cls = conv(tower(self.odm_cls_ls, pooled), self.odm_cls_head)
+        odm_reg = conv(tower(self.odm_reg_ls, or_feats), self.odm_reg_head)
+        return [(fam_cls[l], fam_reg[l], odm_cls[l], odm_reg[l],
+                 self.grid_anchors(x.size(2), x.size(3), s, x.device), refines[l])
+                for l, (x, s) in enumerate(zip(feats, self.featmap_strides))]
 
     @torch.no_grad()
     def select_and_decode(self, outs):

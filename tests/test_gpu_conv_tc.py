@@ -119,3 +119,28 @@ def test_multi_level_launch_equals_per_level():
     for x, y, yp in zip(xs, outs, pooled):
         r, rp = orconv_forward_tc(x, m.weight, m.indices, m.bias, with_pool=True)
         assert torch.equal(y, r) and torch.equal(yp, rp)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("C,Co,ks,relu", [(256, 256, 3, True), (32, 256, 3, True), (256, 15, 3, False), (256, 5, 1, False),
+                                          (64, 32, 1, True), (72, 40, 3, False)])
+def test_conv2d_tc_multi_vs_torch(dtype, C, Co, ks, relu):
+    """The stock nn.Conv2d layers of the head on the tcgen05 kernel: kernel 1 / 3, channel counts that need
+    zero-padded k-blocks (32, 72) and padded outputs (5, 15, 40), several levels incl. partial tiles."""
+    from s2anet_b200.conv_tc import conv2d_forward_tc_multi
+    g = torch.Generator().manual_seed(C + Co + ks)
+    sizes = ((24, 40), (13, 21), (3, 5))
+    xs = [torch.randn(2, C, h, w, generator=g).to(DEV).to(dtype).contiguous(memory_format=torch.channels_last) for h, w in sizes]
+    wt = (torch.randn(Co, C, ks, ks, generator=g) * 0.05).to(DEV).to(dtype)
+    bias = (torch.randn(Co, generator=g) * 0.1).to(DEV)
+    ys = conv2d_forward_tc_multi(xs, wt, bias, relu=relu)
+    for x, y in zip(xs, ys):
+        assert tuple(y.shape) == (2, Co, x.size(2), x.size(3)) and y.dtype == dtype
+        ref = torch.nn.functional.conv2d(x.float(), wt.float(), bias, padding=ks // 2)
+        if relu:
+            ref = ref.relu()
+        check(y, ref, dtype)
+    # no bias
+    y0 = conv2d_forward_tc_multi(xs[:1], wt, None, relu=relu)[0]
+    ref0 = torch.nn.functional.conv2d(xs[0].float(), wt.float(), None, padding=ks // 2)
+    check(y0, ref0.relu() if relu else ref0, dtype)
