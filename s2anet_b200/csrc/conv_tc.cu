@@ -51,13 +51,13 @@ enum { TC_ALIGN = 0, TC_PLAIN = 1 };
 //  * ORConv2d (TC_PLAIN) is fed entirely by TMA and bound by the tensor pipe: a CTA PAIR (cta_group::2, one
 //    TPC) shares every weight k-block -- each CTA stages half of the C_out rows -- and A + B of a k-block
 //    travel through one ring of 6 stages with one full/empty barrier pair per stage.
-//  * AlignConv (TC_ALIGN) is bound by the bilinear gather (LSU wavefronts, L1 hit rate).  Shared memory must
-//    stay under the 196 KB carve-out so that ~60 KB of L1 remain for the gather (ncu: 90 % L1 hits at 60 KB,
-//    75 % at 28 KB; measured 0.284 ms at 28 KB vs 0.235 ms at 60 KB).  CTA pairs are used here too because a
-//    half-width weight stage (16 KB) is what makes room for 5 A stages + 3 B stages + the sample tables;
-//    A and B keep separate rings (the producers' ring is the deeper one).
+//  * AlignConv (TC_ALIGN) is bound by the bilinear gather, i.e. by LSU wavefronts: 4 corners x 128 B per
+//    (row, k-block) = 512 wavefronts per k-block next to 512 tensor-pipe cycles.  Its feature-map reads go
+//    through a TMA-fed shared-memory halo (two 39 KB buffers) instead of L1, which needs the whole 227 KB:
+//    CTA pairs are used here too because a half-width weight stage (16 KB) is what makes room for 4 A
+//    stages + 3 B stages + 2 halo buffers + 2 sample tables.  A and B keep separate rings.
 template <int MODE> struct TcCfg;
-template <> struct TcCfg<TC_ALIGN> { static constexpr int CG = 2, SA = 5, SB = 3; static constexpr bool UNIFIED = false; };
+template <> struct TcCfg<TC_ALIGN> { static constexpr int CG = 2, SA = 4, SB = 3; static constexpr bool UNIFIED = false; };
 template <> struct TcCfg<TC_PLAIN> { static constexpr int CG = 2, SA = 6, SB = 6; static constexpr bool UNIFIED = true; };
 constexpr int TC_MAX_STAGES = 8;
 constexpr int TC_PROD_THREADS = TC_GROUPS * 128;
@@ -65,16 +65,27 @@ constexpr int TC_EPI_THREADS = 128;                   // 4 epilogue warps, one p
 constexpr int TC_THREADS = TC_PROD_THREADS + 64 + TC_EPI_THREADS;   // producers | TMA warp | MMA warp | epilogue
 constexpr int TC_ACC_STAGES = 2;                      // double-buffered accumulator: 2 x 256 TMEM columns
 constexpr int TC_TMEM_COLS = 512;
-constexpr int TC_NBAR = 4 * TC_MAX_STAGES + 2 * TC_ACC_STAGES + 2;
+constexpr int TC_NBAR = 4 * TC_MAX_STAGES + 2 * TC_ACC_STAGES + 2 + 4;   // + halo full/empty x 2
 constexpr int TC_MAX_LEVELS = 8;
 constexpr uint32_t kSpinLimit = 1u << 26;            // watchdog: trap instead of hanging the GPU
 
-// One (row, tap) gather recipe, 16 bytes (one LDS.128): byte offset of the (clamped) top-left corner pixel
-// inside the image (a multiple of 16, so the two low bits carry "right corner is one pixel further" /
-// "bottom corners are one row further"), and the four bilinear weights already rounded to the 16-bit
-// type.  Corners that fall outside the map keep a valid (clamped) address and get weight 0, which is
-// the reference's rule (deform_conv_cuda_kernel.cu:97-108, :228).
-struct __align__(16) TapSample { uint32_t base; uint32_t w01; uint32_t w23; uint32_t pad; };
+// AlignConv reads the feature map through a shared-memory HALO: for every (tile, 64-channel block) TMA loads
+// the (8 + 2*3) x (16 + 2*3) pixel window around the tile once (39 KB, zero-filled outside the map, two
+// buffers), and the nine taps of that channel block gather their bilinear corners from it with LDS.128 --
+// fixed latency, no L1 tags, no misses.  Corners outside the window (large or far-shifted anchors) are read
+// from global memory instead, per sample.
+constexpr int TC_HALO = 3;
+constexpr int TC_HW = TC_PW + 2 * TC_HALO, TC_HH = TC_PH + 2 * TC_HALO;      // 22 x 14 pixels
+constexpr int TC_HALO_BYTES = TC_HW * TC_HH * TC_KB * 2;                      // 39,424 B per buffer
+
+// One (row, tap) gather recipe, 12 bytes: the four bilinear weights already rounded to the 16-bit type, and
+// `base`: bit 31 = "all corners are inside the halo window", bits 2..30 = index of the (clamped) top-left
+// corner pixel -- inside the halo window if bit 31 is set, inside the image otherwise -- bit 0 = "right
+// corners are one pixel further", bit 1 = "bottom corners are one row further".  Corners that fall outside
+// the map keep a valid (clamped) address and get weight 0, which is the reference's rule
+// (deform_conv_cuda_kernel.cu:97-108, :228).
+struct __align__(4) TapSample { uint32_t base; uint32_t w01; uint32_t w23; };
+constexpr uint32_t TC_IN_HALO = 0x80000000u;
 
 struct TcLevel {
   const void* x;          // [B, H, W, C] 16-bit (channels_last)
@@ -198,9 +209,13 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t addr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
   return r;
 }
-// arrive on an mbarrier that may live in the peer CTA (shared::cluster address)
+// arrive on an mbarrier that may live in the peer CTA (shared::cluster address).  Default semantics
+// (.release at CTA scope, as CUTLASS's ClusterBarrier::arrive(cta_id) does): the `.release.cluster` form
+// compiles to MEMBAR.ALL.GPU + ERRBAR in front of the arrive, which cost the AlignConv producers ~15 % of
+// their issue samples (ncu source view, profiles/r1_conv_tc_v8).  The data this arrive publishes is only ever
+// read by the tensor core of the WRITING CTA (each SM reads its own A tile), after fence.proxy.async.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 
 // TMA loads.  `bar` is a shared::cluster address: with cta_group::2 the completion may be signalled on
@@ -315,22 +330,11 @@ template <> __device__ __forceinline__ __nv_bfloat162 from_f2<__nv_bfloat16>(flo
 }
 template <> __device__ __forceinline__ __half2 from_f2<__half>(float a, float b) { return __floats2half2_rn(a, b); }
 
-__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
-
-// Pull the 128-byte lines (one 64-channel block per pixel) of the halo region around a tile into L1 a
-// whole channel block ahead of their use: rows [ty0-4, ty0+12), cols [tx0-4, tx0+20) = 384 pixels,
-// one per producer thread.  The gather's L1 hit rate is what bounds AlignConv (each 16-load batch
-// waits for its slowest load), and the first tap of every channel block used to miss on every line.
-constexpr int TC_HALO = 4;
-constexpr int TC_PF_W = TC_PW + 2 * TC_HALO, TC_PF_H = TC_PH + 2 * TC_HALO;     // 24 x 16
-__device__ __forceinline__ void prefetch_halo(const TcParams& p, const TileCoord& tc, int cb, int idx) {
-  if (idx >= TC_PF_W * TC_PF_H) return;
-  const TcLevel& L = p.lv[tc.lvl];
-  const int y = tc.ty0 - TC_HALO + idx / TC_PF_W, x = tc.tx0 - TC_HALO + idx % TC_PF_W;
-  if (y < 0 || y >= L.H || x < 0 || x >= L.W) return;
-  prefetch_l1(reinterpret_cast<const uint8_t*>(L.x) + (((size_t)(tc.b * L.H + y) * L.W + x) * p.C + (size_t)cb * TC_KB) * 2);
+__device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
+  uint4 r;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+  return r;
 }
-
 __device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
   uint4 r;
   asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
@@ -382,7 +386,7 @@ __device__ __forceinline__ void build_tap_table(const TcParams& p, const TileCoo
     const int r = e / 9, t = e - 9 * r;
     const int y = tc.ty0 + r / TC_PW, x = tc.tx0 + r % TC_PW;
     TapSample s;
-    s.base = 0u; s.w01 = 0u; s.w23 = 0u; s.pad = 0u;
+    s.base = TC_IN_HALO; s.w01 = 0u; s.w23 = 0u;          // weight-0 sample: reads halo pixel 0
     if (y < H && x < W) {
       const float* a = L.anchors + ((size_t)(tc.b * H + y) * W + x) * 5;
       const float ax = a[0] / L.stride, ay = a[1] / L.stride, aw = a[2] / L.stride, ah = a[3] / L.stride;
@@ -409,7 +413,10 @@ __device__ __forceinline__ void build_tap_table(const TcParams& p, const TileCoo
         const H2 p23 = from_f2<T>((b_ok && l_ok) ? ly * hx : 0.0f, (b_ok && r_ok) ? ly * lx : 0.0f);
         s.w01 = *reinterpret_cast<const uint32_t*>(&p01);
         s.w23 = *reinterpret_cast<const uint32_t*>(&p23);
-        s.base = (uint32_t)(((size_t)yt * W + xl) * p.C * 2) | (xrr > xl ? 1u : 0u) | (yb > yt ? 2u : 0u);
+        const int hy0 = yt - (tc.ty0 - TC_HALO), hx0 = xl - (tc.tx0 - TC_HALO);     // top-left corner inside the halo window?
+        const bool in_halo = hy0 >= 0 && hx0 >= 0 && yb - (tc.ty0 - TC_HALO) < TC_HH && xrr - (tc.tx0 - TC_HALO) < TC_HW;
+        const uint32_t pix = in_halo ? (uint32_t)(hy0 * TC_HW + hx0) : (uint32_t)(yt * W + xl);
+        s.base = (in_halo ? TC_IN_HALO : 0u) | (pix << 2) | (xrr > xl ? 1u : 0u) | (yb > yt ? 2u : 0u);
       }
     }
     tab[e] = s;
@@ -435,23 +442,27 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
   // SWIZZLE_128B operands need 1024-byte aligned tiles: align the dynamic window by hand (the offset is
   // the same in both CTAs of a pair, which the paired MMA and the multicast commits rely on)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  // carve: A stages | B stages | 2 output staging buffers (PLAIN) or 2 sample tables (ALIGN) | barriers | tmem pointer.
-  // In ALIGN mode the epilogue of a tile stages its output in that tile's own sample table, which is dead by
-  // then (every A k-block of the tile has been produced) and is rebuilt for tile + 2 right after the stores.
+  // carve: A stages | B stages | PLAIN: 2 output staging buffers / ALIGN: 2 halo buffers, 2 sample tables | barriers
+  // | tmem pointer.  In ALIGN mode the epilogue of a tile stages its output (one 8 KB buffer) in that tile's own
+  // sample table, which is dead by then (every A k-block of the tile has been produced) and is rebuilt for
+  // tile + 2 right after the stores.
   uint8_t* sA = smem;
   uint8_t* sB = sA + SA * TC_A_BYTES;
   uint8_t* s_out_plain = sB + SB * B_STAGE_BYTES;
-  TapSample* s_tab = reinterpret_cast<TapSample*>(s_out_plain);
-  static_assert(sizeof(TapSample) * TC_M * 9 >= 2 * TC_OUT_BYTES && (sizeof(TapSample) * TC_M * 9) % 512 == 0, "staging aliases a table");
-  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_out_plain + (MODE == TC_ALIGN ? 2 * sizeof(TapSample) * TC_M * 9
-                                                                                    : (size_t)2 * TC_OUT_BYTES));
+  uint8_t* s_halo = s_out_plain;                                         // ALIGN only
+  TapSample* s_tab = reinterpret_cast<TapSample*>(s_halo + 2 * TC_HALO_BYTES);
+  static_assert(sizeof(TapSample) * TC_M * 9 >= TC_OUT_BYTES && (sizeof(TapSample) * TC_M * 9) % 512 == 0 &&
+                    (2 * TC_HALO_BYTES) % 512 == 0 && TC_HALO_BYTES % 128 == 0, "staging aliases a table; 512-byte aligned for SWIZZLE_64B");
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(
+      s_out_plain + (MODE == TC_ALIGN ? 2 * TC_HALO_BYTES + 2 * sizeof(TapSample) * TC_M * 9 : (size_t)2 * TC_OUT_BYTES));
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + TC_NBAR);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t bar_full_a = smem_u32(s_bar), bar_empty_a = bar_full_a + 8 * TC_MAX_STAGES,
                  bar_full_b = bar_empty_a + 8 * TC_MAX_STAGES, bar_empty_b = bar_full_b + 8 * TC_MAX_STAGES,
                  bar_acc_full = bar_empty_b + 8 * TC_MAX_STAGES, bar_acc_empty = bar_acc_full + 8 * TC_ACC_STAGES,
-                 bar_tab_full = bar_acc_empty + 8 * TC_ACC_STAGES;       // 2 barriers
+                 bar_tab_full = bar_acc_empty + 8 * TC_ACC_STAGES,       // 2 barriers
+                 bar_halo_full = bar_tab_full + 16, bar_halo_empty = bar_halo_full + 16;   // 2 + 2 barriers
   constexpr int kTmaWarp = TC_PROD_THREADS / 32, kMmaWarp = kTmaWarp + 1, kEpiWarp0 = kTmaWarp + 2;
 
   const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;     // 0 = leader (issues the MMAs, owns the "full" barriers)
@@ -488,6 +499,8 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       mbar_init(bar_acc_full + 8 * s, 1);       // tcgen05.commit after the last k-block of a tile group
       mbar_init(bar_acc_empty + 8 * s, CG * TC_EPI_THREADS);
       mbar_init(bar_tab_full + 8 * s, TC_EPI_THREADS);
+      mbar_init(bar_halo_full + 8 * s, 1);                   // the TMA thread's expect_tx arrive (+ bytes)
+      mbar_init(bar_halo_empty + 8 * s, TC_PROD_THREADS / 32);   // one elected arrive per producer warp
     }
     fence_barrier_init();
   }
@@ -517,6 +530,8 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     int kb = group;                            // k-block inside the current tile
     int s = group % SA;                        // A stage of that k-block
     uint32_t ph = (uint32_t)(group / SA) & 1u;
+    uint32_t hseq = 0;                         // running (tile, channel block) counter: halo buffer = hseq & 1
+    const uint32_t halo_u32 = smem_u32(s_halo) + (uint32_t)chunk * 16u;
     int it = 0;
     for (int q = first_q; MODE == TC_ALIGN && q < ngroups; q += q_step, ++it) {
       const int tile = S2A_TILE_OF(q);
@@ -531,52 +546,92 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       for (; kb < nkb; kb += TC_GROUPS, tap += TC_GROUPS, s += TC_GROUPS) {
         if (tap >= 9) { tap -= 9; ++cb; }
         if (s >= SA) { s -= SA; ph ^= 1u; }
-        if (tap < TC_GROUPS && !(p.debug & 4)) {
-          // this group's first k-block of channel block cb: prefetch its third of the halo of the NEXT
-          // channel block (or of the next tile's first one) -- 9 k-blocks ahead of the loads that need it
-          if (cb + 1 < ncb) prefetch_halo(p, tc, cb + 1, group * 128 + gt);
-          else if (q + q_step < ngroups) prefetch_halo(p, decode_tile(p, S2A_TILE_OF(q + q_step)), 0, group * 128 + gt);
-        }
+        const uint32_t hcur = hseq + (uint32_t)cb;                  // this k-block's (tile, channel block)
+        mbar_wait(bar_halo_full + 8 * (hcur & 1u), (hcur >> 1) & 1u);
         mbar_wait(bar_empty_a + 8 * s, ph ^ 1u);
         uint8_t* a_stage = sA + s * TC_A_BYTES;
         if (!(p.debug & 2)) {
           // 128-byte row r = j*16 + rsub of the stage; chunk position swizzled by (r & 7) == (rsub & 7)
           uint8_t* a_dst = a_stage + rsub * 128 + ((chunk ^ (rsub & 7)) << 4);
           const uint8_t* src = xb + ((size_t)cb * TC_KB + chunk * 8) * 2;   // this thread's 16 bytes inside a pixel
+          const uint32_t hsrc = halo_u32 + (hcur & 1u) * TC_HALO_BYTES;
           const TapSample* trow = tab + rsub * 9 + tap;
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
             uint4 v[4][4];
-            uint32_t w01[4], w23[4];
+            TapSample sm[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const uint4 sm = *reinterpret_cast<const uint4*>(trow + (half * 4 + i) * 16 * 9);   // one LDS.128
-              w01[i] = sm.y; w23[i] = sm.z;
-              const uint8_t* q0 = src + (sm.x & ~3u);
-              const uint32_t dx = (sm.x & 1u) ? pix_stride : 0u, dy = (sm.x & 2u) ? row_stride : 0u;
-              v[i][0] = ldg_nc_v4(q0);
-              v[i][1] = ldg_nc_v4(q0 + dx);
-              v[i][2] = ldg_nc_v4(q0 + dy);
-              v[i][3] = ldg_nc_v4(q0 + dy + dx);
+            for (int i = 0; i < 4; ++i) sm[i] = trow[(half * 4 + i) * 16 * 9];       // the four recipes first ...
+            const bool fast = (sm[0].base & sm[1].base & sm[2].base & sm[3].base & TC_IN_HALO) != 0u;
+            if (__all_sync(0xffffffffu, fast)) {
+              // ... so that the common case -- every corner of the warp's 16 samples inside the halo -- is one
+              // straight-line batch of 16 LDS.128 with no dependent branch in between
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const uint32_t q0 = hsrc + ((sm[i].base & ~TC_IN_HALO) >> 2) * (TC_KB * 2);
+                const uint32_t dx = (sm[i].base & 1u) ? (uint32_t)(TC_KB * 2) : 0u;
+                const uint32_t dy = (sm[i].base & 2u) ? (uint32_t)(TC_HW * TC_KB * 2) : 0u;
+                v[i][0] = lds_v4(q0);
+                v[i][1] = lds_v4(q0 + dx);
+                v[i][2] = lds_v4(q0 + dy);
+                v[i][3] = lds_v4(q0 + dy + dx);
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const uint32_t pix = (sm[i].base & ~TC_IN_HALO) >> 2;
+                if (sm[i].base & TC_IN_HALO) {
+                  const uint32_t q0 = hsrc + pix * (TC_KB * 2);
+                  const uint32_t dx = (sm[i].base & 1u) ? (uint32_t)(TC_KB * 2) : 0u;
+                  const uint32_t dy = (sm[i].base & 2u) ? (uint32_t)(TC_HW * TC_KB * 2) : 0u;
+                  v[i][0] = lds_v4(q0);
+                  v[i][1] = lds_v4(q0 + dx);
+                  v[i][2] = lds_v4(q0 + dy);
+                  v[i][3] = lds_v4(q0 + dy + dx);
+                } else {                               // a corner outside the halo window: straight from global memory
+                  const uint8_t* q0 = src + (size_t)pix * pix_stride;
+                  const uint32_t dx = (sm[i].base & 1u) ? pix_stride : 0u, dy = (sm[i].base & 2u) ? row_stride : 0u;
+                  v[i][0] = ldg_nc_v4(q0);
+                  v[i][1] = ldg_nc_v4(q0 + dx);
+                  v[i][2] = ldg_nc_v4(q0 + dy);
+                  v[i][3] = ldg_nc_v4(q0 + dy + dx);
+                }
+              }
             }
 #pragma unroll
             for (int i = 0; i < 4; ++i)
               *reinterpret_cast<uint4*>(a_dst + (half * 4 + i) * 2048) =
-                  blend4<T>(v[i][0], v[i][1], v[i][2], v[i][3], w01[i], w23[i]);
+                  blend4<T>(v[i][0], v[i][1], v[i][2], v[i][3], sm[i].w01, sm[i].w23);
           }
         }
         fence_proxy_async_smem();          // generic-proxy stores -> visible to the tensor core (async proxy)
         __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(ld_full_a + 8 * s);     // on the leader CTA's barrier
+        if (lane == 0) {
+          mbar_arrive_cluster(ld_full_a + 8 * s);                  // on the leader CTA's barrier
+          if (tap >= 9 - TC_GROUPS) mbar_arrive(bar_halo_empty + 8 * (hcur & 1u));   // this warp's last tap of the channel block
+        }
       }
       kb -= nkb;                           // first k-block of this group in the next tile
+      hseq += (uint32_t)ncb;
     }
   } else if (warp == kTmaWarp) {
     // ===================== TMA: this CTA's C_out/CG weight rows (and, PLAIN, its A tile) =====================
     if (lane == 0) {
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;                   // phase bits of the stage rings
+      uint32_t hseq = 0;                         // running (tile, channel block) counter of the halo buffers
       bool warm = false;
+      // AlignConv: halo of one (tile, channel block) = the 14 x 22 pixel window around the tile as one 4-D box
+      // {64, 22, 14, 1}, zero-filled outside the map, into buffer (sequence number & 1)
+      auto load_halo = [&](const TileCoord& t, int cblk) {
+        const uint32_t hb = hseq & 1u;
+        mbar_wait(bar_halo_empty + 8 * hb, ((hseq >> 1) & 1u) ^ 1u);
+        mbar_arrive_expect_tx(bar_halo_full + 8 * hb, TC_HALO_BYTES);
+        tma_load_4d<1>(smem_u32(s_halo + hb * TC_HALO_BYTES), &maps.x[t.lvl], cblk * TC_KB, t.tx0 - TC_HALO, t.ty0 - TC_HALO,
+                       t.b, bar_halo_full + 8 * hb);
+        ++hseq;
+      };
+      if (MODE == TC_ALIGN && first_q < ngroups) load_halo(decode_tile(p, S2A_TILE_OF(first_q)), 0);
       for (int q = first_q; q < ngroups; q += q_step) {
         const TileCoord tc = decode_tile(p, S2A_TILE_OF(q));
         int cb = 0, tap = 0;
@@ -596,6 +651,11 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
             }
             if (++sa == SA) { sa = 0; pa ^= 1u; }
           } else {
+            if (MODE == TC_ALIGN && tap == 3) {
+              // halo of the NEXT (tile, channel block), requested six k-blocks before its first use
+              if (cb + 1 < ncb) load_halo(tc, cb + 1);
+              else if (q + q_step < ngroups) load_halo(decode_tile(p, S2A_TILE_OF(q + q_step)), 0);
+            }
             mbar_wait(bar_empty_b + 8 * sb, pb ^ 1u);
             if ((p.debug & 1) && warm) {
               if (leader) mbar_arrive(bar_full_b + 8 * sb);
@@ -741,16 +801,21 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
           const float mx = fmaxf(t0, t1);
           m[i >> 3] = (i & 7) == 0 ? mx : fmaxf(m[i >> 3], mx);
         }
-        if (et == 0) tma_store_wait_read();        // the store issued one iteration ago has left its buffer ...
-        uint8_t* row = s_out + (ci & 1) * TC_OUT_BYTES + r * (TC_OUT_CH * 2);
+        // PLAIN: two staging buffers -- the store issued one iteration ago must have left ITS buffer before the
+        // barrier below lets anybody write the other one again next iteration.  ALIGN: one buffer (inside the dead
+        // sample table) -- the previous store must be gone before anybody writes it: one more barrier.
+        if (et == 0) tma_store_wait_read();
+        if (MODE == TC_ALIGN) epi_bar_sync();
+        uint8_t* sbuf = s_out + (MODE == TC_ALIGN ? 0 : (ci & 1) * TC_OUT_BYTES);
+        uint8_t* row = sbuf + r * (TC_OUT_CH * 2);
 #pragma unroll
         for (int j = 0; j < 4; ++j)
           *reinterpret_cast<uint4*>(row + ((j ^ ((r >> 1) & 3)) << 4)) =
               make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
         fence_proxy_async_smem();
-        epi_bar_sync();                            // ... and, after this barrier, everybody knows it
+        epi_bar_sync();
         if (et == 0 && !ghost && !(p.debug & 64))
-          tma_store_4d(&maps.y[tc.lvl], smem_u32(s_out + (ci & 1) * TC_OUT_BYTES), c0, tc.tx0, tc.ty0, tc.b);
+          tma_store_4d(&maps.y[tc.lvl], smem_u32(sbuf), c0, tc.tx0, tc.ty0, tc.b);
         if (valid && L.pooled) {
           uint2 o;
           H2* oh = reinterpret_cast<H2*>(&o);
@@ -871,7 +936,8 @@ template <int MODE>
 constexpr size_t tc_smem_bytes() {
   using Cfg = TcCfg<MODE>;
   return 1024 /*alignment slack*/ + (size_t)Cfg::SA * TC_A_BYTES + (size_t)Cfg::SB * ((256 / Cfg::CG) * TC_KB * 2) +
-         (MODE == TC_ALIGN ? 2 * sizeof(TapSample) * TC_M * 9 : (size_t)2 * TC_OUT_BYTES) + 8 * TC_NBAR + 16;
+         (MODE == TC_ALIGN ? 2 * (size_t)TC_HALO_BYTES + 2 * sizeof(TapSample) * TC_M * 9 : (size_t)2 * TC_OUT_BYTES) +
+         8 * TC_NBAR + 16;
 }
 
 template <int MODE, typename T>
@@ -880,7 +946,6 @@ static int launch_tc(const TcMaps& tmap, const TcParams& p, cudaStream_t st) {
   auto kern = conv_tc_kernel<MODE, T>;
   constexpr size_t smem = tc_smem_bytes<MODE>();
   static_assert(smem <= 227 * 1024, "shared memory budget");
-  static_assert(MODE != TC_ALIGN || smem <= 195 * 1024, "AlignConv must fit the 196 KB carve-out (L1 for the gather)");
   S2A_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // persistent: at most one CTA per SM, launched as clusters of CG CTAs (CG = 2: a CTA pair = one TPC)
   const int ngroups = (p.total_tiles + CG - 1) / CG;
@@ -939,16 +1004,18 @@ static int conv_tc_common(int mode, int nlevels, const void* const* xs, const fl
   TcMaps tmap;
   memset(&tmap, 0, sizeof(tmap));
   const CUtensorMapDataType tdt = dtype == S2A_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
-  if (mode == TC_PLAIN) {
-    for (int l = 0; l < nlevels; ++l) {
-      const cuuint64_t xd[4] = {(cuuint64_t)C, (cuuint64_t)Ws[l], (cuuint64_t)Hs[l], (cuuint64_t)B};
-      const cuuint64_t xs_[3] = {(cuuint64_t)C * 2, (cuuint64_t)Ws[l] * C * 2, (cuuint64_t)Hs[l] * Ws[l] * C * 2};
-      const cuuint32_t xb[4] = {(cuuint32_t)TC_KB, (cuuint32_t)TC_PW, (cuuint32_t)TC_PH, 1};
-      const cuuint32_t xe[4] = {1, 1, 1, 1};
-      CUresult xr = enc(&tmap.x[l], tdt, 4, const_cast<void*>(xs[l]), xd, xs_, xb, xe, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-      if (xr != CUDA_SUCCESS) { set_error("conv_tc: cuTensorMapEncodeTiled (x, level %d) failed (%d)", l, (int)xr); return S2A_ERR_CUDA; }
-    }
+  for (int l = 0; l < nlevels; ++l) {
+    // TC_PLAIN: A tiles {64 ch, 16, 8, 1} (SWIZZLE_128B, the UMMA operand layout); TC_ALIGN: halo windows
+    // {64 ch, 22, 14, 1}, plain layout (one 128-byte line per pixel), both zero-filled outside the map
+    const cuuint64_t xd[4] = {(cuuint64_t)C, (cuuint64_t)Ws[l], (cuuint64_t)Hs[l], (cuuint64_t)B};
+    const cuuint64_t xs_[3] = {(cuuint64_t)C * 2, (cuuint64_t)Ws[l] * C * 2, (cuuint64_t)Hs[l] * Ws[l] * C * 2};
+    const cuuint32_t xb[4] = {(cuuint32_t)TC_KB, (cuuint32_t)(mode == TC_PLAIN ? TC_PW : TC_HW),
+                              (cuuint32_t)(mode == TC_PLAIN ? TC_PH : TC_HH), 1};
+    const cuuint32_t xe[4] = {1, 1, 1, 1};
+    CUresult xr = enc(&tmap.x[l], tdt, 4, const_cast<void*>(xs[l]), xd, xs_, xb, xe, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      mode == TC_PLAIN ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (xr != CUDA_SUCCESS) { set_error("conv_tc: cuTensorMapEncodeTiled (x, level %d) failed (%d)", l, (int)xr); return S2A_ERR_CUDA; }
   }
   for (int l = 0; l < nlevels; ++l) {
     const cuuint64_t yd[4] = {(cuuint64_t)Co, (cuuint64_t)Ws[l], (cuuint64_t)Hs[l], (cuuint64_t)B};
