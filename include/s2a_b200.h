@@ -241,6 +241,25 @@ S2A_EXPORT int s2a_select_decode(int nlevels, const void* const* cls, const int6
                                  int64_t n_total, void* workspace, size_t workspace_bytes,
                                  void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * assign_labels -- fused max-IoU label assignment, batched over images
+ *   reference: models/utils.py:33-147 (assign_labels: bbox_iou_rotated + range / invalid-anchor filters + row
+ *              max/argmax + negative / positive rules + the per-GT loop), utils/metrics.py:85-107
+ * anchors [batch, num_anchors, 5], gts [batch, max_gts, 5] fp32 contiguous; gt_counts int32 [batch] (number of
+ * real GT rows per image) or NULL (= max_gts everywhere).  assign_out int64 [batch, num_anchors]:
+ * -2 ignored, -1 negative, >= 0 index of the assigned GT -- the reference's assign_gt_ids.  The IoU matrix is
+ * never materialised (two passes over 64 x 256 tiles; IoU values bit-identical to s2a_box_iou_rotated).
+ * img_h / img_w: imgs_size of the reference (anchors outside become ignored when filter_invalid_anchors != 0);
+ * requires pos_iou_thr > 0 and min_pos_iou_thr >= 0 (the reference defaults are 0.5 / 0.4 / 0).
+ */
+S2A_EXPORT size_t s2a_assign_labels_workspace_bytes(int64_t batch, int64_t num_anchors, int64_t max_gts);
+S2A_EXPORT int s2a_assign_labels(const float* anchors, const float* gts, const int32_t* gt_counts,
+                                 int64_t batch, int64_t num_anchors, int64_t max_gts, float img_h,
+                                 float img_w, float pos_iou_thr, float neg_iou_thr,
+                                 float min_pos_iou_thr, int gt_max_assign_all,
+                                 int filter_invalid_anchors, int64_t* assign_out, void* workspace,
+                                 size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

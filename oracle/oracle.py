@@ -316,3 +316,33 @@ def select_decode(cls_preds, bbox_preds, anchors, topk=2000, wh_ratio_clip=16 / 
         out_b.append(delta2bbox_rotated(np.concatenate(al), np.concatenate(dl), wh_ratio_clip))
         out_s.append(np.concatenate(sl)); out_i.append(np.concatenate(il))
     return np.stack(out_b), np.stack(out_s), np.stack(out_i)
+
+
+def assign_labels(anchors, gt_boxes, imgs_size=(1024, 1024), pos_iou_thr=0.5, neg_iou_thr=0.4, min_pos_iou_thr=0,
+                  gt_max_assign_all=True, filter_invalid_anchors=True, ious=None):
+    """models/utils.py:33-147 restated with numpy on top of the oracle IoU (or a given IoU matrix)."""
+    anchors, gt_boxes = _f32(anchors), _f32(gt_boxes)
+    M, N = anchors.shape[0], gt_boxes.shape[0]
+    out = np.full(M, -2, np.int64)
+    flags = np.ones(M, bool)
+    if filter_invalid_anchors:                                                        # :71-77
+        flags = ((anchors[:, 0] >= 0) & (anchors[:, 1] >= 0) & (anchors[:, 0] <= imgs_size[1]) & (anchors[:, 1] <= imgs_size[0])
+                 & (anchors[:, 2] < imgs_size[1]) & (anchors[:, 3] < imgs_size[0]))
+    if N == 0:                                                                        # :79-86
+        out[flags] = -1
+        return out
+    iou = (box_iou_rotated(anchors, gt_boxes) if ious is None else np.array(ious, np.float32)).copy()
+    iou[(iou < 0) | (iou > 1)] = -0.5                                                 # :89-96
+    iou[~flags] = -0.5                                                                # :99-100
+    mx, arg = iou.max(axis=1), iou.argmax(axis=1)                                     # :115 (first index of the maximum)
+    out[(mx >= 0) & (mx < neg_iou_thr)] = -1                                          # :116
+    pos = mx >= pos_iou_thr
+    out[pos] = arg[pos]                                                               # :122-123
+    gmx, garg = iou.max(axis=0), iou.argmax(axis=0)                                   # :128
+    for i in range(N):                                                                # :130-144
+        if gmx[i] > min_pos_iou_thr:
+            if gt_max_assign_all:
+                out[iou[:, i] == gmx[i]] = i
+            else:
+                out[garg[i]] = i
+    return out
