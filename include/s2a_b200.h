@@ -242,6 +242,25 @@ S2A_EXPORT int s2a_select_decode(int nlevels, const void* const* cls, const int6
                                  void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Deformable convolution backward, sampling side -- replace deformable_im2col,
+ * deformable_col2im and deformable_col2im_coord
+ *   reference: models/dcn/src/deform_conv_cuda_kernel.cu:189-275, :278-351, :353-435 as called by
+ *              deform_conv_backward_input_cuda / deform_conv_backward_parameters_cuda
+ *              (models/dcn/src/deform_conv_cuda.cpp:262-489)
+ * fp32, NCHW contiguous.  columns / grad_columns: [B, C*kH*kW, Ho*Wo] with K index c*kH*kW + i*kW + j (the order of
+ * weight.flatten(1)).  s2a_deform_col2im_f32 ACCUMULATES into grad_input [B,C,H,W] and grad_offset
+ * [B, dgroups*2*kH*kW, Ho, Wo] (the caller zeroes them, deform_conv.py:88-89); either may be NULL.  The two dense
+ * contractions around these kernels are library GEMMs issued by the host binding (s2anet_b200/dcn.py).
+ */
+S2A_EXPORT int s2a_deform_im2col_f32(const float* x, const float* offset, float* columns, int B, int C,
+                                     int H, int W, int kH, int kW, int strideH, int strideW, int padH,
+                                     int padW, int dilH, int dilW, int dgroups, void* stream);
+S2A_EXPORT int s2a_deform_col2im_f32(const float* grad_columns, const float* x, const float* offset,
+                                     float* grad_input, float* grad_offset, int B, int C, int H, int W,
+                                     int kH, int kW, int strideH, int strideW, int padH, int padW,
+                                     int dilH, int dilW, int dgroups, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * assign_labels -- fused max-IoU label assignment, batched over images
  *   reference: models/utils.py:33-147 (assign_labels: bbox_iou_rotated + range / invalid-anchor filters + row
  *              max/argmax + negative / positive rules + the per-GT loop), utils/metrics.py:85-107

@@ -78,8 +78,9 @@ class AlignConv(nn.Module):
         return offset.reshape(anchors.size(0), -1).permute(1, 0).reshape(-1, feat_h, feat_w)
 
     def forward(self, x, anchors, stride):
-        if self.kernel_size != (3, 3) or self.deform_conv.deformable_groups != 1:
-            # generic route of the reference: explicit offsets + DeformConv
+        needs_grad = torch.is_grad_enabled() and (x.requires_grad or self.deform_conv.weight.requires_grad)
+        if self.kernel_size != (3, 3) or self.deform_conv.deformable_groups != 1 or needs_grad:
+            # generic route of the reference: explicit offsets + DeformConv (the autograd Function: training)
             num_imgs, H, W = anchors.shape[:3]
             offset = torch.stack([self.get_offset(anchors[i].reshape(-1, 5), (H, W), stride) for i in range(num_imgs)])
             return self.relu(self.deform_conv(x, offset))

@@ -62,6 +62,86 @@ def deform_conv_forward_cuda(input, weight, offset, output, columns, ones, kW, k
     return 1
 
 
+def _bwd_common(input, offset, weight, kW, kH, group, deformable_group, im2col_step, what):
+    dev = _lib.require_cuda(input, offset, weight)
+    if input.dim() != 4:
+        raise RuntimeError("%s: 4D input tensor expected but got: %d" % (what, input.dim()))
+    if weight.size(2) != kH or weight.size(3) != kW:
+        raise RuntimeError("kernel size should be consistent with weight")
+    if im2col_step <= 0 or input.size(0) % im2col_step != 0:
+        raise RuntimeError("im2col step must divide batchsize")
+    if weight.size(1) * group != input.size(1):
+        raise RuntimeError("invalid number of input planes, expected: %d, but got: %d" % (weight.size(1) * group, input.size(1)))
+    if offset.size(1) != deformable_group * 2 * kH * kW or offset.size(0) != input.size(0):
+        raise RuntimeError("invalid shape of offset")
+    return dev
+
+
+def deform_conv_backward_input_cuda(input, offset, gradOutput, gradInput, gradOffset, weight, columns, kW, kH, dW, dH,
+                                    padW, padH, dilationW, dilationH, group, deformable_group, im2col_step):
+    """reference: deform_conv_cuda.cpp:262-373.  ACCUMULATES the input and offset gradients into the caller's
+    pre-zeroed `gradInput` / `gradOffset` (deform_conv.py:88-89); `columns` is the reference's scratch handle and is
+    ignored.  The column gradient W^T x gradOutput is a library GEMM (as `addmm_` is in the reference, :331-337);
+    the bilinear scatter and the coordinate gradient run in one pass of s2a_deform_col2im_f32.  Returns 1."""
+    dev = _bwd_common(input, offset, weight, kW, kH, group, deformable_group, im2col_step, "deform_conv_backward_input_cuda")
+    _lib.require_cuda(gradOutput, gradInput, gradOffset)
+    B, C, H, W = input.shape
+    Co = weight.size(0)
+    x = input.detach().float().contiguous()
+    off = offset.detach().float().contiguous()
+    go = gradOutput.detach().float().contiguous()
+    Ho, Wo = go.shape[2:]
+    kk = kH * kW
+    wg = weight.detach().float().reshape(group, Co // group, (C // group) * kk)
+    gi = gradInput if (gradInput.dtype == torch.float32 and gradInput.is_contiguous()) else gradInput.float().contiguous()
+    gf = gradOffset if (gradOffset.dtype == torch.float32 and gradOffset.is_contiguous()) else gradOffset.float().contiguous()
+    lib = _lib.load()
+    for b0 in range(0, B, im2col_step):                   # the reference's im2col_step chunking bounds the scratch
+        b1 = b0 + im2col_step
+        gcol = torch.matmul(wg.transpose(1, 2)[None], go[b0:b1].reshape(b1 - b0, group, Co // group, Ho * Wo))
+        gcol = gcol.reshape(b1 - b0, C * kk, Ho * Wo).contiguous()
+        with torch.cuda.device(dev):
+            rc = lib.s2a_deform_col2im_f32(_lib.ptr(gcol), _lib.ptr(x[b0:b1]), _lib.ptr(off[b0:b1]), _lib.ptr(gi[b0:b1]),
+                                           _lib.ptr(gf[b0:b1]), b1 - b0, C, H, W, kH, kW, dH, dW, padH, padW, dilationH,
+                                           dilationW, deformable_group, _lib.stream_ptr(dev))
+        _lib.check(rc, "deform_col2im")
+    if gi is not gradInput:
+        gradInput.copy_(gi)
+    if gf is not gradOffset:
+        gradOffset.copy_(gf)
+    return 1
+
+
+def deform_conv_backward_parameters_cuda(input, offset, gradOutput, gradWeight, columns, ones, kW, kH, dW, dH, padW, padH,
+                                         dilationW, dilationH, group, deformable_group, scale, im2col_step):
+    """reference: deform_conv_cuda.cpp:376-489.  gradWeight += scale * gradOutput x columns^T with the columns of
+    s2a_deform_im2col_f32 and a library GEMM (the reference's `addmm_`, :459-467).  Returns 1."""
+    dev = _bwd_common(input, offset, weight=gradWeight, kW=kW, kH=kH, group=group, deformable_group=deformable_group,
+                      im2col_step=im2col_step, what="deform_conv_backward_parameters_cuda")
+    _lib.require_cuda(gradOutput)
+    B, C, H, W = input.shape
+    Co = gradWeight.size(0)
+    x = input.detach().float().contiguous()
+    off = offset.detach().float().contiguous()
+    go = gradOutput.detach().float().contiguous()
+    Ho, Wo = go.shape[2:]
+    kk = kH * kW
+    acc = torch.zeros((group, Co // group, (C // group) * kk), dtype=torch.float32, device=dev)
+    lib = _lib.load()
+    for b0 in range(0, B, im2col_step):
+        b1 = b0 + im2col_step
+        col = torch.empty((b1 - b0, C * kk, Ho * Wo), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            rc = lib.s2a_deform_im2col_f32(_lib.ptr(x[b0:b1]), _lib.ptr(off[b0:b1]), _lib.ptr(col), b1 - b0, C, H, W, kH, kW,
+                                           dH, dW, padH, padW, dilationH, dilationW, deformable_group, _lib.stream_ptr(dev))
+        _lib.check(rc, "deform_im2col")
+        g4 = go[b0:b1].reshape(b1 - b0, group, Co // group, Ho * Wo)
+        c4 = col.reshape(b1 - b0, group, (C // group) * kk, Ho * Wo)
+        acc += torch.matmul(g4, c4.transpose(2, 3)).sum(0)
+    gradWeight.add_(acc.reshape(gradWeight.shape).to(gradWeight.dtype), alpha=float(scale))
+    return 1
+
+
 class DeformConvFunction(Function):
     """reference: models/dcn/deform_conv.py:13-109."""
 
@@ -93,8 +173,27 @@ class DeformConvFunction(Function):
     @staticmethod
     @once_differentiable
     def backward(ctx, grad_output):
-        # SURVEY.md section 8f item 1 ("next"): dgrad / wgrad / offset-grad kernels are not built yet.
-        raise NotImplementedError("s2anet_b200: DeformConv backward is not implemented yet (forward/inference path only)")
+        """reference: models/dcn/deform_conv.py:72-109."""
+        input, offset, weight = ctx.saved_tensors
+        grad_input = grad_offset = grad_weight = None
+        if not grad_output.is_cuda:
+            raise NotImplementedError
+        cur_im2col_step = min(ctx.im2col_step, input.shape[0])
+        assert (input.shape[0] % cur_im2col_step) == 0, 'im2col step must divide batchsize'
+        if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
+            grad_input = torch.zeros_like(input)
+            grad_offset = torch.zeros_like(offset)
+            deform_conv_backward_input_cuda(input, offset, grad_output, grad_input, grad_offset, weight, ctx.bufs_[0],
+                                            weight.size(3), weight.size(2), ctx.stride[1], ctx.stride[0], ctx.padding[1],
+                                            ctx.padding[0], ctx.dilation[1], ctx.dilation[0], ctx.groups,
+                                            ctx.deformable_groups, cur_im2col_step)
+        if ctx.needs_input_grad[2]:
+            grad_weight = torch.zeros_like(weight)
+            deform_conv_backward_parameters_cuda(input, offset, grad_output, grad_weight, ctx.bufs_[0], ctx.bufs_[1],
+                                                 weight.size(3), weight.size(2), ctx.stride[1], ctx.stride[0],
+                                                 ctx.padding[1], ctx.padding[0], ctx.dilation[1], ctx.dilation[0],
+                                                 ctx.groups, ctx.deformable_groups, 1, cur_im2col_step)
+        return (grad_input, grad_offset, grad_weight, None, None, None, None, None, None)
 
     @staticmethod
     def _output_size(input, weight, padding, dilation, stride):

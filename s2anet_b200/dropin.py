@@ -44,8 +44,8 @@ def install(matplotlib_stub=True):
 
     _module("models.dcn.deform_conv_cuda",
             deform_conv_forward_cuda=dcn.deform_conv_forward_cuda,
-            deform_conv_backward_input_cuda=_not_built("deform_conv_backward_input_cuda"),
-            deform_conv_backward_parameters_cuda=_not_built("deform_conv_backward_parameters_cuda"),
+            deform_conv_backward_input_cuda=dcn.deform_conv_backward_input_cuda,
+            deform_conv_backward_parameters_cuda=dcn.deform_conv_backward_parameters_cuda,
             modulated_deform_conv_cuda_forward=_not_built("modulated_deform_conv_cuda_forward"),
             modulated_deform_conv_cuda_backward=_not_built("modulated_deform_conv_cuda_backward"))
     _module("models.dcn.deform_pool_cuda",

@@ -50,7 +50,7 @@ def test_reference_python_imports_on_the_shims(ref_on_path):
     with pytest.raises(NotImplementedError):
         multiclass_nms_rotated(torch.rand(4, 5), torch.rand(4, 15))
     with pytest.raises(NotImplementedError):
-        ext.deform_conv_backward_input_cuda()
+        ext.modulated_deform_conv_cuda_forward()
     # the reference's empty-input short cut never reaches the extension
     assert nms_rotated(torch.zeros(0, 6), 0.5).shape == (0, 6)
 

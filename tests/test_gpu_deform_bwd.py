@@ -1,0 +1,120 @@
+"""Deformable-convolution backward: DeformConvFunction.backward and the extension-level
+deform_conv_backward_input_cuda / deform_conv_backward_parameters_cuda.
+
+Witnesses: torchvision.ops.deform_conv2d's autograd (same operator, fp32/fp64 on the GPU and on the CPU) and, when
+prebuilt, the reference's own deform_conv_cuda extension (unmodified sources compiled for sm_100a) running the
+same three calls.  Tolerance: 1e-4 + 1e-4 * max|ref| in fp32 (summation order differs: atomics, GEMM tiling)."""
+import numpy as np
+import pytest
+import torch
+
+from s2anet_b200 import synth
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def close(a, b, what):
+    err = float((a - b).abs().max())
+    tol = 1e-4 + 1e-4 * float(b.abs().max())
+    assert err <= tol, "%s: max-abs err %g > %g" % (what, err, tol)
+
+
+CASES = [
+    # B, C, H, W, Co, k, stride, pad, dil, groups, dgroups
+    (2, 16, 12, 10, 24, 3, 1, 1, 1, 1, 1),
+    (3, 16, 9, 11, 12, 3, 2, 2, 2, 1, 2),
+    (1, 16, 7, 8, 128, 3, 1, 1, 1, 2, 1),
+    (1, 4, 6, 6, 4, 1, 1, 0, 1, 1, 1),
+]
+
+
+@pytest.mark.parametrize("B,C,H,W,Co,k,stride,pad,dil,groups,dgroups", CASES)
+def test_autograd_matches_torchvision(B, C, H, W, Co, k, stride, pad, dil, groups, dgroups):
+    import torchvision
+    from s2anet_b200.dcn import deform_conv
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g = torch.Generator().manual_seed(B * 100 + C)
+    Ho = (H + 2 * pad - (dil * (k - 1) + 1)) // stride + 1
+    Wo = (W + 2 * pad - (dil * (k - 1) + 1)) // stride + 1
+    x = torch.randn(B, C, H, W, generator=g).to(DEV).requires_grad_()
+    off = (torch.randn(B, dgroups * 2 * k * k, Ho, Wo, generator=g) * 1.5).to(DEV).requires_grad_()
+    w = (torch.randn(Co, C // groups, k, k, generator=g) * 0.2).to(DEV).requires_grad_()
+    gy = torch.randn(B, Co, Ho, Wo, generator=g).to(DEV)
+    y = deform_conv(x, off, w, stride, pad, dil, groups, dgroups)
+    y.backward(gy)
+    x2, off2, w2 = (t_.detach().double().requires_grad_() for t_ in (x, off, w))
+    y2 = torchvision.ops.deform_conv2d(x2, off2, w2, stride=stride, padding=pad, dilation=dil)
+    y2.backward(gy.double())
+    close(y.detach().double(), y2.detach(), "forward")
+    close(x.grad.double(), x2.grad, "grad_input")
+    close(off.grad.double(), off2.grad, "grad_offset")
+    close(w.grad.double(), w2.grad, "grad_weight")
+
+
+def test_alignconv_training_step_p4_vs_torchvision_and_reference_cuda():
+    """AlignConv at P4 size (64x64, 256 -> 256, batch 2) with autograd: gradients of the feature map and of the
+    weight against torchvision, and the three extension-level calls against the reference's own CUDA binary."""
+    import torchvision
+    from oracle import build_oracle
+    from s2anet_b200 import dcn
+    from s2anet_b200.alignconv import AlignConv
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g = torch.Generator().manual_seed(3)
+    B, C, H = 2, 256, 64
+    x = torch.randn(B, C, H, H, generator=g).to(DEV).requires_grad_()
+    anc = torch.from_numpy(synth.refined_anchors(B, H, H, 16, seed=4)).to(DEV)
+    ac = AlignConv(C, C).to(DEV)
+    ac.init_weights()
+    y = ac(x, anc, 16)
+    assert y.requires_grad
+    gy = torch.randn(y.shape, generator=g).to(DEV)
+    y.backward(gy)
+    off = torch.stack([ac.get_offset(anc[i].reshape(-1, 5), (H, H), 16) for i in range(B)])
+    x2 = x.detach().clone().requires_grad_()
+    w2 = ac.deform_conv.weight.detach().clone().requires_grad_()
+    y2 = torch.relu(torchvision.ops.deform_conv2d(x2, off, w2, padding=1))
+    y2.backward(gy)
+    close(y.detach(), y2.detach(), "forward")
+    close(x.grad, x2.grad, "grad_input")
+    close(ac.deform_conv.weight.grad, w2.grad, "grad_weight")
+    ref = build_oracle.load_ref_extension("deform_conv_cuda", "gpu")
+    if ref is None:
+        pytest.skip("oracle/_ref/ext_gpu/deform_conv_cuda not prebuilt")
+    w = ac.deform_conv.weight.detach()
+    xd = x.detach()
+    gpre = gy * (y.detach() > 0)                       # gradient in front of the ReLU
+    outs = []
+    for ext in (ref, dcn):
+        gi, gof, gw = torch.zeros_like(xd), torch.zeros_like(off), torch.zeros_like(w)
+        ext.deform_conv_backward_input_cuda(xd, off, gpre, gi, gof, w, xd.new_empty(0), 3, 3, 1, 1, 1, 1, 1, 1, 1, 1, B)
+        ext.deform_conv_backward_parameters_cuda(xd, off, gpre, gw, xd.new_empty(0), xd.new_empty(0), 3, 3, 1, 1, 1, 1, 1, 1,
+                                                 1, 1, 1.0, B)
+        torch.cuda.synchronize()
+        outs.append((gi, gof, gw))
+    for a, b, name in zip(outs[1], outs[0], ("grad_input", "grad_offset", "grad_weight")):
+        close(a, b, name + " vs the reference CUDA extension")
+
+
+def test_extension_entries_accumulate_and_check_arguments():
+    from s2anet_b200 import dcn
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, 4, 5, 5, generator=g).to(DEV)
+    off = torch.randn(2, 18, 5, 5, generator=g).to(DEV)
+    w = torch.randn(3, 4, 3, 3, generator=g).to(DEV)
+    gy = torch.randn(2, 3, 5, 5, generator=g).to(DEV)
+    gi, gof, gw = torch.zeros_like(x), torch.zeros_like(off), torch.zeros_like(w)
+    e = x.new_empty(0)
+    assert dcn.deform_conv_backward_input_cuda(x, off, gy, gi, gof, w, e, 3, 3, 1, 1, 1, 1, 1, 1, 1, 1, 2) == 1
+    assert dcn.deform_conv_backward_parameters_cuda(x, off, gy, gw, e, e, 3, 3, 1, 1, 1, 1, 1, 1, 1, 1, 0.5, 1) == 1
+    gi2, gof2, gw2 = gi.clone(), gof.clone(), gw.clone()
+    dcn.deform_conv_backward_input_cuda(x, off, gy, gi2, gof2, w, e, 3, 3, 1, 1, 1, 1, 1, 1, 1, 1, 1)
+    dcn.deform_conv_backward_parameters_cuda(x, off, gy, gw2, e, e, 3, 3, 1, 1, 1, 1, 1, 1, 1, 1, 0.5, 2)
+    close(gi2, 2 * gi, "accumulated grad_input")          # the entries ADD to what the caller passes in
+    close(gof2, 2 * gof, "accumulated grad_offset")
+    close(gw2, 2 * gw, "accumulated grad_weight (scale 0.5 twice)")
+    with pytest.raises(RuntimeError):
+        dcn.deform_conv_backward_input_cuda(x, off, gy, gi, gof, w, e, 3, 3, 1, 1, 1, 1, 1, 1, 1, 1, 3)    # 3 does not divide 2
+    with pytest.raises(NotImplementedError):
+        dcn.deform_conv_backward_input_cuda(x.cpu(), off.cpu(), gy.cpu(), gi.cpu(), gof.cpu(), w.cpu(), e.cpu(), 3, 3, 1, 1, 1,
+                                            1, 1, 1, 1, 1, 1)
