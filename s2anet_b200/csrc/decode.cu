@@ -173,9 +173,16 @@ __global__ void __launch_bounds__(DEC_THREADS) select_decode_kernel(const __grid
       for (int i = tid; i < 256; i += DEC_THREADS) s_hist[i] = 0u;
       __syncthreads();
       const unsigned long long prefix = s_prefix;
-      for (int i = tid; i < n; i += DEC_THREADS) {
-        const unsigned long long c = composite_key(keys[i], i);
-        if (shift == 56 || (c >> (shift + 8)) == (prefix >> (shift + 8))) atomicAdd(&s_hist[(c >> shift) & 255u], 1u);
+      for (int base = 0; base < n; base += DEC_THREADS) {
+        const int i = base + tid;
+        unsigned bin = 0xFFFFFFFFu;                       // inactive lanes form their own group
+        if (i < n) {
+          const unsigned long long c = composite_key(keys[i], i);
+          if (shift == 56 || (c >> (shift + 8)) == (prefix >> (shift + 8))) bin = (unsigned)(c >> shift) & 255u;
+        }
+        // scores cluster in a handful of bins: one shared atomic per distinct bin per warp, not per key
+        const unsigned peers = __match_any_sync(0xffffffffu, bin);
+        if (bin != 0xFFFFFFFFu && (tid & 31) == __ffs(peers) - 1) atomicAdd(&s_hist[bin], (unsigned)__popc(peers));
       }
       __syncthreads();
       if (tid < 32) {
@@ -211,11 +218,16 @@ __global__ void __launch_bounds__(DEC_THREADS) select_decode_kernel(const __grid
     // ---- collect the k selected composites and sort them (descending score, ascending index) ----
     for (int i = tid; i < DEC_THREADS * ITEMS; i += DEC_THREADS) s_sel[i] = 0ull;
     __syncthreads();
-    for (int i = tid; i < n; i += DEC_THREADS) {
-      const unsigned long long c = composite_key(keys[i], i);
-      if (c >= thr) {
-        const int pos = atomicAdd(&s_count, 1);
-        if (pos < DEC_THREADS * ITEMS) s_sel[pos] = c;
+    for (int base = 0; base < n; base += DEC_THREADS) {
+      const int i = base + tid;
+      const unsigned long long c = i < n ? composite_key(keys[i], i) : 0ull;
+      const bool take = i < n && c >= thr;
+      const unsigned bal = __ballot_sync(0xffffffffu, take);
+      if (bal) {
+        int pos = 0;
+        if ((tid & 31) == 0) pos = atomicAdd(&s_count, __popc(bal));
+        pos = __shfl_sync(0xffffffffu, pos, 0) + __popc(bal & ((1u << (tid & 31)) - 1u));
+        if (take && pos < DEC_THREADS * ITEMS) s_sel[pos] = c;
       }
     }
     __syncthreads();
