@@ -71,7 +71,7 @@ class ClockSampler(threading.Thread):
                 self.rows.append([c.strip() for c in out.strip().split(",")])
             except Exception:
                 pass
-            self._halt.wait(0.2)
+            self._halt.wait(0.02)
 
     def stop(self):
         self._halt.set()
@@ -219,7 +219,7 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=8, help="images per GPU per step")

@@ -40,9 +40,9 @@ namespace s2a {
 constexpr int TC_M = 128;                 // rows per tile (8 x 16 patch) = one UMMA M
 constexpr int TC_PH = 8, TC_PW = 16;
 constexpr int TC_KB = 64;                 // k-block (elements) = 128 bytes of 16-bit data
-constexpr int TC_GROUPS = 3;               // producer groups of 4 warps; group g fills k-blocks g, g+G, ...
 constexpr int TC_OUT_CH = 32;              // channels per epilogue TMA store (64-byte rows, SWIZZLE_64B)
-constexpr int TC_OUT_BYTES = TC_M * TC_OUT_CH * 2;    // 8 KB, double-buffered
+constexpr int TC_OUT_BYTES = TC_M * TC_OUT_CH * 2;    // 8 KB
+constexpr int TC_OUT_BUFS = 3;             // staging buffers: the TMA store of chunk i-1 may still be reading when chunk i is staged
 constexpr int TC_A_BYTES = TC_M * TC_KB * 2;          // 16 KB
 
 enum { TC_ALIGN = 0, TC_PLAIN = 1 };
@@ -53,16 +53,21 @@ enum { TC_ALIGN = 0, TC_PLAIN = 1 };
 //    travel through one ring of 6 stages with one full/empty barrier pair per stage.
 //  * AlignConv (TC_ALIGN) is bound by the bilinear gather, i.e. by LSU wavefronts: 4 corners x 128 B per
 //    (row, k-block) = 512 wavefronts per k-block next to 512 tensor-pipe cycles.  Its feature-map reads go
-//    through a TMA-fed shared-memory halo (two 39 KB buffers) instead of L1, which needs the whole 227 KB:
-//    CTA pairs are used here too because a half-width weight stage (16 KB) is what makes room for 4 A
-//    stages + 3 B stages + 2 halo buffers + 2 sample tables.  A and B keep separate rings.
+//    through a TMA-fed shared-memory halo (two 39 KB buffers) instead of L1, and the blended A operand never
+//    touches shared memory: the producers write it straight into TENSOR MEMORY (tcgen05.st, 8 stages of 32
+//    columns next to ONE 256-column accumulator) and the MMA takes A from TMEM.  That removes the A-stage
+//    stores (128 + bank-conflict wavefronts per k-block) from the LSU pipe and the A reads from the
+//    tensor core's shared-memory port.  The producers are the bottleneck, so a single accumulator is enough
+//    (they keep filling the 8 A stages while the epilogue drains it).  A and B keep separate rings.
 template <int MODE> struct TcCfg;
-template <> struct TcCfg<TC_ALIGN> { static constexpr int CG = 2, SA = 4, SB = 3; static constexpr bool UNIFIED = false; };
-template <> struct TcCfg<TC_PLAIN> { static constexpr int CG = 2, SA = 6, SB = 6; static constexpr bool UNIFIED = true; };
+// GROUPS = producer groups of 4 warps (group g fills k-blocks g, g + GROUPS, ...): 16 producer warps for AlignConv
+// (its gather is latency-bound), none for the TMA-fed plain conv (256 threads, registers to spare).
+template <> struct TcCfg<TC_ALIGN> { static constexpr int CG = 2, SA = 6, SB = 6, GROUPS = 4; static constexpr bool UNIFIED = true; };
+template <> struct TcCfg<TC_PLAIN> { static constexpr int CG = 2, SA = 6, SB = 6, GROUPS = 0; static constexpr bool UNIFIED = true; };
+template <int MODE> constexpr int tc_threads() { return (TcCfg<MODE>::GROUPS * 4 + 8) * 32; }
 constexpr int TC_MAX_STAGES = 8;
-constexpr int TC_PROD_THREADS = TC_GROUPS * 128;
 constexpr int TC_EPI_THREADS = 128;                   // 4 epilogue warps, one per TMEM lane quadrant
-constexpr int TC_THREADS = TC_PROD_THREADS + 64 + TC_EPI_THREADS;   // producers | TMA warp | MMA warp | epilogue
+// warps: GROUPS x 4 producers | 4 epilogue | TMA | MMA | 2 idle (pad to a multiple of 4 warps)
 constexpr int TC_ACC_STAGES = 2;                      // double-buffered accumulator: 2 x 256 TMEM columns
 constexpr int TC_TMEM_COLS = 512;
 constexpr int TC_NBAR = 4 * TC_MAX_STAGES + 2 * TC_ACC_STAGES + 2 + 4;   // + halo full/empty x 2
@@ -184,6 +189,15 @@ __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.p
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+// one lane of a fully converged warp (the compiler keeps warp-uniform operands of the tcgen05 / TMA instructions
+// issued under it in uniform registers; issuing them from an `if (lane == 0)` region instead costs a
+// per-instruction ELECT/R2UR "waterfall" loop)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 // cluster helpers (CTA pair)
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -253,7 +267,8 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t sr
                : "memory");
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
-__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// all but the most recent store have finished READING their shared-memory source (two staging buffers)
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_THREADS) : "memory"); }
 
@@ -287,6 +302,33 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint6
         "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
         : "memory");
 }
+// D[tmem] (+)= A[TMEM, 128 lanes per CTA x 8 columns (K = 16 packed 16-bit)] * B[smem]
+template <int CG>
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  if (CG == 2)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc)
+        : "memory");
+  else
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+// registers -> TMEM, shape 16x256b.x4: 16 lanes x 32 columns.  Thread T holds, for every 8-column group g,
+// columns 8g + 2(T%4) + {0,1} of lane T/4 in r[4g], r[4g+1] and of lane T/4 + 8 in r[4g+2], r[4g+3].
+__device__ __forceinline__ void tmem_st_16x256b_x4(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.16x256b.x4.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // arrive (once the MMAs issued so far have completed) on the barrier at the same offset in every CTA of the group
 template <int CG> __device__ __forceinline__ void umma_commit(uint32_t bar) {
   if (CG == 2)
@@ -430,31 +472,32 @@ __device__ __forceinline__ void build_tap_table(const TcParams& p, const TileCoo
 // number of tiles is not a multiple of CG the last group's spare CTA runs a "ghost" copy of the last tile
 // and stores nothing.
 template <int MODE, typename T>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(tc_threads<MODE>(), 1)
 conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcParams p) {
   using Cfg = TcCfg<MODE>;
   constexpr int CG = Cfg::CG, SA = Cfg::SA, SB = Cfg::SB;
   constexpr bool UNI = Cfg::UNIFIED;                   // B shares A's stage index and barriers
   static_assert(!UNI || SA == SB, "a unified ring needs equally many A and B stages");
-  static_assert(TC_GROUPS < SA && SA <= TC_MAX_STAGES && SB <= TC_MAX_STAGES, "stage rings");
+  constexpr int GROUPS = Cfg::GROUPS;
+  static_assert(GROUPS < SA && SA <= TC_MAX_STAGES && SB <= TC_MAX_STAGES, "stage rings");
+  static_assert(MODE != TC_ALIGN || 256 + SA * 32 <= TC_TMEM_COLS, "AlignConv: accumulator + A stages must fit tensor memory");
   constexpr int B_STAGE_BYTES = (256 / CG) * TC_KB * 2;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B operands need 1024-byte aligned tiles: align the dynamic window by hand (the offset is
   // the same in both CTAs of a pair, which the paired MMA and the multicast commits rely on)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  // carve: A stages | B stages | PLAIN: 2 output staging buffers / ALIGN: 2 halo buffers, 2 sample tables | barriers
-  // | tmem pointer.  In ALIGN mode the epilogue of a tile stages its output (one 8 KB buffer) in that tile's own
-  // sample table, which is dead by then (every A k-block of the tile has been produced) and is rebuilt for
-  // tile + 2 right after the stores.
-  uint8_t* sA = smem;
-  uint8_t* sB = sA + SA * TC_A_BYTES;
-  uint8_t* s_out_plain = sB + SB * B_STAGE_BYTES;
-  uint8_t* s_halo = s_out_plain;                                         // ALIGN only
+  // carve: A stages (PLAIN) | B stages | 2 output staging buffers | ALIGN: 2 halo buffers, 2 sample tables | barriers
+  // | tmem pointer
+  constexpr int ACC = MODE == TC_ALIGN ? 1 : 2;        // accumulators: PLAIN 2 x 256 TMEM columns; ALIGN 1 (+ 8 A stages x 32 columns)
+  constexpr uint32_t A_TMEM_COL0 = 256;                // ALIGN: first TMEM column of the A stages
+  uint8_t* sA = smem;                                  // PLAIN only (ALIGN keeps A in tensor memory)
+  uint8_t* sB = sA + (MODE == TC_ALIGN ? 0 : SA * TC_A_BYTES);
+  uint8_t* s_out = sB + SB * B_STAGE_BYTES;                              // 2 x 8 KB, 1024-byte aligned (SWIZZLE_64B)
+  uint8_t* s_halo = s_out + TC_OUT_BUFS * TC_OUT_BYTES;                            // ALIGN only
   TapSample* s_tab = reinterpret_cast<TapSample*>(s_halo + 2 * TC_HALO_BYTES);
-  static_assert(sizeof(TapSample) * TC_M * 9 >= TC_OUT_BYTES && (sizeof(TapSample) * TC_M * 9) % 512 == 0 &&
-                    (2 * TC_HALO_BYTES) % 512 == 0 && TC_HALO_BYTES % 128 == 0, "staging aliases a table; 512-byte aligned for SWIZZLE_64B");
+  static_assert(TC_HALO_BYTES % 128 == 0 && (TC_OUT_BUFS * TC_OUT_BYTES) % 1024 == 0, "TMA source / destination alignment");
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(
-      s_out_plain + (MODE == TC_ALIGN ? 2 * TC_HALO_BYTES + 2 * sizeof(TapSample) * TC_M * 9 : (size_t)2 * TC_OUT_BYTES));
+      s_out + TC_OUT_BUFS * TC_OUT_BYTES + (MODE == TC_ALIGN ? 2 * TC_HALO_BYTES + 2 * sizeof(TapSample) * TC_M * 9 : (size_t)0));
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + TC_NBAR);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -463,7 +506,9 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                  bar_acc_full = bar_empty_b + 8 * TC_MAX_STAGES, bar_acc_empty = bar_acc_full + 8 * TC_ACC_STAGES,
                  bar_tab_full = bar_acc_empty + 8 * TC_ACC_STAGES,       // 2 barriers
                  bar_halo_full = bar_tab_full + 16, bar_halo_empty = bar_halo_full + 16;   // 2 + 2 barriers
-  constexpr int kTmaWarp = TC_PROD_THREADS / 32, kMmaWarp = kTmaWarp + 1, kEpiWarp0 = kTmaWarp + 2;
+  // warps 0-15 producers | 16-19 epilogue (one warpgroup) | 20 TMA, 21 MMA, 22-23 idle (one warpgroup)
+  constexpr int kProdWarps = GROUPS * 4, kEpiWarp0 = kProdWarps, kTmaWarp = kEpiWarp0 + TC_EPI_THREADS / 32,
+                kMmaWarp = kTmaWarp + 1;
 
   const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;     // 0 = leader (issues the MMAs, owns the "full" barriers)
   const bool leader = cta_rank == 0;
@@ -488,7 +533,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     for (int s = 0; s < SA; ++s) {
       // full_a: ALIGN -- one elected arrive per producer warp of the owning group, from every CTA of the group;
       //         PLAIN -- the leader TMA thread's expect_tx arrive (+ the TMA bytes of A and B from every CTA)
-      mbar_init(bar_full_a + 8 * s, MODE == TC_ALIGN ? 4 * CG : 1);
+      mbar_init(bar_full_a + 8 * s, MODE == TC_ALIGN ? 1 + 4 * CG : 1);
       mbar_init(bar_empty_a + 8 * s, 1);        // one (multicast) tcgen05.commit
     }
     for (int s = 0; s < SB && !UNI; ++s) {
@@ -500,7 +545,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       mbar_init(bar_acc_empty + 8 * s, CG * TC_EPI_THREADS);
       mbar_init(bar_tab_full + 8 * s, TC_EPI_THREADS);
       mbar_init(bar_halo_full + 8 * s, 1);                   // the TMA thread's expect_tx arrive (+ bytes)
-      mbar_init(bar_halo_empty + 8 * s, TC_PROD_THREADS / 32);   // one elected arrive per producer warp
+      mbar_init(bar_halo_empty + 8 * s, kProdWarps > 0 ? kProdWarps : 1);   // one elected arrive per producer warp
     }
     fence_barrier_init();
   }
@@ -517,21 +562,27 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t0));
   }
 
-  if (warp < kTmaWarp) {
+  if (GROUPS > 0 && warp < kProdWarps) {
     // ===================== A producers (AlignConv: bilinear gather through the LSU) =====================
     // In TC_PLAIN mode (ORConv2d) the A tile is a shifted patch of the NHWC map, which TMA fetches
     // directly (zero-filled outside the map), so these warps have nothing to do.
     const int group = warp >> 2;               // producer group: owns global k-blocks group, group + G, ...
-    const int gt = tid & 127;                  // thread index inside the group
-    const int chunk = gt & 7;                  // 16-byte chunk (8 channels) inside the 128-byte row
-    const int rsub = gt >> 3;                  // 0..15
+    // Thread mapping = the tcgen05.st 16x256b fragment: warp w of a group owns TMEM lanes (tile rows)
+    // 32*(w%4) .. +31; thread T handles rows T/4 + 8k (k = 0..3) and, of each row's 128-byte k-block line, the
+    // 16-byte chunks q = T%4 and q + 4.  In TMEM column order those 32 bytes sit at 32g + 8q (+8) for g = 0..3;
+    // the weight packer applies the same channel permutation inside every 64-channel block (tc_kperm).
+    const int wq = warp & 3;
+    const int q4 = lane & 3, r8 = lane >> 2;
+    // even rows read chunk q first, odd rows chunk q + 4: one LDS.128 of a warp then spreads over all 32 banks
+    const int c_first = (r8 & 1) ? q4 + 4 : q4, c_second = (r8 & 1) ? q4 : q4 + 4;
     // Group g produces the global k-blocks g, g + G, g + 2G, ... (the sequence runs on across tiles).  Stage
     // index and phase bit advance incrementally: no 64-bit div/mod on these latency-critical paths.
     int kb = group;                            // k-block inside the current tile
     int s = group % SA;                        // A stage of that k-block
     uint32_t ph = (uint32_t)(group / SA) & 1u;
     uint32_t hseq = 0;                         // running (tile, channel block) counter: halo buffer = hseq & 1
-    const uint32_t halo_u32 = smem_u32(s_halo) + (uint32_t)chunk * 16u;
+    const uint32_t halo_u32 = smem_u32(s_halo);
+    constexpr int GSTEP = GROUPS > 0 ? GROUPS : 1;      // (GROUPS == 0: this branch is dead code)
     int it = 0;
     for (int q = first_q; MODE == TC_ALIGN && q < ngroups; q += q_step, ++it) {
       const int tile = S2A_TILE_OF(q);
@@ -543,72 +594,67 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       const TapSample* tab = s_tab + (it & 1) * (TC_M * 9);
       mbar_wait(bar_tab_full + 8 * (it & 1), (uint32_t)(it >> 1) & 1u);
       int cb = kb / 9, tap = kb - 9 * cb;
-      for (; kb < nkb; kb += TC_GROUPS, tap += TC_GROUPS, s += TC_GROUPS) {
+      for (; kb < nkb; kb += GSTEP, tap += GSTEP, s += GSTEP) {
         if (tap >= 9) { tap -= 9; ++cb; }
         if (s >= SA) { s -= SA; ph ^= 1u; }
         const uint32_t hcur = hseq + (uint32_t)cb;                  // this k-block's (tile, channel block)
         mbar_wait(bar_halo_full + 8 * (hcur & 1u), (hcur >> 1) & 1u);
         mbar_wait(bar_empty_a + 8 * s, ph ^ 1u);
-        uint8_t* a_stage = sA + s * TC_A_BYTES;
+        tc_fence_after();
         if (!(p.debug & 2)) {
-          // 128-byte row r = j*16 + rsub of the stage; chunk position swizzled by (r & 7) == (rsub & 7)
-          uint8_t* a_dst = a_stage + rsub * 128 + ((chunk ^ (rsub & 7)) << 4);
-          const uint8_t* src = xb + ((size_t)cb * TC_KB + chunk * 8) * 2;   // this thread's 16 bytes inside a pixel
+          const uint8_t* src = xb + (size_t)cb * TC_KB * 2;                    // channel block inside a pixel (global fallback)
           const uint32_t hsrc = halo_u32 + (hcur & 1u) * TC_HALO_BYTES;
-          const TapSample* trow = tab + rsub * 9 + tap;
+          const TapSample* trow = tab + (wq * 32 + r8) * 9 + tap;
 #pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            uint4 v[4][4];
-            TapSample sm[4];
+          for (int half = 0; half < 2; ++half) {                               // TMEM lanes 32*wq + 16*half .. +15
+            uint32_t frag[16];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) sm[i] = trow[(half * 4 + i) * 16 * 9];       // the four recipes first ...
-            const bool fast = (sm[0].base & sm[1].base & sm[2].base & sm[3].base & TC_IN_HALO) != 0u;
-            if (__all_sync(0xffffffffu, fast)) {
-              // ... so that the common case -- every corner of the warp's 16 samples inside the halo -- is one
-              // straight-line batch of 16 LDS.128 with no dependent branch in between
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const uint32_t q0 = hsrc + ((sm[i].base & ~TC_IN_HALO) >> 2) * (TC_KB * 2);
-                const uint32_t dx = (sm[i].base & 1u) ? (uint32_t)(TC_KB * 2) : 0u;
-                const uint32_t dy = (sm[i].base & 2u) ? (uint32_t)(TC_HW * TC_KB * 2) : 0u;
-                v[i][0] = lds_v4(q0);
-                v[i][1] = lds_v4(q0 + dx);
-                v[i][2] = lds_v4(q0 + dy);
-                v[i][3] = lds_v4(q0 + dy + dx);
+            for (int i = 0; i < 2; ++i) {                                      // rows r8 and r8 + 8 of this half
+              const TapSample sm = trow[(half * 16 + i * 8) * 9];
+              uint4 va[4], vb[4];                                              // [corner]: first / second chunk
+              const uint32_t pix = (sm.base & ~TC_IN_HALO) >> 2;
+              const uint32_t o1 = (uint32_t)c_first * 16u, o2 = (uint32_t)c_second * 16u;
+              if (__all_sync(0xffffffffu, (sm.base & TC_IN_HALO) != 0u)) {     // warp-uniform: no dependent divergence
+                const uint32_t q0 = hsrc + pix * (TC_KB * 2);
+                const uint32_t dx = (sm.base & 1u) ? (uint32_t)(TC_KB * 2) : 0u;
+                const uint32_t dy = (sm.base & 2u) ? (uint32_t)(TC_HW * TC_KB * 2) : 0u;
+                va[0] = lds_v4(q0 + o1); va[1] = lds_v4(q0 + dx + o1);
+                va[2] = lds_v4(q0 + dy + o1); va[3] = lds_v4(q0 + dy + dx + o1);
+                vb[0] = lds_v4(q0 + o2); vb[1] = lds_v4(q0 + dx + o2);
+                vb[2] = lds_v4(q0 + dy + o2); vb[3] = lds_v4(q0 + dy + dx + o2);
+              } else if (sm.base & TC_IN_HALO) {
+                const uint32_t q0 = hsrc + pix * (TC_KB * 2);
+                const uint32_t dx = (sm.base & 1u) ? (uint32_t)(TC_KB * 2) : 0u;
+                const uint32_t dy = (sm.base & 2u) ? (uint32_t)(TC_HW * TC_KB * 2) : 0u;
+                va[0] = lds_v4(q0 + o1); va[1] = lds_v4(q0 + dx + o1);
+                va[2] = lds_v4(q0 + dy + o1); va[3] = lds_v4(q0 + dy + dx + o1);
+                vb[0] = lds_v4(q0 + o2); vb[1] = lds_v4(q0 + dx + o2);
+                vb[2] = lds_v4(q0 + dy + o2); vb[3] = lds_v4(q0 + dy + dx + o2);
+              } else {                               // a corner outside the halo window: straight from global memory
+                const uint8_t* q0 = src + (size_t)pix * pix_stride;
+                const uint32_t dx = (sm.base & 1u) ? pix_stride : 0u, dy = (sm.base & 2u) ? row_stride : 0u;
+                va[0] = ldg_nc_v4(q0 + o1); va[1] = ldg_nc_v4(q0 + dx + o1);
+                va[2] = ldg_nc_v4(q0 + dy + o1); va[3] = ldg_nc_v4(q0 + dy + dx + o1);
+                vb[0] = ldg_nc_v4(q0 + o2); vb[1] = ldg_nc_v4(q0 + dx + o2);
+                vb[2] = ldg_nc_v4(q0 + dy + o2); vb[3] = ldg_nc_v4(q0 + dy + dx + o2);
               }
-            } else {
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const uint32_t pix = (sm[i].base & ~TC_IN_HALO) >> 2;
-                if (sm[i].base & TC_IN_HALO) {
-                  const uint32_t q0 = hsrc + pix * (TC_KB * 2);
-                  const uint32_t dx = (sm[i].base & 1u) ? (uint32_t)(TC_KB * 2) : 0u;
-                  const uint32_t dy = (sm[i].base & 2u) ? (uint32_t)(TC_HW * TC_KB * 2) : 0u;
-                  v[i][0] = lds_v4(q0);
-                  v[i][1] = lds_v4(q0 + dx);
-                  v[i][2] = lds_v4(q0 + dy);
-                  v[i][3] = lds_v4(q0 + dy + dx);
-                } else {                               // a corner outside the halo window: straight from global memory
-                  const uint8_t* q0 = src + (size_t)pix * pix_stride;
-                  const uint32_t dx = (sm[i].base & 1u) ? pix_stride : 0u, dy = (sm[i].base & 2u) ? row_stride : 0u;
-                  v[i][0] = ldg_nc_v4(q0);
-                  v[i][1] = ldg_nc_v4(q0 + dx);
-                  v[i][2] = ldg_nc_v4(q0 + dy);
-                  v[i][3] = ldg_nc_v4(q0 + dy + dx);
-                }
-              }
+              const uint4 b1 = blend4<T>(va[0], va[1], va[2], va[3], sm.w01, sm.w23);
+              const uint4 b2 = blend4<T>(vb[0], vb[1], vb[2], vb[3], sm.w01, sm.w23);
+              const uint4 lo = (r8 & 1) ? b2 : b1, hi = (r8 & 1) ? b1 : b2;     // chunk q / chunk q + 4
+              frag[0 + 2 * i] = lo.x; frag[1 + 2 * i] = lo.y;                   // column group 0
+              frag[4 + 2 * i] = lo.z; frag[5 + 2 * i] = lo.w;                   // group 1
+              frag[8 + 2 * i] = hi.x; frag[9 + 2 * i] = hi.y;                   // group 2
+              frag[12 + 2 * i] = hi.z; frag[13 + 2 * i] = hi.w;                 // group 3
             }
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-              *reinterpret_cast<uint4*>(a_dst + (half * 4 + i) * 2048) =
-                  blend4<T>(v[i][0], v[i][1], v[i][2], v[i][3], sm[i].w01, sm[i].w23);
+            tmem_st_16x256b_x4(tmem_base + ((uint32_t)(wq * 32 + half * 16) << 16) + A_TMEM_COL0 + (uint32_t)s * 32u, frag);
           }
+          tmem_st_wait();
         }
-        fence_proxy_async_smem();          // generic-proxy stores -> visible to the tensor core (async proxy)
+        tc_fence_before();                 // tensor-memory stores ordered before the arrive the MMA thread waits on
         __syncwarp();
         if (lane == 0) {
           mbar_arrive_cluster(ld_full_a + 8 * s);                  // on the leader CTA's barrier
-          if (tap >= 9 - TC_GROUPS) mbar_arrive(bar_halo_empty + 8 * (hcur & 1u));   // this warp's last tap of the channel block
+          if (tap >= 9 - GSTEP) mbar_arrive(bar_halo_empty + 8 * (hcur & 1u));   // this warp's last tap of the channel block
         }
       }
       kb -= nkb;                           // first k-block of this group in the next tile
@@ -637,16 +683,24 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         int cb = 0, tap = 0;
         for (int kb = 0; kb < nkb; ++kb) {
           if (UNI) {
-            // one ring: A tile (TC_PLAIN: the 8 x 16 patch shifted by the tap, 64 channels = one 4-D box
-            // {64, 16, 8, 1}, zero-filled outside the map) and the weight k-block complete the same barrier
+            // one ring: the weight k-block and the A operand of a k-block complete the same "full" barrier -- for
+            // TC_PLAIN the A tile is the 8 x 16 patch shifted by the tap (64 channels = one 4-D box {64, 16, 8, 1},
+            // zero-filled outside the map), for TC_ALIGN the producer warps arrive on it after their tcgen05.st
+            if (MODE == TC_ALIGN && tap == 3) {
+              // halo of the NEXT (tile, channel block), requested six k-blocks before its first use
+              if (cb + 1 < ncb) load_halo(tc, cb + 1);
+              else if (q + q_step < ngroups) load_halo(decode_tile(p, S2A_TILE_OF(q + q_step)), 0);
+            }
             mbar_wait(bar_empty_a + 8 * sa, pa ^ 1u);
             if ((p.debug & 1) && warm) {
               if (leader) mbar_arrive(bar_full_a + 8 * sa);
             } else {
-              if (leader) mbar_arrive_expect_tx(bar_full_a + 8 * sa, b_bytes_group + CG * TC_A_BYTES);
-              const int ti = tap / p.ks, half = p.ks >> 1;
-              tma_load_4d<CG>(smem_u32(sA + sa * TC_A_BYTES), &maps.x[tc.lvl], cb * TC_KB, tc.tx0 - half + (tap - p.ks * ti),
-                              tc.ty0 - half + ti, tc.b, ld_full_a + 8 * sa);
+              if (leader) mbar_arrive_expect_tx(bar_full_a + 8 * sa, b_bytes_group + (MODE == TC_PLAIN ? CG * TC_A_BYTES : 0));
+              if (MODE == TC_PLAIN) {
+                const int ti = tap / p.ks, half = p.ks >> 1;
+                tma_load_4d<CG>(smem_u32(sA + sa * TC_A_BYTES), &maps.x[tc.lvl], cb * TC_KB, tc.tx0 - half + (tap - p.ks * ti),
+                                tc.ty0 - half + ti, tc.b, ld_full_a + 8 * sa);
+              }
               tma_load_2d<CG>(smem_u32(sB + sa * B_STAGE_BYTES), &maps.w, kb * TC_KB, (int)cta_rank * co_part, ld_full_a + 8 * sa);
             }
             if (++sa == SA) { sa = 0; pa ^= 1u; }
@@ -672,7 +726,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     }
   } else if (warp == kMmaWarp) {
     // ===================== MMA issuer (leader CTA only) =====================
-    if (lane == 0 && leader) {
+    if (leader) {                                    // the whole warp runs the loop; one elected lane issues
       // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 (1<<4), A/B format (bf16=1, f16=0)
       // at bits 7 / 10, K-major A and B, N>>3 at bit 17, M>>4 at bit 24 (M = 128 per CTA of the group)
       const uint32_t fmt = std::is_same<T, __nv_bfloat16>::value ? 1u : 0u;
@@ -683,79 +737,98 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       // the wait for the NEXT stage (and, at a tile boundary, for the next accumulator) sits between the
       // second and the third MMA of the current k-block.  tools/umma_bench2.cu: 634 -> 528 cycles per
       // k-block (ideal 512) for exactly this change.
-      int sa = 0, sb = 0, it = 0;
-      uint32_t pa = 0, pb = 0;
+      static_assert(UNI, "the MMA thread handles one barrier pair per stage");
+      // Everything this thread touches per k-block advances incrementally (stage barrier addresses, operand
+      // descriptors, TMEM column of the A stage): the instructions between two MMAs are on the critical path.
+      const uint64_t adesc0 = MODE == TC_ALIGN ? 0ull : umma_desc_sw128(smem_u32(sA));
+      const uint64_t bdesc0 = umma_desc_sw128(smem_u32(sB));
+      const uint32_t atm0 = tmem_base + A_TMEM_COL0;
+      uint64_t adesc = adesc0, bdesc = bdesc0;
+      uint32_t atm = atm0, full_bar = bar_full_a, empty_bar = bar_empty_a;
+      int sa = 0, it = 0;
+      uint32_t pa = 0;
       long long tl[10];
+      long long tw_acc = 0, tw_a = 0; int n_block = 0;
       mbar_wait(bar_acc_empty, 1u);
       mbar_wait(bar_full_a, 0u);
-      if (!UNI) mbar_wait(bar_full_b, 0u);
       tc_fence_after();
       for (int q = first_q; q < ngroups; q += q_step, ++it) {
-        const int as = it & 1;
+        const int as = it % ACC;
         if ((p.debug & 8) && it < 9) tl[it] = clock64();
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * 256);
         const bool last_tile = q + q_step >= ngroups;
+        // the accumulator tile group it + 1 will use, and the phase of its "drained" barrier
+        const uint32_t acc_bar = bar_acc_empty + 8 * ((it + 1) % ACC), acc_par = ((uint32_t)((it + 1) / ACC) & 1u) ^ 1u;
+        const uint32_t acc_full_bar = bar_acc_full + 8 * as;
         for (int kb = 0; kb < nkb; ++kb) {
-          const uint64_t adesc = umma_desc_sw128(smem_u32(sA + sa * TC_A_BYTES));
-          const uint64_t bdesc = umma_desc_sw128(smem_u32(sB + (UNI ? sa : sb) * B_STAGE_BYTES));
-          // +32 bytes (>>4 = 2) per K=16 step inside the swizzle atom
-          umma_f16<CG>(d_tmem, adesc, bdesc, idesc, kb != 0 ? 1u : 0u);
-          umma_f16<CG>(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
-          int nsa = sa + 1, nsb = sb + 1;
-          uint32_t npa = pa, npb = pb;
-          if (nsa == SA) { nsa = 0; npa ^= 1u; }
-          if (nsb == SB) { nsb = 0; npb ^= 1u; }
+          // +32 bytes (>>4 = 2) per K=16 step inside the swizzle atom; A in TMEM: +8 columns per K=16 step
+          const bool issuer = elect_one();
+          if (issuer) {
+            if (MODE == TC_ALIGN) {
+              umma_f16_ts<CG>(d_tmem, atm, bdesc, idesc, kb != 0 ? 1u : 0u);
+              umma_f16_ts<CG>(d_tmem, atm + 8u, bdesc + 2, idesc, 1u);
+            } else {
+              umma_f16<CG>(d_tmem, adesc, bdesc, idesc, kb != 0 ? 1u : 0u);
+              umma_f16<CG>(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
+            }
+          }
+          __syncwarp();
+          // next stage
+          uint32_t nfull = full_bar + 8, npa = pa;
+          const bool wrap = sa + 1 == SA;
+          if (wrap) { nfull = bar_full_a; npa ^= 1u; }
+          const bool new_acc = kb + 1 == nkb;
+          const bool more = !new_acc || !last_tile;
+          bool ready = false;
           if (MODE == TC_PLAIN) {
             // tensor-bound: the next stage is (nearly) always there; wait for it in the shadow of the two MMAs
             // just queued (and, at a tile boundary, for the next accumulator to be drained)
-            if (kb + 1 < nkb) {
-              mbar_wait(bar_full_a + 8 * nsa, npa);
-              if (!UNI) mbar_wait(bar_full_b + 8 * nsb, npb);
-              tc_fence_after();
-            } else if (!last_tile) {
-              mbar_wait(bar_acc_empty + 8 * (as ^ 1), ((uint32_t)((it + 1) >> 1) & 1u) ^ 1u);
-              mbar_wait(bar_full_a + 8 * nsa, npa);
-              if (!UNI) mbar_wait(bar_full_b + 8 * nsb, npb);
-              tc_fence_after();
-            }
-            umma_f16<CG>(d_tmem, adesc + 4, bdesc + 4, idesc, 1u);
-            umma_f16<CG>(d_tmem, adesc + 6, bdesc + 6, idesc, 1u);
-            umma_commit<CG>(bar_empty_a + 8 * sa);  // stage (of every CTA of the group) reusable once these MMAs have read it
-            if (!UNI) umma_commit<CG>(bar_empty_b + 8 * sb);
-            if (kb + 1 == nkb) umma_commit<CG>(bar_acc_full + 8 * as);   // accumulators of this tile group complete
-          } else {
-            // producer-bound (AlignConv): the next stage is usually NOT ready yet.  Probe without blocking; if
-            // it is not there, release this k-block's stage FIRST -- blocking here with two MMAs unissued would
-            // hold the stage until the next one is full and cost the producers one stage of their ring.
-            const bool more = kb + 1 < nkb || !last_tile;
-            const bool new_acc = kb + 1 == nkb;
-            const uint32_t acc_bar = bar_acc_empty + 8 * (as ^ 1), acc_par = ((uint32_t)((it + 1) >> 1) & 1u) ^ 1u;
-            const bool ready = more && mbar_test(bar_full_a + 8 * nsa, npa) && (UNI || mbar_test(bar_full_b + 8 * nsb, npb)) &&
-                               (!new_acc || mbar_test(acc_bar, acc_par));
-            if (ready) tc_fence_after();
-            umma_f16<CG>(d_tmem, adesc + 4, bdesc + 4, idesc, 1u);
-            umma_f16<CG>(d_tmem, adesc + 6, bdesc + 6, idesc, 1u);
-            umma_commit<CG>(bar_empty_a + 8 * sa);
-            if (!UNI) umma_commit<CG>(bar_empty_b + 8 * sb);
-            if (new_acc) umma_commit<CG>(bar_acc_full + 8 * as);
-            if (more && !ready) {
+            if (more) {
               if (new_acc) mbar_wait(acc_bar, acc_par);
-              mbar_wait(bar_full_a + 8 * nsa, npa);
-              if (!UNI) mbar_wait(bar_full_b + 8 * nsb, npb);
+              mbar_wait(nfull, npa);
               tc_fence_after();
+              ready = true;
             }
+          } else {
+            // AlignConv: probe without blocking; if the next stage is not there yet, release this k-block's stage
+            // FIRST -- blocking here with two MMAs unissued would hold a stage the producers need.  With a single
+            // accumulator the next tile always has to wait for the epilogue: never "ready" across tiles.
+            ready = __all_sync(0xffffffffu, more && !new_acc && mbar_test(nfull, npa));
+            if (ready) tc_fence_after();
           }
-          sa = nsa; pa = npa; sb = nsb; pb = npb;
+          if (issuer) {
+            if (MODE == TC_ALIGN) {
+              umma_f16_ts<CG>(d_tmem, atm + 16u, bdesc + 4, idesc, 1u);
+              umma_f16_ts<CG>(d_tmem, atm + 24u, bdesc + 6, idesc, 1u);
+            } else {
+              umma_f16<CG>(d_tmem, adesc + 4, bdesc + 4, idesc, 1u);
+              umma_f16<CG>(d_tmem, adesc + 6, bdesc + 6, idesc, 1u);
+            }
+            umma_commit<CG>(empty_bar);             // stage (of every CTA of the group) reusable once these MMAs have read it
+            if (new_acc) umma_commit<CG>(acc_full_bar);   // accumulators of this tile group complete
+          }
+          __syncwarp();
+          if (more && !ready) {
+            long long w0 = (p.debug & 8) ? clock64() : 0;
+            if (new_acc) mbar_wait(acc_bar, acc_par);
+            long long w1 = (p.debug & 8) ? clock64() : 0;
+            mbar_wait(nfull, npa);
+            tc_fence_after();
+            if (p.debug & 8) { tw_acc += w1 - w0; tw_a += clock64() - w1; ++n_block; }
+          }
+          if (wrap) { sa = 0; adesc = adesc0; bdesc = bdesc0; atm = atm0; empty_bar = bar_empty_a; }
+          else { ++sa; adesc += TC_A_BYTES >> 4; bdesc += B_STAGE_BYTES >> 4; atm += 32u; empty_bar += 8; }
+          full_bar = nfull; pa = npa;
         }
       }
-      if ((p.debug & 8) && blockIdx.x == 0) {
+      if ((p.debug & 8) && blockIdx.x == 0 && lane == 0) {
         tl[min(it, 9)] = clock64();
-        printf("s2a conv_tc MMA thread: start +%lld;", tl[0] - dbg_c0);
+        printf("s2a conv_tc MMA thread: blocked %d times: acc %lld, full %lld cycles; start +%lld;", n_block, tw_acc, tw_a, tl[0] - dbg_c0);
         for (int i = 0; i < min(it, 9); ++i) printf(" tile%d %lld", i, tl[i + 1] - tl[i]);
         printf("\n");
       }
     }
-  } else {
+  } else if (warp >= kEpiWarp0 && warp < kTmaWarp) {
     // ===================== epilogue warps (also build the sample tables) =====================
     const int et = tid - kEpiWarp0 * 32;          // 0..127
     const int quad = warp & 3;                    // TMEM lane quadrant this warp may read (warp id % 4)
@@ -772,13 +845,12 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     }
     int it = 0;
     for (int q = first_q; q < ngroups; q += q_step, ++it) {
-      const int as = it & 1;
+      const int as = it % ACC, tb = it & 1;         // accumulator / sample-table buffer of this tile
       const bool ghost = S2A_IS_GHOST(q);
       const TileCoord tc = decode_tile(p, S2A_TILE_OF(q));
       const TcLevel& L = p.lv[tc.lvl];
-      mbar_wait(bar_acc_full + 8 * as, (uint32_t)(it >> 1) & 1u);
+      mbar_wait(bar_acc_full + 8 * as, (uint32_t)(it / ACC) & 1u);
       tc_fence_after();
-      uint8_t* s_out = MODE == TC_ALIGN ? reinterpret_cast<uint8_t*>(s_tab + as * (TC_M * 9)) : s_out_plain;
       const int r = quad * 32 + lane;
       const int y = tc.ty0 + r / TC_PW, x = tc.tx0 + r % TC_PW;
       const bool valid = (y < L.H && x < L.W) && !ghost;
@@ -789,24 +861,37 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       for (int c0 = 0, ci = 0; c0 < p.Co && !(p.debug & 32); c0 += TC_OUT_CH, ++ci) {
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * 256 + c0), v);
+        if (c0 + TC_OUT_CH >= p.Co) {               // last columns are in registers: the accumulator is free
+          tc_fence_before();
+          mbar_arrive_cluster(ld_acc_empty + 8 * as);
+        }
         uint32_t pk[16];
         float m[4];
+        if (MODE == TC_ALIGN) {
+          // AlignConv: ReLU only (alignconv.py:97), no bias, no pooling -- the epilogue warps share their issue
+          // slots with 16 producer warps, so every instruction here delays the hand-back of the accumulator
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float t0 = __uint_as_float(v[i]), t1 = __uint_as_float(v[i + 1]);
-          if (p.bias) { t0 += __ldg(p.bias + c0 + i); t1 += __ldg(p.bias + c0 + i + 1); }
-          if (p.relu) { t0 = fmaxf(t0, 0.0f); t1 = fmaxf(t1, 0.0f); }
-          const H2 h = from_f2<T>(t0, t1);
-          pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&h);
-          const float mx = fmaxf(t0, t1);
-          m[i >> 3] = (i & 7) == 0 ? mx : fmaxf(m[i >> 3], mx);
+          for (int i = 0; i < 32; i += 2) {
+            const H2 h = from_f2<T>(fmaxf(__uint_as_float(v[i]), 0.0f), fmaxf(__uint_as_float(v[i + 1]), 0.0f));
+            pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&h);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            float t0 = __uint_as_float(v[i]), t1 = __uint_as_float(v[i + 1]);
+            if (p.bias) { t0 += __ldg(p.bias + c0 + i); t1 += __ldg(p.bias + c0 + i + 1); }
+            if (p.relu) { t0 = fmaxf(t0, 0.0f); t1 = fmaxf(t1, 0.0f); }
+            const H2 h = from_f2<T>(t0, t1);
+            pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&h);
+            const float mx = fmaxf(t0, t1);
+            m[i >> 3] = (i & 7) == 0 ? mx : fmaxf(m[i >> 3], mx);
+          }
         }
-        // PLAIN: two staging buffers -- the store issued one iteration ago must have left ITS buffer before the
-        // barrier below lets anybody write the other one again next iteration.  ALIGN: one buffer (inside the dead
-        // sample table) -- the previous store must be gone before anybody writes it: one more barrier.
+        // three staging buffers: when this wait returns, every store but the most recent one has finished reading its
+        // buffer; the barrier below publishes that, so the chunk after this one may overwrite the buffer used two
+        // chunks before it while the store of the chunk in between is still in flight
         if (et == 0) tma_store_wait_read();
-        if (MODE == TC_ALIGN) epi_bar_sync();
-        uint8_t* sbuf = s_out + (MODE == TC_ALIGN ? 0 : (ci & 1) * TC_OUT_BYTES);
+        uint8_t* sbuf = s_out + (ci % TC_OUT_BUFS) * TC_OUT_BYTES;
         uint8_t* row = sbuf + r * (TC_OUT_CH * 2);
 #pragma unroll
         for (int j = 0; j < 4; ++j)
@@ -816,7 +901,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         epi_bar_sync();
         if (et == 0 && !ghost && !(p.debug & 64))
           tma_store_4d(&maps.y[tc.lvl], smem_u32(sbuf), c0, tc.tx0, tc.ty0, tc.b);
-        if (valid && L.pooled) {
+        if (MODE == TC_PLAIN && valid && L.pooled) {
           uint2 o;
           H2* oh = reinterpret_cast<H2*>(&o);
           oh[0] = from_f2<T>(m[0], m[1]);
@@ -824,17 +909,14 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
           *reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(L.pooled) + (pos * (p.Co / 8) + c0 / 8) * 2) = o;
         }
       }
-      tc_fence_before();
-      mbar_arrive_cluster(ld_acc_empty + 8 * as);    // accumulator may be overwritten by tile group it + 2
+      if (p.debug & 32) { tc_fence_before(); mbar_arrive_cluster(ld_acc_empty + 8 * as); }
       if (MODE == TC_ALIGN) {
         // every A k-block of tile `it` has been produced (its MMAs completed), so table (it & 1) is free:
         // build the table of tile it + 2 into it
         const int nxt = q + 2 * q_step;
         if (nxt < ngroups) {
-          if (et == 0) tma_store_wait_read();      // the last output box has left the buffer
-          epi_bar_sync();
-          build_tap_table<T>(p, decode_tile(p, S2A_TILE_OF(nxt)), s_tab + as * (TC_M * 9), et, TC_EPI_THREADS);
-          mbar_arrive(bar_tab_full + 8 * as);
+          build_tap_table<T>(p, decode_tile(p, S2A_TILE_OF(nxt)), s_tab + tb * (TC_M * 9), et, TC_EPI_THREADS);
+          mbar_arrive(bar_tab_full + 8 * tb);
         }
       }
     }
@@ -862,6 +944,16 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
 // weight packing: [Co][C][3][3] (any of f32/bf16/f16) -> [Co][(cb, tap, c64)] 16-bit, optionally
 // through the ARF map (ORConv: w [O, I, nOri, 3, 3], indices [nOri*9, nRot])
 // ---------------------------------------------------------------------------------------------
+// AlignConv keeps its A operand in tensor memory, written with tcgen05.st 16x256b fragments: thread q = T%4 of a
+// row holds the row's 16-byte chunks q and q + 4, which land at TMEM K-byte offsets 32g + 8q (g = 0..3).  This is
+// the channel (inside a 64-channel block) that sits at K position p of the A operand; the packed AlignConv
+// weights use the same order.
+__host__ __device__ inline int tc_kperm(int p) {
+  const int b = 2 * p, g = b >> 5, q = (b & 31) >> 3, t = b & 7;
+  const int pix_byte = g < 2 ? 16 * q + 8 * g + t : 64 + 16 * q + 8 * (g - 2) + t;
+  return pix_byte >> 1;
+}
+
 template <typename TIn, typename TOut>
 __global__ void pack_weight_kernel(const TIn* __restrict__ w, const uint8_t* __restrict__ arf_idx, TOut* __restrict__ wp,
                                    int Co, int C, int nOri, int nRot, int arfI) {
@@ -883,7 +975,7 @@ __global__ void pack_weight_kernel(const TIn* __restrict__ w, const uint8_t* __r
     r /= 9;
     const int cb = (int)(r % (C / 64));
     const int n = (int)(r / (C / 64));
-    const int cin = cb * 64 + c;
+    const int cin = cb * 64 + (arf_idx ? c : tc_kperm(c));   // no ARF map = AlignConv weights: TMEM A operand order
     float v;
     if (arf_idx) {
       const int o = n / nRot, k = n % nRot;
@@ -935,9 +1027,9 @@ static EncodeTiledFn get_encode_fn() {
 template <int MODE>
 constexpr size_t tc_smem_bytes() {
   using Cfg = TcCfg<MODE>;
-  return 1024 /*alignment slack*/ + (size_t)Cfg::SA * TC_A_BYTES + (size_t)Cfg::SB * ((256 / Cfg::CG) * TC_KB * 2) +
-         (MODE == TC_ALIGN ? 2 * (size_t)TC_HALO_BYTES + 2 * sizeof(TapSample) * TC_M * 9 : (size_t)2 * TC_OUT_BYTES) +
-         8 * TC_NBAR + 16;
+  return 1024 /*alignment slack*/ + (MODE == TC_ALIGN ? 0 : (size_t)Cfg::SA * TC_A_BYTES) +
+         (size_t)Cfg::SB * ((256 / Cfg::CG) * TC_KB * 2) + (size_t)TC_OUT_BUFS * TC_OUT_BYTES +
+         (MODE == TC_ALIGN ? 2 * (size_t)TC_HALO_BYTES + 2 * sizeof(TapSample) * TC_M * 9 : (size_t)0) + 8 * TC_NBAR + 16;
 }
 
 template <int MODE, typename T>
@@ -952,7 +1044,7 @@ static int launch_tc(const TcMaps& tmap, const TcParams& p, cudaStream_t st) {
   const int nclusters = std::max(1, std::min(ngroups, sm_count() / CG));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(nclusters * CG));
-  cfg.blockDim = dim3(TC_THREADS);
+  cfg.blockDim = dim3(tc_threads<MODE>());
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
