@@ -16,14 +16,14 @@
 //       deform_conv_cuda_kernel.cu:210-228); for ORConv it is the plain shifted pixel.
 //   Wp: weights pre-packed to [C_out][K'] 16-bit (ARF rotation folded into the packing for ORConv).
 //
-// Warp roles (576 threads, persistent CTA pairs): warps 0-11 are three producer groups that build AlignConv's
-// A tiles (per (row, tap) recipe -> 4 corner loads of 16 bytes from the NHWC map -> packed 16-bit blend -> 16-byte
-// store into the 128B-swizzled K-major stage); warp 12 is the TMA warp (weight k-blocks, and for ORConv the A
-// tile as one 4-D box); warp 13 allocates TMEM and one of its threads issues tcgen05.mma.cta_group::2
-// (M = 256 across the pair, N = C_out, K = 16, kind::f16); warps 14-17 are the epilogue (tcgen05.ld -> bias /
-// ReLU / 8-way orientation max -> staging -> TMA store) and build the gather recipes two tiles ahead.  Stages
-// are recycled through full/empty mbarriers; tcgen05.commit (multicast to both CTAs) releases a stage when its
-// MMAs retire; two 256-column TMEM accumulators let the epilogue of one tile overlap the next main loop.
+// Warp roles (persistent CTA pairs; AlignConv 24 warps, plain conv / ORConv 8): 16 producer warps (AlignConv only)
+// build the A tiles -- per (row, tap) recipe -> 8 LDS.128 from a TMA-fed shared-memory halo of the feature map ->
+// packed 16-bit blend -> tcgen05.st straight into the A stage in TENSOR MEMORY; 4 epilogue warps (tcgen05.ld ->
+// bias / ReLU / 8-way orientation max -> staging -> TMA store; they also build the gather recipes two tiles
+// ahead); one TMA warp (weight k-blocks, halos, and for ORConv / plain convs the A tile as one 4-D box); one MMA
+// warp that allocates TMEM and issues tcgen05.mma.cta_group::2 (M = 256 across the pair, N = C_out, K = 16,
+// kind::f16; A from shared memory or from TMEM) under elect.sync.  Stages are recycled through one full/empty
+// mbarrier pair each; tcgen05.commit (multicast to both CTAs) releases a stage when its MMAs retire.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -662,7 +662,8 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     }
   } else if (warp == kTmaWarp) {
     // ===================== TMA: this CTA's C_out/CG weight rows (and, PLAIN, its A tile) =====================
-    if (lane == 0) {
+    // (the whole warp walks the loop and waits; one elected lane arms the barrier and issues the copies)
+    {
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;                   // phase bits of the stage rings
       uint32_t hseq = 0;                         // running (tile, channel block) counter of the halo buffers
@@ -672,9 +673,12 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       auto load_halo = [&](const TileCoord& t, int cblk) {
         const uint32_t hb = hseq & 1u;
         mbar_wait(bar_halo_empty + 8 * hb, ((hseq >> 1) & 1u) ^ 1u);
-        mbar_arrive_expect_tx(bar_halo_full + 8 * hb, TC_HALO_BYTES);
-        tma_load_4d<1>(smem_u32(s_halo + hb * TC_HALO_BYTES), &maps.x[t.lvl], cblk * TC_KB, t.tx0 - TC_HALO, t.ty0 - TC_HALO,
-                       t.b, bar_halo_full + 8 * hb);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(bar_halo_full + 8 * hb, TC_HALO_BYTES);
+          tma_load_4d<1>(smem_u32(s_halo + hb * TC_HALO_BYTES), &maps.x[t.lvl], cblk * TC_KB, t.tx0 - TC_HALO, t.ty0 - TC_HALO,
+                         t.b, bar_halo_full + 8 * hb);
+        }
+        __syncwarp();
         ++hseq;
       };
       if (MODE == TC_ALIGN && first_q < ngroups) load_halo(decode_tile(p, S2A_TILE_OF(first_q)), 0);
@@ -692,17 +696,20 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
               else if (q + q_step < ngroups) load_halo(decode_tile(p, S2A_TILE_OF(q + q_step)), 0);
             }
             mbar_wait(bar_empty_a + 8 * sa, pa ^ 1u);
-            if ((p.debug & 1) && warm) {
-              if (leader) mbar_arrive(bar_full_a + 8 * sa);
-            } else {
-              if (leader) mbar_arrive_expect_tx(bar_full_a + 8 * sa, b_bytes_group + (MODE == TC_PLAIN ? CG * TC_A_BYTES : 0));
-              if (MODE == TC_PLAIN) {
-                const int ti = tap / p.ks, half = p.ks >> 1;
-                tma_load_4d<CG>(smem_u32(sA + sa * TC_A_BYTES), &maps.x[tc.lvl], cb * TC_KB, tc.tx0 - half + (tap - p.ks * ti),
-                                tc.ty0 - half + ti, tc.b, ld_full_a + 8 * sa);
+            if (elect_one()) {
+              if ((p.debug & 1) && warm) {
+                if (leader) mbar_arrive(bar_full_a + 8 * sa);
+              } else {
+                if (leader) mbar_arrive_expect_tx(bar_full_a + 8 * sa, b_bytes_group + (MODE == TC_PLAIN ? CG * TC_A_BYTES : 0));
+                if (MODE == TC_PLAIN) {
+                  const int ti = tap / p.ks, half = p.ks >> 1;
+                  tma_load_4d<CG>(smem_u32(sA + sa * TC_A_BYTES), &maps.x[tc.lvl], cb * TC_KB, tc.tx0 - half + (tap - p.ks * ti),
+                                  tc.ty0 - half + ti, tc.b, ld_full_a + 8 * sa);
+                }
+                tma_load_2d<CG>(smem_u32(sB + sa * B_STAGE_BYTES), &maps.w, kb * TC_KB, (int)cta_rank * co_part, ld_full_a + 8 * sa);
               }
-              tma_load_2d<CG>(smem_u32(sB + sa * B_STAGE_BYTES), &maps.w, kb * TC_KB, (int)cta_rank * co_part, ld_full_a + 8 * sa);
             }
+            __syncwarp();
             if (++sa == SA) { sa = 0; pa ^= 1u; }
           } else {
             if (MODE == TC_ALIGN && tap == 3) {
@@ -711,12 +718,15 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
               else if (q + q_step < ngroups) load_halo(decode_tile(p, S2A_TILE_OF(q + q_step)), 0);
             }
             mbar_wait(bar_empty_b + 8 * sb, pb ^ 1u);
-            if ((p.debug & 1) && warm) {
-              if (leader) mbar_arrive(bar_full_b + 8 * sb);
-            } else {
-              if (leader) mbar_arrive_expect_tx(bar_full_b + 8 * sb, b_bytes_group);
-              tma_load_2d<CG>(smem_u32(sB + sb * B_STAGE_BYTES), &maps.w, kb * TC_KB, (int)cta_rank * co_part, ld_full_b + 8 * sb);
+            if (elect_one()) {
+              if ((p.debug & 1) && warm) {
+                if (leader) mbar_arrive(bar_full_b + 8 * sb);
+              } else {
+                if (leader) mbar_arrive_expect_tx(bar_full_b + 8 * sb, b_bytes_group);
+                tma_load_2d<CG>(smem_u32(sB + sb * B_STAGE_BYTES), &maps.w, kb * TC_KB, (int)cta_rank * co_part, ld_full_b + 8 * sb);
+              }
             }
+            __syncwarp();
             if (++sb == SB) { sb = 0; pb ^= 1u; }
           }
           if (++tap == ntap) { tap = 0; ++cb; }
