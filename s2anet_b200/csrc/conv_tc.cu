@@ -62,8 +62,10 @@ enum { TC_ALIGN = 0, TC_PLAIN = 1 };
 template <int MODE> struct TcCfg;
 // GROUPS = producer groups of 4 warps (group g fills k-blocks g, g + GROUPS, ...): 16 producer warps for AlignConv
 // (its gather is latency-bound), none for the TMA-fed plain conv (256 threads, registers to spare).
-template <> struct TcCfg<TC_ALIGN> { static constexpr int CG = 2, SA = 6, SB = 6, GROUPS = 4; static constexpr bool UNIFIED = true; };
-template <> struct TcCfg<TC_PLAIN> { static constexpr int CG = 2, SA = 6, SB = 6, GROUPS = 0; static constexpr bool UNIFIED = true; };
+// KPS = k-blocks per stage: the MMA warp pays ~200 cycles of wait / commit / bookkeeping per STAGE and the tensor
+// pipe only holds two MMAs ahead, so the tensor-bound plain conv moves two k-blocks (8 MMAs) per stage.
+template <> struct TcCfg<TC_ALIGN> { static constexpr int CG = 2, SA = 6, SB = 6, GROUPS = 4, KPS = 1; static constexpr bool UNIFIED = true; };
+template <> struct TcCfg<TC_PLAIN> { static constexpr int CG = 2, SA = 3, SB = 3, GROUPS = 0, KPS = 2; static constexpr bool UNIFIED = true; };
 template <int MODE> constexpr int tc_threads() { return (TcCfg<MODE>::GROUPS * 4 + 8) * 32; }
 constexpr int TC_MAX_STAGES = 8;
 constexpr int TC_EPI_THREADS = 128;                   // 4 epilogue warps, one per TMEM lane quadrant
@@ -478,10 +480,11 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
   constexpr int CG = Cfg::CG, SA = Cfg::SA, SB = Cfg::SB;
   constexpr bool UNI = Cfg::UNIFIED;                   // B shares A's stage index and barriers
   static_assert(!UNI || SA == SB, "a unified ring needs equally many A and B stages");
-  constexpr int GROUPS = Cfg::GROUPS;
+  constexpr int GROUPS = Cfg::GROUPS, KPS = Cfg::KPS;
   static_assert(GROUPS < SA && SA <= TC_MAX_STAGES && SB <= TC_MAX_STAGES, "stage rings");
   static_assert(MODE != TC_ALIGN || 256 + SA * 32 <= TC_TMEM_COLS, "AlignConv: accumulator + A stages must fit tensor memory");
-  constexpr int B_STAGE_BYTES = (256 / CG) * TC_KB * 2;
+  constexpr int B_KB_BYTES = (256 / CG) * TC_KB * 2;            // one k-block of this CTA's weight rows
+  constexpr int B_STAGE_BYTES = KPS * B_KB_BYTES, A_STAGE_BYTES = KPS * TC_A_BYTES;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B operands need 1024-byte aligned tiles: align the dynamic window by hand (the offset is
   // the same in both CTAs of a pair, which the paired MMA and the multicast commits rely on)
@@ -491,7 +494,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
   constexpr int ACC = MODE == TC_ALIGN ? 1 : 2;        // accumulators: PLAIN 2 x 256 TMEM columns; ALIGN 1 (+ 8 A stages x 32 columns)
   constexpr uint32_t A_TMEM_COL0 = 256;                // ALIGN: first TMEM column of the A stages
   uint8_t* sA = smem;                                  // PLAIN only (ALIGN keeps A in tensor memory)
-  uint8_t* sB = sA + (MODE == TC_ALIGN ? 0 : SA * TC_A_BYTES);
+  uint8_t* sB = sA + (MODE == TC_ALIGN ? 0 : SA * A_STAGE_BYTES);
   uint8_t* s_out = sB + SB * B_STAGE_BYTES;                              // 2 x 8 KB, 1024-byte aligned (SWIZZLE_64B)
   uint8_t* s_halo = s_out + TC_OUT_BUFS * TC_OUT_BYTES;                            // ALIGN only
   TapSample* s_tab = reinterpret_cast<TapSample*>(s_halo + 2 * TC_HALO_BYTES);
@@ -682,7 +685,44 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         ++hseq;
       };
       if (MODE == TC_ALIGN && first_q < ngroups) load_halo(decode_tile(p, S2A_TILE_OF(first_q)), 0);
-      for (int q = first_q; q < ngroups; q += q_step) {
+      for (int q = first_q; MODE == TC_PLAIN && q < ngroups; q += q_step) {
+        // plain conv / ORConv: a stage carries KPS k-blocks; per k-block the A tile is the 8 x 16 patch shifted by the
+        // tap (64 channels = one 4-D box {64, 16, 8, 1}, zero-filled outside the map) plus this CTA's weight rows
+        const TileCoord tc = decode_tile(p, S2A_TILE_OF(q));
+        int cb = 0, tap = 0;
+        for (int kb = 0; kb < nkb; kb += KPS) {
+          const int nk = min(KPS, nkb - kb);
+          int cbj[KPS], dxj[KPS], dyj[KPS];
+          const int half = p.ks >> 1;
+#pragma unroll
+          for (int j = 0; j < KPS; ++j) {
+            const int ti = tap / p.ks;
+            cbj[j] = cb; dyj[j] = ti - half; dxj[j] = tap - p.ks * ti - half;
+            if (j < nk && ++tap == ntap) { tap = 0; ++cb; }
+          }
+          mbar_wait(bar_empty_a + 8 * sa, pa ^ 1u);
+          if (elect_one()) {
+            if ((p.debug & 1) && warm) {
+              if (leader) mbar_arrive(bar_full_a + 8 * sa);
+            } else {
+              if (leader) mbar_arrive_expect_tx(bar_full_a + 8 * sa, (uint32_t)nk * (b_bytes_group + CG * TC_A_BYTES));
+#pragma unroll
+              for (int j = 0; j < KPS; ++j) {
+                if (j < nk) {
+                  tma_load_4d<CG>(smem_u32(sA + sa * A_STAGE_BYTES + j * TC_A_BYTES), &maps.x[tc.lvl], cbj[j] * TC_KB, tc.tx0 + dxj[j],
+                                  tc.ty0 + dyj[j], tc.b, ld_full_a + 8 * sa);
+                  tma_load_2d<CG>(smem_u32(sB + sa * B_STAGE_BYTES + j * B_KB_BYTES), &maps.w, (kb + j) * TC_KB,
+                                  (int)cta_rank * co_part, ld_full_a + 8 * sa);
+                }
+              }
+            }
+          }
+          __syncwarp();
+          if (++sa == SA) { sa = 0; pa ^= 1u; }
+        }
+        warm = true;
+      }
+      for (int q = first_q; MODE == TC_ALIGN && q < ngroups; q += q_step) {
         const TileCoord tc = decode_tile(p, S2A_TILE_OF(q));
         int cb = 0, tap = 0;
         for (int kb = 0; kb < nkb; ++kb) {
@@ -770,29 +810,41 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         // the accumulator tile group it + 1 will use, and the phase of its "drained" barrier
         const uint32_t acc_bar = bar_acc_empty + 8 * ((it + 1) % ACC), acc_par = ((uint32_t)((it + 1) / ACC) & 1u) ^ 1u;
         const uint32_t acc_full_bar = bar_acc_full + 8 * as;
-        for (int kb = 0; kb < nkb; ++kb) {
-          // +32 bytes (>>4 = 2) per K=16 step inside the swizzle atom; A in TMEM: +8 columns per K=16 step
+        for (int kb = 0; kb < nkb; kb += KPS) {
+          const int nk = KPS == 1 ? 1 : min(KPS, nkb - kb);          // k-blocks in this stage
+          // +32 bytes (>>4 = 2) per K=16 step inside the swizzle atom; A in TMEM: +8 columns per K=16 step.
+          // Every MMA of the stage but the last two is issued first ...
           const bool issuer = elect_one();
           if (issuer) {
             if (MODE == TC_ALIGN) {
               umma_f16_ts<CG>(d_tmem, atm, bdesc, idesc, kb != 0 ? 1u : 0u);
               umma_f16_ts<CG>(d_tmem, atm + 8u, bdesc + 2, idesc, 1u);
             } else {
-              umma_f16<CG>(d_tmem, adesc, bdesc, idesc, kb != 0 ? 1u : 0u);
-              umma_f16<CG>(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
+#pragma unroll
+              for (int j = 0; j < KPS; ++j) {
+                if (j < nk) {
+                  const uint64_t aj = adesc + (uint64_t)(j * (TC_A_BYTES >> 4)), bj = bdesc + (uint64_t)(j * (B_KB_BYTES >> 4));
+                  umma_f16<CG>(d_tmem, aj, bj, idesc, (kb | j) != 0 ? 1u : 0u);
+                  umma_f16<CG>(d_tmem, aj + 2, bj + 2, idesc, 1u);
+                  if (j + 1 < nk) {
+                    umma_f16<CG>(d_tmem, aj + 4, bj + 4, idesc, 1u);
+                    umma_f16<CG>(d_tmem, aj + 6, bj + 6, idesc, 1u);
+                  }
+                }
+              }
             }
           }
           __syncwarp();
-          // next stage
+          // ... then the next stage is awaited in the shadow of the MMAs just queued ...
           uint32_t nfull = full_bar + 8, npa = pa;
           const bool wrap = sa + 1 == SA;
           if (wrap) { nfull = bar_full_a; npa ^= 1u; }
-          const bool new_acc = kb + 1 == nkb;
+          const bool new_acc = kb + KPS >= nkb;
           const bool more = !new_acc || !last_tile;
           bool ready = false;
           if (MODE == TC_PLAIN) {
-            // tensor-bound: the next stage is (nearly) always there; wait for it in the shadow of the two MMAs
-            // just queued (and, at a tile boundary, for the next accumulator to be drained)
+            // tensor-bound: the next stage is (nearly) always there (and, at a tile boundary, the next accumulator
+            // has to be drained)
             if (more) {
               if (new_acc) mbar_wait(acc_bar, acc_par);
               mbar_wait(nfull, npa);
@@ -806,13 +858,15 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
             ready = __all_sync(0xffffffffu, more && !new_acc && mbar_test(nfull, npa));
             if (ready) tc_fence_after();
           }
+          // ... and the last two MMAs and the commit follow
           if (issuer) {
             if (MODE == TC_ALIGN) {
               umma_f16_ts<CG>(d_tmem, atm + 16u, bdesc + 4, idesc, 1u);
               umma_f16_ts<CG>(d_tmem, atm + 24u, bdesc + 6, idesc, 1u);
             } else {
-              umma_f16<CG>(d_tmem, adesc + 4, bdesc + 4, idesc, 1u);
-              umma_f16<CG>(d_tmem, adesc + 6, bdesc + 6, idesc, 1u);
+              const uint64_t aj = adesc + (uint64_t)((nk - 1) * (TC_A_BYTES >> 4)), bj = bdesc + (uint64_t)((nk - 1) * (B_KB_BYTES >> 4));
+              umma_f16<CG>(d_tmem, aj + 4, bj + 4, idesc, 1u);
+              umma_f16<CG>(d_tmem, aj + 6, bj + 6, idesc, 1u);
             }
             umma_commit<CG>(empty_bar);             // stage (of every CTA of the group) reusable once these MMAs have read it
             if (new_acc) umma_commit<CG>(acc_full_bar);   // accumulators of this tile group complete
@@ -827,7 +881,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
             if (p.debug & 8) { tw_acc += w1 - w0; tw_a += clock64() - w1; ++n_block; }
           }
           if (wrap) { sa = 0; adesc = adesc0; bdesc = bdesc0; atm = atm0; empty_bar = bar_empty_a; }
-          else { ++sa; adesc += TC_A_BYTES >> 4; bdesc += B_STAGE_BYTES >> 4; atm += 32u; empty_bar += 8; }
+          else { ++sa; adesc += A_STAGE_BYTES >> 4; bdesc += B_STAGE_BYTES >> 4; atm += 32u; empty_bar += 8; }
           full_bar = nfull; pa = npa;
         }
       }
@@ -1037,8 +1091,8 @@ static EncodeTiledFn get_encode_fn() {
 template <int MODE>
 constexpr size_t tc_smem_bytes() {
   using Cfg = TcCfg<MODE>;
-  return 1024 /*alignment slack*/ + (MODE == TC_ALIGN ? 0 : (size_t)Cfg::SA * TC_A_BYTES) +
-         (size_t)Cfg::SB * ((256 / Cfg::CG) * TC_KB * 2) + (size_t)TC_OUT_BUFS * TC_OUT_BYTES +
+  return 1024 /*alignment slack*/ + (MODE == TC_ALIGN ? 0 : (size_t)Cfg::SA * Cfg::KPS * TC_A_BYTES) +
+         (size_t)Cfg::SB * Cfg::KPS * ((256 / Cfg::CG) * TC_KB * 2) + (size_t)TC_OUT_BUFS * TC_OUT_BYTES +
          (MODE == TC_ALIGN ? 2 * (size_t)TC_HALO_BYTES + 2 * sizeof(TapSample) * TC_M * 9 : (size_t)0) + 8 * TC_NBAR + 16;
 }
 
