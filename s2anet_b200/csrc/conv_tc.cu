@@ -936,7 +936,9 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
           // slots with 16 producer warps, so every instruction here delays the hand-back of the accumulator
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
-            const H2 h = from_f2<T>(fmaxf(__uint_as_float(v[i]), 0.0f), fmaxf(__uint_as_float(v[i + 1]), 0.0f));
+            // ReLU on the packed pair after rounding (rounding is monotone and keeps 0): one HMNMX2 instead of two FMNMX
+            H2 h = from_f2<T>(__uint_as_float(v[i]), __uint_as_float(v[i + 1]));
+            h = __hmax2(h, from_f2<T>(0.0f, 0.0f));
             pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&h);
           }
         } else {
@@ -951,20 +953,23 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
             m[i >> 3] = (i & 7) == 0 ? mx : fmaxf(m[i >> 3], mx);
           }
         }
-        // three staging buffers: when this wait returns, every store but the most recent one has finished reading its
-        // buffer; the barrier below publishes that, so the chunk after this one may overwrite the buffer used two
-        // chunks before it while the store of the chunk in between is still in flight
-        if (et == 0) tma_store_wait_read();
-        uint8_t* sbuf = s_out + (ci % TC_OUT_BUFS) * TC_OUT_BYTES;
-        uint8_t* row = sbuf + r * (TC_OUT_CH * 2);
+        // Each epilogue warp stores its own 32 tile rows (2 spatial rows x 16 pixels) -- no barrier across the four
+        // warps.  Three 2 KB staging buffers per warp: when the elected lane's wait returns, every store of this warp
+        // but the most recent one has finished reading its buffer; __syncwarp publishes that, so the chunk after this
+        // one may overwrite the buffer used two chunks before it while the store in between is still in flight.
+        const bool issuer = elect_one();
+        if (issuer) tma_store_wait_read();
+        __syncwarp();
+        uint8_t* sbuf = s_out + (ci % TC_OUT_BUFS) * TC_OUT_BYTES + quad * (32 * TC_OUT_CH * 2);
+        uint8_t* row = sbuf + lane * (TC_OUT_CH * 2);
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-          *reinterpret_cast<uint4*>(row + ((j ^ ((r >> 1) & 3)) << 4)) =
+          *reinterpret_cast<uint4*>(row + ((j ^ ((lane >> 1) & 3)) << 4)) =
               make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
         fence_proxy_async_smem();
-        epi_bar_sync();
-        if (et == 0 && !ghost && !(p.debug & 64))
-          tma_store_4d(&maps.y[tc.lvl], smem_u32(sbuf), c0, tc.tx0, tc.ty0, tc.b);
+        __syncwarp();
+        if (issuer && !ghost && !(p.debug & 64))
+          tma_store_4d(&maps.y[tc.lvl], smem_u32(sbuf), c0, tc.tx0, tc.ty0 + 2 * quad, tc.b);
         if (MODE == TC_PLAIN && valid && L.pooled) {
           uint2 o;
           H2* oh = reinterpret_cast<H2*>(&o);
@@ -987,7 +992,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
   }
 #undef S2A_TILE_OF
 #undef S2A_IS_GHOST
-  if (tid == kEpiWarp0 * 32) tma_store_wait_all();     // this thread issued every output store of the CTA
+  if (warp >= kEpiWarp0 && warp < kTmaWarp) tma_store_wait_all();   // (the lanes that issued output stores wait for them)
   tc_fence_before();
   if (CG == 2) cluster_sync_all();   // no CTA may exit (or free TMEM) while its partner can still signal / read it
   else __syncthreads();
@@ -1176,7 +1181,7 @@ static int conv_tc_common(int mode, int nlevels, const void* const* xs, const fl
   for (int l = 0; l < nlevels; ++l) {
     const cuuint64_t yd[4] = {(cuuint64_t)Co, (cuuint64_t)Ws[l], (cuuint64_t)Hs[l], (cuuint64_t)B};
     const cuuint64_t ys_[3] = {(cuuint64_t)Co * 2, (cuuint64_t)Ws[l] * Co * 2, (cuuint64_t)Hs[l] * Ws[l] * Co * 2};
-    const cuuint32_t yb[4] = {(cuuint32_t)TC_OUT_CH, (cuuint32_t)TC_PW, (cuuint32_t)TC_PH, 1};
+    const cuuint32_t yb[4] = {(cuuint32_t)TC_OUT_CH, (cuuint32_t)TC_PW, 2, 1};      // one epilogue warp's 32 tile rows
     const cuuint32_t ye[4] = {1, 1, 1, 1};
     CUresult yr = enc(&tmap.y[l], tdt, 4, outs[l], yd, ys_, yb, ye, CU_TENSOR_MAP_INTERLEAVE_NONE,
                       CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
