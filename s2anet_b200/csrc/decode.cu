@@ -16,6 +16,9 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
+#include <cstdlib>
+#include <type_traits>
+
 #include <cub/block/block_radix_sort.cuh>
 
 #include "common.cuh"
@@ -26,11 +29,36 @@ constexpr int DEC_MAX_LEVELS = 8;
 constexpr int DEC_THREADS = 1024;
 
 template <typename T> __device__ __forceinline__ float ld_as_float(const T* p);
-template <> __device__ __forceinline__ float ld_as_float<float>(const float* p) { return __ldg(p); }
+template <> __device__ __forceinline__ float ld_as_float<float>(const float* p) { return *p; }
 template <> __device__ __forceinline__ float ld_as_float<__nv_bfloat16>(const __nv_bfloat16* p) {
   return __bfloat162float(*p);
 }
 template <> __device__ __forceinline__ float ld_as_float<__half>(const __half* p) { return __half2float(*p); }
+
+template <typename T> __device__ __forceinline__ float bits16_to_float(unsigned short b);
+template <> __device__ __forceinline__ float bits16_to_float<float>(unsigned short) { return 0.0f; }   // (never used)
+template <> __device__ __forceinline__ float bits16_to_float<__nv_bfloat16>(unsigned short b) {
+  return __uint_as_float((uint32_t)b << 16);
+}
+template <> __device__ __forceinline__ float bits16_to_float<__half>(unsigned short b) { return __half2float(__ushort_as_half(b)); }
+
+// The first `n` (<= 16) consecutive channels of one location as floats.  16-bit channels-last tensors whose
+// locations are at least 16 (8) elements apart and 16-byte aligned are read with two (one) 16-byte loads --
+// otherwise a warp would pull one 32-byte sector per 2-byte element.
+template <typename T>
+__device__ __forceinline__ void load_channels(const T* q, long long cstride, long long pstride, int n, float* out) {
+  if (sizeof(T) == 2 && cstride == 1 && (reinterpret_cast<uintptr_t>(q) & 15) == 0 && pstride >= (n <= 8 ? 8 : 16) && n <= 16) {
+    const uint4 v0 = __ldg(reinterpret_cast<const uint4*>(q));
+    uint4 v1 = make_uint4(0u, 0u, 0u, 0u);
+    if (n > 8) v1 = __ldg(reinterpret_cast<const uint4*>(q) + 1);
+    const uint32_t w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+    for (int c = 0; c < 16; ++c)
+      if (c < n) out[c] = bits16_to_float<T>((unsigned short)(w[c >> 1] >> ((c & 1) * 16)));
+  } else {
+    for (int c = 0; c < n; ++c) out[c] = ld_as_float(q + c * cstride);
+  }
+}
 
 // round a float through T (what storing a T tensor element does)
 template <typename T> __device__ __forceinline__ float round_through(float v);
@@ -130,6 +158,9 @@ struct SelParams {
   float* scores;          // [B, n_total, C]
   int32_t* index_out;     // optional [B, n_total]: position (y*W + x) of every candidate inside its level
   float lim;
+  int debug;
+  int smem_keys;          // keys of a level with at most this many locations live in shared memory
+  int sort_bytes;         // offset of that key array inside the dynamic shared memory (behind the sort scratch)
 };
 
 __device__ __forceinline__ unsigned long long composite_key(uint32_t key, int i) {
@@ -152,24 +183,61 @@ __global__ void __launch_bounds__(DEC_THREADS) select_decode_kernel(const __grid
   const T* cls = reinterpret_cast<const T*>(L.cls) + b * L.cs[0];
   const T* reg = reinterpret_cast<const T*>(L.reg) + b * L.rs[0];
   const bool select = n > k;
+  long long t0 = clock64(), t1 = t0, t2 = t0, t3 = t0;
 
+  // composite sort key: (score bits, 16 significant bits for 16-bit inputs) . (index bits, lower location first)
+  const int nb = 32 - __clz(max(n - 1, 1));                 // bits of a location index
+  // a bf16 (fp16) score widened to fp32 has 16 (13) zero low bits
+  const int kshift = std::is_same<T, __nv_bfloat16>::value ? 16 : (std::is_same<T, __half>::value ? 13 : 0);
+  const int total_bits = 32 - kshift + nb;
+  const unsigned idx_mask = (1u << nb) - 1u;
+  auto composite = [&](uint32_t key, int i) -> unsigned long long {
+    return ((unsigned long long)(key >> kshift) << nb) | (unsigned long long)(idx_mask - (unsigned)i);
+  };
   if (select) {
-    // ---- keys: best class score of every location (models/head.py:700-701) -------------------
-    uint32_t* keys = p.keys + (long long)b * p.keys_per_image + L.key_off;
-    for (int i = tid; i < n; i += DEC_THREADS) {
-      const int y = i / L.W, x = i - y * L.W;
-      const T* q = cls + y * L.cs[2] + x * L.cs[3];
-      float m = -INFINITY;
-      for (int c = 0; c < C; ++c) m = fmaxf(m, ld_as_float(q + c * L.cs[1]));
+    // ---- keys: best class score of every location (models/head.py:700-701); kept in shared memory when they fit
+    uint32_t* keys = n <= p.smem_keys ? reinterpret_cast<uint32_t*>(dsm + p.sort_bytes)
+                                      : p.keys + (long long)b * p.keys_per_image + L.key_off;
+    constexpr int UNR = 4;                                  // locations in flight per thread (latency-bound loop)
+    for (int i0 = tid; i0 < n; i0 += UNR * DEC_THREADS) {
+      float m[UNR];
+      if (C <= 16) {
+        float v[UNR][16];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+          const int i = min(i0 + u * DEC_THREADS, n - 1);
+          const int y = i / L.W, x = i - y * L.W;
+          load_channels<T>(cls + y * L.cs[2] + x * L.cs[3], L.cs[1], L.cs[3], C, v[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+          m[u] = -INFINITY;
+#pragma unroll
+          for (int c = 0; c < 16; ++c)
+            if (c < C) m[u] = fmaxf(m[u], v[u][c]);
+        }
+      } else {
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+          const int i = min(i0 + u * DEC_THREADS, n - 1);
+          const int y = i / L.W, x = i - y * L.W;
+          const T* q = cls + y * L.cs[2] + x * L.cs[3];
+          m[u] = -INFINITY;
+          for (int c = 0; c < C; ++c) m[u] = fmaxf(m[u], ld_as_float(q + c * L.cs[1]));
+        }
+      }
       // sigmoid is monotone, so max_c sigmoid(x_c) == sigmoid(max_c x_c) bit for bit; scores are >= 0,
       // so their bit patterns order like unsigned integers
-      keys[i] = __float_as_uint(sigmoid_t<T>(m));
+#pragma unroll
+      for (int u = 0; u < UNR; ++u)
+        if (i0 + u * DEC_THREADS < n) keys[i0 + u * DEC_THREADS] = __float_as_uint(sigmoid_t<T>(m[u]));
     }
     if (tid == 0) { s_prefix = 0ull; s_remaining = k; s_done = 0; s_count = 0; }
     __syncthreads();
+    t1 = clock64();
     // ---- radix select of the k-th largest composite (score, lower index first): exact top-k with a
     // defined tie rule (torch.topk leaves ties unspecified) --------------------------------------
-    for (int shift = 56; shift >= 0; shift -= 8) {
+    for (int shift = ((total_bits - 1) / 8) * 8; shift >= 0; shift -= 8) {
       for (int i = tid; i < 256; i += DEC_THREADS) s_hist[i] = 0u;
       __syncthreads();
       const unsigned long long prefix = s_prefix;
@@ -177,8 +245,8 @@ __global__ void __launch_bounds__(DEC_THREADS) select_decode_kernel(const __grid
         const int i = base + tid;
         unsigned bin = 0xFFFFFFFFu;                       // inactive lanes form their own group
         if (i < n) {
-          const unsigned long long c = composite_key(keys[i], i);
-          if (shift == 56 || (c >> (shift + 8)) == (prefix >> (shift + 8))) bin = (unsigned)(c >> shift) & 255u;
+          const unsigned long long c = composite(keys[i], i);
+          if (shift + 8 >= 64 || (c >> (shift + 8)) == (prefix >> (shift + 8))) bin = (unsigned)(c >> shift) & 255u;
         }
         // scores cluster in a handful of bins: one shared atomic per distinct bin per warp, not per key
         const unsigned peers = __match_any_sync(0xffffffffu, bin);
@@ -215,12 +283,13 @@ __global__ void __launch_bounds__(DEC_THREADS) select_decode_kernel(const __grid
       if (s_done) break;
     }
     const unsigned long long thr = s_prefix;
+    t2 = clock64();
     // ---- collect the k selected composites and sort them (descending score, ascending index) ----
     for (int i = tid; i < DEC_THREADS * ITEMS; i += DEC_THREADS) s_sel[i] = 0ull;
     __syncthreads();
     for (int base = 0; base < n; base += DEC_THREADS) {
       const int i = base + tid;
-      const unsigned long long c = i < n ? composite_key(keys[i], i) : 0ull;
+      const unsigned long long c = i < n ? composite(keys[i], i) : 0ull;
       const bool take = i < n && c >= thr;
       const unsigned bal = __ballot_sync(0xffffffffu, take);
       if (bal) {
@@ -235,31 +304,43 @@ __global__ void __launch_bounds__(DEC_THREADS) select_decode_kernel(const __grid
 #pragma unroll
     for (int j = 0; j < ITEMS; ++j) items[j] = s_sel[tid * ITEMS + j];
     __syncthreads();
-    Sort(sort_tmp).SortDescending(items);
+    Sort(sort_tmp).SortDescending(items, 0, total_bits);       // only the bits that carry information
 #pragma unroll
     for (int j = 0; j < ITEMS; ++j) s_sel[tid * ITEMS + j] = items[j];
     __syncthreads();
   }
 
+  t3 = clock64();
   // ---- gather + sigmoid + final decode (models/head.py:703-717) ---------------------------------
   for (int j = tid; j < k; j += DEC_THREADS) {
-    const int i = select ? (int)(0xFFFFFFFFu - (uint32_t)(s_sel[j] & 0xFFFFFFFFull)) : j;
+    const int i = select ? (int)(idx_mask - (unsigned)(s_sel[j] & (unsigned long long)idx_mask)) : j;
     const int y = i / L.W, x = i - y * L.W;
     const long long row = (long long)b * p.n_total + L.out_off + j;
     const T* q = cls + y * L.cs[2] + x * L.cs[3];
     float* so = p.scores + row * C;
-    for (int c = 0; c < C; ++c) so[c] = sigmoid_t<T>(ld_as_float(q + c * L.cs[1]));
-    const T* d = reg + y * L.rs[2] + x * L.rs[3];
+    if (C <= 16) {
+      float v[16];
+      load_channels<T>(q, L.cs[1], L.cs[3], C, v);
+#pragma unroll
+      for (int c = 0; c < 16; ++c)
+        if (c < C) so[c] = sigmoid_t<T>(v[c]);
+    } else {
+      for (int c = 0; c < C; ++c) so[c] = sigmoid_t<T>(ld_as_float(q + c * L.cs[1]));
+    }
+    float d[5];
+    load_channels<T>(reg + y * L.rs[2] + x * L.rs[3], L.rs[1], L.rs[3], 5, d);
     const float* ap = L.anchors + ((long long)b * n + i) * 5;
     const float a[5] = {__ldg(ap), __ldg(ap + 1), __ldg(ap + 2), __ldg(ap + 3), __ldg(ap + 4)};
     float o[5];
-    delta2bbox_rotated<T>(a, ld_as_float(d), ld_as_float(d + L.rs[1]), ld_as_float(d + 2 * L.rs[1]),
-                          ld_as_float(d + 3 * L.rs[1]), ld_as_float(d + 4 * L.rs[1]), p.lim, o);
+    delta2bbox_rotated<T>(a, d[0], d[1], d[2], d[3], d[4], p.lim, o);
     float* bo = p.bboxes + row * 5;
 #pragma unroll
     for (int e = 0; e < 5; ++e) bo[e] = o[e];
     if (p.index_out) p.index_out[row] = i;
   }
+  if (p.debug && tid == 0 && blockIdx.y == 0)
+    printf("select_decode level %d: keys %lld, select %lld, collect+sort %lld, gather+decode %lld cycles\n", (int)blockIdx.x, t1 - t0, t2 - t1,
+           t3 - t2, clock64() - t3);
 }
 
 template <typename T> static float limit_in(float max_ratio);
@@ -272,10 +353,15 @@ static float clamp_limit(double wh_ratio_clip, int dtype) {
 }
 
 template <typename T, int ITEMS>
-static int launch_select(const SelParams& p, cudaStream_t st) {
+static int launch_select(SelParams p, cudaStream_t st) {
   using Sort = cub::BlockRadixSort<unsigned long long, DEC_THREADS, ITEMS>;
   auto kern = select_decode_kernel<T, ITEMS>;
-  const size_t smem = sizeof(typename Sort::TempStorage);
+  p.sort_bytes = (int)align_up(sizeof(typename Sort::TempStorage), 16);
+  p.smem_keys = 16384;                                          // 64 KB: P3 of a 1024^2 image
+  int need = 0;
+  for (int l = 0; l < p.nlevels; ++l)
+    if (p.lv[l].n > p.lv[l].k && p.lv[l].n <= p.smem_keys) need = std::max(need, p.lv[l].n);
+  const size_t smem = (size_t)p.sort_bytes + (size_t)need * sizeof(uint32_t);
   S2A_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<dim3(p.nlevels, p.B), DEC_THREADS, smem, st>>>(p);
   S2A_LAUNCH_OK("select_decode_kernel");
@@ -363,6 +449,7 @@ extern "C" int s2a_select_decode(int nlevels, const void* const* cls, const int6
   p.nlevels = nlevels; p.B = B; p.C = num_classes; p.n_total = off; p.keys_per_image = keys;
   p.keys = reinterpret_cast<uint32_t*>(workspace); p.bboxes = bboxes_out; p.scores = scores_out; p.index_out = index_out;
   p.lim = clamp_limit(wh_ratio_clip, dtype);
+  { const char* e = getenv("S2A_DEC_DEBUG"); p.debug = e ? atoi(e) : 0; }
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == S2A_F32) return launch_select_items<float>(p, kmax, st);
   if (dtype == S2A_BF16) return launch_select_items<__nv_bfloat16>(p, kmax, st);
