@@ -31,7 +31,8 @@ def _newer(target, deps):
 
 
 def _compile(src, obj, verbose):
-    cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+    extra = os.environ.get("S2A_NVCC_EXTRA", "").split()      # e.g. -DS2A_TC_TIMELINE (in-kernel clock probes)
+    cmd = ["nvcc"] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed for %s:\n%s" % (src, r.stdout))

@@ -37,6 +37,13 @@
 
 namespace s2a {
 
+// -DS2A_TC_TIMELINE: in-kernel clock probes of the MMA warp (printed under S2A_TC_DEBUG=8); off in normal builds
+#ifdef S2A_TC_TIMELINE
+#define S2A_TL(...) __VA_ARGS__
+#else
+#define S2A_TL(...)
+#endif
+
 constexpr int TC_M = 128;                 // rows per tile (8 x 16 patch) = one UMMA M
 constexpr int TC_PH = 8, TC_PW = 16;
 constexpr int TC_KB = 64;                 // k-block (elements) = 128 bytes of 16-bit data
@@ -558,12 +565,11 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
-  long long dbg_c0 = 0;
-  unsigned long long dbg_t0 = 0;
-  if ((p.debug & 8) && blockIdx.x == 0) {
-    dbg_c0 = clock64();
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t0));
-  }
+  S2A_TL(long long dbg_c0 = 0; unsigned long long dbg_t0 = 0;
+         if ((p.debug & 8) && blockIdx.x == 0) {
+           dbg_c0 = clock64();
+           asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t0));
+         })
 
   if (GROUPS > 0 && warp < kProdWarps) {
     // ===================== A producers (AlignConv: bilinear gather through the LSU) =====================
@@ -797,14 +803,13 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       uint32_t atm = atm0, full_bar = bar_full_a, empty_bar = bar_empty_a;
       int sa = 0, it = 0;
       uint32_t pa = 0;
-      long long tl[10];
-      long long tw_acc = 0, tw_a = 0; int n_block = 0;
+      S2A_TL(long long tl[10]; long long tw_acc = 0, tw_a = 0; int n_block = 0;)
       mbar_wait(bar_acc_empty, 1u);
       mbar_wait(bar_full_a, 0u);
       tc_fence_after();
       for (int q = first_q; q < ngroups; q += q_step, ++it) {
         const int as = it % ACC;
-        if ((p.debug & 8) && it < 9) tl[it] = clock64();
+        S2A_TL(if ((p.debug & 8) && it < 9) tl[it] = clock64();)
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * 256);
         const bool last_tile = q + q_step >= ngroups;
         // the accumulator tile group it + 1 will use, and the phase of its "drained" barrier
@@ -873,24 +878,26 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
           }
           __syncwarp();
           if (more && !ready) {
-            long long w0 = (p.debug & 8) ? clock64() : 0;
+            S2A_TL(long long w0 = (p.debug & 8) ? clock64() : 0;)
             if (new_acc) mbar_wait(acc_bar, acc_par);
-            long long w1 = (p.debug & 8) ? clock64() : 0;
+            S2A_TL(long long w1 = (p.debug & 8) ? clock64() : 0;)
             mbar_wait(nfull, npa);
             tc_fence_after();
-            if (p.debug & 8) { tw_acc += w1 - w0; tw_a += clock64() - w1; ++n_block; }
+            S2A_TL(if (p.debug & 8) { tw_acc += w1 - w0; tw_a += clock64() - w1; ++n_block; })
           }
           if (wrap) { sa = 0; adesc = adesc0; bdesc = bdesc0; atm = atm0; empty_bar = bar_empty_a; }
           else { ++sa; adesc += A_STAGE_BYTES >> 4; bdesc += B_STAGE_BYTES >> 4; atm += 32u; empty_bar += 8; }
           full_bar = nfull; pa = npa;
         }
       }
+#ifdef S2A_TC_TIMELINE
       if ((p.debug & 8) && blockIdx.x == 0 && lane == 0) {
         tl[min(it, 9)] = clock64();
         printf("s2a conv_tc MMA thread: blocked %d times: acc %lld, full %lld cycles; start +%lld;", n_block, tw_acc, tw_a, tl[0] - dbg_c0);
         for (int i = 0; i < min(it, 9); ++i) printf(" tile%d %lld", i, tl[i + 1] - tl[i]);
         printf("\n");
       }
+#endif
     }
   } else if (warp >= kEpiWarp0 && warp < kTmaWarp) {
     // ===================== epilogue warps (also build the sample tables) =====================
@@ -996,6 +1003,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
   tc_fence_before();
   if (CG == 2) cluster_sync_all();   // no CTA may exit (or free TMEM) while its partner can still signal / read it
   else __syncthreads();
+#ifdef S2A_TC_TIMELINE
   if ((p.debug & 8) && blockIdx.x == 0 && tid == 0) {
     unsigned long long t1;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
@@ -1003,6 +1011,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     printf("s2a conv_tc clock probe: %lld cycles in %llu ns = %.0f MHz\n", c1 - dbg_c0, t1 - dbg_t0,
            (double)(c1 - dbg_c0) * 1e3 / (double)(t1 - dbg_t0));
   }
+#endif
   if (warp == kMmaWarp) {
     tc_fence_after();
     tmem_dealloc<CG>(tmem_base, TC_TMEM_COLS);

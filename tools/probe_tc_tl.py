@@ -1,3 +1,6 @@
+"""MMA-warp timeline probe.  Needs a library built with the clock probes compiled in:
+    S2A_NVCC_EXTRA=-DS2A_TC_TIMELINE python -m s2anet_b200.build --force
+then run with the S2A_TC_DEBUG values to try (8 = timeline; +1 no weight TMA, +2 no gather, +32 no epilogue)."""
 import os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
