@@ -144,3 +144,23 @@ def test_conv2d_tc_multi_vs_torch(dtype, C, Co, ks, relu):
     y0 = conv2d_forward_tc_multi(xs[:1], wt, None, relu=relu)[0]
     ref0 = torch.nn.functional.conv2d(xs[0].float(), wt.float(), None, padding=ks // 2)
     check(y0, ref0.relu() if relu else ref0, dtype)
+
+
+@pytest.mark.parametrize("scale", [0.05, 1.0, 12.0])
+def test_alignconv_tc_halo_and_global_fallback(scale):
+    """The tcgen05 AlignConv reads the feature map through a 14 x 22-pixel shared-memory halo and falls back to
+    global loads, per sample, for corners outside it.  Tiny anchors keep every sample in the halo, huge anchors
+    (12x: tap offsets of ~16 pixels, many samples outside the map) send almost everything through the fallback."""
+    from s2anet_b200.alignconv import alignconv_forward
+    dtype = torch.bfloat16
+    B, C, H, W, Co, stride = 2, 128, 40, 56, 64, 8
+    g = torch.Generator().manual_seed(int(scale * 100))
+    x = torch.randn(B, C, H, W, generator=g).to(DEV).to(dtype).contiguous(memory_format=torch.channels_last)
+    w = (torch.randn(Co, C, 3, 3, generator=g) * 0.05).to(DEV).to(dtype)
+    anc = synth.refined_anchors(B, H, W, stride, seed=3)
+    anc[..., 2:4] *= scale
+    anc[0, 0, 0] = [-5000.0, 9000.0, 300.0, 2.0, 0.3]          # far outside the image: contributes zeros
+    anc = torch.from_numpy(anc).to(DEV)
+    y = alignconv_forward(x, anc, w, stride)
+    ref = alignconv_forward(x.float(), anc, w.float(), stride)
+    check(y, ref, dtype)
