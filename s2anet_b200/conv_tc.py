@@ -2,11 +2,34 @@
 packed-weight cache.  Activations are bf16 / fp16 tensors in torch.channels_last memory format
 (physically NHWC), which is what cuDNN's tensor-core convolutions around these ops produce, so
 no layout copies happen inside a channels-last model."""
+import weakref
+
 import torch
 
 from . import _lib
 
-_PACK_CACHE = {}      # (data_ptr, version, dtype, device, kind) -> packed tensor
+# Packed weights are cached per source TENSOR OBJECT (not per address: a freed weight's address is reused by the
+# allocator): (id, dtype, kind) -> (weak refs to the sources, their versions, packed result).  An entry is valid only
+# while every source is still the same live object at the same in-place version; entries die with their tensors.
+_PACK_CACHE = {}
+
+
+def _cache_get(key, sources):
+    hit = _PACK_CACHE.get(key)
+    if hit is None:
+        return None
+    refs, versions, value = hit
+    if all(r() is t for r, t in zip(refs, sources)) and versions == tuple(t._version for t in sources):
+        return value
+    return None
+
+
+def _cache_put(key, sources, value):
+    if len(_PACK_CACHE) > 256:
+        _PACK_CACHE.clear()
+    drop = lambda _ref, k=key: _PACK_CACHE.pop(k, None)
+    _PACK_CACHE[key] = (tuple(weakref.ref(t, drop) for t in sources), tuple(t._version for t in sources), value)
+    return value
 
 
 def _nhwc(x):
@@ -18,8 +41,9 @@ def _nhwc(x):
 
 def pack_weight(weight, dtype, indices=None):
     """Pack (and cache) conv weights for the tensor-core kernel; ORConv banks go through the ARF map."""
-    key = (weight.data_ptr(), weight._version, dtype, weight.device, None if indices is None else indices.data_ptr())
-    hit = _PACK_CACHE.get(key)
+    sources = (weight,) if indices is None else (weight, indices)
+    key = (tuple(id(t) for t in sources), dtype, "arf")
+    hit = _cache_get(key, sources)
     if hit is not None:
         return hit
     dev = weight.device
@@ -38,10 +62,7 @@ def pack_weight(weight, dtype, indices=None):
         rc = _lib.load().s2a_conv_pack_weight(_lib.ptr(w), _lib.dtype_code(w), _lib.ptr(idx), _lib.ptr(packed),
                                               _lib.dtype_code(packed), Co, C, nOri, nRot, _lib.stream_ptr(dev))
     _lib.check(rc, "conv_pack_weight")
-    if len(_PACK_CACHE) > 64:
-        _PACK_CACHE.clear()
-    _PACK_CACHE[key] = packed
-    return packed
+    return _cache_put(key, sources, packed)
 
 
 def alignconv_forward_tc(x, anchors, weight, stride):
@@ -137,9 +158,9 @@ def orconv_forward_tc_multi(xs, weight, indices, bias, with_pool=False):
 
 def pack_conv2d_weight(weight, bias, dtype):
     """Pack (and cache) a stock [Co,C,ks,ks] conv weight (+ fp32 bias padded to Co_pad) for conv2d_forward_tc_multi."""
-    key = (weight.data_ptr(), weight._version, dtype, weight.device, "conv2d",
-           None if bias is None else (bias.data_ptr(), bias._version))
-    hit = _PACK_CACHE.get(key)
+    sources = (weight,) if bias is None else (weight, bias)
+    key = (tuple(id(t) for t in sources), dtype, "conv2d")
+    hit = _cache_get(key, sources)
     if hit is not None:
         return hit
     dev = weight.device
@@ -157,10 +178,7 @@ def pack_conv2d_weight(weight, bias, dtype):
     if bias is not None:
         b = torch.zeros((Co_pad,), dtype=torch.float32, device=dev)
         b[:Co] = bias.detach().float()
-    if len(_PACK_CACHE) > 64:
-        _PACK_CACHE.clear()
-    _PACK_CACHE[key] = (packed, b, Co_pad, ks)
-    return _PACK_CACHE[key]
+    return _cache_put(key, sources, (packed, b, Co_pad, ks))
 
 
 def conv2d_forward_tc_multi(xs, weight, bias=None, relu=False):

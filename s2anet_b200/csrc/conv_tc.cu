@@ -45,12 +45,22 @@ namespace s2a {
 #endif
 
 constexpr int TC_M = 128;                 // rows per tile (8 x 16 patch) = one UMMA M
-constexpr int TC_PH = 8, TC_PW = 16;
+constexpr int TC_PH = 8, TC_PW = 16;       // AlignConv tile: 8 rows x 16 pixels
+// Plain conv / ORConv tile: 16 rows x 8 pixels.  Its A operand is read by the tensor core straight out of a
+// shared-memory HALO of the feature map (18 rows x 16 pixels x 64 channels, SWIZZLE_128B, written by ONE TMA box per
+// (tile, 64-channel block)): tap (dy, dx) is the same halo seen through a descriptor whose start address is shifted
+// by (dy * 16 + dx) pixels.  An 8-row core group of the UMMA operand = 8 x-consecutive pixels of one halo row
+// (8 x 128 B), consecutive groups are one halo row (16 pixels = 2048 B = SBO) apart; a row pitch of 16 pixels keeps
+// every group on the same swizzle phase, and the shift by dx 128-byte lines goes into the descriptor's base-offset
+// field.  Every pixel travels L2 -> shared memory 2.25 times per 3 x 3 conv instead of 9 times (the convs were
+// bound by the L2 -> SM fabric: 11.6 TB/s of TMA loads with one box per tap).
+constexpr int TC_PPH = 16, TC_PPW = 8;
+constexpr int TC_PHALO_PITCH = 16, TC_PHALO_ROWS = TC_PPH + 2;
+constexpr int TC_PHALO_BYTES = TC_PHALO_ROWS * TC_PHALO_PITCH * 128;   // 36,864 B (a multiple of 1024)
 constexpr int TC_KB = 64;                 // k-block (elements) = 128 bytes of 16-bit data
 constexpr int TC_OUT_CH = 32;              // channels per epilogue TMA store (64-byte rows, SWIZZLE_64B)
 constexpr int TC_OUT_BYTES = TC_M * TC_OUT_CH * 2;    // 8 KB
 constexpr int TC_OUT_BUFS = 3;             // staging buffers: the TMA store of chunk i-1 may still be reading when chunk i is staged
-constexpr int TC_A_BYTES = TC_M * TC_KB * 2;          // 16 KB
 
 enum { TC_ALIGN = 0, TC_PLAIN = 1 };
 
@@ -72,7 +82,7 @@ template <int MODE> struct TcCfg;
 // KPS = k-blocks per stage: the MMA warp pays ~200 cycles of wait / commit / bookkeeping per STAGE and the tensor
 // pipe only holds two MMAs ahead, so the tensor-bound plain conv moves two k-blocks (8 MMAs) per stage.
 template <> struct TcCfg<TC_ALIGN> { static constexpr int CG = 2, SA = 6, SB = 6, GROUPS = 4, KPS = 1; static constexpr bool UNIFIED = true; };
-template <> struct TcCfg<TC_PLAIN> { static constexpr int CG = 2, SA = 3, SB = 3, GROUPS = 0, KPS = 2; static constexpr bool UNIFIED = true; };
+template <> struct TcCfg<TC_PLAIN> { static constexpr int CG = 2, SA = 4, SB = 4, GROUPS = 0, KPS = 2; static constexpr bool UNIFIED = true; };
 template <int MODE> constexpr int tc_threads() { return (TcCfg<MODE>::GROUPS * 4 + 8) * 32; }
 constexpr int TC_MAX_STAGES = 8;
 constexpr int TC_EPI_THREADS = 128;                   // 4 epilogue warps, one per TMEM lane quadrant
@@ -130,6 +140,10 @@ struct TcMaps {
   CUtensorMap y[TC_MAX_LEVELS];   // outputs: the epilogue stores 8 x 16 x 32-channel boxes through these
 };
 
+template <int MODE> __host__ __device__ constexpr int tc_pw() { return MODE == 1 ? TC_PPW : TC_PW; }
+template <int MODE> __host__ __device__ constexpr int tc_ph() { return MODE == 1 ? TC_PPH : TC_PH; }
+
+template <int MODE>
 __device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int tile) {
   int l = 0;
 #pragma unroll 1
@@ -141,8 +155,8 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int tile) {
   c.lvl = l;
   c.b = t / tpi;
   t -= c.b * tpi;
-  c.ty0 = (t / L.tiles_x) * TC_PH;
-  c.tx0 = (t % L.tiles_x) * TC_PW;
+  c.ty0 = (t / L.tiles_x) * tc_ph<MODE>();
+  c.tx0 = (t % L.tiles_x) * tc_pw<MODE>();
   return c;
 }
 
@@ -192,6 +206,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       __trap();
     }
   }
+}
+// A try_wait costs the issuing thread ~150 cycles even when the phase is already complete, a test_wait ~40
+// (tools/umma_bench2.cu): on the MMA warp's critical path, where the awaited phase is nearly always complete, probe
+// first and fall back to the suspending wait only if it is not.
+__device__ __forceinline__ void mbar_wait_likely_ready(uint32_t bar, uint32_t parity) {
+  if (!mbar_test(bar, parity)) mbar_wait(bar, parity);
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -364,8 +384,9 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
 // start address >> 4 | LBO (unused for swizzled K-major, 1) << 16 | SBO (8 rows * 128 B = 1024 B) >> 4
 // << 32 | version 1 << 46 | layout SWIZZLE_128B (2) << 61.
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
-  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
+// Bits 49-51 (base offset) are added by the caller when the start address is not 1024-byte aligned.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr, uint32_t sbo_bytes = 1024) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) |
          (2ull << 61);
 }
 
@@ -491,23 +512,23 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
   static_assert(GROUPS < SA && SA <= TC_MAX_STAGES && SB <= TC_MAX_STAGES, "stage rings");
   static_assert(MODE != TC_ALIGN || 256 + SA * 32 <= TC_TMEM_COLS, "AlignConv: accumulator + A stages must fit tensor memory");
   constexpr int B_KB_BYTES = (256 / CG) * TC_KB * 2;            // one k-block of this CTA's weight rows
-  constexpr int B_STAGE_BYTES = KPS * B_KB_BYTES, A_STAGE_BYTES = KPS * TC_A_BYTES;
+  constexpr int B_STAGE_BYTES = KPS * B_KB_BYTES;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B operands need 1024-byte aligned tiles: align the dynamic window by hand (the offset is
   // the same in both CTAs of a pair, which the paired MMA and the multicast commits rely on)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  // carve: A stages (PLAIN) | B stages | 2 output staging buffers | ALIGN: 2 halo buffers, 2 sample tables | barriers
-  // | tmem pointer
+  // carve: B stages | 3 output staging buffers | 2 halo buffers | ALIGN: 2 sample tables | barriers | tmem pointer
   constexpr int ACC = MODE == TC_ALIGN ? 1 : 2;        // accumulators: PLAIN 2 x 256 TMEM columns; ALIGN 1 (+ 8 A stages x 32 columns)
   constexpr uint32_t A_TMEM_COL0 = 256;                // ALIGN: first TMEM column of the A stages
-  uint8_t* sA = smem;                                  // PLAIN only (ALIGN keeps A in tensor memory)
-  uint8_t* sB = sA + (MODE == TC_ALIGN ? 0 : SA * A_STAGE_BYTES);
-  uint8_t* s_out = sB + SB * B_STAGE_BYTES;                              // 2 x 8 KB, 1024-byte aligned (SWIZZLE_64B)
-  uint8_t* s_halo = s_out + TC_OUT_BUFS * TC_OUT_BYTES;                            // ALIGN only
-  TapSample* s_tab = reinterpret_cast<TapSample*>(s_halo + 2 * TC_HALO_BYTES);
-  static_assert(TC_HALO_BYTES % 128 == 0 && (TC_OUT_BUFS * TC_OUT_BYTES) % 1024 == 0, "TMA source / destination alignment");
+  constexpr int HALO_BYTES = MODE == TC_ALIGN ? TC_HALO_BYTES : TC_PHALO_BYTES;
+  uint8_t* sB = smem;
+  uint8_t* s_out = sB + SB * B_STAGE_BYTES;                              // 3 x 8 KB, 1024-byte aligned (SWIZZLE_64B)
+  uint8_t* s_halo = s_out + TC_OUT_BUFS * TC_OUT_BYTES;                  // 1024-byte aligned (PLAIN: SWIZZLE_128B operand)
+  TapSample* s_tab = reinterpret_cast<TapSample*>(s_halo + 2 * HALO_BYTES);          // ALIGN only
+  static_assert(TC_HALO_BYTES % 128 == 0 && TC_PHALO_BYTES % 1024 == 0 && (TC_OUT_BUFS * TC_OUT_BYTES) % 1024 == 0 &&
+                B_STAGE_BYTES % 1024 == 0, "TMA source / destination alignment");
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(
-      s_out + TC_OUT_BUFS * TC_OUT_BYTES + (MODE == TC_ALIGN ? 2 * TC_HALO_BYTES + 2 * sizeof(TapSample) * TC_M * 9 : (size_t)0));
+      s_halo + 2 * HALO_BYTES + (MODE == TC_ALIGN ? 2 * sizeof(TapSample) * TC_M * 9 : (size_t)0));
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + TC_NBAR);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -552,7 +573,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     }
     for (int s = 0; s < TC_ACC_STAGES; ++s) {
       mbar_init(bar_acc_full + 8 * s, 1);       // tcgen05.commit after the last k-block of a tile group
-      mbar_init(bar_acc_empty + 8 * s, CG * TC_EPI_THREADS);
+      mbar_init(bar_acc_empty + 8 * s, CG * (TC_EPI_THREADS / 32));   // one elected arrive per epilogue warp of the group
       mbar_init(bar_tab_full + 8 * s, TC_EPI_THREADS);
       mbar_init(bar_halo_full + 8 * s, 1);                   // the TMA thread's expect_tx arrive (+ bytes)
       mbar_init(bar_halo_empty + 8 * s, kProdWarps > 0 ? kProdWarps : 1);   // one elected arrive per producer warp
@@ -595,7 +616,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     int it = 0;
     for (int q = first_q; MODE == TC_ALIGN && q < ngroups; q += q_step, ++it) {
       const int tile = S2A_TILE_OF(q);
-      const TileCoord tc = decode_tile(p, tile);
+      const TileCoord tc = decode_tile<MODE>(p, tile);
       const TcLevel& L = p.lv[tc.lvl];
       const int H = L.H, W = L.W;
       const uint32_t pix_stride = (uint32_t)p.C * 2u, row_stride = (uint32_t)W * pix_stride;
@@ -690,36 +711,23 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         __syncwarp();
         ++hseq;
       };
-      if (MODE == TC_ALIGN && first_q < ngroups) load_halo(decode_tile(p, S2A_TILE_OF(first_q)), 0);
+      if (MODE == TC_ALIGN && first_q < ngroups) load_halo(decode_tile<MODE>(p, S2A_TILE_OF(first_q)), 0);
       for (int q = first_q; MODE == TC_PLAIN && q < ngroups; q += q_step) {
-        // plain conv / ORConv: a stage carries KPS k-blocks; per k-block the A tile is the 8 x 16 patch shifted by the
-        // tap (64 channels = one 4-D box {64, 16, 8, 1}, zero-filled outside the map) plus this CTA's weight rows
-        const TileCoord tc = decode_tile(p, S2A_TILE_OF(q));
-        int cb = 0, tap = 0;
+        // plain conv / ORConv: a stage carries KPS weight k-blocks (this CTA's C_out/CG rows of each); the A operand
+        // is the halo the halo warp loads
         for (int kb = 0; kb < nkb; kb += KPS) {
           const int nk = min(KPS, nkb - kb);
-          int cbj[KPS], dxj[KPS], dyj[KPS];
-          const int half = p.ks >> 1;
-#pragma unroll
-          for (int j = 0; j < KPS; ++j) {
-            const int ti = tap / p.ks;
-            cbj[j] = cb; dyj[j] = ti - half; dxj[j] = tap - p.ks * ti - half;
-            if (j < nk && ++tap == ntap) { tap = 0; ++cb; }
-          }
           mbar_wait(bar_empty_a + 8 * sa, pa ^ 1u);
           if (elect_one()) {
             if ((p.debug & 1) && warm) {
               if (leader) mbar_arrive(bar_full_a + 8 * sa);
             } else {
-              if (leader) mbar_arrive_expect_tx(bar_full_a + 8 * sa, (uint32_t)nk * (b_bytes_group + CG * TC_A_BYTES));
+              if (leader) mbar_arrive_expect_tx(bar_full_a + 8 * sa, (uint32_t)nk * b_bytes_group);
 #pragma unroll
               for (int j = 0; j < KPS; ++j) {
-                if (j < nk) {
-                  tma_load_4d<CG>(smem_u32(sA + sa * A_STAGE_BYTES + j * TC_A_BYTES), &maps.x[tc.lvl], cbj[j] * TC_KB, tc.tx0 + dxj[j],
-                                  tc.ty0 + dyj[j], tc.b, ld_full_a + 8 * sa);
+                if (j < nk)
                   tma_load_2d<CG>(smem_u32(sB + sa * B_STAGE_BYTES + j * B_KB_BYTES), &maps.w, (kb + j) * TC_KB,
                                   (int)cta_rank * co_part, ld_full_a + 8 * sa);
-                }
               }
             }
           }
@@ -729,29 +737,23 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         warm = true;
       }
       for (int q = first_q; MODE == TC_ALIGN && q < ngroups; q += q_step) {
-        const TileCoord tc = decode_tile(p, S2A_TILE_OF(q));
+        const TileCoord tc = decode_tile<MODE>(p, S2A_TILE_OF(q));
         int cb = 0, tap = 0;
         for (int kb = 0; kb < nkb; ++kb) {
           if (UNI) {
-            // one ring: the weight k-block and the A operand of a k-block complete the same "full" barrier -- for
-            // TC_PLAIN the A tile is the 8 x 16 patch shifted by the tap (64 channels = one 4-D box {64, 16, 8, 1},
-            // zero-filled outside the map), for TC_ALIGN the producer warps arrive on it after their tcgen05.st
+            // one ring: the weight k-block and the A operand of a k-block complete the same "full" barrier (the
+            // producer warps arrive on it after their tcgen05.st)
             if (MODE == TC_ALIGN && tap == 3) {
               // halo of the NEXT (tile, channel block), requested six k-blocks before its first use
               if (cb + 1 < ncb) load_halo(tc, cb + 1);
-              else if (q + q_step < ngroups) load_halo(decode_tile(p, S2A_TILE_OF(q + q_step)), 0);
+              else if (q + q_step < ngroups) load_halo(decode_tile<MODE>(p, S2A_TILE_OF(q + q_step)), 0);
             }
             mbar_wait(bar_empty_a + 8 * sa, pa ^ 1u);
             if (elect_one()) {
               if ((p.debug & 1) && warm) {
                 if (leader) mbar_arrive(bar_full_a + 8 * sa);
               } else {
-                if (leader) mbar_arrive_expect_tx(bar_full_a + 8 * sa, b_bytes_group + (MODE == TC_PLAIN ? CG * TC_A_BYTES : 0));
-                if (MODE == TC_PLAIN) {
-                  const int ti = tap / p.ks, half = p.ks >> 1;
-                  tma_load_4d<CG>(smem_u32(sA + sa * TC_A_BYTES), &maps.x[tc.lvl], cb * TC_KB, tc.tx0 - half + (tap - p.ks * ti),
-                                  tc.ty0 - half + ti, tc.b, ld_full_a + 8 * sa);
-                }
+                if (leader) mbar_arrive_expect_tx(bar_full_a + 8 * sa, b_bytes_group);
                 tma_load_2d<CG>(smem_u32(sB + sa * B_STAGE_BYTES), &maps.w, kb * TC_KB, (int)cta_rank * co_part, ld_full_a + 8 * sa);
               }
             }
@@ -761,7 +763,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
             if (MODE == TC_ALIGN && tap == 3) {
               // halo of the NEXT (tile, channel block), requested six k-blocks before its first use
               if (cb + 1 < ncb) load_halo(tc, cb + 1);
-              else if (q + q_step < ngroups) load_halo(decode_tile(p, S2A_TILE_OF(q + q_step)), 0);
+              else if (q + q_step < ngroups) load_halo(decode_tile<MODE>(p, S2A_TILE_OF(q + q_step)), 0);
             }
             mbar_wait(bar_empty_b + 8 * sb, pb ^ 1u);
             if (elect_one()) {
@@ -780,6 +782,26 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         warm = true;
       }
     }
+  } else if (MODE == TC_PLAIN && warp == kMmaWarp + 1) {
+    // ===================== plain conv: halo loads (the A operand) =====================
+    // One box {64 ch, 16, 18, 1} per (tile, 64-channel block) at (tx0 - 1, ty0 - 1), zero-filled outside the map and
+    // beyond C, into buffer (sequence number & 1).  A buffer is recycled when the last tap's MMAs of its channel
+    // block have retired (tcgen05.commit, multicast to both CTAs); both CTAs' boxes complete the leader's barrier.
+    const uint32_t ld_halo_full = CG == 2 ? map_to_cta(bar_halo_full, 0) : bar_halo_full;
+    uint32_t hseq = 0;
+    for (int q = first_q; q < ngroups; q += q_step) {
+      const TileCoord tc = decode_tile<MODE>(p, S2A_TILE_OF(q));
+      for (int cb = 0; cb < ncb; ++cb, ++hseq) {
+        const uint32_t hb = hseq & 1u;
+        mbar_wait(bar_halo_empty + 8 * hb, ((hseq >> 1) & 1u) ^ 1u);
+        if (elect_one()) {
+          if (leader) mbar_arrive_expect_tx(bar_halo_full + 8 * hb, (uint32_t)(CG * TC_PHALO_BYTES));
+          tma_load_4d<CG>(smem_u32(s_halo + hb * TC_PHALO_BYTES), &maps.x[tc.lvl], cb * TC_KB, tc.tx0 - 1, tc.ty0 - 1, tc.b,
+                          ld_halo_full + 8 * hb);
+        }
+        __syncwarp();
+      }
+    }
   } else if (warp == kMmaWarp) {
     // ===================== MMA issuer (leader CTA only) =====================
     if (leader) {                                    // the whole warp runs the loop; one elected lane issues
@@ -796,14 +818,20 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       static_assert(UNI, "the MMA thread handles one barrier pair per stage");
       // Everything this thread touches per k-block advances incrementally (stage barrier addresses, operand
       // descriptors, TMEM column of the A stage): the instructions between two MMAs are on the critical path.
-      const uint64_t adesc0 = MODE == TC_ALIGN ? 0ull : umma_desc_sw128(smem_u32(sA));
+      // plain conv: the A operand of tap (ti, tj) is the halo buffer seen from pixel (ti, tj) on: start address
+      // + (ti * 16 + tj) 128-byte lines, SBO = one halo row (2048 B), base offset = tj (the swizzle phase of the
+      // first line; rows are a multiple of 8 lines apart and do not change it)
+      static_assert(MODE == TC_ALIGN || KPS == 2, "plain conv: two k-blocks per stage");
+      const uint64_t hdesc0 = umma_desc_sw128(smem_u32(s_halo), TC_PHALO_PITCH * 128);
       const uint64_t bdesc0 = umma_desc_sw128(smem_u32(sB));
       const uint32_t atm0 = tmem_base + A_TMEM_COL0;
-      uint64_t adesc = adesc0, bdesc = bdesc0;
+      uint64_t bdesc = bdesc0;
+      int tap = 0;                                   // plain conv: tap of the next k-block, and the running
+      uint32_t hseq = 0;                             // (tile, channel block) counter: halo buffer = hseq & 1
       uint32_t atm = atm0, full_bar = bar_full_a, empty_bar = bar_empty_a;
       int sa = 0, it = 0;
       uint32_t pa = 0;
-      S2A_TL(long long tl[10]; long long tw_acc = 0, tw_a = 0; int n_block = 0;)
+      S2A_TL(long long tl[10]; long long tw_acc = 0, tw_a = 0, tw_halo = 0; int n_block = 0;)
       mbar_wait(bar_acc_empty, 1u);
       mbar_wait(bar_full_a, 0u);
       tc_fence_after();
@@ -819,23 +847,39 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
           const int nk = KPS == 1 ? 1 : min(KPS, nkb - kb);          // k-blocks in this stage
           // +32 bytes (>>4 = 2) per K=16 step inside the swizzle atom; A in TMEM: +8 columns per K=16 step.
           // Every MMA of the stage but the last two is issued first ...
+          uint64_t a_desc0 = 0ull, a_desc1 = 0ull;   // plain conv: A descriptors of the stage's k-blocks,
+          uint32_t a_rel0 = 0u, a_rel1 = 0u;         // and the halo barrier to release after a block's last tap
+          if (MODE == TC_PLAIN) {
+            auto next_block = [&](uint64_t& desc, uint32_t& rel) {
+              if (tap == 0) {                        // first tap of a channel block: its halo (requested nine k-blocks ago)
+                S2A_TL(long long w0 = (p.debug & 8) ? clock64() : 0;)
+                mbar_wait_likely_ready(bar_halo_full + 8 * (hseq & 1u), (hseq >> 1) & 1u);
+                tc_fence_after();
+                S2A_TL(if (p.debug & 8) tw_halo += clock64() - w0;)
+              }
+              const int ti = p.ks == 3 ? (tap * 11) >> 5 : 1, tj = p.ks == 3 ? tap - 3 * ti : 1;
+              desc = hdesc0 + (uint64_t)((hseq & 1u) * (uint32_t)(TC_PHALO_BYTES >> 4)) +
+                     (uint64_t)((ti * TC_PHALO_PITCH + tj) * (128 >> 4)) + ((p.debug & 4) ? ((uint64_t)tj << 49) : 0ull);
+              if (++tap == ntap) { tap = 0; rel = bar_halo_empty + 8 * (hseq & 1u); ++hseq; }
+            };
+            next_block(a_desc0, a_rel0);
+            if (nk == 2) next_block(a_desc1, a_rel1);
+          }
           const bool issuer = elect_one();
           if (issuer) {
             if (MODE == TC_ALIGN) {
               umma_f16_ts<CG>(d_tmem, atm, bdesc, idesc, kb != 0 ? 1u : 0u);
               umma_f16_ts<CG>(d_tmem, atm + 8u, bdesc + 2, idesc, 1u);
             } else {
-#pragma unroll
-              for (int j = 0; j < KPS; ++j) {
-                if (j < nk) {
-                  const uint64_t aj = adesc + (uint64_t)(j * (TC_A_BYTES >> 4)), bj = bdesc + (uint64_t)(j * (B_KB_BYTES >> 4));
-                  umma_f16<CG>(d_tmem, aj, bj, idesc, (kb | j) != 0 ? 1u : 0u);
-                  umma_f16<CG>(d_tmem, aj + 2, bj + 2, idesc, 1u);
-                  if (j + 1 < nk) {
-                    umma_f16<CG>(d_tmem, aj + 4, bj + 4, idesc, 1u);
-                    umma_f16<CG>(d_tmem, aj + 6, bj + 6, idesc, 1u);
-                  }
-                }
+              umma_f16<CG>(d_tmem, a_desc0, bdesc, idesc, kb != 0 ? 1u : 0u);
+              umma_f16<CG>(d_tmem, a_desc0 + 2, bdesc + 2, idesc, 1u);
+              if (nk == 2) {
+                umma_f16<CG>(d_tmem, a_desc0 + 4, bdesc + 4, idesc, 1u);
+                umma_f16<CG>(d_tmem, a_desc0 + 6, bdesc + 6, idesc, 1u);
+                if (a_rel0) umma_commit<CG>(a_rel0);
+                const uint64_t b1 = bdesc + (uint64_t)(B_KB_BYTES >> 4);
+                umma_f16<CG>(d_tmem, a_desc1, b1, idesc, 1u);
+                umma_f16<CG>(d_tmem, a_desc1 + 2, b1 + 2, idesc, 1u);
               }
             }
           }
@@ -851,9 +895,12 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
             // tensor-bound: the next stage is (nearly) always there (and, at a tile boundary, the next accumulator
             // has to be drained)
             if (more) {
-              if (new_acc) mbar_wait(acc_bar, acc_par);
-              mbar_wait(nfull, npa);
+              S2A_TL(long long w0 = (p.debug & 8) ? clock64() : 0;)
+              if (new_acc) mbar_wait_likely_ready(acc_bar, acc_par);
+              S2A_TL(long long w1 = (p.debug & 8) ? clock64() : 0;)
+              mbar_wait_likely_ready(nfull, npa);
               tc_fence_after();
+              S2A_TL(if (p.debug & 8) { if (new_acc) tw_acc += w1 - w0; tw_a += clock64() - w1; ++n_block; })
               ready = true;
             }
           } else {
@@ -869,9 +916,11 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
               umma_f16_ts<CG>(d_tmem, atm + 16u, bdesc + 4, idesc, 1u);
               umma_f16_ts<CG>(d_tmem, atm + 24u, bdesc + 6, idesc, 1u);
             } else {
-              const uint64_t aj = adesc + (uint64_t)((nk - 1) * (TC_A_BYTES >> 4)), bj = bdesc + (uint64_t)((nk - 1) * (B_KB_BYTES >> 4));
+              const uint64_t aj = nk == 2 ? a_desc1 : a_desc0, bj = bdesc + (uint64_t)((nk - 1) * (B_KB_BYTES >> 4));
               umma_f16<CG>(d_tmem, aj + 4, bj + 4, idesc, 1u);
               umma_f16<CG>(d_tmem, aj + 6, bj + 6, idesc, 1u);
+              const uint32_t rel = nk == 2 ? a_rel1 : a_rel0;
+              if (rel) umma_commit<CG>(rel);        // halo buffer (of both CTAs) reusable
             }
             umma_commit<CG>(empty_bar);             // stage (of every CTA of the group) reusable once these MMAs have read it
             if (new_acc) umma_commit<CG>(acc_full_bar);   // accumulators of this tile group complete
@@ -885,15 +934,15 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
             tc_fence_after();
             S2A_TL(if (p.debug & 8) { tw_acc += w1 - w0; tw_a += clock64() - w1; ++n_block; })
           }
-          if (wrap) { sa = 0; adesc = adesc0; bdesc = bdesc0; atm = atm0; empty_bar = bar_empty_a; }
-          else { ++sa; adesc += A_STAGE_BYTES >> 4; bdesc += B_STAGE_BYTES >> 4; atm += 32u; empty_bar += 8; }
+          if (wrap) { sa = 0; bdesc = bdesc0; atm = atm0; empty_bar = bar_empty_a; }
+          else { ++sa; bdesc += B_STAGE_BYTES >> 4; atm += 32u; empty_bar += 8; }
           full_bar = nfull; pa = npa;
         }
       }
 #ifdef S2A_TC_TIMELINE
       if ((p.debug & 8) && blockIdx.x == 0 && lane == 0) {
         tl[min(it, 9)] = clock64();
-        printf("s2a conv_tc MMA thread: blocked %d times: acc %lld, full %lld cycles; start +%lld;", n_block, tw_acc, tw_a, tl[0] - dbg_c0);
+        printf("s2a conv_tc MMA thread: blocked %d times: acc %lld, full %lld, halo %lld cycles; start +%lld;", n_block, tw_acc, tw_a, tw_halo, tl[0] - dbg_c0);
         for (int i = 0; i < min(it, 9); ++i) printf(" tile%d %lld", i, tl[i + 1] - tl[i]);
         printf("\n");
       }
@@ -909,7 +958,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       for (int j = 0; j < 2; ++j) {
         const int q = first_q + j * q_step;
         if (q < ngroups) {
-          build_tap_table<T>(p, decode_tile(p, S2A_TILE_OF(q)), s_tab + j * (TC_M * 9), et, TC_EPI_THREADS);
+          build_tap_table<T>(p, decode_tile<MODE>(p, S2A_TILE_OF(q)), s_tab + j * (TC_M * 9), et, TC_EPI_THREADS);
           mbar_arrive(bar_tab_full + 8 * j);
         }
       }
@@ -918,12 +967,12 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     for (int q = first_q; q < ngroups; q += q_step, ++it) {
       const int as = it % ACC, tb = it & 1;         // accumulator / sample-table buffer of this tile
       const bool ghost = S2A_IS_GHOST(q);
-      const TileCoord tc = decode_tile(p, S2A_TILE_OF(q));
+      const TileCoord tc = decode_tile<MODE>(p, S2A_TILE_OF(q));
       const TcLevel& L = p.lv[tc.lvl];
       mbar_wait(bar_acc_full + 8 * as, (uint32_t)(it / ACC) & 1u);
       tc_fence_after();
       const int r = quad * 32 + lane;
-      const int y = tc.ty0 + r / TC_PW, x = tc.tx0 + r % TC_PW;
+      const int y = tc.ty0 + r / tc_pw<MODE>(), x = tc.tx0 + r % tc_pw<MODE>();
       const bool valid = (y < L.H && x < L.W) && !ghost;
       const size_t pos = (size_t)(tc.b * L.H + y) * L.W + x;
       // 32 channels at a time: TMEM -> registers -> bias / ReLU / 8-way orientation max -> 16-bit -> a 64-byte row
@@ -933,8 +982,11 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * 256 + c0), v);
         if (c0 + TC_OUT_CH >= p.Co) {               // last columns are in registers: the accumulator is free
+          // (one arrive per warp: 128 per-thread arrives on the leader's barrier -- half of them remote -- took
+          // ~3,000 cycles to get through, on the critical path of the accumulator hand-off)
           tc_fence_before();
-          mbar_arrive_cluster(ld_acc_empty + 8 * as);
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(ld_acc_empty + 8 * as);
         }
         uint32_t pk[16];
         float m[4];
@@ -976,7 +1028,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         fence_proxy_async_smem();
         __syncwarp();
         if (issuer && !ghost && !(p.debug & 64))
-          tma_store_4d(&maps.y[tc.lvl], smem_u32(sbuf), c0, tc.tx0, tc.ty0 + 2 * quad, tc.b);
+          tma_store_4d(&maps.y[tc.lvl], smem_u32(sbuf), c0, tc.tx0, tc.ty0 + (32 / tc_pw<MODE>()) * quad, tc.b);
         if (MODE == TC_PLAIN && valid && L.pooled) {
           uint2 o;
           H2* oh = reinterpret_cast<H2*>(&o);
@@ -985,13 +1037,13 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
           *reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(L.pooled) + (pos * (p.Co / 8) + c0 / 8) * 2) = o;
         }
       }
-      if (p.debug & 32) { tc_fence_before(); mbar_arrive_cluster(ld_acc_empty + 8 * as); }
+      if (p.debug & 32) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive_cluster(ld_acc_empty + 8 * as); }
       if (MODE == TC_ALIGN) {
         // every A k-block of tile `it` has been produced (its MMAs completed), so table (it & 1) is free:
         // build the table of tile it + 2 into it
         const int nxt = q + 2 * q_step;
         if (nxt < ngroups) {
-          build_tap_table<T>(p, decode_tile(p, S2A_TILE_OF(nxt)), s_tab + tb * (TC_M * 9), et, TC_EPI_THREADS);
+          build_tap_table<T>(p, decode_tile<MODE>(p, S2A_TILE_OF(nxt)), s_tab + tb * (TC_M * 9), et, TC_EPI_THREADS);
           mbar_arrive(bar_tab_full + 8 * tb);
         }
       }
@@ -1105,9 +1157,10 @@ static EncodeTiledFn get_encode_fn() {
 template <int MODE>
 constexpr size_t tc_smem_bytes() {
   using Cfg = TcCfg<MODE>;
-  return 1024 /*alignment slack*/ + (MODE == TC_ALIGN ? 0 : (size_t)Cfg::SA * Cfg::KPS * TC_A_BYTES) +
-         (size_t)Cfg::SB * Cfg::KPS * ((256 / Cfg::CG) * TC_KB * 2) + (size_t)TC_OUT_BUFS * TC_OUT_BYTES +
-         (MODE == TC_ALIGN ? 2 * (size_t)TC_HALO_BYTES + 2 * sizeof(TapSample) * TC_M * 9 : (size_t)0) + 8 * TC_NBAR + 16;
+  return 1024 /*alignment slack*/ + (size_t)Cfg::SB * Cfg::KPS * ((256 / Cfg::CG) * TC_KB * 2) +
+         (size_t)TC_OUT_BUFS * TC_OUT_BYTES +
+         (MODE == TC_ALIGN ? 2 * (size_t)TC_HALO_BYTES + 2 * sizeof(TapSample) * TC_M * 9 : 2 * (size_t)TC_PHALO_BYTES) +
+         8 * TC_NBAR + 16;
 }
 
 template <int MODE, typename T>
@@ -1161,7 +1214,8 @@ static int conv_tc_common(int mode, int nlevels, const void* const* xs, const fl
     TcLevel& L = p.lv[l];
     L.x = xs[l]; L.anchors = anchors ? anchors[l] : nullptr; L.out = outs[l]; L.pooled = pooleds ? pooleds[l] : nullptr;
     L.H = Hs[l]; L.W = Ws[l];
-    L.tiles_x = (Ws[l] + TC_PW - 1) / TC_PW; L.tiles_y = (Hs[l] + TC_PH - 1) / TC_PH;
+    const int pw = mode == TC_PLAIN ? TC_PPW : TC_PW, ph = mode == TC_PLAIN ? TC_PPH : TC_PH;
+    L.tiles_x = (Ws[l] + pw - 1) / pw; L.tiles_y = (Hs[l] + ph - 1) / ph;
     L.tile_begin = (int)tiles;
     L.stride = strides ? strides[l] : 1.0f;
     S2A_CHECK_ARG(mode == TC_PLAIN || L.stride > 0.0f, "alignconv_tc: stride must be positive");
@@ -1175,12 +1229,13 @@ static int conv_tc_common(int mode, int nlevels, const void* const* xs, const fl
   memset(&tmap, 0, sizeof(tmap));
   const CUtensorMapDataType tdt = dtype == S2A_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   for (int l = 0; l < nlevels; ++l) {
-    // TC_PLAIN: A tiles {64 ch, 16, 8, 1} (SWIZZLE_128B, the UMMA operand layout); TC_ALIGN: halo windows
-    // {64 ch, 22, 14, 1}, plain layout (one 128-byte line per pixel), both zero-filled outside the map
+    // TC_PLAIN: halo windows {64 ch, 16, 18, 1} (SWIZZLE_128B, read by the tensor core as the A operand of every
+    // tap); TC_ALIGN: halo windows {64 ch, 22, 14, 1}, plain layout (one 128-byte line per pixel, gathered by
+    // LDS); both zero-filled outside the map
     const cuuint64_t xd[4] = {(cuuint64_t)C, (cuuint64_t)Ws[l], (cuuint64_t)Hs[l], (cuuint64_t)B};
     const cuuint64_t xs_[3] = {(cuuint64_t)C * 2, (cuuint64_t)Ws[l] * C * 2, (cuuint64_t)Hs[l] * Ws[l] * C * 2};
-    const cuuint32_t xb[4] = {(cuuint32_t)TC_KB, (cuuint32_t)(mode == TC_PLAIN ? TC_PW : TC_HW),
-                              (cuuint32_t)(mode == TC_PLAIN ? TC_PH : TC_HH), 1};
+    const cuuint32_t xb[4] = {(cuuint32_t)TC_KB, (cuuint32_t)(mode == TC_PLAIN ? TC_PHALO_PITCH : TC_HW),
+                              (cuuint32_t)(mode == TC_PLAIN ? TC_PHALO_ROWS : TC_HH), 1};
     const cuuint32_t xe[4] = {1, 1, 1, 1};
     CUresult xr = enc(&tmap.x[l], tdt, 4, const_cast<void*>(xs[l]), xd, xs_, xb, xe, CU_TENSOR_MAP_INTERLEAVE_NONE,
                       mode == TC_PLAIN ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
@@ -1190,7 +1245,8 @@ static int conv_tc_common(int mode, int nlevels, const void* const* xs, const fl
   for (int l = 0; l < nlevels; ++l) {
     const cuuint64_t yd[4] = {(cuuint64_t)Co, (cuuint64_t)Ws[l], (cuuint64_t)Hs[l], (cuuint64_t)B};
     const cuuint64_t ys_[3] = {(cuuint64_t)Co * 2, (cuuint64_t)Ws[l] * Co * 2, (cuuint64_t)Hs[l] * Ws[l] * Co * 2};
-    const cuuint32_t yb[4] = {(cuuint32_t)TC_OUT_CH, (cuuint32_t)TC_PW, 2, 1};      // one epilogue warp's 32 tile rows
+    const int pw = mode == TC_PLAIN ? TC_PPW : TC_PW;
+    const cuuint32_t yb[4] = {(cuuint32_t)TC_OUT_CH, (cuuint32_t)pw, (cuuint32_t)(32 / pw), 1};      // one epilogue warp's 32 tile rows
     const cuuint32_t ye[4] = {1, 1, 1, 1};
     CUresult yr = enc(&tmap.y[l], tdt, 4, outs[l], yd, ys_, yb, ye, CU_TENSOR_MAP_INTERLEAVE_NONE,
                       CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

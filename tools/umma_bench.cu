@@ -22,7 +22,7 @@ template <int CG> __device__ __forceinline__ void commit(uint32_t bar) {
 }
 
 template <int CG>
-__global__ void __launch_bounds__(128, 1) bench(int N, int alt, int iters, int kstep_bytes, long long* out, int mode) {
+__global__ void __launch_bounds__(128, 1) bench(int N, int alt, int iters, int kstep_bytes, long long* out, int mode, int mper) {
   extern __shared__ uint8_t raw[];
   uint8_t* sm = raw + ((1024u - (smem_u32(raw) & 1023u)) & 1023u);
   uint8_t* sA = sm;                  // 4 stages x 16 KB
@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(128, 1) bench(int N, int alt, int iters, int k
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tm = *tptr;
   if (threadIdx.x == 0 && rank == 0) {
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)((128 * CG) >> 4) << 24);
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)((mper * CG) >> 4) << 24);
     const long long c0 = clock64();
     for (int i = 0; i < iters; ++i) {
       const int st = i & 3;
@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(128, 1) bench(int N, int alt, int iters, int k
   }
 }
 
-template <int CG> void run(int grid, int N, int alt, int kstep, int mode = 0) {
+template <int CG> void run(int grid, int N, int alt, int kstep, int mode = 0, int mper = 128) {
   long long* d;
   cudaMalloc(&d, 8);
   const size_t smem = 1024 + 4 * 16384 + 4 * 32768 + 64;
@@ -102,7 +102,7 @@ template <int CG> void run(int grid, int N, int alt, int kstep, int mode = 0) {
     cfg.attrs = at; cfg.numAttrs = 1;
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     cudaEventRecord(e0);
-    cudaError_t e = cudaLaunchKernelEx(&cfg, bench<CG>, N, alt, iters, kstep, d, mode);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, bench<CG>, N, alt, iters, kstep, d, mode, mper);
     cudaEventRecord(e1);
     cudaError_t e2 = cudaDeviceSynchronize();
     if (e != cudaSuccess || e2 != cudaSuccess) { printf("error %s %s\n", cudaGetErrorString(e), cudaGetErrorString(e2)); return; }
@@ -110,15 +110,29 @@ template <int CG> void run(int grid, int N, int alt, int kstep, int mode = 0) {
     long long cyc; cudaMemcpy(&cyc, d, 8, cudaMemcpyDeviceToHost);
     if (rep == 1) {
       const double per = (double)cyc / (iters * 4.0);
-      const double flop = 2.0 * 128 * CG * N * 16;              // per MMA (whole group)
-      printf("mode=%d cg=%d grid=%3d N=%3d alt=%d kstep=%3dB : %7.1f cyc/MMA  -> %6.0f flop/clk/SM, %.3f ms, %7.0f TFLOP/s chip\n", mode, CG, grid, N, alt,
+      const double flop = 2.0 * mper * CG * N * 16;              // per MMA (whole group)
+      printf("mode=%d Mper=%d cg=%d grid=%3d N=%3d alt=%d kstep=%3dB : %7.1f cyc/MMA  -> %6.0f flop/clk/SM, %.3f ms, %7.0f TFLOP/s chip\n", mode, mper, CG, grid, N, alt,
              kstep, per, flop / per / CG, ms, flop * iters * 4.0 * (grid / CG) / (ms * 1e-3) / 1e12);
     }
   }
   cudaFree(d);
 }
 
-int main() {
+int main(int argc, char** argv) {
+  if (argc > 2) {          // commit cost: two commits per 4 MMAs (mode 2) vs none, small and large N
+    for (int N : {32, 256})
+      for (int mode : {0, 2}) { run<1>(148, N, 0, 32, mode); run<2>(148, N, 0, 32, mode); }
+    return 0;
+  }
+  if (argc > 1) {          // shape sweep: MMA time vs M (rows per CTA) and N
+    for (int mper : {128, 64}) {
+      for (int N : {16, 32, 64, 128, 256}) {
+        run<1>(148, N, 0, 32, 0, mper);
+        run<2>(148, N, 0, 32, 0, mper);
+      }
+    }
+    return 0;
+  }
   for (int grid : {2, 148}) {
     for (int N : {64, 128, 256}) {
       run<1>(grid, N, 0, 32);

@@ -4,6 +4,7 @@
 // Prints cycles per k-block (ideal 512).
 #include <cstdio>
 #include <cstdint>
+#include <cstdlib>
 #include <cuda_runtime.h>
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -31,7 +32,7 @@ __device__ __forceinline__ void arrive(uint32_t bar) {
 #endif
 constexpr int S = RING;   // barrier ring depth (operand buffers alias modulo 4)
 
-__global__ void __launch_bounds__(192, 1) bench(int iters, int mode, long long* out) {
+__global__ void __launch_bounds__(192, 1) bench(int iters, int mode, long long* out, int N) {
   extern __shared__ uint8_t raw[];
   uint8_t* sm = raw + ((1024u - (smem_u32(raw) & 1023u)) & 1023u);
   uint8_t* sA = sm;
@@ -74,7 +75,7 @@ __global__ void __launch_bounds__(192, 1) bench(int iters, int mode, long long* 
   const int tiles = iters / KB;
   if (warp == 0) {
     if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (((uint32_t)N >> 3) << 17) | ((128u >> 4) << 24);
       const long long c0 = clock64();
       int s = 0; uint32_t ph = 0;
       for (int t = 0; t < tiles; ++t) {
@@ -98,9 +99,19 @@ __global__ void __launch_bounds__(192, 1) bench(int iters, int mode, long long* 
         } else
         for (int kb = 0; kb < KB; ++kb) {
           if (mode & 1) { wait(full + 8 * s, ph); if (mode & 8) wait(full2 + 8 * s, ph); asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+          // cost of the pieces, without a partner thread: a try_wait that always succeeds (fresh barrier, parity 1),
+          // a test_wait, a fence
+          if (mode & 32) wait(accempty + 8, 1u);
+          if (mode & 128) {
+            uint32_t ok;
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(accempty + 8), "r"(1u) : "memory");
+            if (!ok) __trap();
+          }
+          if (mode & 64) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint64_t ad = desc_sw128(smem_u32(sA + (s & 3) * 16384)), bd = desc_sw128(smem_u32(sB + (s & 3) * 32768));
 #pragma unroll
           for (int k = 0; k < 4; ++k) mma1(tm + as * 256, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0);
+          if (mode & 256) commit1(dummy);
           if (mode & 1) { commit1(empty + 8 * s); if (mode & 4) commit1(dummy); if (mode & 8) commit1(empty2 + 8 * s); }
           if (++s == S) { s = 0; ph ^= 1u; }
         }
@@ -158,17 +169,18 @@ __global__ void __launch_bounds__(192, 1) bench(int iters, int mode, long long* 
   }
 }
 
-int main() {
+int main(int argc, char** argv) {
+  const int N = argc > 1 ? atoi(argv[1]) : 256;
   long long* d;
   cudaMalloc(&d, 16);
   const size_t smem = 1024 + 4 * 16384 + 4 * 32768 + 1024;
   cudaFuncSetAttribute(bench, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const int iters = 36 * 28;
-  printf("ring depth %d\n", S);
+  printf("ring depth %d, N = %d\n", S, N);
   for (int grid : {148})
-    for (int mode : {1, 17}) {
+    for (int mode : {0, 32, 64, 96, 128, 192, 256, 288, 352}) {
       for (int rep = 0; rep < 2; ++rep) {
-        bench<<<grid, 192, smem>>>(iters, mode, d);
+        bench<<<grid, 192, smem>>>(iters, mode, d, N);
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
       }
