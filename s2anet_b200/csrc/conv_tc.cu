@@ -62,7 +62,7 @@ constexpr int TC_OUT_CH = 32;              // channels per epilogue TMA store (6
 constexpr int TC_OUT_BYTES = TC_M * TC_OUT_CH * 2;    // 8 KB
 constexpr int TC_OUT_BUFS = 3;             // staging buffers: the TMA store of chunk i-1 may still be reading when chunk i is staged
 
-enum { TC_ALIGN = 0, TC_PLAIN = 1 };
+enum { TC_ALIGN = 0, TC_PLAIN = 1, TC_PLAIN_S = 2 };
 
 // Per-mode pipeline shape.
 //  * ORConv2d (TC_PLAIN) is fed entirely by TMA and bound by the tensor pipe: a CTA PAIR (cta_group::2, one
@@ -81,15 +81,24 @@ template <int MODE> struct TcCfg;
 // (its gather is latency-bound), none for the TMA-fed plain conv (256 threads, registers to spare).
 // KPS = k-blocks per stage: the MMA warp pays ~200 cycles of wait / commit / bookkeeping per STAGE and the tensor
 // pipe only holds two MMAs ahead, so the tensor-bound plain conv moves two k-blocks (8 MMAs) per stage.
-template <> struct TcCfg<TC_ALIGN> { static constexpr int CG = 2, SA = 6, SB = 6, GROUPS = 4, KPS = 1; static constexpr bool UNIFIED = true; };
-template <> struct TcCfg<TC_PLAIN> { static constexpr int CG = 2, SA = 4, SB = 4, GROUPS = 0, KPS = 2; static constexpr bool UNIFIED = true; };
+// BROWS = weight rows (output channels) one CTA stages per k-block.
+// TC_PLAIN_S is the plain conv for C_out = 32 (the 15- and 5-channel prediction convs, padded): a tcgen05.mma takes
+// >= 69 cycles however small N is and the MMA warp pays a fixed few hundred cycles of waits / commits / bookkeeping
+// per STAGE, so with 2 KB of weights per k-block a stage carries all NINE taps of a channel block (36 MMAs).
+// NHALO = halo buffers (a power of two).  A halo is requested when the buffer it goes to is released, NHALO - 1
+// channel blocks ahead of its first use: 2 buffers give the 512-cycle k-blocks of the wide conv 4,600 cycles for
+// the load; the narrow conv runs a channel block in ~2,500 cycles -- less than the load takes -- and keeps 4.
+template <> struct TcCfg<TC_ALIGN> { static constexpr int CG = 2, SA = 6, SB = 6, GROUPS = 4, KPS = 1, BROWS = 128, NHALO = 2; static constexpr bool UNIFIED = true; };
+template <> struct TcCfg<TC_PLAIN> { static constexpr int CG = 2, SA = 4, SB = 4, GROUPS = 0, KPS = 2, BROWS = 128, NHALO = 2; static constexpr bool UNIFIED = true; };
+template <> struct TcCfg<TC_PLAIN_S> { static constexpr int CG = 2, SA = 3, SB = 3, GROUPS = 0, KPS = 9, BROWS = 16, NHALO = 4; static constexpr bool UNIFIED = true; };
 template <int MODE> constexpr int tc_threads() { return (TcCfg<MODE>::GROUPS * 4 + 8) * 32; }
 constexpr int TC_MAX_STAGES = 8;
 constexpr int TC_EPI_THREADS = 128;                   // 4 epilogue warps, one per TMEM lane quadrant
 // warps: GROUPS x 4 producers | 4 epilogue | TMA | MMA | 2 idle (pad to a multiple of 4 warps)
 constexpr int TC_ACC_STAGES = 2;                      // double-buffered accumulator: 2 x 256 TMEM columns
 constexpr int TC_TMEM_COLS = 512;
-constexpr int TC_NBAR = 4 * TC_MAX_STAGES + 2 * TC_ACC_STAGES + 2 + 4;   // + halo full/empty x 2
+constexpr int TC_MAX_HALOS = 4;
+constexpr int TC_NBAR = 4 * TC_MAX_STAGES + 2 * TC_ACC_STAGES + 2 + 2 * TC_MAX_HALOS;   // + table full x 2, halo full/empty
 constexpr int TC_MAX_LEVELS = 8;
 constexpr uint32_t kSpinLimit = 1u << 26;            // watchdog: trap instead of hanging the GPU
 
@@ -140,8 +149,8 @@ struct TcMaps {
   CUtensorMap y[TC_MAX_LEVELS];   // outputs: the epilogue stores 8 x 16 x 32-channel boxes through these
 };
 
-template <int MODE> __host__ __device__ constexpr int tc_pw() { return MODE == 1 ? TC_PPW : TC_PW; }
-template <int MODE> __host__ __device__ constexpr int tc_ph() { return MODE == 1 ? TC_PPH : TC_PH; }
+template <int MODE> __host__ __device__ constexpr int tc_pw() { return MODE != 0 ? TC_PPW : TC_PW; }
+template <int MODE> __host__ __device__ constexpr int tc_ph() { return MODE != 0 ? TC_PPH : TC_PH; }
 
 template <int MODE>
 __device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int tile) {
@@ -511,7 +520,8 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
   constexpr int GROUPS = Cfg::GROUPS, KPS = Cfg::KPS;
   static_assert(GROUPS < SA && SA <= TC_MAX_STAGES && SB <= TC_MAX_STAGES, "stage rings");
   static_assert(MODE != TC_ALIGN || 256 + SA * 32 <= TC_TMEM_COLS, "AlignConv: accumulator + A stages must fit tensor memory");
-  constexpr int B_KB_BYTES = (256 / CG) * TC_KB * 2;            // one k-block of this CTA's weight rows
+  constexpr bool IS_PLAIN = MODE != TC_ALIGN;                   // TC_PLAIN or TC_PLAIN_S
+  constexpr int B_KB_BYTES = Cfg::BROWS * TC_KB * 2;            // one k-block of this CTA's weight rows
   constexpr int B_STAGE_BYTES = KPS * B_KB_BYTES;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B operands need 1024-byte aligned tiles: align the dynamic window by hand (the offset is
@@ -524,11 +534,13 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
   uint8_t* sB = smem;
   uint8_t* s_out = sB + SB * B_STAGE_BYTES;                              // 3 x 8 KB, 1024-byte aligned (SWIZZLE_64B)
   uint8_t* s_halo = s_out + TC_OUT_BUFS * TC_OUT_BYTES;                  // 1024-byte aligned (PLAIN: SWIZZLE_128B operand)
-  TapSample* s_tab = reinterpret_cast<TapSample*>(s_halo + 2 * HALO_BYTES);          // ALIGN only
+  constexpr int NH = Cfg::NHALO, NHL = NH == 4 ? 2 : 1;
+  static_assert((NH == 2 || NH == 4) && NH <= TC_MAX_HALOS && (MODE != TC_ALIGN || NH == 2), "halo buffers");
+  TapSample* s_tab = reinterpret_cast<TapSample*>(s_halo + NH * HALO_BYTES);          // ALIGN only
   static_assert(TC_HALO_BYTES % 128 == 0 && TC_PHALO_BYTES % 1024 == 0 && (TC_OUT_BUFS * TC_OUT_BYTES) % 1024 == 0 &&
                 B_STAGE_BYTES % 1024 == 0, "TMA source / destination alignment");
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(
-      s_halo + 2 * HALO_BYTES + (MODE == TC_ALIGN ? 2 * sizeof(TapSample) * TC_M * 9 : (size_t)0));
+      s_halo + NH * HALO_BYTES + (MODE == TC_ALIGN ? 2 * sizeof(TapSample) * TC_M * 9 : (size_t)0));
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + TC_NBAR);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -536,7 +548,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
                  bar_full_b = bar_empty_a + 8 * TC_MAX_STAGES, bar_empty_b = bar_full_b + 8 * TC_MAX_STAGES,
                  bar_acc_full = bar_empty_b + 8 * TC_MAX_STAGES, bar_acc_empty = bar_acc_full + 8 * TC_ACC_STAGES,
                  bar_tab_full = bar_acc_empty + 8 * TC_ACC_STAGES,       // 2 barriers
-                 bar_halo_full = bar_tab_full + 16, bar_halo_empty = bar_halo_full + 16;   // 2 + 2 barriers
+                 bar_halo_full = bar_tab_full + 16, bar_halo_empty = bar_halo_full + 8 * TC_MAX_HALOS;   // 4 + 4 barriers
   // warps 0-15 producers | 16-19 epilogue (one warpgroup) | 20 TMA, 21 MMA, 22-23 idle (one warpgroup)
   constexpr int kProdWarps = GROUPS * 4, kEpiWarp0 = kProdWarps, kTmaWarp = kEpiWarp0 + TC_EPI_THREADS / 32,
                 kMmaWarp = kTmaWarp + 1;
@@ -575,8 +587,11 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       mbar_init(bar_acc_full + 8 * s, 1);       // tcgen05.commit after the last k-block of a tile group
       mbar_init(bar_acc_empty + 8 * s, CG * (TC_EPI_THREADS / 32));   // one elected arrive per epilogue warp of the group
       mbar_init(bar_tab_full + 8 * s, TC_EPI_THREADS);
+    }
+    for (int s = 0; s < NH; ++s) {
       mbar_init(bar_halo_full + 8 * s, 1);                   // the TMA thread's expect_tx arrive (+ bytes)
-      mbar_init(bar_halo_empty + 8 * s, kProdWarps > 0 ? kProdWarps : 1);   // one elected arrive per producer warp
+      // ALIGN: one elected arrive per producer warp; plain conv: one (multicast) tcgen05.commit
+      mbar_init(bar_halo_empty + 8 * s, kProdWarps > 0 ? kProdWarps : 1);
     }
     fence_barrier_init();
   }
@@ -712,7 +727,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         ++hseq;
       };
       if (MODE == TC_ALIGN && first_q < ngroups) load_halo(decode_tile<MODE>(p, S2A_TILE_OF(first_q)), 0);
-      for (int q = first_q; MODE == TC_PLAIN && q < ngroups; q += q_step) {
+      for (int q = first_q; IS_PLAIN && q < ngroups; q += q_step) {
         // plain conv / ORConv: a stage carries KPS weight k-blocks (this CTA's C_out/CG rows of each); the A operand
         // is the halo the halo warp loads
         for (int kb = 0; kb < nkb; kb += KPS) {
@@ -782,7 +797,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         warm = true;
       }
     }
-  } else if (MODE == TC_PLAIN && warp == kMmaWarp + 1) {
+  } else if (IS_PLAIN && warp == kMmaWarp + 1) {
     // ===================== plain conv: halo loads (the A operand) =====================
     // One box {64 ch, 16, 18, 1} per (tile, 64-channel block) at (tx0 - 1, ty0 - 1), zero-filled outside the map and
     // beyond C, into buffer (sequence number & 1).  A buffer is recycled when the last tap's MMAs of its channel
@@ -792,12 +807,13 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     for (int q = first_q; q < ngroups; q += q_step) {
       const TileCoord tc = decode_tile<MODE>(p, S2A_TILE_OF(q));
       for (int cb = 0; cb < ncb; ++cb, ++hseq) {
-        const uint32_t hb = hseq & 1u;
-        mbar_wait(bar_halo_empty + 8 * hb, ((hseq >> 1) & 1u) ^ 1u);
+        const uint32_t hb = hseq & (uint32_t)(NH - 1);
+        mbar_wait(bar_halo_empty + 8 * hb, ((hseq >> NHL) & 1u) ^ 1u);
         if (elect_one()) {
-          if (leader) mbar_arrive_expect_tx(bar_halo_full + 8 * hb, (uint32_t)(CG * TC_PHALO_BYTES));
-          tma_load_4d<CG>(smem_u32(s_halo + hb * TC_PHALO_BYTES), &maps.x[tc.lvl], cb * TC_KB, tc.tx0 - 1, tc.ty0 - 1, tc.b,
-                          ld_halo_full + 8 * hb);
+          // (a 1 x 1 conv needs no border: its box is the 8 x 16 tile itself, pitch 8 pixels)
+          if (leader) mbar_arrive_expect_tx(bar_halo_full + 8 * hb, (uint32_t)CG * (p.ks == 3 ? TC_PHALO_BYTES : TC_M * 128));
+          tma_load_4d<CG>(smem_u32(s_halo + hb * TC_PHALO_BYTES), &maps.x[tc.lvl], cb * TC_KB, tc.tx0 - (p.ks >> 1),
+                          tc.ty0 - (p.ks >> 1), tc.b, ld_halo_full + 8 * hb);
         }
         __syncwarp();
       }
@@ -821,13 +837,13 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       // plain conv: the A operand of tap (ti, tj) is the halo buffer seen from pixel (ti, tj) on: start address
       // + (ti * 16 + tj) 128-byte lines, SBO = one halo row (2048 B), base offset = tj (the swizzle phase of the
       // first line; rows are a multiple of 8 lines apart and do not change it)
-      static_assert(MODE == TC_ALIGN || KPS == 2, "plain conv: two k-blocks per stage");
-      const uint64_t hdesc0 = umma_desc_sw128(smem_u32(s_halo), TC_PHALO_PITCH * 128);
+      const int hpitch = p.ks == 3 ? TC_PHALO_PITCH : TC_PPW;      // halo row pitch in pixels (1 x 1: the bare tile)
+      const uint64_t hdesc0 = umma_desc_sw128(smem_u32(s_halo), (uint32_t)hpitch * 128u);
       const uint64_t bdesc0 = umma_desc_sw128(smem_u32(sB));
       const uint32_t atm0 = tmem_base + A_TMEM_COL0;
       uint64_t bdesc = bdesc0;
       int tap = 0;                                   // plain conv: tap of the next k-block, and the running
-      uint32_t hseq = 0;                             // (tile, channel block) counter: halo buffer = hseq & 1
+      uint32_t hseq = 0;                             // (tile, channel block) counter: halo buffer = hseq % NHALO
       uint32_t atm = atm0, full_bar = bar_full_a, empty_bar = bar_empty_a;
       int sa = 0, it = 0;
       uint32_t pa = 0;
@@ -847,23 +863,24 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
           const int nk = KPS == 1 ? 1 : min(KPS, nkb - kb);          // k-blocks in this stage
           // +32 bytes (>>4 = 2) per K=16 step inside the swizzle atom; A in TMEM: +8 columns per K=16 step.
           // Every MMA of the stage but the last two is issued first ...
-          uint64_t a_desc0 = 0ull, a_desc1 = 0ull;   // plain conv: A descriptors of the stage's k-blocks,
-          uint32_t a_rel0 = 0u, a_rel1 = 0u;         // and the halo barrier to release after a block's last tap
-          if (MODE == TC_PLAIN) {
-            auto next_block = [&](uint64_t& desc, uint32_t& rel) {
-              if (tap == 0) {                        // first tap of a channel block: its halo (requested nine k-blocks ago)
-                S2A_TL(long long w0 = (p.debug & 8) ? clock64() : 0;)
-                mbar_wait_likely_ready(bar_halo_full + 8 * (hseq & 1u), (hseq >> 1) & 1u);
-                tc_fence_after();
-                S2A_TL(if (p.debug & 8) tw_halo += clock64() - w0;)
+          uint64_t a_last = 0ull;                    // plain conv: A descriptor of the stage's last k-block, and the
+          uint32_t rel_last = 0u;                    // halo barrier to release after it (if it is a block's last tap)
+          if (IS_PLAIN) {
+            // (all lanes) the halo of every channel block that starts inside this stage -- requested nine k-blocks ago
+            int t = tap;
+            uint32_t h = hseq;
+#pragma unroll
+            for (int j = 0; j < KPS; ++j) {
+              if (j < nk) {
+                if (t == 0) {
+                  S2A_TL(long long w0 = (p.debug & 8) ? clock64() : 0;)
+                  mbar_wait_likely_ready(bar_halo_full + 8 * (h & (uint32_t)(NH - 1)), (h >> NHL) & 1u);
+                  tc_fence_after();
+                  S2A_TL(if (p.debug & 8) tw_halo += clock64() - w0;)
+                }
+                if (++t == ntap) { t = 0; ++h; }
               }
-              const int ti = p.ks == 3 ? (tap * 11) >> 5 : 1, tj = p.ks == 3 ? tap - 3 * ti : 1;
-              desc = hdesc0 + (uint64_t)((hseq & 1u) * (uint32_t)(TC_PHALO_BYTES >> 4)) +
-                     (uint64_t)((ti * TC_PHALO_PITCH + tj) * (128 >> 4)) + ((p.debug & 4) ? ((uint64_t)tj << 49) : 0ull);
-              if (++tap == ntap) { tap = 0; rel = bar_halo_empty + 8 * (hseq & 1u); ++hseq; }
-            };
-            next_block(a_desc0, a_rel0);
-            if (nk == 2) next_block(a_desc1, a_rel1);
+            }
           }
           const bool issuer = elect_one();
           if (issuer) {
@@ -871,17 +888,34 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
               umma_f16_ts<CG>(d_tmem, atm, bdesc, idesc, kb != 0 ? 1u : 0u);
               umma_f16_ts<CG>(d_tmem, atm + 8u, bdesc + 2, idesc, 1u);
             } else {
-              umma_f16<CG>(d_tmem, a_desc0, bdesc, idesc, kb != 0 ? 1u : 0u);
-              umma_f16<CG>(d_tmem, a_desc0 + 2, bdesc + 2, idesc, 1u);
-              if (nk == 2) {
-                umma_f16<CG>(d_tmem, a_desc0 + 4, bdesc + 4, idesc, 1u);
-                umma_f16<CG>(d_tmem, a_desc0 + 6, bdesc + 6, idesc, 1u);
-                if (a_rel0) umma_commit<CG>(a_rel0);
-                const uint64_t b1 = bdesc + (uint64_t)(B_KB_BYTES >> 4);
-                umma_f16<CG>(d_tmem, a_desc1, b1, idesc, 1u);
-                umma_f16<CG>(d_tmem, a_desc1 + 2, b1 + 2, idesc, 1u);
+              int t = tap;
+              uint32_t h = hseq;
+#pragma unroll
+              for (int j = 0; j < KPS; ++j) {
+                if (j < nk) {
+                  const int ti = (t * 11) >> 5, tj = t - 3 * ti;         // (1 x 1: t = 0)
+                  const uint64_t aj = hdesc0 + (uint64_t)((h & (uint32_t)(NH - 1)) * (uint32_t)(TC_PHALO_BYTES >> 4)) +
+                                      (uint64_t)((ti * hpitch + tj) * (128 >> 4));
+                  const uint64_t bj = bdesc + (uint64_t)(j * (B_KB_BYTES >> 4));
+                  uint32_t rel = 0u;
+                  if (++t == ntap) { t = 0; rel = bar_halo_empty + 8 * (h & (uint32_t)(NH - 1)); ++h; }
+                  umma_f16<CG>(d_tmem, aj, bj, idesc, (kb | j) != 0 ? 1u : 0u);
+                  umma_f16<CG>(d_tmem, aj + 2, bj + 2, idesc, 1u);
+                  if (j + 1 < nk) {
+                    umma_f16<CG>(d_tmem, aj + 4, bj + 4, idesc, 1u);
+                    umma_f16<CG>(d_tmem, aj + 6, bj + 6, idesc, 1u);
+                    if (rel) umma_commit<CG>(rel);
+                  } else {                           // (the last k-block's second half follows the wait below)
+                    a_last = aj; rel_last = rel;
+                  }
+                }
               }
             }
+          }
+          if (IS_PLAIN) {                            // (all lanes) advance the tap / halo counters past this stage
+#pragma unroll
+            for (int j = 0; j < KPS; ++j)
+              if (j < nk && ++tap == ntap) { tap = 0; ++hseq; }
           }
           __syncwarp();
           // ... then the next stage is awaited in the shadow of the MMAs just queued ...
@@ -891,7 +925,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
           const bool new_acc = kb + KPS >= nkb;
           const bool more = !new_acc || !last_tile;
           bool ready = false;
-          if (MODE == TC_PLAIN) {
+          if (IS_PLAIN) {
             // tensor-bound: the next stage is (nearly) always there (and, at a tile boundary, the next accumulator
             // has to be drained)
             if (more) {
@@ -916,11 +950,10 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
               umma_f16_ts<CG>(d_tmem, atm + 16u, bdesc + 4, idesc, 1u);
               umma_f16_ts<CG>(d_tmem, atm + 24u, bdesc + 6, idesc, 1u);
             } else {
-              const uint64_t aj = nk == 2 ? a_desc1 : a_desc0, bj = bdesc + (uint64_t)((nk - 1) * (B_KB_BYTES >> 4));
-              umma_f16<CG>(d_tmem, aj + 4, bj + 4, idesc, 1u);
-              umma_f16<CG>(d_tmem, aj + 6, bj + 6, idesc, 1u);
-              const uint32_t rel = nk == 2 ? a_rel1 : a_rel0;
-              if (rel) umma_commit<CG>(rel);        // halo buffer (of both CTAs) reusable
+              const uint64_t bj = bdesc + (uint64_t)((nk - 1) * (B_KB_BYTES >> 4));
+              umma_f16<CG>(d_tmem, a_last + 4, bj + 4, idesc, 1u);
+              umma_f16<CG>(d_tmem, a_last + 6, bj + 6, idesc, 1u);
+              if (rel_last) umma_commit<CG>(rel_last);   // halo buffer (of both CTAs) reusable
             }
             umma_commit<CG>(empty_bar);             // stage (of every CTA of the group) reusable once these MMAs have read it
             if (new_acc) umma_commit<CG>(acc_full_bar);   // accumulators of this tile group complete
@@ -1029,7 +1062,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         __syncwarp();
         if (issuer && !ghost && !(p.debug & 64))
           tma_store_4d(&maps.y[tc.lvl], smem_u32(sbuf), c0, tc.tx0, tc.ty0 + (32 / tc_pw<MODE>()) * quad, tc.b);
-        if (MODE == TC_PLAIN && valid && L.pooled) {
+        if (IS_PLAIN && valid && L.pooled) {
           uint2 o;
           H2* oh = reinterpret_cast<H2*>(&o);
           oh[0] = from_f2<T>(m[0], m[1]);
@@ -1157,9 +1190,10 @@ static EncodeTiledFn get_encode_fn() {
 template <int MODE>
 constexpr size_t tc_smem_bytes() {
   using Cfg = TcCfg<MODE>;
-  return 1024 /*alignment slack*/ + (size_t)Cfg::SB * Cfg::KPS * ((256 / Cfg::CG) * TC_KB * 2) +
+  return 1024 /*alignment slack*/ + (size_t)Cfg::SB * Cfg::KPS * (Cfg::BROWS * TC_KB * 2) +
          (size_t)TC_OUT_BUFS * TC_OUT_BYTES +
-         (MODE == TC_ALIGN ? 2 * (size_t)TC_HALO_BYTES + 2 * sizeof(TapSample) * TC_M * 9 : 2 * (size_t)TC_PHALO_BYTES) +
+         (MODE == TC_ALIGN ? 2 * (size_t)TC_HALO_BYTES + 2 * sizeof(TapSample) * TC_M * 9
+                           : (size_t)Cfg::NHALO * TC_PHALO_BYTES) +
          8 * TC_NBAR + 16;
 }
 
@@ -1230,12 +1264,12 @@ static int conv_tc_common(int mode, int nlevels, const void* const* xs, const fl
   const CUtensorMapDataType tdt = dtype == S2A_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   for (int l = 0; l < nlevels; ++l) {
     // TC_PLAIN: halo windows {64 ch, 16, 18, 1} (SWIZZLE_128B, read by the tensor core as the A operand of every
-    // tap); TC_ALIGN: halo windows {64 ch, 22, 14, 1}, plain layout (one 128-byte line per pixel, gathered by
+    // tap; a 1 x 1 conv loads the bare tile {64 ch, 8, 16, 1}); TC_ALIGN: halo windows {64 ch, 22, 14, 1}, plain layout (one 128-byte line per pixel, gathered by
     // LDS); both zero-filled outside the map
     const cuuint64_t xd[4] = {(cuuint64_t)C, (cuuint64_t)Ws[l], (cuuint64_t)Hs[l], (cuuint64_t)B};
     const cuuint64_t xs_[3] = {(cuuint64_t)C * 2, (cuuint64_t)Ws[l] * C * 2, (cuuint64_t)Hs[l] * Ws[l] * C * 2};
-    const cuuint32_t xb[4] = {(cuuint32_t)TC_KB, (cuuint32_t)(mode == TC_PLAIN ? TC_PHALO_PITCH : TC_HW),
-                              (cuuint32_t)(mode == TC_PLAIN ? TC_PHALO_ROWS : TC_HH), 1};
+    const cuuint32_t xb[4] = {(cuuint32_t)TC_KB, (cuuint32_t)(mode == TC_PLAIN ? (ks == 3 ? TC_PHALO_PITCH : TC_PPW) : TC_HW),
+                              (cuuint32_t)(mode == TC_PLAIN ? (ks == 3 ? TC_PHALO_ROWS : TC_PPH) : TC_HH), 1};
     const cuuint32_t xe[4] = {1, 1, 1, 1};
     CUresult xr = enc(&tmap.x[l], tdt, 4, const_cast<void*>(xs[l]), xd, xs_, xb, xe, CU_TENSOR_MAP_INTERLEAVE_NONE,
                       mode == TC_PLAIN ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
@@ -1267,6 +1301,8 @@ static int conv_tc_common(int mode, int nlevels, const void* const* xs, const fl
   if (mode == TC_ALIGN) {
     return dtype == S2A_BF16 ? launch_tc<TC_ALIGN, __nv_bfloat16>(tmap, p, st) : launch_tc<TC_ALIGN, __half>(tmap, p, st);
   }
+  if (Co == 2 * TcCfg<TC_PLAIN_S>::BROWS && ks == 3)          // the narrow prediction convs: nine taps per stage
+    return dtype == S2A_BF16 ? launch_tc<TC_PLAIN_S, __nv_bfloat16>(tmap, p, st) : launch_tc<TC_PLAIN_S, __half>(tmap, p, st);
   return dtype == S2A_BF16 ? launch_tc<TC_PLAIN, __nv_bfloat16>(tmap, p, st) : launch_tc<TC_PLAIN, __half>(tmap, p, st);
 }
 
