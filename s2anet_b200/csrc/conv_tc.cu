@@ -588,7 +588,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       mbar_init(bar_acc_empty + 8 * s, CG * (TC_EPI_THREADS / 32));   // one elected arrive per epilogue warp of the group
       mbar_init(bar_tab_full + 8 * s, TC_EPI_THREADS);
     }
-    for (int s = 0; s < NH; ++s) {
+    for (int s = 0; s < TC_MAX_HALOS; ++s) {
       mbar_init(bar_halo_full + 8 * s, 1);                   // the TMA thread's expect_tx arrive (+ bytes)
       // ALIGN: one elected arrive per producer warp; plain conv: one (multicast) tcgen05.commit
       mbar_init(bar_halo_empty + 8 * s, kProdWarps > 0 ? kProdWarps : 1);
@@ -803,16 +803,20 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
     // beyond C, into buffer (sequence number & 1).  A buffer is recycled when the last tap's MMAs of its channel
     // block have retired (tcgen05.commit, multicast to both CTAs); both CTAs' boxes complete the leader's barrier.
     const uint32_t ld_halo_full = CG == 2 ? map_to_cta(bar_halo_full, 0) : bar_halo_full;
+    // ring depth / buffer size: a 1 x 1 conv's "halo" is the bare 16 KB tile and lives one k-block only, so the
+    // same shared memory holds a ring of four of them (its loads are latency-, not bandwidth-bound)
+    const int nhl = (p.ks == 3) ? NHL : 2;
+    const uint32_t nh_mask = (1u << nhl) - 1u, hstride = p.ks == 3 ? (uint32_t)TC_PHALO_BYTES : (uint32_t)(TC_M * 128);
     uint32_t hseq = 0;
     for (int q = first_q; q < ngroups; q += q_step) {
       const TileCoord tc = decode_tile<MODE>(p, S2A_TILE_OF(q));
       for (int cb = 0; cb < ncb; ++cb, ++hseq) {
-        const uint32_t hb = hseq & (uint32_t)(NH - 1);
-        mbar_wait(bar_halo_empty + 8 * hb, ((hseq >> NHL) & 1u) ^ 1u);
+        const uint32_t hb = hseq & nh_mask;
+        mbar_wait(bar_halo_empty + 8 * hb, ((hseq >> nhl) & 1u) ^ 1u);
         if (elect_one()) {
           // (a 1 x 1 conv needs no border: its box is the 8 x 16 tile itself, pitch 8 pixels)
-          if (leader) mbar_arrive_expect_tx(bar_halo_full + 8 * hb, (uint32_t)CG * (p.ks == 3 ? TC_PHALO_BYTES : TC_M * 128));
-          tma_load_4d<CG>(smem_u32(s_halo + hb * TC_PHALO_BYTES), &maps.x[tc.lvl], cb * TC_KB, tc.tx0 - (p.ks >> 1),
+          if (leader) mbar_arrive_expect_tx(bar_halo_full + 8 * hb, (uint32_t)CG * hstride);
+          tma_load_4d<CG>(smem_u32(s_halo + hb * hstride), &maps.x[tc.lvl], cb * TC_KB, tc.tx0 - (p.ks >> 1),
                           tc.ty0 - (p.ks >> 1), tc.b, ld_halo_full + 8 * hb);
         }
         __syncwarp();
@@ -838,6 +842,8 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       // + (ti * 16 + tj) 128-byte lines, SBO = one halo row (2048 B), base offset = tj (the swizzle phase of the
       // first line; rows are a multiple of 8 lines apart and do not change it)
       const int hpitch = p.ks == 3 ? TC_PHALO_PITCH : TC_PPW;      // halo row pitch in pixels (1 x 1: the bare tile)
+      const int nhl = (p.ks == 3) ? NHL : 2;                       // log2(halo ring depth), see the halo warp
+      const uint32_t nh_mask = (1u << nhl) - 1u, hstride16 = (p.ks == 3 ? (uint32_t)TC_PHALO_BYTES : (uint32_t)(TC_M * 128)) >> 4;
       const uint64_t hdesc0 = umma_desc_sw128(smem_u32(s_halo), (uint32_t)hpitch * 128u);
       const uint64_t bdesc0 = umma_desc_sw128(smem_u32(sB));
       const uint32_t atm0 = tmem_base + A_TMEM_COL0;
@@ -874,7 +880,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
               if (j < nk) {
                 if (t == 0) {
                   S2A_TL(long long w0 = (p.debug & 8) ? clock64() : 0;)
-                  mbar_wait_likely_ready(bar_halo_full + 8 * (h & (uint32_t)(NH - 1)), (h >> NHL) & 1u);
+                  mbar_wait_likely_ready(bar_halo_full + 8 * (h & nh_mask), (h >> nhl) & 1u);
                   tc_fence_after();
                   S2A_TL(if (p.debug & 8) tw_halo += clock64() - w0;)
                 }
@@ -894,11 +900,11 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
               for (int j = 0; j < KPS; ++j) {
                 if (j < nk) {
                   const int ti = (t * 11) >> 5, tj = t - 3 * ti;         // (1 x 1: t = 0)
-                  const uint64_t aj = hdesc0 + (uint64_t)((h & (uint32_t)(NH - 1)) * (uint32_t)(TC_PHALO_BYTES >> 4)) +
+                  const uint64_t aj = hdesc0 + (uint64_t)((h & nh_mask) * hstride16) +
                                       (uint64_t)((ti * hpitch + tj) * (128 >> 4));
                   const uint64_t bj = bdesc + (uint64_t)(j * (B_KB_BYTES >> 4));
                   uint32_t rel = 0u;
-                  if (++t == ntap) { t = 0; rel = bar_halo_empty + 8 * (h & (uint32_t)(NH - 1)); ++h; }
+                  if (++t == ntap) { t = 0; rel = bar_halo_empty + 8 * (h & nh_mask); ++h; }
                   umma_f16<CG>(d_tmem, aj, bj, idesc, (kb | j) != 0 ? 1u : 0u);
                   umma_f16<CG>(d_tmem, aj + 2, bj + 2, idesc, 1u);
                   if (j + 1 < nk) {

@@ -199,6 +199,36 @@ __global__ void __launch_bounds__(DEC_THREADS) select_decode_kernel(const __grid
     uint32_t* keys = n <= p.smem_keys ? reinterpret_cast<uint32_t*>(dsm + p.sort_bytes)
                                       : p.keys + (long long)b * p.keys_per_image + L.key_off;
     constexpr int UNR = 4;                                  // locations in flight per thread (latency-bound loop)
+    // 16-bit channels-last logits with at most 16 classes (the head's own layout): a PAIR of lanes reads one location
+    // -- 16 bytes = 8 classes each -- so that a warp's load covers 16 consecutive pixels (8 cache lines) instead of
+    // 32 pixels with every other 16-byte chunk skipped (32 sectors in 16 lines, and half the lanes' worth of loads)
+    const bool paired = sizeof(T) == 2 && C <= 16 && L.cs[1] == 1 && (L.cs[3] & 7) == 0 && (L.cs[2] & 7) == 0 &&
+                        (L.cs[0] & 7) == 0 && (reinterpret_cast<uintptr_t>(L.cls) & 15) == 0 && L.cs[3] >= (C <= 8 ? 8 : 16);
+    if (paired) {
+      constexpr int HALF_T = DEC_THREADS / 2;
+      const int half = tid & 1, pr = tid >> 1;
+      for (int base = 0; base < n; base += UNR * HALF_T) {
+        uint4 v[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+          const int i = min(base + u * HALF_T + pr, n - 1);
+          const int y = i / L.W, x = i - y * L.W;
+          v[u] = make_uint4(0u, 0u, 0u, 0u);
+          if (half * 8 < C) v[u] = __ldg(reinterpret_cast<const uint4*>(cls + y * L.cs[2] + x * L.cs[3]) + half);
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+          const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+          float m = -INFINITY;
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            if (half * 8 + e < C) m = fmaxf(m, bits16_to_float<T>((unsigned short)(w[e >> 1] >> ((e & 1) * 16))));
+          m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+          const int i = base + u * HALF_T + pr;
+          if (half == 0 && i < n) keys[i] = __float_as_uint(sigmoid_t<T>(m));
+        }
+      }
+    } else
     for (int i0 = tid; i0 < n; i0 += UNR * DEC_THREADS) {
       float m[UNR];
       if (C <= 16) {
@@ -312,31 +342,51 @@ __global__ void __launch_bounds__(DEC_THREADS) select_decode_kernel(const __grid
 
   t3 = clock64();
   // ---- gather + sigmoid + final decode (models/head.py:703-717) ---------------------------------
-  for (int j = tid; j < k; j += DEC_THREADS) {
-    const int i = select ? (int)(idx_mask - (unsigned)(s_sel[j] & (unsigned long long)idx_mask)) : j;
-    const int y = i / L.W, x = i - y * L.W;
-    const long long row = (long long)b * p.n_total + L.out_off + j;
-    const T* q = cls + y * L.cs[2] + x * L.cs[3];
-    float* so = p.scores + row * C;
-    if (C <= 16) {
-      float v[16];
-      load_channels<T>(q, L.cs[1], L.cs[3], C, v);
+  // Output rows of a level are contiguous ([k, C] scores, [k, 5] boxes), but a thread owns a whole row: written
+  // directly that is 20 scattered 4-byte stores per location (32 sectors per warp instruction).  With at most 16
+  // classes the rows of DEC_THREADS locations are staged in shared memory (the sort scratch and the keys are dead by
+  // now; row strides C and 5 words are odd -> conflict-free) and copied out with coalesced stores.
+  const bool staged = C <= 16;
+  float* st_sc = reinterpret_cast<float*>(dsm);
+  float* st_bb = st_sc + DEC_THREADS * C;
+  for (int j0 = 0; j0 < k; j0 += DEC_THREADS) {
+    const int j = j0 + tid;
+    const int cnt = min(DEC_THREADS, k - j0);
+    const long long row0 = (long long)b * p.n_total + L.out_off + j0;
+    if (staged) __syncthreads();                     // (first round: everybody is done with the sort scratch / keys)
+    if (j < k) {
+      const int i = select ? (int)(idx_mask - (unsigned)(s_sel[j] & (unsigned long long)idx_mask)) : j;
+      const int y = i / L.W, x = i - y * L.W;
+      const long long row = row0 + tid;
+      const T* q = cls + y * L.cs[2] + x * L.cs[3];
+      float* so = staged ? st_sc + tid * C : p.scores + row * C;
+      if (C <= 16) {
+        float v[16];
+        load_channels<T>(q, L.cs[1], L.cs[3], C, v);
 #pragma unroll
-      for (int c = 0; c < 16; ++c)
-        if (c < C) so[c] = sigmoid_t<T>(v[c]);
-    } else {
-      for (int c = 0; c < C; ++c) so[c] = sigmoid_t<T>(ld_as_float(q + c * L.cs[1]));
+        for (int c = 0; c < 16; ++c)
+          if (c < C) so[c] = sigmoid_t<T>(v[c]);
+      } else {
+        for (int c = 0; c < C; ++c) so[c] = sigmoid_t<T>(ld_as_float(q + c * L.cs[1]));
+      }
+      float d[5];
+      load_channels<T>(reg + y * L.rs[2] + x * L.rs[3], L.rs[1], L.rs[3], 5, d);
+      const float* ap = L.anchors + ((long long)b * n + i) * 5;
+      const float a[5] = {__ldg(ap), __ldg(ap + 1), __ldg(ap + 2), __ldg(ap + 3), __ldg(ap + 4)};
+      float o[5];
+      delta2bbox_rotated<T>(a, d[0], d[1], d[2], d[3], d[4], p.lim, o);
+      float* bo = staged ? st_bb + tid * 5 : p.bboxes + row * 5;
+#pragma unroll
+      for (int e = 0; e < 5; ++e) bo[e] = o[e];
+      if (p.index_out) p.index_out[row] = i;
     }
-    float d[5];
-    load_channels<T>(reg + y * L.rs[2] + x * L.rs[3], L.rs[1], L.rs[3], 5, d);
-    const float* ap = L.anchors + ((long long)b * n + i) * 5;
-    const float a[5] = {__ldg(ap), __ldg(ap + 1), __ldg(ap + 2), __ldg(ap + 3), __ldg(ap + 4)};
-    float o[5];
-    delta2bbox_rotated<T>(a, d[0], d[1], d[2], d[3], d[4], p.lim, o);
-    float* bo = p.bboxes + row * 5;
-#pragma unroll
-    for (int e = 0; e < 5; ++e) bo[e] = o[e];
-    if (p.index_out) p.index_out[row] = i;
+    if (staged) {
+      __syncthreads();
+      float* gs = p.scores + row0 * C;
+      for (int e = tid; e < cnt * C; e += DEC_THREADS) gs[e] = st_sc[e];
+      float* gb = p.bboxes + row0 * 5;
+      for (int e = tid; e < cnt * 5; e += DEC_THREADS) gb[e] = st_bb[e];
+    }
   }
   if (p.debug && tid == 0 && blockIdx.y == 0)
     printf("select_decode level %d: keys %lld, select %lld, collect+sort %lld, gather+decode %lld cycles\n", (int)blockIdx.x, t1 - t0, t2 - t1,
@@ -361,7 +411,8 @@ static int launch_select(SelParams p, cudaStream_t st) {
   int need = 0;
   for (int l = 0; l < p.nlevels; ++l)
     if (p.lv[l].n > p.lv[l].k && p.lv[l].n <= p.smem_keys) need = std::max(need, p.lv[l].n);
-  const size_t smem = (size_t)p.sort_bytes + (size_t)need * sizeof(uint32_t);
+  size_t smem = (size_t)p.sort_bytes + (size_t)need * sizeof(uint32_t);
+  if (p.C <= 16) smem = std::max(smem, (size_t)DEC_THREADS * (p.C + 5) * sizeof(float));   // output staging (gather phase)
   S2A_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<dim3(p.nlevels, p.B), DEC_THREADS, smem, st>>>(p);
   S2A_LAUNCH_OK("select_decode_kernel");

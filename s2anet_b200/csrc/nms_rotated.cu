@@ -152,7 +152,7 @@ nms_mask_kernel(const RBox* __restrict__ boxes, const float* __restrict__ labels
 
 // Greedy sweep of one score-ordered segment of n boxes.  mask row stride = ld words; only words
 // j >= row/64 of a row are ever read.  Writes kept positions (0..n-1, ascending) through `emit`.
-// s_remv: cb words of shared memory.  Must be called by all kSweepThreads threads of the CTA.
+// s_remv, s_kw: cb words of shared memory each.  Must be called by all kSweepThreads threads of the CTA.
 template <class Emit>
 __device__ __forceinline__ int sweep_segment(const unsigned long long* __restrict__ mask, int n, int ld,
                                              unsigned long long* s_remv, unsigned long long* s_kw,
@@ -160,15 +160,38 @@ __device__ __forceinline__ int sweep_segment(const unsigned long long* __restric
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int cb = (n + kBlk - 1) / kBlk;
   for (int j = tid; j < cb; j += kSweepThreads) s_remv[j] = 0ull;
+  // The sweep is a chain of cb dependent steps, each of them two global-load latencies long if done naively
+  // (diagonal words, then the kept rows).  Neither load depends on the outcome of the step: the diagonal words of
+  // block b + 1 are requested before block b is resolved, and every warp requests the later words of ITS two rows
+  // of block b while warp 0 resolves it, and only masks them with the keep bits afterwards.
+  unsigned long long dlo = 0ull, dhi = 0ull;         // warp 0: diagonal words of the current block, rows lane / lane + 32
+  if (warp == 0 && cb > 0) {
+    if (lane < n) dlo = mask[(size_t)lane * ld];
+    if (lane + 32 < n) dhi = mask[(size_t)(lane + 32) * ld];
+  }
   __syncthreads();
   int total = 0;
   for (int b = 0; b < cb; ++b) {
     const int nb = min(kBlk, n - b * kBlk);
+    const int ra = b * kBlk + 2 * warp, rbb = ra + 1;   // this warp's rows of block b
+    const int j0 = b + 1 + lane, j1 = j0 + 32;
+    unsigned long long va0 = 0ull, va1 = 0ull, vb0 = 0ull, vb1 = 0ull;
+    if (ra < n) {
+      const unsigned long long* pa = mask + (size_t)ra * ld;
+      if (j0 < cb) va0 = pa[j0];
+      if (j1 < cb) va1 = pa[j1];
+    }
+    if (rbb < n) {
+      const unsigned long long* pb = mask + (size_t)rbb * ld;
+      if (j0 < cb) vb0 = pb[j0];
+      if (j1 < cb) vb1 = pb[j1];
+    }
     if (warp == 0) {
+      unsigned long long nlo = 0ull, nhi = 0ull;       // diagonal words of block b + 1
+      const int rlo = (b + 1) * kBlk + lane, rhi = rlo + 32;
+      if (rlo < n) nlo = mask[(size_t)rlo * ld + b + 1];
+      if (rhi < n) nhi = mask[(size_t)rhi * ld + b + 1];
       unsigned long long rem = s_remv[b];
-      const int rlo = b * kBlk + lane, rhi = rlo + 32;
-      unsigned long long dlo = (rlo < n) ? mask[(size_t)rlo * ld + b] : 0ull;
-      unsigned long long dhi = (rhi < n) ? mask[(size_t)rhi * ld + b] : 0ull;
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
         const unsigned long long w = __shfl_sync(0xffffffffu, dlo, i);
@@ -181,23 +204,24 @@ __device__ __forceinline__ int sweep_segment(const unsigned long long* __restric
       }
       const unsigned long long valid = (nb == kBlk) ? ~0ull : ((1ull << nb) - 1ull);
       const unsigned long long kw = ~rem & valid;
-      if (lane == 0) *s_kw = kw;
-      if ((kw >> lane) & 1ull) emit(total + __popcll(kw & ((1ull << lane) - 1ull)), b * kBlk + lane);
-      if ((kw >> (lane + 32)) & 1ull)
-        emit(total + __popcll(kw & ((1ull << (lane + 32)) - 1ull)), b * kBlk + 32 + lane);
+      if (lane == 0) s_kw[b] = kw;                     // (the survivors are written out after the chain, in parallel)
+      dlo = nlo; dhi = nhi;
     }
     __syncthreads();
-    const unsigned long long kw = *s_kw;
+    const unsigned long long kw = s_kw[b];
     total += __popcll(kw);
     // OR the kept rows of this block into the removed-bitmap of all later blocks:
     // lanes walk the columns (coalesced), warps split the 64 rows two each.
     if (b + 1 < cb) {
-      const int ra = 2 * warp, rbb = 2 * warp + 1;
-      const bool ka = (kw >> ra) & 1ull, kb2 = (kw >> rbb) & 1ull;
+      const bool ka = (kw >> (2 * warp)) & 1ull, kb2 = (kw >> (2 * warp + 1)) & 1ull;
       if (ka || kb2) {
-        const unsigned long long* pa = mask + (size_t)(b * kBlk + ra) * ld;
-        const unsigned long long* pb = mask + (size_t)(b * kBlk + rbb) * ld;
-        for (int j = b + 1 + lane; j < cb; j += 32) {
+        const unsigned long long a0 = (ka ? va0 : 0ull) | (kb2 ? vb0 : 0ull);
+        const unsigned long long a1 = (ka ? va1 : 0ull) | (kb2 ? vb1 : 0ull);
+        if (a0) atomicOr(&s_remv[j0], a0);
+        if (a1) atomicOr(&s_remv[j1], a1);
+        const unsigned long long* pa = mask + (size_t)ra * ld;
+        const unsigned long long* pb = mask + (size_t)rbb * ld;
+        for (int j = j1 + 32; j < cb; j += 32) {         // (segments of more than ~4,200 boxes)
           unsigned long long acc = 0ull;
           if (ka) acc |= pa[j];
           if (kb2) acc |= pb[j];
@@ -207,6 +231,18 @@ __device__ __forceinline__ int sweep_segment(const unsigned long long* __restric
     }
     __syncthreads();
   }
+  // emission: warp w writes the survivors of blocks w, w + 32, ...; its first output position is the number of
+  // survivors in the blocks before
+  for (int b = warp; b < cb; b += kSweepThreads / 32) {
+    int before = 0;
+    for (int j = lane; j < b; j += 32) before += __popcll(s_kw[j]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(0xffffffffu, before, o);
+    const unsigned long long kw = s_kw[b];
+    if ((kw >> lane) & 1ull) emit(before + __popcll(kw & ((1ull << lane) - 1ull)), b * kBlk + lane);
+    if ((kw >> (lane + 32)) & 1ull)
+      emit(before + __popcll(kw & ((1ull << (lane + 32)) - 1ull)), b * kBlk + 32 + lane);
+  }
   return total;
 }
 
@@ -214,9 +250,8 @@ __global__ void __launch_bounds__(kSweepThreads)
 nms_sweep_kernel(const unsigned long long* __restrict__ mask, const int* __restrict__ order, int n,
                  int64_t* __restrict__ keep_out, int32_t* __restrict__ num_keep) {
   extern __shared__ unsigned long long s_dyn[];
-  __shared__ unsigned long long s_kw;
   const int cb = (n + kBlk - 1) / kBlk;
-  int total = sweep_segment(mask, n, cb, s_dyn, &s_kw,
+  int total = sweep_segment(mask, n, cb, s_dyn, s_dyn + cb,
                             [&](int pos, int sorted_idx) { keep_out[pos] = (int64_t)order[sorted_idx]; });
   if (threadIdx.x == 0) *num_keep = total;
 }
@@ -385,14 +420,13 @@ mc_sweep_kernel(const unsigned long long* __restrict__ mask, const int* __restri
                 const float* __restrict__ seg_score, const int* __restrict__ seg_box,
                 float* __restrict__ kept_score, int* __restrict__ kept_box, int* __restrict__ kept_count) {
   extern __shared__ unsigned long long s_dyn[];
-  __shared__ unsigned long long s_kw;
   const size_t seg = blockIdx.x;
   const int k = seg_count[seg];
   const float* sc = seg_score + seg * n;
   const int* bx = seg_box + seg * n;
   float* ks = kept_score + seg * n;
   int* kb = kept_box + seg * n;
-  int total = sweep_segment(mask + seg * (size_t)n * ld, k, ld, s_dyn, &s_kw,
+  int total = sweep_segment(mask + seg * (size_t)n * ld, k, ld, s_dyn, s_dyn + ld,
                             [&](int pos, int sorted_idx) { ks[pos] = sc[sorted_idx]; kb[pos] = bx[sorted_idx]; });
   if (threadIdx.x == 0) kept_count[seg] = total;
 }
@@ -518,7 +552,7 @@ extern "C" int s2a_nms_rotated(const float* dets, int64_t det_stride, const floa
   nms_mask_kernel<<<(unsigned)tiles, kMaskThreads, 0, st>>>(w.boxes, labels ? w.labels : nullptr, ni, cb,
                                                             iou_threshold, w.mask);
   S2A_LAUNCH_OK("nms_mask_kernel");
-  const size_t smem = sizeof(unsigned long long) * (size_t)cb;
+  const size_t smem = 2 * sizeof(unsigned long long) * (size_t)cb;
   S2A_CHECK_ARG(smem <= 200 * 1024, "nms_rotated: n too large for the single-CTA sweep");
   if (smem > 48 * 1024)
     S2A_CUDA_OK(cudaFuncSetAttribute(nms_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -578,7 +612,7 @@ extern "C" int s2a_multiclass_nms_rotated(const float* bboxes, const float* scor
   mc_mask_kernel<<<sm_count() * 8, kMaskThreads, 0, st>>>(w.seg_rbox, w.seg_count, w.tile_off, S, ni, ld, iou_thr,
                                                           w.mask);
   S2A_LAUNCH_OK("mc_mask_kernel");
-  const size_t smem = sizeof(unsigned long long) * (size_t)ld;
+  const size_t smem = 2 * sizeof(unsigned long long) * (size_t)ld;
   mc_sweep_kernel<<<S, kSweepThreads, smem, st>>>(w.mask, w.seg_count, ni, ld, w.seg_score, w.seg_box,
                                                   w.kept_score, w.kept_box, w.kept_count);
   S2A_LAUNCH_OK("mc_sweep_kernel");
