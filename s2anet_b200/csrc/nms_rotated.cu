@@ -39,6 +39,9 @@ struct MaskTileSmem {
   float lcol[kBlk];
   unsigned long long word[kBlk];
   uint16_t list[kBlk * kBlk];
+  // one byte per (row, column) pair: "suppresses".  Plain stores -- 64-bit shared-memory atomicOr is a CAS loop, and
+  // up to 64 threads setting bits of the same row word serialised on it.
+  __align__(16) uint8_t flag[kBlk * kBlk];
   int count;
 };
 
@@ -50,12 +53,13 @@ __device__ __forceinline__ void mask_tile(MaskTileSmem& s, const RBox* __restric
                                           const float* __restrict__ lcols, int nr, int nc, bool diag,
                                           float thr) {
   const int tid = threadIdx.x;
+  static_assert(kMaskThreads * 16 == kBlk * kBlk, "one 16-byte store per thread clears the flags");
+  reinterpret_cast<uint4*>(s.flag)[tid] = make_uint4(0u, 0u, 0u, 0u);
   if (tid < kBlk) {
     if (tid < nr) {
       s.row[tid] = rows[tid];
       s.lrow[tid] = lrows ? lrows[tid] : 0.0f;
     }
-    s.word[tid] = 0ull;
   } else if (tid < 2 * kBlk) {
     const int c = tid - kBlk;
     if (c < nc) {
@@ -79,9 +83,17 @@ __device__ __forceinline__ void mask_tile(MaskTileSmem& s, const RBox* __restric
     bool clip = false;
     if (r < nr && c < nc && (!diag || c > r)) {
       int cls = RB_ZERO;
-      if (s.lrow[r] == lc) cls = rbox_classify_fast(s.row[r], cb);   // labels differ -> IoU := 0
-      if (cls != RB_ZERO) clip = true;                               // listed: full classify + clip below
-      else if (zero_suppresses) atomicOr(&s.word[r], 1ull << c);
+      const RBox& rb = s.row[r];
+      if (s.lrow[r] == lc) cls = rbox_classify_fast(rb, cb);         // labels differ -> IoU := 0
+      if (cls != RB_ZERO) {
+        // The sweep only needs "IoU > thr".  intersection <= min(area) and union >= max(area), so a pair whose area
+        // ratio is below thr (with 0.1 % slack for the reference's fp32 polygon area) cannot suppress: no clip.
+        const float ar = rb.w * rb.h, ac = cb.w * cb.h;
+        const bool small = thr > 0.0f && rb.w > 0.0f && rb.h > 0.0f && cb.w > 0.0f && cb.h > 0.0f &&
+                           fminf(ar, ac) < 0.999f * thr * fmaxf(ar, ac);
+        clip = !small;                                               // listed: full classify + clip below
+      }
+      else if (zero_suppresses) s.flag[r * kBlk + c] = 1;
     }
     const unsigned bal = __ballot_sync(0xffffffffu, clip);
     if (bal) {
@@ -96,7 +108,23 @@ __device__ __forceinline__ void mask_tile(MaskTileSmem& s, const RBox* __restric
   for (int k = tid; k < cnt; k += kMaskThreads) {
     const int p = s.list[k];
     const int r = p >> 6, cc = p & (kBlk - 1);
-    if (rbox_iou(s.row[r], s.col[cc]) > thr) atomicOr(&s.word[r], 1ull << cc);
+    if (rbox_iou(s.row[r], s.col[cc]) > thr) s.flag[p] = 1;
+  }
+  __syncthreads();
+  if (tid < kBlk) {                               // row tid: 64 flag bytes -> one word
+    const uint4* f = reinterpret_cast<const uint4*>(s.flag + tid * kBlk);
+    unsigned long long w = 0ull;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint4 v = f[q];
+      const uint32_t x[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const uint32_t nib = (x[e] & 1u) | ((x[e] >> 7) & 2u) | ((x[e] >> 14) & 4u) | ((x[e] >> 21) & 8u);
+        w |= (unsigned long long)nib << (16 * q + 4 * e);
+      }
+    }
+    s.word[tid] = w;
   }
   __syncthreads();
 }
@@ -157,6 +185,8 @@ template <class Emit>
 __device__ __forceinline__ int sweep_segment(const unsigned long long* __restrict__ mask, int n, int ld,
                                              unsigned long long* s_remv, unsigned long long* s_kw,
                                              Emit emit) {
+  static_assert(kSweepThreads == 1024, "the column reduction below transposes a 32 x 32 block of words");
+  __shared__ unsigned long long s_part[32][33];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int cb = (n + kBlk - 1) / kBlk;
   for (int j = tid; j < cb; j += kSweepThreads) s_remv[j] = 0ull;
@@ -210,18 +240,33 @@ __device__ __forceinline__ int sweep_segment(const unsigned long long* __restric
     __syncthreads();
     const unsigned long long kw = s_kw[b];
     total += __popcll(kw);
-    // OR the kept rows of this block into the removed-bitmap of all later blocks:
-    // lanes walk the columns (coalesced), warps split the 64 rows two each.
+    // OR the kept rows of this block into the removed-bitmap of all later blocks.  Every warp holds, per lane, the
+    // words of ITS two rows for columns b + 1 + lane (and + 32); the OR over the 32 warps goes through a padded
+    // 32 x 32 transpose in shared memory and a warp reduction -- one writer per column, no atomics (32 warps
+    // hammering the same 64-bit shared-memory words with atomicOr was most of the sweep's time).
     if (b + 1 < cb) {
       const bool ka = (kw >> (2 * warp)) & 1ull, kb2 = (kw >> (2 * warp + 1)) & 1ull;
-      if (ka || kb2) {
-        const unsigned long long a0 = (ka ? va0 : 0ull) | (kb2 ? vb0 : 0ull);
-        const unsigned long long a1 = (ka ? va1 : 0ull) | (kb2 ? vb1 : 0ull);
-        if (a0) atomicOr(&s_remv[j0], a0);
-        if (a1) atomicOr(&s_remv[j1], a1);
+      const unsigned long long a0 = (ka ? va0 : 0ull) | (kb2 ? vb0 : 0ull);
+      const unsigned long long a1 = (ka ? va1 : 0ull) | (kb2 ? vb1 : 0ull);
+      s_part[warp][lane] = a0;
+      __syncthreads();
+      {
+        const unsigned long long v = s_part[lane][warp];
+        const unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)v), hi = __reduce_or_sync(0xffffffffu, (unsigned)(v >> 32));
+        if (lane == 0 && b + 1 + warp < cb) s_remv[b + 1 + warp] |= ((unsigned long long)hi << 32) | lo;
+      }
+      if (b + 1 + 32 < cb) {
+        __syncthreads();
+        s_part[warp][lane] = a1;
+        __syncthreads();
+        const unsigned long long v = s_part[lane][warp];
+        const unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)v), hi = __reduce_or_sync(0xffffffffu, (unsigned)(v >> 32));
+        if (lane == 0 && b + 1 + 32 + warp < cb) s_remv[b + 1 + 32 + warp] |= ((unsigned long long)hi << 32) | lo;
+      }
+      if (b + 1 + 64 < cb && (ka || kb2)) {              // (segments of more than ~4,200 boxes: the far columns)
         const unsigned long long* pa = mask + (size_t)ra * ld;
         const unsigned long long* pb = mask + (size_t)rbb * ld;
-        for (int j = j1 + 32; j < cb; j += 32) {         // (segments of more than ~4,200 boxes)
+        for (int j = j1 + 32; j < cb; j += 32) {
           unsigned long long acc = 0ull;
           if (ka) acc |= pa[j];
           if (kb2) acc |= pb[j];
