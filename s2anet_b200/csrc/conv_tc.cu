@@ -8,7 +8,8 @@
 // rotation_invariant_pooling.py:19-27).
 //
 // GEMM view:  D[m, n] = sum_k A[m, k] * Wp[n, k]
-//   m : output position (a CTA owns an 8 x 16 spatial patch = 128 rows = one UMMA M)
+//   m : output position (a CTA owns a 128-pixel patch = 128 rows = one UMMA M: 8 rows x 16 pixels for AlignConv,
+//       16 rows x 8 pixels for the plain convs)
 //   n : output channel (N = C_out <= 256, the whole channel dimension in one UMMA N)
 //   k : (64-channel block, tap, channel-in-block) -- 64-wide k-blocks, K' = 9*C_in
 //   A : never exists in global memory.  For AlignConv a[m, (cb,t,c)] is the bilinear sample of x at
@@ -20,9 +21,11 @@
 // build the A tiles -- per (row, tap) recipe -> 8 LDS.128 from a TMA-fed shared-memory halo of the feature map ->
 // packed 16-bit blend -> tcgen05.st straight into the A stage in TENSOR MEMORY; 4 epilogue warps (tcgen05.ld ->
 // bias / ReLU / 8-way orientation max -> staging -> TMA store; they also build the gather recipes two tiles
-// ahead); one TMA warp (weight k-blocks, halos, and for ORConv / plain convs the A tile as one 4-D box); one MMA
-// warp that allocates TMEM and issues tcgen05.mma.cta_group::2 (M = 256 across the pair, N = C_out, K = 16,
-// kind::f16; A from shared memory or from TMEM) under elect.sync.  Stages are recycled through one full/empty
+// ahead); one TMA warp (weight k-blocks, AlignConv halos); for ORConv / plain convs one more warp that loads the
+// OPERAND HALO -- one SWIZZLE_128B box per (tile, channel block) that the tensor core reads for all nine taps
+// through shifted shared-memory descriptors; one MMA warp that allocates TMEM and issues
+// tcgen05.mma.cta_group::2 (M = 256 across the pair, N = C_out, K = 16, kind::f16; A from shared memory or from
+// TMEM) under elect.sync.  Stages are recycled through one full/empty
 // mbarrier pair each; tcgen05.commit (multicast to both CTAs) releases a stage when its MMAs retire.
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -66,8 +69,8 @@ enum { TC_ALIGN = 0, TC_PLAIN = 1, TC_PLAIN_S = 2 };
 
 // Per-mode pipeline shape.
 //  * ORConv2d (TC_PLAIN) is fed entirely by TMA and bound by the tensor pipe: a CTA PAIR (cta_group::2, one
-//    TPC) shares every weight k-block -- each CTA stages half of the C_out rows -- and A + B of a k-block
-//    travel through one ring of 6 stages with one full/empty barrier pair per stage.
+//    TPC) shares every weight k-block -- each CTA stages half of the C_out rows -- in a ring of 4 stages of two
+//    k-blocks with one full/empty barrier pair per stage; the A operand is the shared-memory halo (see TC_PPW).
 //  * AlignConv (TC_ALIGN) is bound by the bilinear gather, i.e. by LSU wavefronts: 4 corners x 128 B per
 //    (row, k-block) = 512 wavefronts per k-block next to 512 tensor-pipe cycles.  Its feature-map reads go
 //    through a TMA-fed shared-memory halo (two 39 KB buffers) instead of L1, and the blended A operand never
