@@ -279,6 +279,23 @@ S2A_EXPORT int s2a_assign_labels(const float* anchors, const float* gts, const i
                                  int filter_invalid_anchors, int64_t* assign_out, void* workspace,
                                  size_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * poly_nms -- DOTA result-merging NMS on quadrilaterals, fp64 (second half)
+ *   reference: DOTA_devkit/ResultMerge_multi_process.py:62-123 (py_cpu_nms_poly_fast),
+ *              DOTA_devkit/polyiou/csrc/polyiou.cpp:9-126 (iou_poly and its helpers)
+ * dets: rows of det_stride >= 9 doubles (x0 y0 x1 y1 x2 y2 x3 y3 score).  A later (lower-score) row is dropped
+ * when its value against a kept row is not <= thresh, where value = overlap ratio of the two axis-aligned
+ * bounding boxes (area (dx + 1)(dy + 1), overlap without the + 1) if that is not > 0, else the polygon IoU.
+ * keep_out int64 [n]: kept row indices in descending-score order (equal scores: input order);
+ * num_keep_out int32.  Every fp64 operation is individually rounded in the reference's order.
+ * s2a_poly_iou_pairs: out[i] = iou_poly(p[i], q[i]) for 8-double polygons (parity probe).
+ */
+S2A_EXPORT size_t s2a_poly_nms_workspace_bytes(int64_t n);
+S2A_EXPORT int s2a_poly_nms(const double* dets, int64_t det_stride, int64_t n, double thresh,
+                            int64_t* keep_out, int32_t* num_keep_out, void* workspace,
+                            size_t workspace_bytes, void* stream);
+S2A_EXPORT int s2a_poly_iou_pairs(const double* p, const double* q, int64_t n, double* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

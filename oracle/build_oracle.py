@@ -35,11 +35,24 @@ def _stale(out, srcs):
 
 
 def build_oracle(force=False):
-    src = os.path.join(HERE, "s2a_oracle.c")
+    srcs = [os.path.join(HERE, "s2a_oracle.c"), os.path.join(HERE, "poly_oracle.c")]
     out = os.path.join(HERE, "libs2a_oracle.so")
-    if force or _stale(out, [src]):
+    if force or _stale(out, srcs):
         _run(["gcc", "-O2", "-std=c11", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math",
-              "-fvisibility=hidden", "-o", out, src, "-lm"])
+              "-fvisibility=hidden", "-o", out] + srcs + ["-lm"])
+    return out
+
+
+def build_ref_polyiou(force=False):
+    """The reference's polygon IoU (DOTA_devkit/polyiou/csrc/polyiou.cpp), compiled where it lies, behind a C shim."""
+    src = os.path.join(REF, "DOTA_devkit/polyiou/csrc/polyiou.cpp")
+    if not os.path.exists(src):
+        return None
+    os.makedirs(REF_OUT, exist_ok=True)
+    shim = os.path.join(HERE, "ref_shim_poly.cpp")
+    out = os.path.join(REF_OUT, "libref_polyiou.so")
+    if force or _stale(out, [shim, src]):
+        _run(["g++", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-o", out, shim, src])
     return out
 
 
@@ -75,6 +88,7 @@ if __name__ == "__main__":
     print(build_oracle(force="--force" in sys.argv))
     for o in build_ref_shims(force="--force" in sys.argv):
         print(o)
+    print(build_ref_polyiou(force="--force" in sys.argv))
 
 
 # ---- the reference's own torch extensions, compiled from /root/reference in place ---------------

@@ -346,3 +346,95 @@ def assign_labels(anchors, gt_boxes, imgs_size=(1024, 1024), pos_iou_thr=0.5, ne
             else:
                 out[garg[i]] = i
     return out
+
+
+# ---- DOTA result-merging NMS (fp64 polygons): oracle/poly_oracle.c and oracle/_ref/libref_polyiou.so -----------
+
+_f64p = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+
+
+def _poly_lib():
+    L = lib()
+    if not getattr(L, "_poly_ready", False):
+        L.s2a_oracle_poly_iou_pairs.restype = None
+        L.s2a_oracle_poly_iou_pairs.argtypes = [_f64p, _f64p, C.c_int64, _f64p]
+        L.s2a_oracle_poly_nms.restype = C.c_int64
+        L.s2a_oracle_poly_nms.argtypes = [_f64p, C.c_int64, C.c_int64, C.c_double, _i64p]
+        L._poly_ready = True
+    return L
+
+
+def poly_iou_pairs(p, q):
+    """polyiou.cpp:110-126 for n pairs: p, q [n, 8] float64 -> [n]."""
+    p = np.ascontiguousarray(p, dtype=np.float64)
+    q = np.ascontiguousarray(q, dtype=np.float64)
+    out = np.empty((p.shape[0],), dtype=np.float64)
+    _poly_lib().s2a_oracle_poly_iou_pairs(p, q, p.shape[0], out)
+    return out
+
+
+def poly_nms(dets, thresh):
+    """ResultMerge_multi_process.py:62-123: dets [n, 9] float64 -> kept row indices (descending score)."""
+    dets = np.ascontiguousarray(dets, dtype=np.float64)
+    n = dets.shape[0]
+    keep = np.empty((max(n, 1),), dtype=np.int64)
+    k = _poly_lib().s2a_oracle_poly_nms(dets, dets.shape[1], n, float(thresh), keep)
+    return keep[:k].copy()
+
+
+def ref_polyiou():
+    """The reference's own iou_poly compiled in place (oracle/_ref/libref_polyiou.so), or None."""
+    path = os.path.join(HERE, "_ref", "libref_polyiou.so")
+    if not os.path.exists(path):
+        return None
+    L = C.CDLL(path)
+    L.ref_iou_poly_pairs.restype = None
+    L.ref_iou_poly_pairs.argtypes = [_f64p, _f64p, C.c_int64, _f64p]
+    return L
+
+
+def ref_poly_iou_pairs(p, q):
+    L = ref_polyiou()
+    if L is None:
+        return None
+    p = np.ascontiguousarray(p, dtype=np.float64)
+    q = np.ascontiguousarray(q, dtype=np.float64)
+    out = np.empty((p.shape[0],), dtype=np.float64)
+    L.ref_iou_poly_pairs(p, q, p.shape[0], out)
+    return out
+
+
+def ref_py_cpu_nms_poly_fast(dets, thresh=0.5):
+    """py_cpu_nms_poly_fast line by line (ResultMerge_multi_process.py:62-123), numpy as in the reference, with the
+    reference's compiled iou_poly for the pair values.  Used to generate and to pin the golden keep lists."""
+    L = ref_polyiou()
+    assert L is not None, "oracle/_ref/libref_polyiou.so is not built"
+    dets = np.asarray(dets, dtype=np.float64)
+    obbs = dets[:, 0:-1]
+    x1 = np.min(obbs[:, 0::2], axis=1)
+    y1 = np.min(obbs[:, 1::2], axis=1)
+    x2 = np.max(obbs[:, 0::2], axis=1)
+    y2 = np.max(obbs[:, 1::2], axis=1)
+    scores = dets[:, 8]
+    areas = (x2 - x1 + 1) * (y2 - y1 + 1)
+    order = scores.argsort()[::-1]
+    keep = []
+    while order.size > 0:
+        i = order[0]
+        keep.append(int(i))
+        xx1 = np.maximum(x1[i], x1[order[1:]])
+        yy1 = np.maximum(y1[i], y1[order[1:]])
+        xx2 = np.minimum(x2[i], x2[order[1:]])
+        yy2 = np.minimum(y2[i], y2[order[1:]])
+        w = np.maximum(0.0, xx2 - xx1)
+        h = np.maximum(0.0, yy2 - yy1)
+        hbb_inter = w * h
+        hbb_ovr = hbb_inter / (areas[i] + areas[order[1:]] - hbb_inter)
+        h_inds = np.where(hbb_ovr > 0)[0]
+        tmp_order = order[h_inds + 1]
+        if tmp_order.size:
+            pi = np.ascontiguousarray(np.repeat(obbs[i][None, :], tmp_order.size, axis=0))
+            hbb_ovr[h_inds] = ref_poly_iou_pairs(pi, np.ascontiguousarray(obbs[tmp_order]))
+        inds = np.where(hbb_ovr <= thresh)[0]
+        order = order[inds + 1]
+    return np.asarray(keep, dtype=np.int64)

@@ -44,6 +44,9 @@ PROTOTYPES = {
     "s2a_deform_col2im_f32": (_i32, [_vp, _vp, _vp, _vp, _vp] + [_i32] * 13 + [_vp]),
     "s2a_assign_labels_workspace_bytes": (_sz, [_i64, _i64, _i64]),
     "s2a_assign_labels": (_i32, [_vp, _vp, _vp, _i64, _i64, _i64, _f32, _f32, _f32, _f32, _f32, _i32, _i32, _vp, _vp, _sz, _vp]),
+    "s2a_poly_nms_workspace_bytes": (_sz, [_i64]),
+    "s2a_poly_nms": (_i32, [_vp, _i64, _i64, _f64, _vp, _vp, _vp, _sz, _vp]),
+    "s2a_poly_iou_pairs": (_i32, [_vp, _vp, _i64, _vp, _vp]),
     "s2a_fam_decode": (_i32, [_i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _f32, _f32, _f64, _i32, _vp]),
     "s2a_select_decode_workspace_bytes": (_sz, [_i32, _vp, _vp, _i32]),
     "s2a_select_decode": (_i32, [_i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _f64, _i32, _vp, _vp, _vp,
@@ -76,6 +79,7 @@ KERNELS_PER_CALL = {
     "orconv_forward": 1, "conv_pack_weight": 1, "alignconv_forward_tc": 1, "orconv_forward_tc": 1,
     "alignconv_forward_tc_multi": 1, "orconv_forward_tc_multi": 1, "fam_decode": 1, "select_decode": 1, "conv2d_pack_weight": 1,
     "conv2d_forward_tc_multi": 1, "assign_labels": 2, "deform_im2col": 1, "deform_col2im": 1,
+    "poly_nms": 4, "poly_iou_pairs": 1,
 }
 launches = 0          # running count, read by bench.py for "gpu_launches"
 

@@ -667,3 +667,204 @@ extern "C" int s2a_multiclass_nms_rotated(const float* bboxes, const float* scor
   S2A_LAUNCH_OK("mc_emit_kernel");
   return S2A_OK;
 }
+
+// ================================================================================================
+// DOTA result-merging NMS on polygons, fp64 (second half)
+//
+// Replaces (reference): py_cpu_nms_poly_fast (DOTA_devkit/ResultMerge_multi_process.py:62-123) and the polygon IoU
+// it calls per pair (DOTA_devkit/polyiou/csrc/polyiou.cpp:108-126, restated in poly_iou.cuh).  Same device
+// structure as nms_rotated: sort by score, upper-triangular 64 x 64 suppression tiles (axis-aligned prefilter for
+// every pair, polygon IoU for the listed survivors), one-CTA sweep.  The reference keeps a later box iff
+// `value <= thresh`, so a NaN value suppresses -- the predicate here is !(value <= thresh).
+// ================================================================================================
+#include "poly_iou.cuh"
+
+namespace s2a {
+
+struct PolyBox { double p[8]; double hb[5]; };      // polygon, (x1, y1, x2, y2, area) of its axis-aligned box
+
+__global__ void poly_keys_kernel(const double* __restrict__ dets, int64_t stride, int n, double* __restrict__ keys,
+                                 int* __restrict__ vals) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { keys[i] = dets[(size_t)i * stride + 8]; vals[i] = i; }
+}
+
+__global__ void poly_prep_kernel(const double* __restrict__ dets, int64_t stride, const int* __restrict__ order, int n,
+                                 PolyBox* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double* d = dets + (size_t)order[i] * stride;
+  PolyBox b;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) b.p[e] = d[e];
+  b.hb[0] = fmin(fmin(b.p[0], b.p[2]), fmin(b.p[4], b.p[6]));
+  b.hb[1] = fmin(fmin(b.p[1], b.p[3]), fmin(b.p[5], b.p[7]));
+  b.hb[2] = fmax(fmax(b.p[0], b.p[2]), fmax(b.p[4], b.p[6]));
+  b.hb[3] = fmax(fmax(b.p[1], b.p[3]), fmax(b.p[5], b.p[7]));
+  // areas = (x2 - x1 + 1) * (y2 - y1 + 1)   (ResultMerge_multi_process.py:69)
+  b.hb[4] = __dmul_rn(__dadd_rn(__dsub_rn(b.hb[2], b.hb[0]), 1.0), __dadd_rn(__dsub_rn(b.hb[3], b.hb[1]), 1.0));
+  out[i] = b;
+}
+
+struct PolyTileSmem {
+  PolyBox row[kBlk];
+  PolyBox col[kBlk];
+  uint16_t list[kBlk * kBlk];
+  __align__(16) uint8_t flag[kBlk * kBlk];
+  int count;
+};
+
+__global__ void __launch_bounds__(kMaskThreads)
+poly_mask_kernel(const PolyBox* __restrict__ boxes, int n, int cb, double thr, unsigned long long* __restrict__ mask) {
+  __shared__ PolyTileSmem s;
+  int rb, cbk;
+  decode_upper((long long)blockIdx.x, cb, rb, cbk);
+  const int nr = min(kBlk, n - rb * kBlk), nc = min(kBlk, n - cbk * kBlk);
+  const bool diag = rb == cbk;
+  const int tid = threadIdx.x;
+  reinterpret_cast<uint4*>(s.flag)[tid] = make_uint4(0u, 0u, 0u, 0u);
+  // 2 x 64 boxes of 13 doubles, copied word by word (coalesced)
+  {
+    const double* src_r = reinterpret_cast<const double*>(boxes + (size_t)rb * kBlk);
+    const double* src_c = reinterpret_cast<const double*>(boxes + (size_t)cbk * kBlk);
+    double* dst_r = reinterpret_cast<double*>(s.row);
+    double* dst_c = reinterpret_cast<double*>(s.col);
+    for (int e = tid; e < nr * 13; e += kMaskThreads) dst_r[e] = src_r[e];
+    for (int e = tid; e < nc * 13; e += kMaskThreads) dst_c[e] = src_c[e];
+  }
+  if (tid == 0) s.count = 0;
+  __syncthreads();
+  const int c = tid & (kBlk - 1), r0 = tid >> 6;
+  const unsigned lane = tid & 31;
+  for (int k = 0; k < kBlk / 4; ++k) {
+    const int r = r0 + 4 * k;
+    bool clip = false;
+    if (r < nr && c < nc && (!diag || c > r)) {
+      const double* hi = s.row[r].hb;
+      const double* hj = s.col[c].hb;
+      const double w = fmax(0.0, __dsub_rn(fmin(hi[2], hj[2]), fmax(hi[0], hj[0])));
+      const double h = fmax(0.0, __dsub_rn(fmin(hi[3], hj[3]), fmax(hi[1], hj[1])));
+      const double inter = __dmul_rn(w, h);
+      const double ovr = __ddiv_rn(inter, __dsub_rn(__dadd_rn(hi[4], hj[4]), inter));
+      if (ovr > 0.0) clip = true;                       // polygon IoU replaces the value (below)
+      else if (!(ovr <= thr)) s.flag[r * kBlk + c] = 1;  // NaN, or a negative threshold
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, clip);
+    if (bal) {
+      int base = 0;
+      if (lane == 0) base = atomicAdd(&s.count, __popc(bal));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (clip) s.list[base + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)(r * kBlk + c);
+    }
+  }
+  __syncthreads();
+  const int cnt = s.count;
+  for (int k = tid; k < cnt; k += kMaskThreads) {
+    const int p = s.list[k];
+    const double v = poly_iou(s.row[p >> 6].p, s.col[p & (kBlk - 1)].p);
+    if (!(v <= thr)) s.flag[p] = 1;
+  }
+  __syncthreads();
+  if (tid < nr) {
+    const uint4* f = reinterpret_cast<const uint4*>(s.flag + tid * kBlk);
+    unsigned long long w = 0ull;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint4 v = f[q];
+      const uint32_t x[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const uint32_t nib = (x[e] & 1u) | ((x[e] >> 7) & 2u) | ((x[e] >> 14) & 4u) | ((x[e] >> 21) & 8u);
+        w |= (unsigned long long)nib << (16 * q + 4 * e);
+      }
+    }
+    mask[((size_t)rb * kBlk + tid) * cb + cbk] = w;
+  }
+}
+
+__global__ void poly_iou_pairs_kernel(const double* __restrict__ p, const double* __restrict__ q, int64_t n,
+                                      double* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = poly_iou(p + 8 * i, q + 8 * i);
+}
+
+struct PolyWorkspace {
+  double* keys_in; double* keys_out; int* vals_in; int* vals_out; PolyBox* boxes; unsigned long long* mask;
+  void* cub_tmp; size_t cub_bytes; size_t total;
+};
+
+static PolyWorkspace carve_poly(void* base, int64_t n) {
+  PolyWorkspace w;
+  const int64_t cb = ceil_div(n, kBlk);
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return (char*)base + o; };
+  w.keys_in = (double*)take(sizeof(double) * n);
+  w.keys_out = (double*)take(sizeof(double) * n);
+  w.vals_in = (int*)take(sizeof(int) * n);
+  w.vals_out = (int*)take(sizeof(int) * n);
+  w.boxes = (PolyBox*)take(sizeof(PolyBox) * n);
+  w.mask = (unsigned long long*)take(sizeof(unsigned long long) * (size_t)n * cb);
+  w.cub_bytes = 0;
+  cub::DeviceRadixSort::SortPairsDescending(nullptr, w.cub_bytes, (const double*)nullptr, (double*)nullptr,
+                                            (const int*)nullptr, (int*)nullptr, (int)n);
+  w.cub_tmp = take(w.cub_bytes);
+  w.total = off;
+  return w;
+}
+
+}  // namespace s2a
+
+extern "C" size_t s2a_poly_nms_workspace_bytes(int64_t n) {
+  if (n <= 0) return 256;
+  return s2a::carve_poly(nullptr, n).total;
+}
+
+extern "C" int s2a_poly_nms(const double* dets, int64_t det_stride, int64_t n, double thresh, int64_t* keep_out,
+                            int32_t* num_keep_out, void* workspace, size_t workspace_bytes, void* stream) {
+  using namespace s2a;
+  cudaStream_t st = (cudaStream_t)stream;
+  S2A_CHECK_ARG(n >= 0 && n < (1ll << 30), "poly_nms: n (%lld) out of range", (long long)n);
+  S2A_CHECK_ARG(num_keep_out != nullptr, "poly_nms: num_keep_out is null");
+  if (n == 0) {
+    S2A_CUDA_OK(cudaMemsetAsync(num_keep_out, 0, sizeof(int32_t), st));
+    return S2A_OK;
+  }
+  S2A_CHECK_ARG(dets && keep_out && workspace, "poly_nms: null pointer");
+  S2A_CHECK_ARG(det_stride >= 9, "poly_nms: rows are 8 polygon coordinates + score (stride %lld)", (long long)det_stride);
+  PolyWorkspace w = carve_poly(workspace, n);
+  if (workspace_bytes < w.total) {
+    set_error("poly_nms: workspace too small (%zu < %zu bytes)", workspace_bytes, w.total);
+    return S2A_ERR_WORKSPACE;
+  }
+  const int ni = (int)n;
+  const int cb = (int)ceil_div(n, kBlk);
+  const int tb = 256, gb = (int)ceil_div(n, tb);
+  poly_keys_kernel<<<gb, tb, 0, st>>>(dets, det_stride, ni, w.keys_in, w.vals_in);
+  S2A_LAUNCH_OK("poly_keys_kernel");
+  size_t cub_bytes = w.cub_bytes;
+  S2A_CUDA_OK(cub::DeviceRadixSort::SortPairsDescending(w.cub_tmp, cub_bytes, w.keys_in, w.keys_out, w.vals_in,
+                                                        w.vals_out, ni, 0, 64, st));
+  poly_prep_kernel<<<gb, tb, 0, st>>>(dets, det_stride, w.vals_out, ni, w.boxes);
+  S2A_LAUNCH_OK("poly_prep_kernel");
+  const long long tiles = (long long)cb * (cb + 1) / 2;
+  S2A_CHECK_ARG(tiles < (1ll << 31), "poly_nms: too many tiles");
+  poly_mask_kernel<<<(unsigned)tiles, kMaskThreads, 0, st>>>(w.boxes, ni, cb, thresh, w.mask);
+  S2A_LAUNCH_OK("poly_mask_kernel");
+  const size_t smem = 2 * sizeof(unsigned long long) * (size_t)cb;
+  S2A_CHECK_ARG(smem <= 200 * 1024, "poly_nms: n too large for the single-CTA sweep");
+  if (smem > 48 * 1024)
+    S2A_CUDA_OK(cudaFuncSetAttribute(nms_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  nms_sweep_kernel<<<1, kSweepThreads, smem, st>>>(w.mask, w.vals_out, ni, keep_out, num_keep_out);
+  S2A_LAUNCH_OK("nms_sweep_kernel");
+  return S2A_OK;
+}
+
+extern "C" int s2a_poly_iou_pairs(const double* p, const double* q, int64_t n, double* out, void* stream) {
+  using namespace s2a;
+  S2A_CHECK_ARG(n >= 0, "poly_iou_pairs: negative n");
+  if (n == 0) return S2A_OK;
+  S2A_CHECK_ARG(p && q && out, "poly_iou_pairs: null pointer");
+  poly_iou_pairs_kernel<<<(unsigned)ceil_div(n, 128), 128, 0, (cudaStream_t)stream>>>(p, q, n, out);
+  S2A_LAUNCH_OK("poly_iou_pairs_kernel");
+  return S2A_OK;
+}

@@ -6,6 +6,7 @@ The reference imports six pybind11 extension modules by name (SURVEY.md section 
     models.dcn.deform_conv_cuda          deform_conv_forward_cuda / backward_* / modulated_*
     models.dcn.deform_pool_cuda          (imported by models/dcn/__init__.py:4, never called by S2ANet)
     models.orn.orn_cuda                  arf_forward / arf_backward / rie_forward / rie_backward
+    DOTA_devkit.polyiou.polyiou          VectorDouble / iou_poly (the SWIG module of the DOTA result merging)
     utils.box_iou_rotated.box_iou_rotated_cuda      box_iou_rotated
     utils.nms_rotated.nms_rotated_cuda              nms_rotated
     utils.ml_nms_rotated.ml_nms_rotated_cuda        ml_nms_rotated
@@ -56,6 +57,13 @@ def install(matplotlib_stub=True):
     _module("utils.box_iou_rotated.box_iou_rotated_cuda", box_iou_rotated=box_iou_rotated)
     _module("utils.nms_rotated.nms_rotated_cuda", nms_rotated=nms_rotated.nms_rotated_op)
     _module("utils.ml_nms_rotated.ml_nms_rotated_cuda", ml_nms_rotated=nms_rotated.ml_nms_rotated)
+    # DOTA result merging (DOTA_devkit/ResultMerge_multi_process.py:15 imports the SWIG module, whose generated
+    # wrapper needs the `imp` module Python 3.12 no longer has): same two names, GPU polygon IoU underneath.  The fast
+    # path is poly_nms.py_cpu_nms_poly_fast, which replaces the whole per-pair Python loop.
+    from . import poly_nms
+    pm = _module("DOTA_devkit.polyiou.polyiou", VectorDouble=poly_nms.VectorDouble, iou_poly=poly_nms.iou_poly)
+    pkg = _module("DOTA_devkit.polyiou", polyiou=pm)
+    pkg.__path__ = []
     if matplotlib_stub:
         try:
             import matplotlib  # noqa: F401

@@ -91,3 +91,18 @@ def all_level_anchors(B, seed, img=1024, strides=STRIDES):
         H = W = img // s
         parts.append(refined_anchors(B, H, W, s, seed * 16 + li).reshape(B, H * W, 5))
     return np.concatenate(parts, 1)
+
+
+def random_quads(n, rng, extent=300.0, lo=8.0, hi=120.0):
+    """n rotated rectangles as 8-number polygons, random orientation (both windings occur)."""
+    c = rng.uniform(0, extent, (n, 2))
+    w = np.exp(rng.uniform(np.log(lo), np.log(hi), n))
+    h = np.exp(rng.uniform(np.log(lo), np.log(hi), n))
+    t = rng.uniform(-np.pi, np.pi, n)
+    dx = np.stack([np.cos(t), np.sin(t)], 1)
+    dy = np.stack([-np.sin(t), np.cos(t)], 1)
+    corners = [c + s1 * dx * w[:, None] / 2 + s2 * dy * h[:, None] / 2 for s1, s2 in ((-1, -1), (1, -1), (1, 1), (-1, 1))]
+    p = np.concatenate(corners, 1)
+    flip = rng.random(n) < 0.5                  # clockwise vertex order for half of them
+    p[flip] = p[flip].reshape(-1, 4, 2)[:, ::-1].reshape(-1, 8)
+    return p

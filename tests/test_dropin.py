@@ -76,3 +76,29 @@ def test_reference_head_builds_and_accelerates(ref_on_path):
     mine = S2ANetHead(15)
     assert sorted(mine.state_dict().keys()) == sorted(head.state_dict().keys())
     mine.load_state_dict(head.state_dict())
+
+
+def test_reference_result_merge_runs_on_the_polyiou_shim(ref_on_path, monkeypatch):
+    """DOTA_devkit/ResultMerge_multi_process.py, unmodified, on the `DOTA_devkit.polyiou.polyiou` shim.  Its own
+    py_cpu_nms_poly_fast (:62-123), fed with the CPU oracle's iou_poly, must reproduce the golden keep lists -- which
+    pins both the oracle's NMS restatement and the golden generator's against the reference function itself."""
+    import types
+    import numpy as np
+    from oracle import oracle as O
+    from s2anet_b200 import dropin
+    dropin.install()
+    for name in ("shapely", "shapely.geometry"):            # dota_utils.py imports shapely at module scope (absent here)
+        if name not in sys.modules:
+            monkeypatch.setitem(sys.modules, name, types.ModuleType(name))
+    sys.modules["shapely"].geometry = sys.modules["shapely.geometry"]
+    import DOTA_devkit.ResultMerge_multi_process as R
+    assert R.polyiou.__s2a_b200__ and callable(R.polyiou.iou_poly) and callable(R.polyiou.VectorDouble)
+    monkeypatch.setattr(R.polyiou, "iou_poly",
+                        lambda p, q: float(O.poly_iou_pairs(np.array([list(p)]), np.array([list(q)]))[0]))
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "poly_small.npz"))
+    for thr, key in ((0.1, "keep_01"), (0.5, "keep_05")):
+        keep = R.py_cpu_nms_poly_fast(g["dets"], thr)
+        assert [int(i) for i in keep] == [int(i) for i in g[key]]
+    for k in list(sys.modules):
+        if k.startswith("DOTA_devkit"):
+            del sys.modules[k]
