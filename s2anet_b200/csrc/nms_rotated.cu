@@ -111,20 +111,19 @@ __device__ __forceinline__ void mask_tile(MaskTileSmem& s, const RBox* __restric
     if (rbox_iou(s.row[r], s.col[cc]) > thr) s.flag[p] = 1;
   }
   __syncthreads();
-  if (tid < kBlk) {                               // row tid: 64 flag bytes -> one word
-    const uint4* f = reinterpret_cast<const uint4*>(s.flag + tid * kBlk);
-    unsigned long long w = 0ull;
+  {
+    // flags -> words with all 256 threads: thread t packs the 16 flag bytes (row t / 4, quarter t % 4) into 16 bits,
+    // the four quarters of a row meet through two shuffles (two warps doing all 64 rows was a third of the tile time)
+    const uint4 v = reinterpret_cast<const uint4*>(s.flag)[tid];
+    const uint32_t x[4] = {v.x, v.y, v.z, v.w};
+    uint32_t bits = 0u;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const uint4 v = f[q];
-      const uint32_t x[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const uint32_t nib = (x[e] & 1u) | ((x[e] >> 7) & 2u) | ((x[e] >> 14) & 4u) | ((x[e] >> 21) & 8u);
-        w |= (unsigned long long)nib << (16 * q + 4 * e);
-      }
-    }
-    s.word[tid] = w;
+    for (int e = 0; e < 4; ++e)
+      bits |= ((x[e] & 1u) | ((x[e] >> 7) & 2u) | ((x[e] >> 14) & 4u) | ((x[e] >> 21) & 8u)) << (4 * e);
+    unsigned long long w = (unsigned long long)bits << (16 * (tid & 3));
+    w |= __shfl_xor_sync(0xffffffffu, w, 1);
+    w |= __shfl_xor_sync(0xffffffffu, w, 2);
+    if ((tid & 3) == 0) s.word[tid >> 2] = w;
   }
   __syncthreads();
 }
@@ -132,8 +131,9 @@ __device__ __forceinline__ void mask_tile(MaskTileSmem& s, const RBox* __restric
 // linear index over the upper triangle (row-major, diagonal included) of a cb x cb tile grid
 __device__ __forceinline__ void decode_upper(long long t, int cb, int& rb, int& cbk) {
   // row r starts at r*cb - r(r-1)/2
-  double fcb = (double)cb + 0.5;
-  int r = (int)floor(fcb - sqrt(fcb * fcb - 2.0 * (double)t));
+  // (a float estimate; the two loops below make it exact)
+  const float fcb = (float)cb + 0.5f;
+  int r = (int)floorf(fcb - sqrtf(fmaxf(fcb * fcb - 2.0f * (float)t, 0.0f)));
   if (r < 0) r = 0;
   if (r > cb - 1) r = cb - 1;
   while (r > 0 && (long long)r * cb - (long long)r * (r - 1) / 2 > t) --r;
