@@ -207,7 +207,9 @@ S2A_EXPORT int s2a_conv2d_forward_tc_multi(int nlevels, const void* const* xs,
                                            void* stream);
 
 /* ---------------------------------------------------------------------------------------------
- * Box decode stages of the head, one launch over all FPN levels and images.
+ * Box decode stages of the head, batched over all FPN levels and images:
+ * s2a_fam_decode is one launch, s2a_select_decode three (keys grid-wide, one CTA per (level, image) for the
+ * exact top-k, gather + decode grid-wide).
  *
  * s2a_fam_decode -- replaces fam_bbox_decode + gen_grid_anchors
  *   reference: models/head.py:27-52 (fam_bbox_decode, wh_ratio_clip=1e-6), models/anchors.py:75-126

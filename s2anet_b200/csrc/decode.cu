@@ -161,10 +161,83 @@ struct SelParams {
   int debug;
   int smem_keys;          // keys of a level with at most this many locations live in shared memory
   int sort_bytes;         // offset of that key array inside the dynamic shared memory (behind the sort scratch)
+  int split;              // 1: keys come from select_keys_kernel, the selection goes to sel_idx, gather_decode_kernel
+                          //    writes the outputs (three launches, the two data-parallel ones grid-wide); 0: one launch
+  int32_t* sel_idx;       // workspace [B][n_total]: selected location per output row (split mode)
 };
 
 __device__ __forceinline__ unsigned long long composite_key(uint32_t key, int i) {
   return ((unsigned long long)key << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)i);
+}
+
+// Best class score of every location of one (level, image) -> keys[i] (bits of the T-rounded sigmoid), models/head.py:700-701.
+// `t` of `NT` threads cooperate (a CTA, or the whole grid row of select_keys_kernel).
+template <typename T>
+__device__ __forceinline__ void compute_keys(const SelLevel& L, const T* cls, int C, int n, uint32_t* keys, int t, int NT) {
+  constexpr int UNR = 4;                                  // locations in flight per thread (latency-bound loop)
+  // 16-bit channels-last logits with at most 16 classes (the head's own layout): a PAIR of lanes reads one location
+  // -- 16 bytes = 8 classes each -- so that a warp's load covers 16 consecutive pixels (8 cache lines) instead of
+  // 32 pixels with every other 16-byte chunk skipped (32 sectors in 16 lines, and half the lanes' worth of loads)
+  const bool paired = sizeof(T) == 2 && C <= 16 && L.cs[1] == 1 && (L.cs[3] & 7) == 0 && (L.cs[2] & 7) == 0 &&
+                      (L.cs[0] & 7) == 0 && (reinterpret_cast<uintptr_t>(L.cls) & 15) == 0 && L.cs[3] >= (C <= 8 ? 8 : 16);
+  if (paired) {
+    const int HALF_T = NT / 2;
+    const int half = t & 1, pr = t >> 1;
+    for (int base = 0; base < n; base += UNR * HALF_T) {
+      uint4 v[UNR];
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const int i = min(base + u * HALF_T + pr, n - 1);
+        const int y = i / L.W, x = i - y * L.W;
+        v[u] = make_uint4(0u, 0u, 0u, 0u);
+        if (half * 8 < C) v[u] = __ldg(reinterpret_cast<const uint4*>(cls + y * L.cs[2] + x * L.cs[3]) + half);
+      }
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+        float m = -INFINITY;
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          if (half * 8 + e < C) m = fmaxf(m, bits16_to_float<T>((unsigned short)(w[e >> 1] >> ((e & 1) * 16))));
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+        const int i = base + u * HALF_T + pr;
+        if (half == 0 && i < n) keys[i] = __float_as_uint(sigmoid_t<T>(m));
+      }
+    }
+  } else
+  for (int i0 = t; i0 < n; i0 += UNR * NT) {
+    float m[UNR];
+    if (C <= 16) {
+      float v[UNR][16];
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const int i = min(i0 + u * NT, n - 1);
+        const int y = i / L.W, x = i - y * L.W;
+        load_channels<T>(cls + y * L.cs[2] + x * L.cs[3], L.cs[1], L.cs[3], C, v[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        m[u] = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < 16; ++c)
+          if (c < C) m[u] = fmaxf(m[u], v[u][c]);
+      }
+    } else {
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const int i = min(i0 + u * NT, n - 1);
+        const int y = i / L.W, x = i - y * L.W;
+        const T* q = cls + y * L.cs[2] + x * L.cs[3];
+        m[u] = -INFINITY;
+        for (int c = 0; c < C; ++c) m[u] = fmaxf(m[u], ld_as_float(q + c * L.cs[1]));
+      }
+    }
+    // sigmoid is monotone, so max_c sigmoid(x_c) == sigmoid(max_c x_c) bit for bit; scores are >= 0,
+    // so their bit patterns order like unsigned integers
+#pragma unroll
+    for (int u = 0; u < UNR; ++u)
+      if (i0 + u * NT < n) keys[i0 + u * NT] = __float_as_uint(sigmoid_t<T>(m[u]));
+  }
 }
 
 template <typename T, int ITEMS>
@@ -183,6 +256,7 @@ __global__ void __launch_bounds__(DEC_THREADS) select_decode_kernel(const __grid
   const T* cls = reinterpret_cast<const T*>(L.cls) + b * L.cs[0];
   const T* reg = reinterpret_cast<const T*>(L.reg) + b * L.rs[0];
   const bool select = n > k;
+  if (p.split && !select) return;                          // nothing to select: gather_decode_kernel takes row j = location j
   long long t0 = clock64(), t1 = t0, t2 = t0, t3 = t0;
 
   // composite sort key: (score bits, 16 significant bits for 16-bit inputs) . (index bits, lower location first)
@@ -198,69 +272,12 @@ __global__ void __launch_bounds__(DEC_THREADS) select_decode_kernel(const __grid
     // ---- keys: best class score of every location (models/head.py:700-701); kept in shared memory when they fit
     uint32_t* keys = n <= p.smem_keys ? reinterpret_cast<uint32_t*>(dsm + p.sort_bytes)
                                       : p.keys + (long long)b * p.keys_per_image + L.key_off;
-    constexpr int UNR = 4;                                  // locations in flight per thread (latency-bound loop)
-    // 16-bit channels-last logits with at most 16 classes (the head's own layout): a PAIR of lanes reads one location
-    // -- 16 bytes = 8 classes each -- so that a warp's load covers 16 consecutive pixels (8 cache lines) instead of
-    // 32 pixels with every other 16-byte chunk skipped (32 sectors in 16 lines, and half the lanes' worth of loads)
-    const bool paired = sizeof(T) == 2 && C <= 16 && L.cs[1] == 1 && (L.cs[3] & 7) == 0 && (L.cs[2] & 7) == 0 &&
-                        (L.cs[0] & 7) == 0 && (reinterpret_cast<uintptr_t>(L.cls) & 15) == 0 && L.cs[3] >= (C <= 8 ? 8 : 16);
-    if (paired) {
-      constexpr int HALF_T = DEC_THREADS / 2;
-      const int half = tid & 1, pr = tid >> 1;
-      for (int base = 0; base < n; base += UNR * HALF_T) {
-        uint4 v[UNR];
-#pragma unroll
-        for (int u = 0; u < UNR; ++u) {
-          const int i = min(base + u * HALF_T + pr, n - 1);
-          const int y = i / L.W, x = i - y * L.W;
-          v[u] = make_uint4(0u, 0u, 0u, 0u);
-          if (half * 8 < C) v[u] = __ldg(reinterpret_cast<const uint4*>(cls + y * L.cs[2] + x * L.cs[3]) + half);
-        }
-#pragma unroll
-        for (int u = 0; u < UNR; ++u) {
-          const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
-          float m = -INFINITY;
-#pragma unroll
-          for (int e = 0; e < 8; ++e)
-            if (half * 8 + e < C) m = fmaxf(m, bits16_to_float<T>((unsigned short)(w[e >> 1] >> ((e & 1) * 16))));
-          m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
-          const int i = base + u * HALF_T + pr;
-          if (half == 0 && i < n) keys[i] = __float_as_uint(sigmoid_t<T>(m));
-        }
-      }
-    } else
-    for (int i0 = tid; i0 < n; i0 += UNR * DEC_THREADS) {
-      float m[UNR];
-      if (C <= 16) {
-        float v[UNR][16];
-#pragma unroll
-        for (int u = 0; u < UNR; ++u) {
-          const int i = min(i0 + u * DEC_THREADS, n - 1);
-          const int y = i / L.W, x = i - y * L.W;
-          load_channels<T>(cls + y * L.cs[2] + x * L.cs[3], L.cs[1], L.cs[3], C, v[u]);
-        }
-#pragma unroll
-        for (int u = 0; u < UNR; ++u) {
-          m[u] = -INFINITY;
-#pragma unroll
-          for (int c = 0; c < 16; ++c)
-            if (c < C) m[u] = fmaxf(m[u], v[u][c]);
-        }
-      } else {
-#pragma unroll
-        for (int u = 0; u < UNR; ++u) {
-          const int i = min(i0 + u * DEC_THREADS, n - 1);
-          const int y = i / L.W, x = i - y * L.W;
-          const T* q = cls + y * L.cs[2] + x * L.cs[3];
-          m[u] = -INFINITY;
-          for (int c = 0; c < C; ++c) m[u] = fmaxf(m[u], ld_as_float(q + c * L.cs[1]));
-        }
-      }
-      // sigmoid is monotone, so max_c sigmoid(x_c) == sigmoid(max_c x_c) bit for bit; scores are >= 0,
-      // so their bit patterns order like unsigned integers
-#pragma unroll
-      for (int u = 0; u < UNR; ++u)
-        if (i0 + u * DEC_THREADS < n) keys[i0 + u * DEC_THREADS] = __float_as_uint(sigmoid_t<T>(m[u]));
+    if (p.split) {                                          // keys were produced grid-wide: bring them on chip
+      const uint32_t* gk = p.keys + (long long)b * p.keys_per_image + L.key_off;
+      if (keys != gk)
+        for (int i = tid; i < n; i += DEC_THREADS) keys[i] = gk[i];
+    } else {
+      compute_keys<T>(L, cls, C, n, keys, tid, DEC_THREADS);
     }
     if (tid == 0) { s_prefix = 0ull; s_remaining = k; s_done = 0; s_count = 0; }
     __syncthreads();
@@ -341,6 +358,14 @@ __global__ void __launch_bounds__(DEC_THREADS) select_decode_kernel(const __grid
   }
 
   t3 = clock64();
+  if (p.split) {                                           // the selected locations, in output order
+    int32_t* dst = p.sel_idx + (long long)b * p.n_total + L.out_off;
+    for (int j = tid; j < k; j += DEC_THREADS) dst[j] = (int32_t)(idx_mask - (unsigned)(s_sel[j] & (unsigned long long)idx_mask));
+    if (p.debug && tid == 0 && blockIdx.y == 0)
+      printf("select_decode level %d (split): keys %lld, select %lld, collect+sort %lld cycles\n", (int)blockIdx.x, t1 - t0, t2 - t1,
+             t3 - t2);
+    return;
+  }
   // ---- gather + sigmoid + final decode (models/head.py:703-717) ---------------------------------
   // Output rows of a level are contiguous ([k, C] scores, [k, 5] boxes), but a thread owns a whole row: written
   // directly that is 20 scattered 4-byte stores per location (32 sectors per warp instruction).  With at most 16
@@ -393,6 +418,69 @@ __global__ void __launch_bounds__(DEC_THREADS) select_decode_kernel(const __grid
            t3 - t2, clock64() - t3);
 }
 
+// ---- split mode, launch 1: keys of every level that needs a selection, grid-wide ------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) select_keys_kernel(const __grid_constant__ SelParams p) {
+  const SelLevel& L = p.lv[blockIdx.y];
+  if (L.n <= L.k) return;
+  const int b = blockIdx.z;
+  const T* cls = reinterpret_cast<const T*>(L.cls) + b * L.cs[0];
+  compute_keys<T>(L, cls, p.C, L.n, p.keys + (long long)b * p.keys_per_image + L.key_off,
+                  (int)(blockIdx.x * blockDim.x + threadIdx.x), (int)(gridDim.x * blockDim.x));
+}
+
+// ---- split mode, launch 3: gather + sigmoid + final decode of every output row (models/head.py:703-717) ----------
+// One thread per row of the concatenated candidate list; a block's 256 rows are contiguous in both outputs and go
+// through shared memory so that the global stores are coalesced (row strides C and 5 words: conflict-free).
+template <typename T>
+__global__ void __launch_bounds__(256) gather_decode_kernel(const __grid_constant__ SelParams p) {
+  extern __shared__ __align__(16) uint8_t dsm[];
+  const int b = blockIdx.y, tid = threadIdx.x, C = p.C;
+  const int r0 = blockIdx.x * 256, r = r0 + tid;
+  const int cnt = min(256, p.n_total - r0);
+  const bool staged = C <= 16;
+  float* st_sc = reinterpret_cast<float*>(dsm);
+  float* st_bb = st_sc + 256 * C;
+  const long long row0 = (long long)b * p.n_total + r0;
+  if (r < p.n_total) {
+    int l = 0;
+    while (l + 1 < p.nlevels && r >= p.lv[l + 1].out_off) ++l;
+    const SelLevel& L = p.lv[l];
+    const int j = r - L.out_off;
+    const int i = L.n > L.k ? p.sel_idx[(long long)b * p.n_total + r] : j;
+    const int y = i / L.W, x = i - y * L.W;
+    const T* q = reinterpret_cast<const T*>(L.cls) + b * L.cs[0] + y * L.cs[2] + x * L.cs[3];
+    const T* g = reinterpret_cast<const T*>(L.reg) + b * L.rs[0] + y * L.rs[2] + x * L.rs[3];
+    float* so = staged ? st_sc + tid * C : p.scores + (row0 + tid) * C;
+    if (C <= 16) {
+      float v[16];
+      load_channels<T>(q, L.cs[1], L.cs[3], C, v);
+#pragma unroll
+      for (int c = 0; c < 16; ++c)
+        if (c < C) so[c] = sigmoid_t<T>(v[c]);
+    } else {
+      for (int c = 0; c < C; ++c) so[c] = sigmoid_t<T>(ld_as_float(q + c * L.cs[1]));
+    }
+    float d[5];
+    load_channels<T>(g, L.rs[1], L.rs[3], 5, d);
+    const float* ap = L.anchors + ((long long)b * L.n + i) * 5;
+    const float a[5] = {__ldg(ap), __ldg(ap + 1), __ldg(ap + 2), __ldg(ap + 3), __ldg(ap + 4)};
+    float o[5];
+    delta2bbox_rotated<T>(a, d[0], d[1], d[2], d[3], d[4], p.lim, o);
+    float* bo = staged ? st_bb + tid * 5 : p.bboxes + (row0 + tid) * 5;
+#pragma unroll
+    for (int e = 0; e < 5; ++e) bo[e] = o[e];
+    if (p.index_out) p.index_out[row0 + tid] = i;
+  }
+  if (staged) {
+    __syncthreads();
+    float* gs = p.scores + row0 * C;
+    for (int e = tid; e < cnt * C; e += 256) gs[e] = st_sc[e];
+    float* gb = p.bboxes + row0 * 5;
+    for (int e = tid; e < cnt * 5; e += 256) gb[e] = st_bb[e];
+  }
+}
+
 template <typename T> static float limit_in(float max_ratio);
 template <> float limit_in<__nv_bfloat16>(float m) { return __bfloat162float(__float2bfloat16_rn(m)); }
 template <> float limit_in<__half>(float m) { return __half2float(__float2half_rn(m)); }
@@ -414,6 +502,23 @@ static int launch_select(SelParams p, cudaStream_t st) {
   size_t smem = (size_t)p.sort_bytes + (size_t)need * sizeof(uint32_t);
   if (p.C <= 16) smem = std::max(smem, (size_t)DEC_THREADS * (p.C + 5) * sizeof(float));   // output staging (gather phase)
   S2A_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (p.split) {
+    int nmax = 0;
+    for (int l = 0; l < p.nlevels; ++l)
+      if (p.lv[l].n > p.lv[l].k) nmax = std::max(nmax, p.lv[l].n);
+    if (nmax > 0) {
+      // pairs of threads, four locations in flight each: enough blocks to cover the largest level once
+      const int bx = (int)std::min<long long>(ceil_div((long long)nmax * 2, 256 * 4), (long long)sm_count() * 4);
+      select_keys_kernel<T><<<dim3(std::max(bx, 1), p.nlevels, p.B), 256, 0, st>>>(p);
+      S2A_LAUNCH_OK("select_keys_kernel");
+      kern<<<dim3(p.nlevels, p.B), DEC_THREADS, smem, st>>>(p);
+      S2A_LAUNCH_OK("select_decode_kernel");
+    }
+    const size_t gsm = p.C <= 16 ? (size_t)256 * (p.C + 5) * sizeof(float) : 0;
+    gather_decode_kernel<T><<<dim3((unsigned)ceil_div(p.n_total, 256), p.B), 256, gsm, st>>>(p);
+    S2A_LAUNCH_OK("gather_decode_kernel");
+    return S2A_OK;
+  }
   kern<<<dim3(p.nlevels, p.B), DEC_THREADS, smem, st>>>(p);
   S2A_LAUNCH_OK("select_decode_kernel");
   return S2A_OK;
@@ -459,7 +564,8 @@ extern "C" int s2a_fam_decode(int nlevels, const void* const* deltas, const int6
 extern "C" size_t s2a_select_decode_workspace_bytes(int nlevels, const int* Hs, const int* Ws, int B) {
   size_t keys = 0;
   for (int l = 0; l < nlevels; ++l) keys += (size_t)Hs[l] * Ws[l];
-  return keys * sizeof(uint32_t) * (size_t)(B > 0 ? B : 0) + 256;
+  // keys [B][sum H*W] uint32 + selected locations [B][n_total <= sum H*W] int32
+  return 2 * keys * sizeof(uint32_t) * (size_t)(B > 0 ? B : 0) + 512;
 }
 
 extern "C" int s2a_select_decode(int nlevels, const void* const* cls, const int64_t* cls_strides, const void* const* reg,
@@ -499,8 +605,11 @@ extern "C" int s2a_select_decode(int nlevels, const void* const* cls, const int6
   }
   p.nlevels = nlevels; p.B = B; p.C = num_classes; p.n_total = off; p.keys_per_image = keys;
   p.keys = reinterpret_cast<uint32_t*>(workspace); p.bboxes = bboxes_out; p.scores = scores_out; p.index_out = index_out;
+  p.sel_idx = reinterpret_cast<int32_t*>(reinterpret_cast<uint8_t*>(workspace) + align_up((size_t)keys * sizeof(uint32_t) * B, 256));
   p.lim = clamp_limit(wh_ratio_clip, dtype);
   { const char* e = getenv("S2A_DEC_DEBUG"); p.debug = e ? atoi(e) : 0; }
+  p.split = (p.debug & 2) ? 0 : 1;                          // S2A_DEC_DEBUG=2: the single-launch form (timing comparisons)
+  p.debug &= 1;
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == S2A_F32) return launch_select_items<float>(p, kmax, st);
   if (dtype == S2A_BF16) return launch_select_items<__nv_bfloat16>(p, kmax, st);
