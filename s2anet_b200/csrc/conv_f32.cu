@@ -20,10 +20,13 @@
 
 namespace s2a {
 
-constexpr int BM = 64, BN = 64, CK = 8;
+// Output tile BM positions x BN channels per CTA of 16 x 16 threads: 64 x 64 (4 x 4 outputs per thread) or, for
+// ungrouped convs with >= 128 output channels, 128 x 128 (8 x 8 per thread): 16 FMAs per 16-byte shared-memory load
+// instead of 8, and every gathered A value reused by twice as many output channels.
+constexpr int CK = 8;
 constexpr int kConvThreads = 256;
 constexpr int kMaxTaps = 9;           // kH*kW <= 9 on this path (3x3 and smaller)
-constexpr int BNP = BN + 4;            // padded B-tile row (keeps float4 alignment, breaks store conflicts)
+constexpr int kNarrowBN = 64;         // the narrow tile's channel extent (groups > 1 need (Co/groups) % 64 == 0)
 
 enum { MODE_DEFORM = 0, MODE_ALIGN = 1, MODE_PLAIN = 2 };
 
@@ -52,9 +55,12 @@ __device__ __forceinline__ void make_sample(float h, float w, int H, int W, Samp
   if (hh <= H - 1 && wh <= W - 1) { s.off[3] = hh * W + wh; s.wt[3] = lh * lw; }
 }
 
-template <int MODE>
+template <int MODE, int BM, int BN>
 __global__ void __launch_bounds__(kConvThreads)
 conv_gather_f32_kernel(const ConvParams p) {
+  constexpr int BNP = BN + 4;            // padded B-tile row (keeps float4 alignment, breaks store conflicts)
+  constexpr int RM = BM / 16, RN = BN / 16;      // outputs per thread: RM positions x RN channels
+  static_assert((BM == 64 || BM == 128) && (BN == 64 || BN == 128 || BN == 256) && RM * RN <= 64, "tile shapes");
   extern __shared__ __align__(16) unsigned char s_raw[];
   Sample* s_samp = reinterpret_cast<Sample*>(s_raw);                                    // [BM*9]   18 KB
   float (*s_a)[BM] = reinterpret_cast<float (*)[BM]>(s_raw + sizeof(Sample) * BM * kMaxTaps);   // [72][64] 18 KB
@@ -125,12 +131,13 @@ conv_gather_f32_kernel(const ConvParams p) {
     }
   };
 
-  const int tx = tid & 15, ty = tid >> 4;          // 16 x 16 threads, 4 (m) x 4 (n) outputs each
-  float acc[4][4];
+  // 16 x 16 threads; thread (tx, ty) owns positions 64*q + 4*tx + i and channels 64*q + 4*ty + j (i, j < 4; q < RM/4, RN/4)
+  const int tx = tid & 15, ty = tid >> 4;
+  float acc[RM][RN];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < RM; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+    for (int j = 0; j < RN; ++j) acc[i][j] = 0.0f;
 
   int cur_dg = -1;
   const int kk = CK * taps;                          // rows of the smem K chunk actually used
@@ -146,7 +153,7 @@ conv_gather_f32_kernel(const ConvParams p) {
     // A tile: s_a[c*taps + t][m] = sum_q wt_q * x[cin0 + c][off_q]
     for (int i = tid; i < kk * BM; i += kConvThreads) {
       const int m = i & (BM - 1);
-      const int kr = i >> 6;
+      const int kr = i / BM;
       const int c = kr / taps, t = kr - c * taps;
       float v = 0.0f;
       if (c0 + c < Cg) {
@@ -186,24 +193,31 @@ conv_gather_f32_kernel(const ConvParams p) {
     __syncthreads();
 #pragma unroll 8
     for (int k = 0; k < kk; ++k) {
-      const float4 av = *reinterpret_cast<const float4*>(&s_a[k][tx * 4]);
-      const float4 bv = *reinterpret_cast<const float4*>(&s_b[k][ty * 4]);
-      const float a4[4] = {av.x, av.y, av.z, av.w};
-      const float b4[4] = {bv.x, bv.y, bv.z, bv.w};
+      float a4[RM], b4[RN];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int q = 0; q < RM / 4; ++q) {
+        const float4 av = *reinterpret_cast<const float4*>(&s_a[k][q * 64 + tx * 4]);
+        a4[4 * q] = av.x; a4[4 * q + 1] = av.y; a4[4 * q + 2] = av.z; a4[4 * q + 3] = av.w;
+      }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a4[i], b4[j], acc[i][j]);
+      for (int q = 0; q < RN / 4; ++q) {
+        const float4 bv = *reinterpret_cast<const float4*>(&s_b[k][q * 64 + ty * 4]);
+        b4[4 * q] = bv.x; b4[4 * q + 1] = bv.y; b4[4 * q + 2] = bv.z; b4[4 * q + 3] = bv.w;
+      }
+#pragma unroll
+      for (int i = 0; i < RM; ++i)
+#pragma unroll
+        for (int j = 0; j < RN; ++j) acc[i][j] = fmaf(a4[i], b4[j], acc[i][j]);
     }
   }
 
   // ---- epilogue: bias, ReLU, NCHW store, optional orientation max-pool ----
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int co = n0 + ty * 4 + j;
+  for (int j = 0; j < RN; ++j) {
+    const int co = n0 + (j >> 2) * 64 + ty * 4 + (j & 3);
     const float bv = (p.bias && co < p.Co) ? p.bias[co] : 0.0f;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < RM; ++i) {
       float v = acc[i][j] + bv;
       if (p.relu) v = fmaxf(v, 0.0f);
       acc[i][j] = v;
@@ -211,28 +225,29 @@ conv_gather_f32_kernel(const ConvParams p) {
     if (co < p.Co) {
       float* o = p.out + ((size_t)b * p.Co + co) * HoWo;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int pos = m0 + tx * 4 + i;
+      for (int i = 0; i < RM; ++i) {
+        const int pos = m0 + (i >> 2) * 64 + tx * 4 + (i & 3);
         if (pos < HoWo) o[pos] = acc[i][j];
       }
     }
   }
   if (p.pooled) {
     // groups of `pool` (= 8) consecutive output channels: this thread's 4 + the partner's 4 (lane ^ 16)
-    float mx[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      float v = fmaxf(fmaxf(acc[i][0], acc[i][1]), fmaxf(acc[i][2], acc[i][3]));
-      const float o = __shfl_xor_sync(0xffffffffu, v, 16);
-      mx[i] = fmaxf(v, o);
-    }
-    if ((ty & 1) == 0) {
-      const int cg = (n0 + ty * 4) / 8;
-      if (n0 + ty * 4 < p.Co) {
-        float* o = p.pooled + ((size_t)b * (p.Co / 8) + cg) * HoWo;
+    for (int qn = 0; qn < RN / 4; ++qn) {
+      float mx[RM];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int pos = m0 + tx * 4 + i;
+      for (int i = 0; i < RM; ++i) {
+        float v = fmaxf(fmaxf(acc[i][4 * qn], acc[i][4 * qn + 1]), fmaxf(acc[i][4 * qn + 2], acc[i][4 * qn + 3]));
+        const float o = __shfl_xor_sync(0xffffffffu, v, 16);
+        mx[i] = fmaxf(v, o);
+      }
+      const int cbase = n0 + qn * 64 + ty * 4;
+      if ((ty & 1) == 0 && cbase < p.Co) {
+        float* o = p.pooled + ((size_t)b * (p.Co / 8) + cbase / 8) * HoWo;
+#pragma unroll
+        for (int i = 0; i < RM; ++i) {
+          const int pos = m0 + (i >> 2) * 64 + tx * 4 + (i & 3);
           if (pos < HoWo) o[pos] = mx[i];
         }
       }
@@ -240,22 +255,38 @@ conv_gather_f32_kernel(const ConvParams p) {
   }
 }
 
-constexpr size_t kConvSmem = sizeof(Sample) * BM * kMaxTaps + sizeof(float) * CK * kMaxTaps * (BM + BNP);
+template <int BM, int BN>
+constexpr size_t conv_smem_bytes() {
+  return sizeof(Sample) * BM * kMaxTaps + sizeof(float) * CK * kMaxTaps * (BM + BN + 4);
+}
 
-template <int MODE>
-static cudaError_t launch_conv_mode(dim3 grid, const ConvParams& p, cudaStream_t st) {
-  auto kern = conv_gather_f32_kernel<MODE>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kConvSmem);
+template <int MODE, int BM, int BN>
+static cudaError_t launch_conv_tile(const ConvParams& p, cudaStream_t st) {
+  auto kern = conv_gather_f32_kernel<MODE, BM, BN>;
+  constexpr size_t smem = conv_smem_bytes<BM, BN>();
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  kern<<<grid, kConvThreads, kConvSmem, st>>>(p);
+  dim3 grid((unsigned)ceil_div((int64_t)p.Ho * p.Wo, BM), (unsigned)ceil_div(p.Co, BN), (unsigned)p.B);
+  kern<<<grid, kConvThreads, smem, st>>>(p);
   return cudaSuccess;
 }
 
+template <int MODE>
+static cudaError_t launch_conv_mode(const ConvParams& p, cudaStream_t st) {
+  // Wide tiles when a tile cannot straddle channel groups and there is enough work to fill the GPU with them.
+  // (64 x 256 -- every gathered A value reused by all output channels -- was tried too: no faster for AlignConv and
+  // slower for ORConv, whose weight-tile build pays the ARF index arithmetic per element; the build phases, which do
+  // not overlap the FMA loop, are what bounds this kernel.)
+  if (p.groups == 1 && p.Co >= 128 &&
+      ceil_div((int64_t)p.Ho * p.Wo, 128) * ceil_div(p.Co, 128) * p.B >= sm_count())
+    return launch_conv_tile<MODE, 128, 128>(p, st);
+  return launch_conv_tile<MODE, 64, kNarrowBN>(p, st);
+}
+
 static int launch_conv(int mode, const ConvParams& p, cudaStream_t st) {
-  dim3 grid((unsigned)ceil_div((int64_t)p.Ho * p.Wo, BM), (unsigned)ceil_div(p.Co, BN), (unsigned)p.B);
-  if (mode == MODE_DEFORM) S2A_CUDA_OK(launch_conv_mode<MODE_DEFORM>(grid, p, st));
-  else if (mode == MODE_ALIGN) S2A_CUDA_OK(launch_conv_mode<MODE_ALIGN>(grid, p, st));
-  else S2A_CUDA_OK(launch_conv_mode<MODE_PLAIN>(grid, p, st));
+  if (mode == MODE_DEFORM) S2A_CUDA_OK(launch_conv_mode<MODE_DEFORM>(p, st));
+  else if (mode == MODE_ALIGN) S2A_CUDA_OK(launch_conv_mode<MODE_ALIGN>(p, st));
+  else S2A_CUDA_OK(launch_conv_mode<MODE_PLAIN>(p, st));
   S2A_LAUNCH_OK("conv_gather_f32_kernel");
   return S2A_OK;
 }
@@ -280,8 +311,8 @@ extern "C" int s2a_deform_conv_forward_f32(const float* x, const float* offset, 
   const int Wo = (W + 2 * padW - (dilW * (kW - 1) + 1)) / strideW + 1;
   S2A_CHECK_ARG(Ho >= 1 && Wo >= 1, "deform_conv: output size is too small");
   if (kH * kW > kMaxTaps) { set_error("deform_conv: kernels larger than 3x3 are not supported"); return S2A_ERR_UNSUPPORTED; }
-  if (groups > 1 && (Co / groups) % BN != 0) {
-    set_error("deform_conv: groups > 1 needs (Co/groups) %% %d == 0", BN);
+  if (groups > 1 && (Co / groups) % kNarrowBN != 0) {
+    set_error("deform_conv: groups > 1 needs (Co/groups) %% %d == 0", kNarrowBN);
     return S2A_ERR_UNSUPPORTED;
   }
   if (dgroups > 1 && ((C / dgroups) % CK != 0 || (C / groups) % CK != 0)) {
