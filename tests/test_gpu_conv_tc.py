@@ -123,10 +123,12 @@ def test_multi_level_launch_equals_per_level():
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
 @pytest.mark.parametrize("C,Co,ks,relu", [(256, 256, 3, True), (32, 256, 3, True), (256, 15, 3, False), (256, 5, 1, False),
-                                          (64, 32, 1, True), (72, 40, 3, False)])
+                                          (64, 32, 1, True), (72, 40, 3, False), (512, 128, 3, True), (320, 32, 3, False),
+                                          (512, 96, 1, False)])
 def test_conv2d_tc_multi_vs_torch(dtype, C, Co, ks, relu):
     """The stock nn.Conv2d layers of the head on the tcgen05 kernel: kernel 1 / 3, channel counts that need
-    zero-padded k-blocks (32, 72) and padded outputs (5, 15, 40), several levels incl. partial tiles."""
+    zero-padded k-blocks (32, 72) and padded outputs (5, 15, 40), several levels incl. partial tiles; 5 to 8 channel
+    blocks per tile so that the operand-halo ring (2 buffers; 4 in the narrow and the 1 x 1 mode) wraps many times."""
     from s2anet_b200.conv_tc import conv2d_forward_tc_multi
     g = torch.Generator().manual_seed(C + Co + ks)
     sizes = ((24, 40), (13, 21), (3, 5))
@@ -164,3 +166,29 @@ def test_alignconv_tc_halo_and_global_fallback(scale):
     y = alignconv_forward(x, anc, w, stride)
     ref = alignconv_forward(x.float(), anc, w.float(), stride)
     check(y, ref, dtype)
+
+
+@pytest.mark.parametrize("Co,ks", [(64, 3), (15, 3), (40, 1)])
+def test_conv2d_tc_several_tiles_per_cta(Co, ks):
+    """More tiles than CTAs (3 x 136 x 128 pixels = 408 tiles on 148 CTAs): the persistent loop carries the weight
+    ring, the operand-halo ring and the two accumulators across tile boundaries, the last CTA pairs run a ghost tile."""
+    from s2anet_b200.conv_tc import conv2d_forward_tc_multi
+    dtype = torch.bfloat16
+    g = torch.Generator().manual_seed(Co * 10 + ks)
+    x = torch.randn(3, 128, 136, 128, generator=g).to(DEV).to(dtype).contiguous(memory_format=torch.channels_last)
+    wt = (torch.randn(Co, 128, ks, ks, generator=g) * 0.05).to(DEV).to(dtype)
+    bias = torch.randn(Co, generator=g).to(DEV)
+    y = conv2d_forward_tc_multi([x], wt, bias, relu=True)[0]
+    ref = torch.relu(torch.nn.functional.conv2d(x.float(), wt.float(), bias, padding=ks // 2))
+    check(y, ref, dtype)
+
+
+def test_alignconv_tc_several_tiles_per_cta():
+    from s2anet_b200.alignconv import alignconv_forward
+    dtype = torch.bfloat16
+    B, C, H, W, Co, stride = 3, 64, 128, 128, 64, 8
+    g = torch.Generator().manual_seed(77)
+    x = torch.randn(B, C, H, W, generator=g).to(DEV).to(dtype).contiguous(memory_format=torch.channels_last)
+    w = (torch.randn(Co, C, 3, 3, generator=g) * 0.05).to(DEV).to(dtype)
+    anc = torch.from_numpy(synth.refined_anchors(B, H, W, stride, seed=4)).to(DEV)
+    check(alignconv_forward(x, anc, w, stride), alignconv_forward(x.float(), anc, w.float(), stride), dtype)
