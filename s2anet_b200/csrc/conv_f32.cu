@@ -67,6 +67,8 @@ conv_gather_f32_kernel(const ConvParams p) {
   float (*s_b)[BNP] = reinterpret_cast<float (*)[BNP]>(s_raw + sizeof(Sample) * BM * kMaxTaps +
                                                        sizeof(float) * CK * kMaxTaps * BM);     // [72][68] 19 KB
   __shared__ uint8_t s_inv[8 * 72];                        // ARF inverse map [nRot][nEntry]
+  __shared__ uint8_t s_ct[CK * kMaxTaps];                  // K row -> (channel in chunk << 4) | tap
+  __shared__ uint16_t s_ok[BN];                            // ORConv: output channel -> (filter << 3) | rotation
 
   const int tid = threadIdx.x;
   const int taps = p.kH * p.kW;
@@ -141,6 +143,13 @@ conv_gather_f32_kernel(const ConvParams p) {
 
   int cur_dg = -1;
   const int kk = CK * taps;                          // rows of the smem K chunk actually used
+  const int HW = p.H * p.W, wrow = Cg * taps;
+  // index tables: (c, t) of K row kr; (o, k) = (filter, rotation) of output channel n0 + nn (ORConv)
+  for (int kr = tid; kr < kk; kr += kConvThreads) s_ct[kr] = (uint8_t)(((kr / taps) << 4) | (kr % taps));
+  if (MODE == MODE_PLAIN && p.arf_idx)
+    for (int nn = tid; nn < BN; nn += kConvThreads) s_ok[nn] = (uint16_t)((((n0 + nn) / p.nRot) << 3) | ((n0 + nn) % p.nRot));
+  const int step_n = kConvThreads / kk, step_k = kConvThreads - step_n * kk;   // thread stride in (nn, kr)
+  const int kr0 = tid % kk, nn0 = tid / kk;
   for (int c0 = 0; c0 < Cg; c0 += CK) {
     const int cin0 = g * Cg + c0;                    // first input channel of this chunk
     const int dg = (MODE == MODE_DEFORM) ? cin0 / cpd : 0;
@@ -150,47 +159,55 @@ conv_gather_f32_kernel(const ConvParams p) {
       cur_dg = dg;
     }
     __syncthreads();                                 // previous chunk consumed; samples visible
-    // A tile: s_a[c*taps + t][m] = sum_q wt_q * x[cin0 + c][off_q]
+    // A tile: s_a[c*taps + t][m] = sum_q wt_q * x[cin0 + c][off_q].  A thread keeps its position m and walks the
+    // K rows; (c, t) of a row come from a table -- the per-element divisions were half of this kernel's instructions.
+    {
+      const int m = tid & (BM - 1);
+      const Sample* sm = s_samp + m * kMaxTaps;
+      const float* xc = xb + (size_t)cin0 * HW;
 #pragma unroll 4
-    for (int i = tid; i < kk * BM; i += kConvThreads) {
-      const int m = i & (BM - 1);
-      const int kr = i / BM;
-      const int c = kr / taps, t = kr - c * taps;
-      float v = 0.0f;
-      if (c0 + c < Cg) {
-        const Sample& s = s_samp[m * kMaxTaps + t];
-        const float* plane = xb + (size_t)(cin0 + c) * p.H * p.W;
-        if (MODE == MODE_PLAIN) {
-          v = s.wt[0] != 0.0f ? plane[s.off[0]] : 0.0f;
-        } else {
-          v = s.wt[0] * plane[s.off[0]] + s.wt[1] * plane[s.off[1]] + s.wt[2] * plane[s.off[2]] +
-              s.wt[3] * plane[s.off[3]];
+      for (int kr = tid / BM; kr < kk; kr += kConvThreads / BM) {
+        const int ct = s_ct[kr], c = ct >> 4, t = ct & 15;
+        float v = 0.0f;
+        if (c0 + c < Cg) {
+          const Sample& s = sm[t];
+          const float* plane = xc + c * HW;
+          if (MODE == MODE_PLAIN) {
+            v = s.wt[0] != 0.0f ? plane[s.off[0]] : 0.0f;
+          } else {
+            v = s.wt[0] * plane[s.off[0]] + s.wt[1] * plane[s.off[1]] + s.wt[2] * plane[s.off[2]] +
+                s.wt[3] * plane[s.off[3]];
+          }
         }
+        s_a[kr][m] = v;
       }
-      s_a[kr][m] = v;
     }
-    // B tile: s_b[c*taps + t][n] = W[n0 + n][c0 + c][t]
-#pragma unroll 4
-    for (int i = tid; i < kk * BN; i += kConvThreads) {
-      const int kr = i % kk;
-      const int nn = i / kk;
-      const int c = kr / taps, t = kr - c * taps;
-      const int co = n0 + nn;
-      float v = 0.0f;
-      if (co < p.Co && c0 + c < Cg) {
-        if (MODE == MODE_PLAIN && p.arf_idx) {
-          // rotated filter (o, k): entry dst of input plane i comes from base entry inv[k][dst]
-          const int o = co / p.nRot, k = co % p.nRot;
-          const int cin = c0 + c;
-          const int ii = cin / p.nOri, lay = cin % p.nOri;
-          const int nEntry = p.nOri * taps;
-          const int l = s_inv[k * nEntry + lay * taps + t];
-          v = p.w[((size_t)o * p.arfI + ii) * nEntry + l];
-        } else {
-          v = p.w[((size_t)co * Cg + (c0 + c)) * taps + t];
+    // B tile: s_b[c*taps + t][n] = W[n0 + n][c0 + c][t]; consecutive threads read consecutive K rows of one filter
+    // (contiguous in memory: (c0 + c) * taps + t = c0 * taps + row), the (row, n) pair advances incrementally
+    {
+      const float* wc = p.w + (size_t)c0 * taps;
+      int kr = kr0, nn = nn0;
+      while (nn < BN) {
+        const int ct = s_ct[kr], c = ct >> 4, t = ct & 15;
+        const int co = n0 + nn;
+        float v = 0.0f;
+        if (co < p.Co && c0 + c < Cg) {
+          if (MODE == MODE_PLAIN && p.arf_idx) {
+            // rotated filter (o, k): entry dst of input plane i comes from base entry inv[k][dst]
+            const int ok = s_ok[nn], o = ok >> 3, k = ok & 7;
+            const int cin = c0 + c;
+            const int ii = p.nOri == 1 ? cin : cin / p.nOri, lay = p.nOri == 1 ? 0 : cin % p.nOri;
+            const int nEntry = p.nOri * taps;
+            const int l = s_inv[k * nEntry + lay * taps + t];
+            v = p.w[((size_t)o * p.arfI + ii) * nEntry + l];
+          } else {
+            v = wc[(size_t)co * wrow + kr];
+          }
         }
+        s_b[kr][nn] = v;
+        kr += step_k; nn += step_n;
+        if (kr >= kk) { kr -= kk; ++nn; }
       }
-      s_b[kr][nn] = v;
     }
     __syncthreads();
 #pragma unroll 8
