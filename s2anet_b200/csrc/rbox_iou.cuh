@@ -139,6 +139,25 @@ RB_HD int rbox_classify(const RBox& A, const RBox& B) {
   return RB_CLIP;
 }
 
+// Upper bound of the intersection AREA of two boxes with positive sizes (used by the NMS kernels only, to skip clips
+// that cannot reach the threshold; never used for an IoU VALUE).  In A's frame B lies inside its axis-aligned extent
+// (half sizes eu, ev around (du, dv)); the overlap of that rectangle with A bounds the intersection; same from B's
+// side; and the intersection cannot exceed either area.
+RB_HD float rbox_inter_upper_bound(const RBox& A, const RBox& B) {
+  const float dx = B.x - A.x, dy = B.y - A.y;
+  const float sd = B.s2 * A.c2 - B.c2 * A.s2, cd = A.c2 * B.c2 + A.s2 * B.s2;      // sin, cos of (tB - tA), / 4
+  const float S = 4.0f * fabsf(sd), C = 4.0f * fabsf(cd);
+  const float duA = 2.0f * (dx * A.c2 + dy * A.s2), dvA = 2.0f * (dy * A.c2 - dx * A.s2);
+  const float duB = 2.0f * (dx * B.c2 + dy * B.s2), dvB = 2.0f * (dy * B.c2 - dx * B.s2);
+  const float euA = 0.5f * (B.w * C + B.h * S), evA = 0.5f * (B.w * S + B.h * C);  // B's half extents on A's axes
+  const float euB = 0.5f * (A.w * C + A.h * S), evB = 0.5f * (A.w * S + A.h * C);
+  const float ouA = fmaxf(0.0f, fminf(0.5f * A.w, duA + euA) - fmaxf(-0.5f * A.w, duA - euA));
+  const float ovA = fmaxf(0.0f, fminf(0.5f * A.h, dvA + evA) - fmaxf(-0.5f * A.h, dvA - evA));
+  const float ouB = fmaxf(0.0f, fminf(0.5f * B.w, euB - duB) - fmaxf(-0.5f * B.w, -duB - euB));
+  const float ovB = fmaxf(0.0f, fminf(0.5f * B.h, evB - dvB) - fmaxf(-0.5f * B.h, -dvB - evB));
+  return fminf(fminf(ouA * ovA, ouB * ovB), fminf(A.w * A.h, B.w * B.h));
+}
+
 struct RPt { float x, y; };
 RB_HD float rb_cross(float ax, float ay, float bx, float by) {   // A.x*B.y - B.x*A.y  (:50-53)
   return RB_SUB(RB_MUL(ax, by), RB_MUL(bx, ay));
