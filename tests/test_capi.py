@@ -53,6 +53,15 @@ def test_argument_validation_without_gpu(lib):
     assert lib.s2a_arf_forward(None, None, None, 4, 4, 16, 3, 3, 8, 0, None) == -1          # nOri*9 > 72
     assert lib.s2a_ri_pool_forward(None, None, 1, 12, 4, 8, 0, None) == -1                  # 12 % 8 != 0
     assert lib.s2a_multiclass_nms_rotated_workspace_bytes(5344, 15, 1) > 0
+    # polygon NMS (DOTA result merging): n == 0 needs no pointers but num_keep_out; a row is 8 coordinates + score
+    assert lib.s2a_poly_nms_workspace_bytes(0) > 0
+    assert lib.s2a_poly_nms_workspace_bytes(3000) > 3000 * 47 * 8 + 3000 * 104
+    assert lib.s2a_poly_nms(None, 9, 5, 0.3, None, None, None, 0, None) == -1
+    assert b"num_keep_out" in lib.s2a_last_error()
+    assert lib.s2a_poly_iou_pairs(None, None, 0, None, None) == 0
+    assert lib.s2a_poly_iou_pairs(None, None, -1, None, None) == -1
+    # conv entry points: shape constraints are reported, never rerouted
+    assert lib.s2a_select_decode_workspace_bytes(0, None, None, 8) > 0
 
 
 def test_ops_refuse_cpu_tensors():
@@ -76,6 +85,19 @@ def test_ops_refuse_cpu_tensors():
         AlignConv(8, 8)(torch.rand(1, 8, 4, 4), torch.rand(1, 4, 4, 5), 8)
     with pytest.raises(NotImplementedError):
         RotationInvariantPooling(16, 8)(torch.rand(1, 16, 2, 2))
+    from s2anet_b200.assign import assign_labels
+    from s2anet_b200.decode import fam_decode, select_decode
+    from s2anet_b200.poly_nms import iou_poly_pairs, poly_nms
+    with pytest.raises(NotImplementedError):
+        poly_nms(torch.rand(4, 9, dtype=torch.float64), 0.3)
+    with pytest.raises(NotImplementedError):
+        iou_poly_pairs(torch.rand(4, 8, dtype=torch.float64), torch.rand(4, 8, dtype=torch.float64))
+    with pytest.raises(NotImplementedError):
+        fam_decode([torch.rand(1, 5, 4, 4)], [8])
+    with pytest.raises(NotImplementedError):
+        select_decode([torch.rand(1, 15, 4, 4)], [torch.rand(1, 5, 4, 4)], [torch.rand(1, 4, 4, 5)])
+    with pytest.raises(NotImplementedError):
+        assign_labels(torch.rand(8, 5), torch.rand(2, 5))
     m = ORConv2d(8, 2, 3, padding=1, arf_config=(1, 8))
     assert tuple(m.weight.shape) == (2, 8, 1, 3, 3) and tuple(m.bias.shape) == (16,)
     assert tuple(m.indices.shape) == (1, 3, 3, 8) and m.indices.dtype == torch.uint8
