@@ -205,6 +205,15 @@ S2A_EXPORT int s2a_conv2d_forward_tc_multi(int nlevels, const void* const* xs,
                                            void* const* outs, const int* Hs, const int* Ws, int B,
                                            int C, int Co_pad, int ks, int relu, int dtype,
                                            void* stream);
+/* Two such convolutions of one shape class (same C, Co_pad, ks, relu, dtype, B; own inputs / weights / biases /
+ * outputs) in one persistent launch -- e.g. the classification and the regression tower layer of the head
+ * (models/head.py:296-348 runs them one after the other): levels [0, split) use packed_weight0 / bias0, levels
+ * [split, nlevels) packed_weight1 / bias1; nlevels <= 16.  Fills the 74 CTA pairs better than two launches. */
+S2A_EXPORT int s2a_conv2d_forward_tc_multi2(int nlevels, int split, const void* const* xs,
+                                            const void* packed_weight0, const void* packed_weight1,
+                                            const float* bias0, const float* bias1, void* const* outs,
+                                            const int* Hs, const int* Ws, int B, int C, int Co_pad, int ks,
+                                            int relu, int dtype, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Box decode stages of the head, batched over all FPN levels and images:

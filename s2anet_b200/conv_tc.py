@@ -202,3 +202,38 @@ def conv2d_forward_tc_multi(xs, weight, bias=None, relu=False):
     _lib.check(rc, "conv2d_forward_tc_multi")
     Co = weight.size(0)
     return outs if Co == Co_pad else [o[:, :Co] for o in outs]
+
+
+def conv2d_forward_tc_pair(xs0, weight0, bias0, xs1, weight1, bias1, relu=False):
+    """Two convolutions of one shape class -- same C, padded C_out, kernel size, ReLU and batch, e.g. the
+    classification and the regression tower layer of the head -- in ONE persistent launch (two launches of 682 tile
+    groups fill the 74 CTA pairs to 92 %, one launch of 1,364 to 97 %).  Falls back to two launches when the shapes
+    differ or the levels do not fit one launch.  Returns (outs0, outs1) like two conv2d_forward_tc_multi calls."""
+    same = (weight0.shape[1:] == weight1.shape[1:] and (weight0.size(0) + 31) // 32 == (weight1.size(0) + 31) // 32 and
+            xs0[0].dtype == xs1[0].dtype and xs0[0].size(0) == xs1[0].size(0) and len(xs0) + len(xs1) <= 16 and
+            (bias0 is None) == (bias1 is None))
+    if not same:
+        return (conv2d_forward_tc_multi(xs0, weight0, bias0, relu=relu), conv2d_forward_tc_multi(xs1, weight1, bias1, relu=relu))
+    xs = list(xs0) + list(xs1)
+    dev = _lib.require_cuda(*xs, weight0, weight1, bias0, bias1)
+    B, C = xs[0].shape[:2]
+    if weight0.size(1) != C or any(x.size(1) != C for x in xs):
+        raise ValueError("conv2d_forward_tc: input has %d channels, weight expects %d" % (C, weight0.size(1)))
+    if C % 8:
+        raise ValueError("conv2d_forward_tc: C must be a multiple of 8")
+    p0, b0, Co_pad, ks = pack_conv2d_weight(weight0, bias0, xs[0].dtype)
+    p1, b1, _, _ = pack_conv2d_weight(weight1, bias1, xs[0].dtype)
+    xc = [_nhwc(x) for x in xs]
+    outs = [torch.empty((B, Co_pad, x.size(2), x.size(3)), dtype=x.dtype, device=dev, memory_format=torch.channels_last)
+            for x in xs]
+    with torch.cuda.device(dev):
+        rc = _lib.load().s2a_conv2d_forward_tc_multi2(len(xs), len(xs0), _ptr_array(xc), _lib.ptr(p0), _lib.ptr(p1),
+                                                      _lib.ptr(b0), _lib.ptr(b1), _ptr_array(outs),
+                                                      _int_array([x.size(2) for x in xs]), _int_array([x.size(3) for x in xs]),
+                                                      B, C, Co_pad, ks, 1 if relu else 0, _lib.dtype_code(xc[0]),
+                                                      _lib.stream_ptr(dev))
+    _lib.check(rc, "conv2d_forward_tc_multi2")
+    n0 = len(xs0)
+    o0 = outs[:n0] if weight0.size(0) == Co_pad else [o[:, :weight0.size(0)] for o in outs[:n0]]
+    o1 = outs[n0:] if weight1.size(0) == Co_pad else [o[:, :weight1.size(0)] for o in outs[n0:]]
+    return o0, o1

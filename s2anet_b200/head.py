@@ -193,16 +193,34 @@ class S2ANetHead(nn.Module):
                 xs = conv(xs, block[0], relu=True)
             return xs
 
+        def pair(xs0, m0, xs1, m1, relu=False):      # two same-shaped convs in one launch (fills the CTA pairs better)
+            return conv_tc.conv2d_forward_tc_pair(xs0, m0.weight, m0.bias, xs1, m1.weight, m1.bias, relu=relu)
+
+        def towers(seq0, xs0, seq1, xs1):
+            """Two towers layer by layer; layers of the same shape class share a launch."""
+            for b0, b1 in zip(seq0, seq1):
+                xs0, xs1 = pair(xs0, b0[0], xs1, b1[0], relu=True)
+            return xs0, xs1
+
         feats = list(feats)
-        fam_reg = conv(tower(self.fam_reg_ls, feats), self.fam_reg_head)
-        fam_cls = conv(tower(self.fam_cls_ls, feats), self.fam_cls_head)
+        if len(self.fam_reg_ls) == len(self.fam_cls_ls):
+            reg_feat, cls_feat = towers(self.fam_reg_ls, feats, self.fam_cls_ls, feats)
+            fam_reg, fam_cls = pair(reg_feat, self.fam_reg_head, cls_feat, self.fam_cls_head)
+        else:
+            fam_reg = conv(tower(self.fam_reg_ls, feats), self.fam_reg_head)
+            fam_cls = conv(tower(self.fam_cls_ls, feats), self.fam_cls_head)
         refines = decode.fam_decode(fam_reg, self.featmap_strides, self.anchor_scale, self.anchor_angle, 1e-6)
         aligned = conv_tc.alignconv_forward_tc_multi(feats, refines, self.align_conv.deform_conv.weight,
                                                      self.featmap_strides)
         or_feats, pooled = conv_tc.orconv_forward_tc_multi(aligned, self.or_conv.weight, self.or_conv.indices,
                                                            self.or_conv.bias, with_pool=True)
-        odm_cls = conv(tower(self.odm_cls_ls, pooled), self.odm_cls_head)
-        odm_reg = conv(tower(self.odm_reg_ls, or_feats), self.odm_reg_head)
+        if len(self.odm_cls_ls) == len(self.odm_reg_ls):
+            # (the first layers differ in C -- 32 pooled vs 256 channels -- and fall back to two launches inside pair())
+            cls_feat, reg_feat = towers(self.odm_cls_ls, pooled, self.odm_reg_ls, or_feats)
+            odm_cls, odm_reg = pair(cls_feat, self.odm_cls_head, reg_feat, self.odm_reg_head)
+        else:
+            odm_cls = conv(tower(self.odm_cls_ls, pooled), self.odm_cls_head)
+            odm_reg = conv(tower(self.odm_reg_ls, or_feats), self.odm_reg_head)
         return [(fam_cls[l], fam_reg[l], odm_cls[l], odm_reg[l],
                  self.grid_anchors(x.size(2), x.size(3), s, x.device), refines[l])
                 for l, (x, s) in enumerate(zip(feats, self.featmap_strides))]

@@ -192,3 +192,31 @@ def test_alignconv_tc_several_tiles_per_cta():
     w = (torch.randn(Co, C, 3, 3, generator=g) * 0.05).to(DEV).to(dtype)
     anc = torch.from_numpy(synth.refined_anchors(B, H, W, stride, seed=4)).to(DEV)
     check(alignconv_forward(x, anc, w, stride), alignconv_forward(x.float(), anc, w.float(), stride), dtype)
+
+
+@pytest.mark.parametrize("Co0,Co1,ks", [(256, 256, 3), (15, 5, 1), (15, 5, 3)])
+def test_conv2d_tc_pair_equals_two_launches(Co0, Co1, ks):
+    """Two convs of one shape class in ONE launch (levels >= split use the second weights / bias; the second problem
+    starts at an even tile so a CTA pair never mixes weights -- odd tile counts get a padding tile): bit-identical to
+    two separate launches, also when both read the same inputs and when the shapes force the two-launch fallback."""
+    from s2anet_b200.conv_tc import conv2d_forward_tc_multi, conv2d_forward_tc_pair
+    dtype = torch.bfloat16
+    g = torch.Generator().manual_seed(Co0 + Co1 + ks)
+    sizes = ((24, 40), (13, 21), (3, 5))                     # 2 * (10 + 4 + 1) = 15 tiles per problem: odd
+    xs0 = [torch.randn(1, 128, h, w, generator=g).to(DEV).to(dtype).contiguous(memory_format=torch.channels_last) for h, w in sizes]
+    xs1 = [torch.randn(1, 128, h, w, generator=g).to(DEV).to(dtype).contiguous(memory_format=torch.channels_last) for h, w in sizes]
+    w0 = (torch.randn(Co0, 128, ks, ks, generator=g) * 0.05).to(DEV).to(dtype)
+    w1 = (torch.randn(Co1, 128, ks, ks, generator=g) * 0.05).to(DEV).to(dtype)
+    b0, b1 = torch.randn(Co0, generator=g).to(DEV), torch.randn(Co1, generator=g).to(DEV)
+    for a, b in ((xs0, xs1), (xs0, xs0)):
+        o0, o1 = conv2d_forward_tc_pair(a, w0, b0, b, w1, b1, relu=True)
+        r0 = conv2d_forward_tc_multi(a, w0, b0, relu=True)
+        r1 = conv2d_forward_tc_multi(b, w1, b1, relu=True)
+        for x, y in zip(o0 + o1, r0 + r1):
+            assert x.shape == y.shape and torch.equal(x, y)
+    # different input channel counts: falls back to two launches, same results
+    w2 = (torch.randn(Co1, 64, ks, ks, generator=g) * 0.05).to(DEV).to(dtype)
+    xs2 = [x[:, :64].contiguous(memory_format=torch.channels_last) for x in xs1]
+    o0, o2 = conv2d_forward_tc_pair(xs0, w0, b0, xs2, w2, b1, relu=False)
+    for x, y in zip(o2, conv2d_forward_tc_multi(xs2, w2, b1, relu=False)):
+        assert torch.equal(x, y)
