@@ -3,6 +3,7 @@
 // compile can be checked against the oracle without a GPU.  Test infrastructure only.
 #include <cstdint>
 #include "../s2anet_b200/csrc/rbox_iou.cuh"
+#include "../s2anet_b200/csrc/poly_iou.cuh"
 
 extern "C" {
 
@@ -25,6 +26,24 @@ void hh_pairwise(const float* b1, int64_t n, const float* b2, int64_t m, float* 
       out[i * m + j] = v;
     }
   delete[] A; delete[] B;
+}
+
+// the product's fp64 polygon IoU (DOTA result merging), pair by pair
+void hh_poly_iou_pairs(const double* p, const double* q, int64_t n, double* out) {
+  for (int64_t i = 0; i < n; ++i) out[i] = s2a::poly_iou(p + 8 * i, q + 8 * i);
+}
+
+// the NMS kernels' upper bound of the intersection area (never used for an IoU value, only to skip clips)
+void hh_inter_upper_bound(const float* b1, int64_t n, const float* b2, int64_t m, float* out) {
+  for (int64_t i = 0; i < n; ++i) {
+    s2a::RBox A;
+    s2a::rbox_prep(b1[5*i], b1[5*i+1], b1[5*i+2], b1[5*i+3], b1[5*i+4], A);
+    for (int64_t j = 0; j < m; ++j) {
+      s2a::RBox B;
+      s2a::rbox_prep(b2[5*j], b2[5*j+1], b2[5*j+2], b2[5*j+3], b2[5*j+4], B);
+      out[i * m + j] = s2a::rbox_inter_upper_bound(A, B);
+    }
+  }
 }
 
 }

@@ -146,19 +146,37 @@ def host_harness():
     out = os.path.join(ROOT, "tests", "_build", "libhost_harness.so")
     src = os.path.join(ROOT, "tests", "host_harness.cu")
     hdr = os.path.join(ROOT, "s2anet_b200", "csrc", "rbox_iou.cuh")
+    hdr2 = os.path.join(ROOT, "s2anet_b200", "csrc", "poly_iou.cuh")
     os.makedirs(os.path.dirname(out), exist_ok=True)
-    if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+    if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(src), os.path.getmtime(hdr), os.path.getmtime(hdr2)):
         subprocess.check_call(["nvcc", "-O2", "-x", "cu", "-shared", "-Xcompiler", "-fPIC,-ffp-contract=off",
                                "-gencode", "arch=compute_100a,code=sm_100a", "-o", out, src])
     L = C.CDLL(out)
     f32p = np.ctypeslib.ndpointer(np.float32, flags="C")
     L.hh_pairwise.argtypes = [f32p, C.c_int64, f32p, C.c_int64, f32p, C.c_int]
 
+    f64p = np.ctypeslib.ndpointer(np.float64, flags="C")
+    L.hh_poly_iou_pairs.argtypes = [f64p, f64p, C.c_int64, f64p]
+    L.hh_inter_upper_bound.argtypes = [f32p, C.c_int64, f32p, C.c_int64, f32p]
+
     def run(b1, b2, mode):
         b1, b2 = np.ascontiguousarray(b1, np.float32), np.ascontiguousarray(b2, np.float32)
         out_ = np.empty((len(b1), len(b2)), np.float32)
         L.hh_pairwise(b1, len(b1), b2, len(b2), out_, mode)
         return out_
+
+    def poly(p, q):
+        p, q = np.ascontiguousarray(p, np.float64), np.ascontiguousarray(q, np.float64)
+        out_ = np.empty((len(p),), np.float64)
+        L.hh_poly_iou_pairs(p, q, len(p), out_)
+        return out_
+
+    def bound(b1, b2):
+        b1, b2 = np.ascontiguousarray(b1, np.float32), np.ascontiguousarray(b2, np.float32)
+        out_ = np.empty((len(b1), len(b2)), np.float32)
+        L.hh_inter_upper_bound(b1, len(b1), b2, len(b2), out_)
+        return out_
+    run.poly, run.bound = poly, bound
     return run
 
 
@@ -178,3 +196,33 @@ def test_product_iou_source_on_host(oracle, host_harness):
         ref = oracle.box_iou_rotated(b1, b2)
         for mode in (0, 1):
             np.testing.assert_array_equal(bits(host_harness(b1, b2, mode)), bits(ref))
+
+
+def test_product_poly_iou_source_on_host(oracle, host_harness):
+    """csrc/poly_iou.cuh (the fp64 polygon IoU of the DOTA result merging) on the CPU: bit-identical to the oracle --
+    and therefore to the reference's compiled polyiou.cpp -- on the golden pairs and 5,000 random ones."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "poly_small.npz"))
+    with np.errstate(invalid="ignore", divide="ignore"):
+        got = host_harness.poly(g["p"], g["q"])
+    assert np.all((got.view(np.uint64) == g["iou"].view(np.uint64)) | (np.isnan(got) & np.isnan(g["iou"])))
+    p = synth.random_quads(5000, np.random.default_rng(31))
+    q = p + np.random.default_rng(32).normal(0, 6, p.shape)
+    np.testing.assert_array_equal(host_harness.poly(p, q).view(np.uint64), oracle.poly_iou_pairs(p, q).view(np.uint64))
+
+
+def test_nms_intersection_bound_is_an_upper_bound(oracle, host_harness):
+    """rbox_inter_upper_bound (NMS kernels: skip a clip when even this bound cannot reach the threshold) never
+    undercuts the intersection area the reference's IoU implies, on clustered and adversarial boxes."""
+    for boxes in (synth.clustered_boxes(n_seed=150, rep=5, seed=5)[0], synth.adversarial_boxes()):
+        b = boxes[(boxes[:, 2] > 0) & (boxes[:, 3] > 0)]
+        iou = oracle.box_iou_rotated(b, b).astype(np.float64)
+        a = (b[:, 2] * b[:, 3]).astype(np.float64)
+        inter = iou * (a[:, None] + a[None, :]) / (1.0 + iou)
+        ub = host_harness.bound(b, b).astype(np.float64)
+        assert np.all(inter <= ub * 1.001 + 1e-6 * (a[:, None] + a[None, :])), float((inter - ub).max())
+        # and it is useful: most overlapping-but-not-suppressing pairs are decided without a clip at thr = 0.5
+        cand = (iou > 0) & (iou <= 0.5)
+        skipped = 1.001 * ub < 0.999 * 0.5 * (a[:, None] + a[None, :] - 1.001 * ub)
+        assert not np.any(skipped & (iou > 0.5))
+        if cand.sum() > 1000:
+            assert (skipped & cand).sum() > 0.5 * cand.sum()
