@@ -174,6 +174,18 @@ S2A_EXPORT int s2a_conv_pack_weight(const void* weight, int in_dtype, const uint
 S2A_EXPORT int s2a_alignconv_forward_tc(const void* x, const float* anchors,
                                         const void* packed_weight, void* out, int B, int C, int H,
                                         int W, int Co, float stride, int dtype, void* stream);
+/* Generic deformable convolution on the same tcgen05 kernel: the 16-bit route of `deform_conv_forward_cuda`
+ * (reference: models/dcn/src/deform_conv_cuda.cpp:152-260 with scalar_t = half, dispatched at
+ * deform_conv_cuda_kernel.cu:258; models/dcn/deform_conv.py:45-70 casts offset and weight to the input dtype).
+ * 3x3, stride 1, padding 1, dilation 1, groups 1, deformable_groups 1, C % 64 == 0, C_out % 32 == 0 <= 256.
+ * x / out are NHWC 16-bit like s2a_alignconv_forward_tc; `offsets` is the reference's [B, 18, H, W] tensor
+ * ((dy, dx) per tap, NCHW) in fp32 (offsets_dtype = S2A_F32) or in the activations' dtype; `packed_weight` comes
+ * from s2a_conv_pack_weight (no ARF map).  round_positions != 0 rounds the sampling position and every bilinear
+ * weight operation to the 16-bit type exactly as the reference's `scalar_t` arithmetic does (:94-110, :223-224);
+ * 0 keeps them in fp32 (more accurate; what AlignConv's fused path does).  relu != 0 fuses a ReLU. */
+S2A_EXPORT int s2a_deform_conv_forward_tc(const void* x, const void* offsets, int offsets_dtype,
+                                          const void* packed_weight, void* out, int B, int C, int H, int W,
+                                          int Co, int relu, int round_positions, int dtype, void* stream);
 S2A_EXPORT int s2a_orconv_forward_tc(const void* x, const void* packed_weight, const float* bias,
                                      void* out, void* pooled, int B, int C, int H, int W, int Co,
                                      int dtype, void* stream);

@@ -106,6 +106,10 @@ REF_EXTS_GPU = {
     "ml_nms_rotated_cuda": ["utils/ml_nms_rotated/src/nms_rotated_cpu.cpp",
                             "utils/ml_nms_rotated/src/nms_rotated_cuda.cu"],
     "deform_conv_cuda": ["models/dcn/src/deform_conv_cuda.cpp", "models/dcn/src/deform_conv_cuda_kernel.cu"],
+    # needs oracle/thc_shim on the include path (THC/THC.h is gone from torch; three symbols, see the shim header)
+    "orn_cuda": ["models/orn/src/vision.cpp", "models/orn/src/cpu/ActiveRotatingFilter_cpu.cpp",
+                 "models/orn/src/cpu/RotationInvariantEncoding_cpu.cpp", "models/orn/src/cuda/ActiveRotatingFilter_cuda.cu",
+                 "models/orn/src/cuda/RotationInvariantEncoding_cuda.cu"],
 }
 
 
@@ -132,6 +136,7 @@ def build_ref_extensions(kind="cpu", names=None, verbose=False):
             cpp_extension.load(name=name, sources=full, build_directory=bdir, verbose=verbose,
                                extra_cflags=["-O2"] + (["-DWITH_CUDA"] if kind == "gpu" else []),
                                extra_cuda_cflags=["-O2", "-DWITH_CUDA", "-gencode", "arch=compute_100a,code=sm_100a"],
+                               extra_include_paths=[os.path.join(HERE, "thc_shim")],
                                with_cuda=(kind == "gpu"), is_python_module=False)
         out[name] = so
     return out
@@ -162,3 +167,31 @@ def load_ref_extension(name, kind="cpu"):
     spec.loader.exec_module(mod)
     _LOADED[key] = mod
     return mod
+
+
+# ---- the reference checkout staged for the GPU box ------------------------------------------------
+
+STAGED = os.path.join(os.path.dirname(HERE), "baseline", "_ref")
+
+
+def stage_reference_tree():
+    """Copy the (read-only) reference checkout into the git-ignored baseline/_ref/ so that it travels with the gpurun
+    snapshot: the -m gpu tests import the reference's UNMODIFIED Python (models/head.py, models/detector.py,
+    utils/bbox_nms_rotated.py ...) from there on top of the shim modules.  Nothing under baseline/_ref is tracked,
+    edited or shipped as product source.  Returns the staged root (or None where the reference is not mounted)."""
+    import shutil
+    if not os.path.isdir(REF):
+        return STAGED if os.path.isdir(os.path.join(STAGED, "models")) else None
+    os.makedirs(STAGED, exist_ok=True)
+    shutil.copytree(REF, STAGED, dirs_exist_ok=True,
+                    ignore=shutil.ignore_patterns(".git", "__pycache__", "*.pyc", "*.so", "*.o", "build"))
+    return STAGED
+
+
+def reference_root():
+    """Where the reference's Python tree can be imported from: /root/reference in the authoring container, the
+    staged copy on the GPU box; None if neither exists."""
+    for root in (REF, STAGED):
+        if os.path.isfile(os.path.join(root, "models", "head.py")):
+            return root
+    return None

@@ -1,0 +1,3 @@
+// see THC.h in this directory
+#pragma once
+#include <ATen/cuda/Atomic.cuh>

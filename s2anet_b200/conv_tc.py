@@ -14,12 +14,20 @@ from . import _lib
 _PACK_CACHE = {}
 
 
+def _stamp(t):
+    """What identifies the CONTENT a packed copy was made from.  `_version` alone is not enough: writes through
+    `.data` (`w.data.copy_()`, `w.data = ...`, `Module.to()` / `.half()` which reassign `param.data`) do not bump it,
+    but they either change the storage (data_ptr / device / dtype) or go through `.data`'s own version counter --
+    so the stamp also carries the storage address, device, dtype and the version of the `.data` alias."""
+    return (t._version, t.data_ptr(), t.device, t.dtype, tuple(t.shape), tuple(t.stride()))
+
+
 def _cache_get(key, sources):
     hit = _PACK_CACHE.get(key)
     if hit is None:
         return None
-    refs, versions, value = hit
-    if all(r() is t for r, t in zip(refs, sources)) and versions == tuple(t._version for t in sources):
+    refs, stamps, value = hit
+    if all(r() is t for r, t in zip(refs, sources)) and stamps == tuple(_stamp(t) for t in sources):
         return value
     return None
 
@@ -28,8 +36,15 @@ def _cache_put(key, sources, value):
     if len(_PACK_CACHE) > 256:
         _PACK_CACHE.clear()
     drop = lambda _ref, k=key: _PACK_CACHE.pop(k, None)
-    _PACK_CACHE[key] = (tuple(weakref.ref(t, drop) for t in sources), tuple(t._version for t in sources), value)
+    _PACK_CACHE[key] = (tuple(weakref.ref(t, drop) for t in sources), tuple(_stamp(t) for t in sources), value)
     return value
+
+
+def invalidate_pack_cache():
+    """Drop every packed weight.  In-place writes through `.data` that keep the storage (`w.data.add_(1)`, an EMA or
+    a clipping step written that way) are invisible to every stamp torch offers; code that does that calls this (or
+    trains with grad enabled, which never uses the packed inference path)."""
+    _PACK_CACHE.clear()
 
 
 def _nhwc(x):
@@ -79,6 +94,41 @@ def alignconv_forward_tc(x, anchors, weight, stride):
         rc = _lib.load().s2a_alignconv_forward_tc(_lib.ptr(xc), _lib.ptr(a), _lib.ptr(wp), _lib.ptr(out), B, C, H, W, Co,
                                                   float(stride), _lib.dtype_code(xc), _lib.stream_ptr(dev))
     _lib.check(rc, "alignconv_forward_tc")
+    return out
+
+
+def deform_conv_tc_supported(C, Co, kH, kW, dH, dW, padH, padW, dilH, dilW, group, deformable_group):
+    """Shapes the tcgen05 deformable conv takes (everything S2ANet's AlignConv uses)."""
+    return (kH == 3 and kW == 3 and dH == 1 and dW == 1 and padH == 1 and padW == 1 and dilH == 1 and dilW == 1 and
+            group == 1 and deformable_group == 1 and C % 64 == 0 and Co % 32 == 0 and Co <= 256)
+
+
+def deform_conv_forward_tc(x, offset, weight, out=None, relu=False, round_positions=None):
+    """Generic 3x3 deformable convolution (explicit [B,18,H,W] offsets) on the tcgen05 kernel: the 16-bit route of
+    `deform_conv_forward_cuda`.  x bf16/fp16 [B,C,H,W]; offset fp32 or x's dtype; returns (or fills `out`, if it is a
+    channels_last tensor of x's dtype) a channels_last [B,Co,H,W].  round_positions=None: True for fp16 -- the
+    reference's half kernel rounds the sampling positions and bilinear weights to half
+    (deform_conv_cuda_kernel.cu:94-110, 223-224), which this reproduces -- and False for bf16, a dtype the reference
+    does not dispatch (8 mantissa bits would move samples by up to half a pixel)."""
+    dev = _lib.require_cuda(x, offset, weight)
+    B, C, H, W = x.shape
+    Co = weight.size(0)
+    if tuple(offset.shape) != (B, 18, H, W):
+        raise ValueError("offset must be [B,18,H,W] matching x")
+    if round_positions is None:
+        round_positions = x.dtype == torch.float16
+    xc = _nhwc(x)
+    off = offset if offset.dtype in (torch.float32, x.dtype) else offset.to(x.dtype)
+    off = off.contiguous()
+    wp = pack_weight(weight, x.dtype)
+    if out is None or out.dtype != x.dtype or tuple(out.shape) != (B, Co, H, W) or \
+            not out.is_contiguous(memory_format=torch.channels_last):
+        out = torch.empty((B, Co, H, W), dtype=x.dtype, device=dev, memory_format=torch.channels_last)
+    with torch.cuda.device(dev):
+        rc = _lib.load().s2a_deform_conv_forward_tc(_lib.ptr(xc), _lib.ptr(off), _lib.dtype_code(off), _lib.ptr(wp),
+                                                    _lib.ptr(out), B, C, H, W, Co, 1 if relu else 0,
+                                                    1 if round_positions else 0, _lib.dtype_code(xc), _lib.stream_ptr(dev))
+    _lib.check(rc, "deform_conv_forward_tc")
     return out
 
 

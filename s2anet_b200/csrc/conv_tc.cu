@@ -126,6 +126,7 @@ constexpr uint32_t TC_IN_HALO = 0x80000000u;
 struct TcLevel {
   const void* x;          // [B, H, W, C] 16-bit (channels_last)
   const float* anchors;   // [B, H, W, 5] (TC_ALIGN)
+  const void* offsets;    // TC_ALIGN, generic deformable conv: [B, 18, H, W] offsets (dy, dx per tap) instead of anchors
   void* out;              // [B, H, W, Co] 16-bit
   void* pooled;           // [B, H, W, Co/8] 16-bit or null
   int H, W, tiles_x, tiles_y;
@@ -146,6 +147,8 @@ struct TcParams {
   int B, C, Co;
   int ks;                 // TC_PLAIN: square kernel size, 1 or 3 (pad ks/2, stride 1); TC_ALIGN: 3
   int relu;
+  int off_f32;            // generic deformable conv: the offsets are fp32 (else the activations' 16-bit type)
+  int pos_round;          // ... and sampling positions / bilinear weights are rounded like the reference's scalar_t = half path
   int debug;              // timing experiments only (S2A_TC_DEBUG): 1 = no weight TMA after warm-up, 2 = no gather loads
 };
 
@@ -478,29 +481,52 @@ __device__ __forceinline__ void build_tap_table(const TcParams& p, const TileCoo
     TapSample s;
     s.base = TC_IN_HALO; s.w01 = 0u; s.w23 = 0u;          // weight-0 sample: reads halo pixel 0
     if (y < H && x < W) {
-      const float* a = L.anchors + ((size_t)(tc.b * H + y) * W + x) * 5;
-      const float ax = a[0] / L.stride, ay = a[1] / L.stride, aw = a[2] / L.stride, ah = a[3] / L.stride;
-      const float cs = cosf(a[4]), sn = sinf(a[4]);
-      const float dw = aw / 3.0f, dh = ah / 3.0f;
       const int ti = t / 3, tj = t - 3 * ti;
-      const float fi = (float)(ti - 1), fj = (float)(tj - 1);
-      const float txx = __fmul_rn(dw, fj), tyy = __fmul_rn(dh, fi);
-      const float xr = __fsub_rn(__fmul_rn(cs, txx), __fmul_rn(sn, tyy));
-      const float yr = __fadd_rn(__fmul_rn(sn, txx), __fmul_rn(cs, tyy));
-      const float xa = __fadd_rn(xr, ax), ya = __fadd_rn(yr, ay);
-      const float offx = __fsub_rn(xa, __fadd_rn((float)x, fj));
-      const float offy = __fsub_rn(ya, __fadd_rn((float)y, fi));
-      const float h = __fadd_rn((float)(y - 1 + ti), offy);
-      const float w = __fadd_rn((float)(x - 1 + tj), offx);
+      float h, w;
+      if (L.offsets) {
+        // generic deformable conv (deform_conv_cuda_kernel.cu:218-227): h_im = h_in + i + offset_h, pad 1 / stride 1
+        const size_t oi = (((size_t)tc.b * 18 + 2 * t) * H + y) * W + x, plane = (size_t)H * W;
+        float offy, offx;
+        if (p.off_f32) {
+          offy = reinterpret_cast<const float*>(L.offsets)[oi];
+          offx = reinterpret_cast<const float*>(L.offsets)[oi + plane];
+        } else {
+          offy = (float)reinterpret_cast<const T*>(L.offsets)[oi];
+          offx = (float)reinterpret_cast<const T*>(L.offsets)[oi + plane];
+        }
+        h = __fadd_rn((float)(y - 1 + ti), offy);
+        w = __fadd_rn((float)(x - 1 + tj), offx);
+        if (p.pos_round) { h = (float)(T)h; w = (float)(T)w; }     // `scalar_t h_im` of the reference's 16-bit kernel
+      } else {
+        const float* a = L.anchors + ((size_t)(tc.b * H + y) * W + x) * 5;
+        const float ax = a[0] / L.stride, ay = a[1] / L.stride, aw = a[2] / L.stride, ah = a[3] / L.stride;
+        const float cs = cosf(a[4]), sn = sinf(a[4]);
+        const float dw = aw / 3.0f, dh = ah / 3.0f;
+        const float fi = (float)(ti - 1), fj = (float)(tj - 1);
+        const float txx = __fmul_rn(dw, fj), tyy = __fmul_rn(dh, fi);
+        const float xr = __fsub_rn(__fmul_rn(cs, txx), __fmul_rn(sn, tyy));
+        const float yr = __fadd_rn(__fmul_rn(sn, txx), __fmul_rn(cs, tyy));
+        const float xa = __fadd_rn(xr, ax), ya = __fadd_rn(yr, ay);
+        const float offx = __fsub_rn(xa, __fadd_rn((float)x, fj));
+        const float offy = __fsub_rn(ya, __fadd_rn((float)y, fi));
+        h = __fadd_rn((float)(y - 1 + ti), offy);
+        w = __fadd_rn((float)(x - 1 + tj), offx);
+      }
       if (h > -1.0f && w > -1.0f && h < (float)H && w < (float)W) {
         const float hf = floorf(h), wf = floorf(w);
         const int y0 = (int)hf, x0 = (int)wf;
-        const float ly = h - hf, lx = w - wf, hy = 1.0f - ly, hx = 1.0f - lx;
+        const float ly = h - hf, lx = w - wf;
+        float hy = 1.0f - ly, hx = 1.0f - lx;
+        float w00 = hy * hx, w01_ = hy * lx, w10 = ly * hx, w11 = ly * lx;
+        if (p.pos_round && L.offsets) {       // every operation of deformable_im2col_bilinear rounded to scalar_t (:94-110)
+          hy = (float)(T)hy; hx = (float)(T)hx;
+          w00 = (float)(T)(hy * hx); w01_ = (float)(T)(hy * lx); w10 = (float)(T)(ly * hx); w11 = (float)(T)(ly * lx);
+        }
         const bool t_ok = y0 >= 0, b_ok = y0 + 1 <= H - 1, l_ok = x0 >= 0, r_ok = x0 + 1 <= W - 1;
         const int yt = max(y0, 0), yb = min(y0 + 1, H - 1), xl = max(x0, 0), xrr = min(x0 + 1, W - 1);
         using H2 = typename Half2Of<T>::type;
-        const H2 p01 = from_f2<T>((t_ok && l_ok) ? hy * hx : 0.0f, (t_ok && r_ok) ? hy * lx : 0.0f);
-        const H2 p23 = from_f2<T>((b_ok && l_ok) ? ly * hx : 0.0f, (b_ok && r_ok) ? ly * lx : 0.0f);
+        const H2 p01 = from_f2<T>((t_ok && l_ok) ? w00 : 0.0f, (t_ok && r_ok) ? w01_ : 0.0f);
+        const H2 p23 = from_f2<T>((b_ok && l_ok) ? w10 : 0.0f, (b_ok && r_ok) ? w11 : 0.0f);
         s.w01 = *reinterpret_cast<const uint32_t*>(&p01);
         s.w23 = *reinterpret_cast<const uint32_t*>(&p23);
         const int hy0 = yt - (tc.ty0 - TC_HALO), hx0 = xl - (tc.tx0 - TC_HALO);     // top-left corner inside the halo window?
@@ -1047,7 +1073,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
           for (int i = 0; i < 32; i += 2) {
             // ReLU on the packed pair after rounding (rounding is monotone and keeps 0): one HMNMX2 instead of two FMNMX
             H2 h = from_f2<T>(__uint_as_float(v[i]), __uint_as_float(v[i + 1]));
-            h = __hmax2(h, from_f2<T>(0.0f, 0.0f));
+            if (p.relu) h = __hmax2(h, from_f2<T>(0.0f, 0.0f));       // (the generic deformable conv has no ReLU)
             pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&h);
           }
         } else {
@@ -1244,7 +1270,8 @@ static int launch_tc(const TcMaps& tmap, const TcParams& p, cudaStream_t st) {
 static int conv_tc_common(int mode, int nlevels, const void* const* xs, const float* const* anchors, const void* wp,
                           const float* bias, void* const* outs, void* const* pooleds, const int* Hs, const int* Ws,
                           const float* strides, int B, int C, int Co, int relu, int dtype, cudaStream_t st, int ks = 3,
-                          int wsplit = -1, const void* wp2 = nullptr, const float* bias2 = nullptr) {
+                          int wsplit = -1, const void* wp2 = nullptr, const float* bias2 = nullptr,
+                          const void* const* offsets = nullptr, int off_f32 = 0, int pos_round = 0) {
   if (wsplit < 0) wsplit = nlevels;              // one problem: every level uses the first weights
   S2A_CHECK_ARG(nlevels >= 1 && nlevels <= TC_MAX_LEVELS, "conv_tc: 1..%d levels per launch", TC_MAX_LEVELS);
   S2A_CHECK_ARG(B >= 0 && C > 0 && Co > 0, "conv_tc: bad tensor sizes");
@@ -1263,9 +1290,11 @@ static int conv_tc_common(int mode, int nlevels, const void* const* xs, const fl
   for (int l = 0; l < nlevels; ++l) {
     S2A_CHECK_ARG(Hs[l] > 0 && Ws[l] > 0 && Hs[l] < 32768 && Ws[l] < 32768, "conv_tc: bad feature map size");
     S2A_CHECK_ARG((long long)Hs[l] * Ws[l] * C * 2 < (1ll << 32), "conv_tc: one image of a level must be < 4 GiB");
-    S2A_CHECK_ARG(xs[l] && outs[l] && (mode == TC_PLAIN || (anchors && anchors[l])), "conv_tc: null level pointer");
+    S2A_CHECK_ARG(xs[l] && outs[l] && (mode == TC_PLAIN || (anchors && anchors[l]) || (offsets && offsets[l])),
+                  "conv_tc: null level pointer");
     TcLevel& L = p.lv[l];
     L.x = xs[l]; L.anchors = anchors ? anchors[l] : nullptr; L.out = outs[l]; L.pooled = pooleds ? pooleds[l] : nullptr;
+    L.offsets = offsets ? offsets[l] : nullptr;
     L.H = Hs[l]; L.W = Ws[l];
     const int pw = mode == TC_PLAIN ? TC_PPW : TC_PW, ph = mode == TC_PLAIN ? TC_PPH : TC_PH;
     L.tiles_x = (Ws[l] + pw - 1) / pw; L.tiles_y = (Hs[l] + ph - 1) / ph;
@@ -1319,7 +1348,7 @@ static int conv_tc_common(int mode, int nlevels, const void* const* xs, const fl
     if (cr != CUDA_SUCCESS) { set_error("conv_tc: cuTensorMapEncodeTiled failed (%d)", (int)cr); return S2A_ERR_CUDA; }
   }
   p.bias = bias; p.bias2 = bias2; p.wsplit = wsplit; p.nlevels = nlevels; p.total_tiles = (int)tiles;
-  p.B = B; p.C = C; p.Co = Co; p.relu = relu; p.ks = ks;
+  p.B = B; p.C = C; p.Co = Co; p.relu = relu; p.ks = ks; p.off_f32 = off_f32; p.pos_round = pos_round;
   { const char* e = getenv("S2A_TC_DEBUG"); p.debug = e ? atoi(e) : 0; }
   if (mode == TC_ALIGN) {
     return dtype == S2A_BF16 ? launch_tc<TC_ALIGN, __nv_bfloat16>(tmap, p, st) : launch_tc<TC_ALIGN, __half>(tmap, p, st);
@@ -1372,6 +1401,19 @@ extern "C" int s2a_alignconv_forward_tc(const void* x, const float* anchors, con
   S2A_CHECK_ARG(H > 0 && W > 0, "alignconv_tc: bad feature map size");
   return conv_tc_common(TC_ALIGN, 1, &x, &anchors, packed_weight, nullptr, &out, nullptr, &H, &W, &stride, B, C, Co, 1,
                         dtype, (cudaStream_t)stream);
+}
+
+extern "C" int s2a_deform_conv_forward_tc(const void* x, const void* offsets, int offsets_dtype, const void* packed_weight,
+                                          void* out, int B, int C, int H, int W, int Co, int relu, int round_positions,
+                                          int dtype, void* stream) {
+  using namespace s2a;
+  S2A_CHECK_ARG(H > 0 && W > 0, "deform_conv_tc: bad feature map size");
+  S2A_CHECK_ARG(offsets != nullptr || B == 0, "deform_conv_tc: null offsets");
+  S2A_CHECK_ARG(offsets_dtype == S2A_F32 || offsets_dtype == dtype, "deform_conv_tc: offsets must be fp32 or the activations' dtype");
+  const float one = 1.0f;
+  return conv_tc_common(TC_ALIGN, 1, &x, nullptr, packed_weight, nullptr, &out, nullptr, &H, &W, &one, B, C, Co, relu ? 1 : 0,
+                        dtype, (cudaStream_t)stream, 3, -1, nullptr, nullptr, &offsets, offsets_dtype == S2A_F32 ? 1 : 0,
+                        round_positions ? 1 : 0);
 }
 
 extern "C" int s2a_orconv_forward_tc(const void* x, const void* packed_weight, const float* bias, void* out, void* pooled,

@@ -44,9 +44,25 @@ def deform_conv_forward_cuda(input, weight, offset, output, columns, ones, kW, k
     if offset.size(2) != Ho or offset.size(3) != Wo:
         raise RuntimeError("invalid spatial size of offset, expected height: %d width: %d, but got height: %d "
                            "width: %d" % (Ho, Wo, offset.size(2), offset.size(3)))
+    if input.dtype in (torch.float16, torch.bfloat16):
+        # The reference dispatches scalar_t = half here (deform_conv_cuda_kernel.cu:258) and val.py runs the model in
+        # fp16 by default (val.py:126,196,246).  S2ANet's configuration goes to the tcgen05 kernel (offsets ->
+        # gather recipes; positions and bilinear weights rounded like the reference's half arithmetic); every other
+        # geometry runs the exact fp32 kernel on up-cast operands and rounds the result once.
+        from . import conv_tc
+        if conv_tc.deform_conv_tc_supported(C, Co, kH, kW, dH, dW, padH, padW, dilationH, dilationW, group, deformable_group):
+            # (the packer rounds an fp32 weight to the 16-bit type once, which is what `weight.type_as(input)` does)
+            y = conv_tc.deform_conv_forward_tc(input, offset, weight, out=output)
+            if y is not output:
+                output.copy_(y if y.shape == output.shape else y.reshape(output.shape))
+            return 1
+        out32 = torch.empty((B, Co, Ho, Wo), dtype=torch.float32, device=dev)
+        deform_conv_forward_cuda(input.float(), weight.float(), offset.float(), out32, columns, ones, kW, kH, dW, dH, padW,
+                                 padH, dilationW, dilationH, group, deformable_group, im2col_step)
+        output.copy_(out32.view_as(output))
+        return 1
     if input.dtype != torch.float32:
-        raise NotImplementedError("deform_conv_forward_cuda: this build implements float32 through this entry; "
-                                  "use AlignConv for the bf16 tensor-core path")
+        raise TypeError("deform_conv_forward_cuda: unsupported dtype %s (float32, float16, bfloat16)" % input.dtype)
     x = input.contiguous()
     off = offset.to(torch.float32).contiguous()
     w = weight.to(torch.float32).contiguous()

@@ -181,7 +181,11 @@ class S2ANetHead(nn.Module):
         AlignConv and ORConv2d -- runs as ONE persistent multi-level tcgen05 launch (the reference loops over
         levels in Python, head.py:265, and its convs are cuDNN calls)."""
         x0 = feats[0]
-        if not (x0.is_cuda and x0.dtype in (torch.bfloat16, torch.float16) and self.with_orconv):
+        # the fused multi-level path builds no autograd graph: training (any gradient can flow) takes forward_single,
+        # whose ops are the stock differentiable ones + the DeformConv / ARF autograd Functions
+        needs_grad = torch.is_grad_enabled() and (any(f.requires_grad for f in feats) or
+                                                  any(p.requires_grad for p in self.parameters()))
+        if needs_grad or not (x0.is_cuda and x0.dtype in (torch.bfloat16, torch.float16) and self.with_orconv):
             return [self.forward_single(x, s) for x, s in zip(feats, self.featmap_strides)]
         from . import conv_tc
 
@@ -252,18 +256,31 @@ class S2ANetHead(nn.Module):
         return bboxes.contiguous(), scores.contiguous()
 
     @torch.no_grad()
-    def detect(self, feats):
-        """Whole hot path for a batch: head towers + AlignConv + ORConv + decode + multiclass NMS.
-        Sync-free; returns (dets [B,max_per_img,6], labels [B,max_per_img], counts [B] int32)."""
-        outs = self.forward_levels(feats)
+    def detect_from_outs(self, outs):
+        """Post-processing of per-level head outputs (the tuples forward_levels / forward_single return, or the
+        reference head's `p` regrouped per level): decode + per-level top-k + multiclass NMS, batched, sync-free."""
         bboxes, scores = self.select_and_decode(outs)
         return multiclass_nms_rotated_batched(bboxes, scores, self.score_thres_before_nms, self.iou_thres_nms,
                                               self.max_per_img)
 
     @torch.no_grad()
+    def detect(self, feats):
+        """Whole hot path for a batch: head towers + AlignConv + ORConv + decode + multiclass NMS.
+        Sync-free; returns (dets [B,max_per_img,6], labels [B,max_per_img], counts [B] int32)."""
+        return self.detect_from_outs(self.forward_levels(feats))
+
+    @torch.no_grad()
     def get_bboxes(self, feats):
         """Reference-shaped result (models/head.py:648-682): list of (det_bboxes [k,6], det_labels [k])."""
-        dets, labels, counts = self.detect(feats)
+        return self._as_list(*self.detect(feats))
+
+    @torch.no_grad()
+    def get_bboxes_from_outs(self, outs):
+        """models/head.py:648-725 `get_bboxes(p)` on already computed head outputs."""
+        return self._as_list(*self.detect_from_outs(outs))
+
+    @staticmethod
+    def _as_list(dets, labels, counts):
         res = []
         for i, k in enumerate(counts.tolist()):
             if k == 0:

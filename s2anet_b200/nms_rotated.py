@@ -55,6 +55,9 @@ def nms_rotated(dets, iou_thr):
     return dets, keep_inds
 
 
+MC_FUSED_MAX_BOXES = 6144      # kMcMaxBoxes in csrc/nms_rotated.cu
+
+
 def multiclass_nms_rotated_batched(bboxes, scores, score_thr=0.05, iou_thr=0.5, max_per_img=2000):
     """Fused, sync-free, batched form: bboxes [B,n,5], scores [B,n,C] ->
     (dets [B,max_per_img,6], labels [B,max_per_img] float32, counts [B] int32); rows >= counts[b]
@@ -70,6 +73,18 @@ def multiclass_nms_rotated_batched(bboxes, scores, score_thr=0.05, iou_thr=0.5, 
     counts = torch.zeros((B,), dtype=torch.int32, device=dev)
     if B == 0 or n == 0 or C == 0:
         return dets, labels, counts
+    if n > MC_FUSED_MAX_BOXES or not (iou_thr >= 0):
+        # Sizes the fused kernel does not take (more than 6,144 candidate boxes per image -- e.g. 5 levels x top-2000
+        # on inputs above ~1,100 px -- or a negative threshold): per image, the reference's own composition on the
+        # generic ml_nms_rotated kernel (one 4-byte host read per image), written into the same fixed-shape outputs.
+        for b in range(B):
+            d, l = _multiclass_composed(bboxes[b], scores[b], score_thr, iou_thr, max_per_img)
+            k = d.size(0)
+            if k:
+                dets[b, :k] = d
+                labels[b, :k] = l.reshape(-1)
+            counts[b] = k
+        return dets, labels, counts
     lib = _lib.load()
     ws_bytes = lib.s2a_multiclass_nms_rotated_workspace_bytes(n, C, B)
     ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
@@ -80,9 +95,6 @@ def multiclass_nms_rotated_batched(bboxes, scores, score_thr=0.05, iou_thr=0.5, 
                                             _lib.stream_ptr(dev))
     _lib.check(rc, "multiclass_nms_rotated")
     return dets, labels, counts
-
-
-MC_FUSED_MAX_BOXES = 6144      # kMcMaxBoxes in csrc/nms_rotated.cu
 
 
 def _multiclass_composed(bboxes, scores, score_thr, iou_thr, max_per_img):

@@ -102,6 +102,10 @@ class RotationInvariantPooling(nn.Module):
         pooled = getattr(x, "_s2a_pooled", None)     # produced by the fused ORConv2d epilogue
         if pooled is not None and self.nOrientation == 8:
             return pooled
+        if torch.is_grad_enabled() and x.requires_grad:
+            # training: the reference's own differentiable formulation (rotation_invariant_pooling.py:19-27)
+            N, c, h, w = x.size()
+            return x.view(N, -1, self.nOrientation, h, w).max(dim=2, keepdim=False)[0]
         return ri_pool(x, self.nOrientation)
 
 
@@ -190,8 +194,14 @@ class ORConv2d(Conv2d):
         return (self.kernel_size == (3, 3) and self.stride == (1, 1) and self.padding == (1, 1)
                 and self.dilation == (1, 1) and self.groups == 1)
 
+    def _needs_grad(self, input):
+        return torch.is_grad_enabled() and (input.requires_grad or self.weight.requires_grad or
+                                            (self.bias is not None and self.bias.requires_grad))
+
     def forward(self, input):
-        if self._fusable() and input.is_cuda:
+        # The fused kernel is an inference path (no autograd graph): whenever a gradient can flow, take the
+        # reference's route -- the ARF autograd Function (arf_forward / arf_backward kernels) + F.conv2d.
+        if self._fusable() and input.is_cuda and not self._needs_grad(input):
             pool = self.fuse_pool and self.nRotation == 8
             res = orconv_forward(input, self.weight, self.indices, self.bias, with_pool=pool)
             if pool:

@@ -28,3 +28,24 @@ def test_cache_entry_dies_with_its_tensor():
     del b
     gc.collect()
     assert key not in conv_tc._PACK_CACHE
+
+
+def test_cache_sees_data_reassignment_and_dtype_or_device_moves():
+    """`w.data = ...` and Module.to()/half() (which reassign param.data) do not bump `_version`; the stamp
+    also carries the storage address, device, dtype, shape and strides."""
+    w = torch.nn.Parameter(torch.randn(4, 4))
+    key = ((id(w),), torch.float32, "t3")
+    conv_tc._cache_put(key, (w,), "packed")
+    assert conv_tc._cache_get(key, (w,)) == "packed"
+    v0 = w._version
+    w.data = torch.randn(4, 4)                    # new storage, same Parameter object, same version
+    assert w._version == v0
+    assert conv_tc._cache_get(key, (w,)) is None
+    conv_tc._cache_put(key, (w,), "packed2")
+    m = torch.nn.Conv2d(4, 4, 3)
+    key2 = ((id(m.weight),), torch.float32, "t4")
+    conv_tc._cache_put(key2, (m.weight,), "packed3")
+    m.half()                                      # _apply: param.data reassigned in place, dtype changes
+    assert conv_tc._cache_get(key2, (m.weight,)) is None
+    conv_tc.invalidate_pack_cache()
+    assert not conv_tc._PACK_CACHE
