@@ -87,7 +87,21 @@ RB_HD void rbox_prep(float x, float y, float w, float h, float a, RBox& o) {
 //     are ill-conditioned; its answer there is reproduced by the clipper, never predicted.
 // NaN/Inf inputs fail the comparisons and fall through to RB_CLIP.  See DESIGN.md "IoU reject test".
 
-// Stage 1 (every pair, ~25 flops, no divergence): the common case "circles clearly apart, edges clearly
+// Sliver guard (why a side may be as short as 2.5e-4 of the pair's extent).  Vertex coordinates carry an absolute
+// rounding error eps_v <= 2^-22 * ext (ext = |dx| + |dy| + r1 + r2 bounds every coordinate after the centre shift), so
+// an edge of length L has a direction error <= 5e-7 * ext / L: 2e-3 rad at L = 2.5e-4 * ext, a fifth of the 0.01 rad
+// every edge pair keeps from parallel under the angle test -- the determinants stay well conditioned and a computed
+// (t1, t2) in [0,1]^2 would put a common point within 3 * 2^-22 * ext / |sin phi| < 1e-4 * ext of both segments,
+// impossible when they are `gap` apart.  The vertex-in-box test (:131-166) of a point at distance >= gap violates
+// one of its four inequalities by >= (gap / sqrt 2) * L against an evaluation error <= 5e-7 * ext^2 + 7e-7 * ext * L;
+// with a 4x safety factor that needs  gap * L > 3e-6 * ext^2.  The fast test's 10 % circle margin gives
+// gap > 0.039 * ext, so L > 2.5e-4 * ext suffices there; the full test states the product rule explicitly.
+// (Round 1 required L > 2e-3 * ext, which sent every far-away pair with a < 4 px box side -- 57 % of all clipped
+// pairs of BASELINE config 4 -- through the clipper for a result of exactly zero.)
+#define RB_SLIVER 2.5e-4f
+#define RB_GAPRULE 3e-6f
+
+// Stage 1 (every pair, ~25 flops, no divergence): the common case "circles clearly apart (10 %), edges clearly
 // not parallel, no sliver" -> exactly zero.  Everything else is RB_MAYBE and goes to stage 2.
 // `ext` over-estimates the pair's extent with the L1 norm (conservative: margins only grow).
 enum { RB_ZERO = 0, RB_CLIP = 1, RB_MAYBE = 2 };
@@ -98,9 +112,26 @@ RB_HD int rbox_classify_fast(const RBox& A, const RBox& B) {
   const float sd = B.s2 * A.c2 - B.c2 * A.s2;        // sin(tB - tA)/4
   const float cd = A.c2 * B.c2 + A.s2 * B.s2;        // cos(tB - tA)/4
   const float ext = fabsf(dx) + fabsf(dy) + rs;
-  const bool ok = (dx * dx + dy * dy > 1.0201f * rs * rs) && (fabsf(sd * cd) > 0.000625f) &&
-                  (fminf(A.mn, B.mn) > 2e-3f * ext);
+  const bool ok = (dx * dx + dy * dy > 1.21f * rs * rs) && (fabsf(sd * cd) > 0.000625f) &&
+                  (fminf(A.mn, B.mn) > RB_SLIVER * ext);
   return ok ? RB_ZERO : RB_MAYBE;
+}
+
+// The same test on the 24-byte per-box summary the IoU kernel keeps for its all-pairs pass: (x, y, r, mn) and
+// (sin 2t, cos 2t).  |sin 2(tB - tA)| > 0.02 is the angle condition above (|sd * cd| = |sin 2 dT| / 32).
+struct RFast { float x, y, r, mn; };
+struct RAng { float s2t, c2t; };
+RB_HD void rbox_fast_of(const RBox& b, RFast& f, RAng& a) {
+  f.x = b.x; f.y = b.y; f.r = b.r; f.mn = b.mn;
+  a.s2t = 8.0f * b.s2 * b.c2;                        // 2 sin cos
+  a.c2t = 4.0f * (b.c2 * b.c2 - b.s2 * b.s2);        // cos^2 - sin^2
+}
+RB_HD bool rbox_fast_zero(const RFast& A, const RAng& aA, const RFast& B, const RAng& aB) {
+  const float dx = B.x - A.x, dy = B.y - A.y;
+  const float rs = A.r + B.r;
+  const float ext = fabsf(dx) + fabsf(dy) + rs;
+  const float s2d = aB.s2t * aA.c2t - aB.c2t * aA.s2t;
+  return (dx * dx + dy * dy > 1.21f * rs * rs) && (fabsf(s2d) > 0.02f) && (fminf(A.mn, B.mn) > RB_SLIVER * ext);
 }
 
 RB_HD int rbox_classify(const RBox& A, const RBox& B) {
@@ -118,13 +149,18 @@ RB_HD int rbox_classify(const RBox& A, const RBox& B) {
   // centre offset in A's frame and in B's frame
   const float duA = 2.0f * (dx * A.c2 + dy * A.s2), dvA = 2.0f * (dy * A.c2 - dx * A.s2);
   bool sep = d2 > 1.0201f * rs * rs;
+  // lower bound of the distance between the boxes: circles |d| - rs = (d2 - rs^2) / (|d| + rs) >= (d2 - rs^2) / ext;
+  // separating axis: the margin itself
+  float gap = (d2 - rs * rs) / ext;
   if (!sep) {
     const float mg = 4e-3f * ext;
+    gap = mg;
     const float duB = 2.0f * (dx * B.c2 + dy * B.s2), dvB = 2.0f * (dy * B.c2 - dx * B.s2);
     sep = (fabsf(duA) > 0.5f * (wA + wB * C + hB * S) + mg) || (fabsf(dvA) > 0.5f * (hA + wB * S + hB * C) + mg) ||
           (fabsf(duB) > 0.5f * (wB + wA * C + hA * S) + mg) || (fabsf(dvB) > 0.5f * (hB + wA * S + hA * C) + mg);
   }
-  if (sep && fminf(A.mn, B.mn) > 2e-3f * ext) {
+  const float mnp = fminf(A.mn, B.mn);
+  if (sep && mnp > RB_SLIVER * ext && gap * mnp > RB_GAPRULE * ext * ext) {
     // |sd*cd| = |sin(2 dT)|/32
     if (fabsf(sd * cd) > 0.000625f) return RB_ZERO;
     // near-parallel (C >= S) or near-perpendicular: B's half extents along A's axes

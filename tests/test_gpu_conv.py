@@ -191,3 +191,43 @@ def test_p3_full_size_vs_torch_and_reference_cuda():
                                         3, 3, 1, 1, 1, 1, 1, 1, 1, 1, 1)
         e2 = float((y - torch.relu(out)).abs().max())
         assert e2 <= ATOL + RTOL * float(out.abs().max()), e2
+
+
+def test_orconv2d_and_pooling_keep_the_autograd_graph(oracle):
+    """with grad enabled ORConv2d must take the differentiable route (ARF autograd Function +
+    F.conv2d, reference ORConv.py:77-82) -- the fused kernel builds no graph.  Gradients are compared with a pure
+    torch formulation of the same layer (index gather of the rotated bank + F.conv2d + view/max)."""
+    from s2anet_b200.orn import ORConv2d, RotationInvariantPooling
+    torch.backends.cudnn.allow_tf32 = False
+    g = torch.Generator().manual_seed(4)
+    m = ORConv2d(16, 4, 3, padding=1, arf_config=(1, 8)).to(DEV)
+    m.fuse_pool = True
+    pool = RotationInvariantPooling(32, 8)
+    x = torch.randn(2, 16, 9, 11, generator=g).to(DEV).requires_grad_(True)
+    y = m(x)
+    assert y.requires_grad and getattr(y, "_s2a_pooled", None) is None
+    z = pool(y)
+    assert z.requires_grad
+    (y.square().sum() + z.sum()).backward()
+    gw, gb, gx = m.weight.grad.clone(), m.bias.grad.clone(), x.grad.clone()
+    # pure-torch twin
+    w2 = m.weight.detach().clone().requires_grad_(True)
+    b2 = m.bias.detach().clone().requires_grad_(True)
+    x2 = x.detach().clone().requires_grad_(True)
+    idx = m.indices.long().reshape(9, 8) - 1                           # [entry l, rotation k] -> source tap (nOri = 1)
+    # ARF forward (ActiveRotatingFilter_cuda.cu:31-45): out[o*8 + k, i, idx[l, k]] = w[o, i, l]
+    wf = w2.reshape(4, 16, 9)
+    bank = torch.zeros(4, 8, 16, 9, device=DEV)
+    bank = bank.scatter(3, idx.t()[None, :, None, :].expand(4, 8, 16, 9), wf[:, None].expand(4, 8, 16, 9))
+    bank = bank.reshape(32, 16, 3, 3)
+    assert torch.equal(bank.detach(), m.rotate_arf().detach())
+    y2 = torch.nn.functional.conv2d(x2, bank, b2, padding=1)
+    z2 = y2.view(2, 4, 8, 9, 11).max(dim=2)[0]
+    (y2.square().sum() + z2.sum()).backward()
+    for a, b in ((gw, w2.grad), (gb, b2.grad), (gx, x2.grad)):
+        assert float((a - b).abs().max()) <= 1e-4 * float(b.abs().max()) + 1e-6
+    # inference keeps the fused kernel (and its pooled by-product)
+    with torch.no_grad():
+        yi = m(x.detach())
+    assert getattr(yi, "_s2a_pooled", None) is not None
+    np.testing.assert_allclose(yi.cpu().numpy(), y.detach().cpu().numpy(), rtol=RTOL, atol=ATOL)

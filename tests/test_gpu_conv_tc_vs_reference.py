@@ -140,10 +140,17 @@ def test_generic_16bit_entry_other_geometries_and_autograd_function(ref_dc):
     off = (torch.randn(2, 18, 9, 10, generator=g) * 2).to(DEV).half()
     with torch.no_grad():
         y = m(x, off)
-    out = y.new_empty(y.shape)
-    ref_dc.deform_conv_forward_cuda(x, m.weight, off, out, x.new_empty(0), x.new_empty(0), 3, 3, 2, 2, 1, 1, 1, 1, 1, 1, 2)
-    e = errs(y, out)
-    assert y.dtype == torch.float16 and e["rel_l2"] <= 5e-3, e
+    w = m.weight.detach()
+    out16 = y.new_empty(y.shape)
+    ref_dc.deform_conv_forward_cuda(x, w, off, out16, x.new_empty(0), x.new_empty(0), 3, 3, 2, 2, 1, 1, 1, 1, 1, 1, 2)
+    out32 = y.new_empty(y.shape, dtype=torch.float32)
+    ref_dc.deform_conv_forward_cuda(x.float(), w.float(), off.float(), out32, x.new_empty(0).float(), x.new_empty(0).float(),
+                                    3, 3, 2, 2, 1, 1, 1, 1, 1, 1, 2)
+    # exact fp32 arithmetic on the half operands, rounded once: tight against the reference's fp32 run; the reference's
+    # own half run (positions rounded to half, measured 5e-3 .. 3e-2 from its fp32 run) is further away than we are
+    e32, e16 = errs(y, out32), errs(y, out16)
+    assert y.dtype == torch.float16 and e32["rel_l2"] <= 1e-3, e32
+    assert e16["rel_l2"] <= 2e-2 and e32["rel_l2"] <= errs(out16, out32)["rel_l2"], (e16, e32)
 
 
 def test_orconv_tc_vs_reference_arf_binary_and_cudnn():
