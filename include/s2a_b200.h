@@ -60,6 +60,17 @@ S2A_EXPORT const char* s2a_last_error(void);
 S2A_EXPORT int s2a_box_iou_rotated(const float* boxes1, int64_t n, const float* boxes2, int64_t m,
                                    int64_t batch, float* out, int64_t ld_out, int64_t row_begin,
                                    int64_t row_end, int flags, void* stream);
+/* The same matrix, sharded by ROW TILES for several GPUs (the anchor x GT matrix shards by anchor
+ * rows): the n rows are cut into tiles of tile_rows (a multiple of 32, <= 256; 0 = 256) and this call computes the
+ * tiles tile_first, tile_first + tile_step, tile_first + 2 tile_step, ... -- rank r of w ranks passes (r, w), which
+ * deals the tiles out cyclically (contiguous row blocks would hand one rank all the large P5-P7 anchors, whose pairs
+ * mostly reach the clipper).  compact = 0: rows are written at their global index of a [batch, n, ld_out] output;
+ * compact != 0: out holds only this call's tiles, packed in order ([batch, ntiles_mine * tile_rows, ld_out]).
+ * out_batch_stride (elements) = 0 selects the dense value of either layout. */
+S2A_EXPORT int s2a_box_iou_rotated_tiles(const float* boxes1, int64_t n, const float* boxes2, int64_t m,
+                                         int64_t batch, float* out, int64_t ld_out, int64_t out_batch_stride,
+                                         int tile_rows, int tile_first, int tile_step, int compact, int flags,
+                                         void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * nms_rotated / ml_nms_rotated -- replace nms_rotated_cuda()

@@ -51,6 +51,43 @@ def box_iou_rotated_batched(boxes1, boxes2, row_begin=0, row_end=None, out=None,
     return out
 
 
+IOU_TILE_ROWS = 256     # kIouRowsMax in csrc/box_iou_rotated.cu: the unit the anchor rows are dealt out in
+
+
+def tile_rows_of(n, tile_first, tile_step, tile_rows=IOU_TILE_ROWS):
+    """Global row indices (a LongTensor on the CPU) of the row tiles tile_first, tile_first + tile_step, ... of an
+    n-row matrix, in the packed order s2a_box_iou_rotated_tiles(compact=1) writes them."""
+    ntiles = -(-n // tile_rows)
+    rows = [torch.arange(t * tile_rows, min(n, (t + 1) * tile_rows)) for t in range(tile_first, ntiles, tile_step)]
+    return torch.cat(rows) if rows else torch.zeros((0,), dtype=torch.long)
+
+
+def box_iou_rotated_tiles(boxes1, boxes2, tile_first, tile_step, compact=True, out=None, tile_rows=IOU_TILE_ROWS,
+                          _flags=0):
+    """The anchor-row shard of one rank: boxes1 [B,N,5], boxes2 [B,M,5]; the N rows are cut into tiles
+    of `tile_rows` and tiles tile_first, tile_first + tile_step, ... are computed (rank r of w: (r, w) -- a cyclic
+    deal, so every rank gets the same mix of FPN levels).  compact=True returns [B, n_mine_padded, M] holding only
+    those tiles, packed (n_mine_padded = tiles x tile_rows; `tile_rows_of` maps packed rows back to anchors);
+    compact=False writes them at their global rows of a [B,N,M] tensor (`out`, or a new uninitialised one)."""
+    dev = _lib.require_cuda(boxes1, boxes2)
+    B, n, _ = boxes1.shape
+    m = boxes2.size(1)
+    if boxes2.size(0) != B:
+        raise ValueError("batch mismatch")
+    ntiles = -(-n // tile_rows)
+    mine = len(range(tile_first, ntiles, tile_step))
+    if out is None:
+        out = torch.empty((B, mine * tile_rows if compact else n, m), dtype=torch.float32, device=dev)
+    b1 = boxes1.to(torch.float32).contiguous()
+    b2 = boxes2.to(torch.float32).contiguous()
+    with torch.cuda.device(dev):
+        rc = _lib.load().s2a_box_iou_rotated_tiles(_lib.ptr(b1), n, _lib.ptr(b2), m, B, _lib.ptr(out), out.stride(1),
+                                                   out.stride(0), tile_rows, tile_first, tile_step, 1 if compact else 0,
+                                                   _flags, _lib.stream_ptr(dev))
+    _lib.check(rc, "box_iou_rotated_tiles")
+    return out
+
+
 def bbox_iou_rotated(rboxes1, rboxes2):
     """reference: utils/metrics.py:85-107 -- accepts 5- or 6-column boxes, casts to fp32."""
     assert rboxes1.size(-1) in [0, 5, 6]

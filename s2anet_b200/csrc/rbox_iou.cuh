@@ -119,8 +119,8 @@ RB_HD int rbox_classify_fast(const RBox& A, const RBox& B) {
 
 // The same test on the 24-byte per-box summary the IoU kernel keeps for its all-pairs pass: (x, y, r, mn) and
 // (sin 2t, cos 2t).  |sin 2(tB - tA)| > 0.02 is the angle condition above (|sd * cd| = |sin 2 dT| / 32).
-struct RFast { float x, y, r, mn; };
-struct RAng { float s2t, c2t; };
+struct __align__(16) RFast { float x, y, r, mn; };
+struct __align__(8) RAng { float s2t, c2t; };
 RB_HD void rbox_fast_of(const RBox& b, RFast& f, RAng& a) {
   f.x = b.x; f.y = b.y; f.r = b.r; f.mn = b.mn;
   a.s2t = 8.0f * b.s2 * b.c2;                        // 2 sin cos
@@ -217,10 +217,11 @@ RB_HD void rbox_vertices(float xc, float yc, const RBox& b, float (&px)[4], floa
   py[3] = RB_SUB(ty, py[1]);
 }
 
-// The clipper: candidate points (:77-167), in-place Graham hull in the CUDA build's exchange-sort
-// order (:169-282), fan area (:284-296), iou = inter / (a1 + a2 - inter) (:361-362, unclamped).
-// Returns the IoU.  Precondition: both areas >= 1e-14 (rbox_classify handled the early-out).
-RB_HD float rbox_iou_clip(const RBox& A, const RBox& B) {
+// Candidate points of the intersection polygon (:77-167): the edge-edge crossings in (i, j) order, then the vertices
+// of box 1 inside box 2, then the vertices of box 2 inside box 1 -- up to 24.  Every point goes to `sink.put(k, x, y)`
+// (k = its ordinal); returns the count.  One source for all clippers below, so they see bit-identical points.
+template <class Sink>
+RB_HD int rbox_candidates(const RBox& A, const RBox& B, Sink& sink) {
   // centre shift (:340-349): fp32 sum, exact halving, subtraction that is exact in double and
   // rounds once -- identical to the fp32 expression below for all finite pixel-scale inputs.
   float shx = RB_MUL(RB_ADD(A.x, B.x), 0.5f);
@@ -238,7 +239,6 @@ RB_HD float rbox_iou_clip(const RBox& A, const RBox& B) {
     e2y[i] = RB_SUB(p2y[(i + 1) & 3], p2y[i]);
   }
 
-  float qx[24], qy[24];
   int n = 0;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -259,8 +259,7 @@ RB_HD float rbox_iou_clip(const RBox& A, const RBox& B) {
       float t1 = RB_DIV(n1, det);
       float t2 = RB_DIV(n2, det);
       if (t1 >= 0.0f && t1 <= 1.0f && t2 >= 0.0f && t2 <= 1.0f) {
-        qx[n] = RB_ADD(p1x[i], RB_MUL(e1x[i], t1));
-        qy[n] = RB_ADD(p1y[i], RB_MUL(e1y[i], t1));
+        sink.put(n, RB_ADD(p1x[i], RB_MUL(e1x[i], t1)), RB_ADD(p1y[i], RB_MUL(e1y[i], t1)));
         ++n;
       }
     }
@@ -274,7 +273,7 @@ RB_HD float rbox_iou_clip(const RBox& A, const RBox& B) {
       float apab = rb_dot(apx, apy, e2x[0], e2y[0]);
       float apad = -rb_dot(apx, apy, e2x[3], e2y[3]);
       if (apab >= 0.0f && apad >= 0.0f && apab <= abab && apad <= adad) {
-        qx[n] = p1x[i]; qy[n] = p1y[i]; ++n;
+        sink.put(n, p1x[i], p1y[i]); ++n;
       }
     }
   }
@@ -287,12 +286,16 @@ RB_HD float rbox_iou_clip(const RBox& A, const RBox& B) {
       float apab = rb_dot(apx, apy, e1x[0], e1y[0]);
       float apad = -rb_dot(apx, apy, e1x[3], e1y[3]);
       if (apab >= 0.0f && apad >= 0.0f && apab <= abab && apad <= adad) {
-        qx[n] = p2x[i]; qy[n] = p2y[i]; ++n;
+        sink.put(n, p2x[i], p2y[i]); ++n;
       }
     }
   }
+  return n;
+}
 
-  float a1 = RB_MUL(A.w, A.h), a2 = RB_MUL(B.w, B.h);
+// Hull + area on a 24-point array (the general path): in-place Graham hull in the CUDA build's exchange-sort order
+// (:169-282), fan area (:284-296).  Returns the intersection area.
+RB_HD float rbox_hull_area(float* qx, float* qy, int n) {
   float inter = 0.0f;
   if (n > 2) {
     // lowest point (min y, then min x), shift every point by it, move it to slot 0
@@ -344,7 +347,122 @@ RB_HD float rbox_iou_clip(const RBox& A, const RBox& B) {
       }
     }
   }
+  return inter;
+}
+
+struct RbArraySink {
+  float* qx; float* qy;
+  RB_HD void put(int k, float x, float y) { qx[k] = x; qy[k] = y; }
+};
+
+// The general clipper (thread-local 24-point arrays): iou = inter / (a1 + a2 - inter) (:361-362, unclamped).
+// Precondition: both areas >= 1e-14 (rbox_classify handled the early-out).
+RB_HD float rbox_iou_clip(const RBox& A, const RBox& B) {
+  float qx[24], qy[24];
+  RbArraySink sink{qx, qy};
+  const int n = rbox_candidates(A, B, sink);
+  const float inter = rbox_hull_area(qx, qy, n);
+  const float a1 = RB_MUL(A.w, A.h), a2 = RB_MUL(B.w, B.h);
   return RB_DIV(inter, RB_SUB(RB_ADD(a1, a2), inter));
+}
+
+// ---- register-resident hull for 3 <= n <= 8 ------------------------------------------------------------------
+// Two convex quadrilaterals in general position intersect in at most 8 points and every candidate is a vertex of the
+// intersection polygon (21.8 M anchor x GT pairs of BASELINE config 4: n in {0, 3..8}, never more).  For those the
+// reference's hull construction is a fixed sequence: the exchange sort (:209-226) is the comparator network
+// (i, j), 1 <= i < j < n, whatever the data -- 21 compare-exchanges on 8 named registers, predicated on j < n -- and the
+// Graham scan (:243-268) pops nothing when the sorted points are strictly convex.  This routine runs exactly the
+// reference's operations in that case and REPORTS (returns false) instead of guessing in every other: the second
+// point coincides with the first (:234-241 would skip it) or any scan step would pop (cr >= 0, :254).  The caller
+// then runs the general clipper.  All indices are compile-time constants: no local memory.
+RB_HD bool rbox_hull8(float (&qx)[8], float (&qy)[8], int n, float& inter) {
+  // lowest point (min y, then min x)
+  int t = 0;
+  float sx = qx[0], sy = qy[0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i)
+    if (i < n && (qy[i] < sy || (qy[i] == sy && qx[i] < sx))) { t = i; sx = qx[i]; sy = qy[i]; }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { qx[i] = RB_SUB(qx[i], sx); qy[i] = RB_SUB(qy[i], sy); }
+  {  // swap q[0] <-> q[t]
+    const float t0x = qx[0], t0y = qy[0];
+    float zx = t0x, zy = t0y;
+#pragma unroll
+    for (int i = 1; i < 8; ++i)
+      if (i == t) { zx = qx[i]; zy = qy[i]; qx[i] = t0x; qy[i] = t0y; }
+    qx[0] = zx; qy[0] = zy;
+  }
+  // exchange sort by polar angle; 1e-6 collinearity band, squared-distance tie break
+#pragma unroll
+  for (int i = 1; i < 7; ++i) {
+    float ax = qx[i], ay = qy[i];
+#pragma unroll
+    for (int j = i + 1; j < 8; ++j) {
+      if (j < n) {
+        const float bx = qx[j], by = qy[j];
+        const float cp = rb_cross(ax, ay, bx, by);
+        bool sw = (cp <= -RB_HI_1E6);
+        if (!sw && fabsf(cp) <= RB_LO_1E6) sw = rb_dot(ax, ay, ax, ay) > rb_dot(bx, by, bx, by);
+        if (sw) { qx[j] = ax; qy[j] = ay; ax = bx; ay = by; }
+      }
+    }
+    qx[i] = ax; qy[i] = ay;
+  }
+  bool ok = rb_dot(qx[1], qy[1], qx[1], qy[1]) >= RB_HI_1E8;      // k == 1: the second point is not a copy of the first
+#pragma unroll
+  for (int i = 2; i < 8; ++i) {
+    if (i < n) {
+      const float ox = qx[i - 2], oy = qy[i - 2];
+      const float cr = rb_cross(RB_SUB(qx[i], ox), RB_SUB(qy[i], oy), RB_SUB(qx[i - 1], ox), RB_SUB(qy[i - 1], oy));
+      ok = ok && !(cr >= 0.0f);                                   // the scan would not pop
+    }
+  }
+  float area = 0.0f;
+  const float ox = qx[0], oy = qy[0];
+#pragma unroll
+  for (int i = 1; i < 7; ++i)
+    if (i < n - 1)
+      area = RB_ADD(area, fabsf(rb_cross(RB_SUB(qx[i], ox), RB_SUB(qy[i], oy), RB_SUB(qx[i + 1], ox), RB_SUB(qy[i + 1], oy))));
+  inter = RB_MUL(area, 0.5f);
+  return ok;
+}
+
+// Candidate points staged through a caller-provided scratch column (shared memory on the device: element k of this
+// thread at scratch[k * stride], x in [0, 8), y in [8, 16)) -- dynamic indexing happens in the ADDRESS, the points
+// then come back into 16 named registers for rbox_hull8.  Falls back to the general clipper when n > 8 or the hull is
+// not the generic strictly convex one.  Bit-identical to rbox_iou_clip.
+struct RbScratchSink {
+  float* s; int stride;
+  RB_HD void put(int k, float x, float y) {
+    if (k < 8) { s[k * stride] = x; s[(8 + k) * stride] = y; }
+  }
+};
+
+// `ok` = false: not the generic case, the value is meaningless and the caller must run rbox_iou_clip instead (kept
+// out of line by the kernels: it is the only code that touches local memory).
+RB_HD float rbox_iou_clip_try(const RBox& A, const RBox& B, float* scratch, int stride, bool& ok) {
+  RbScratchSink sink{scratch, stride};
+  const int n = rbox_candidates(A, B, sink);
+  const float a1 = RB_MUL(A.w, A.h), a2 = RB_MUL(B.w, B.h);
+  float inter = 0.0f;
+  ok = n <= 8;
+  if (n > 2 && ok) {
+    float qx[8], qy[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      // (slots >= n hold stale values of earlier pairs: never read by a predicated step)
+      qx[k] = scratch[k * stride];
+      qy[k] = scratch[(8 + k) * stride];
+    }
+    ok = rbox_hull8(qx, qy, n, inter);
+  }
+  return RB_DIV(inter, RB_SUB(RB_ADD(a1, a2), inter));
+}
+
+RB_HD float rbox_iou_clip_fast(const RBox& A, const RBox& B, float* scratch, int stride) {
+  bool ok;
+  const float v = rbox_iou_clip_try(A, B, scratch, stride, ok);
+  return ok ? v : rbox_iou_clip(A, B);
 }
 
 // Full semantic of single_box_iou_rotated on prepared boxes (:333-375).

@@ -7,7 +7,7 @@
 
 extern "C" {
 
-// mode 0: classify + clip (what the kernels do); mode 1: clip for every pair that passes the
+// mode 0: classify + clip (what the NMS kernels do); modes 3 / 4: the IoU kernel's path (see below); mode 1: clip for every pair that passes the
 // reference's own area early-out (no disjointness shortcut); mode 2: returns the class (0/1).
 void hh_pairwise(const float* b1, int64_t n, const float* b2, int64_t m, float* out, int mode) {
   s2a::RBox* A = new s2a::RBox[n > 0 ? n : 1];
@@ -17,8 +17,18 @@ void hh_pairwise(const float* b1, int64_t n, const float* b2, int64_t m, float* 
   for (int64_t i = 0; i < n; ++i)
     for (int64_t j = 0; j < m; ++j) {
       float v;
+      float scratch[16];
       if (mode == 0) v = s2a::rbox_iou(A[i], B[j]);
       else if (mode == 2) v = (float)s2a::rbox_classify(A[i], B[j]);
+      else if (mode == 3) {          // what box_iou_rotated_kernel does: fast test -> full classify -> register clipper
+        s2a::RFast fa, fb; s2a::RAng aa, ab;
+        s2a::rbox_fast_of(A[i], fa, aa); s2a::rbox_fast_of(B[j], fb, ab);
+        if (s2a::rbox_fast_zero(fa, aa, fb, ab) || s2a::rbox_classify(A[i], B[j]) == s2a::RB_ZERO) v = 0.0f;
+        else v = s2a::rbox_iou_clip_fast(A[i], B[j], scratch, 1);
+      } else if (mode == 4) {        // register clipper for every pair that passes the area early-out
+        float a1 = A[i].w * A[i].h, a2 = B[j].w * B[j].h;
+        v = ((double)a1 < 1e-14 || (double)a2 < 1e-14) ? 0.0f : s2a::rbox_iou_clip_fast(A[i], B[j], scratch, 1);
+      }
       else {
         float a1 = A[i].w * A[i].h, a2 = B[j].w * B[j].h;
         v = ((double)a1 < 1e-14 || (double)a2 < 1e-14) ? 0.0f : s2a::rbox_iou_clip(A[i], B[j]);

@@ -20,10 +20,17 @@ def _free_port():
     return p
 
 
-def _oracle_iou_fn(a, g, rb, re, out):
+def _oracle_iou_fn(a, g, tile_first, tile_step, tile_rows):
+    """Same contract as box_iou_rotated_tiles(compact=True), computed by the CPU oracle."""
     from oracle import oracle as O
-    for b in range(a.size(0)):
-        out[b, rb:re] = torch.from_numpy(O.box_iou_rotated(a[b, rb:re].numpy(), g[b].numpy()))
+    B, N, M = a.size(0), a.size(1), g.size(1)
+    ntiles = -(-N // tile_rows)
+    tiles = list(range(tile_first, ntiles, tile_step))
+    out = torch.full((B, len(tiles) * tile_rows, M), float("nan"))
+    for k, t in enumerate(tiles):
+        r0, r1 = t * tile_rows, min(N, (t + 1) * tile_rows)
+        for b in range(B):
+            out[b, k * tile_rows:k * tile_rows + (r1 - r0)] = torch.from_numpy(O.box_iou_rotated(a[b, r0:r1].numpy(), g[b].numpy()))
     return out
 
 
@@ -36,17 +43,17 @@ def _worker(rank, world, port, q):
     from s2anet_b200 import dist as sd
     from s2anet_b200 import synth
     try:
-        B, N, M = 2, 333, 40
+        B, N, M, T = 2, 333, 40, 32            # 11 tiles of 32 rows (the last one partial): ranks get 6 and 5
         an = torch.from_numpy(synth.all_level_anchors(B, 3)[:, :N].copy())
         gt = torch.from_numpy(np.stack([synth.dota_like_gt(M, 50 + i) for i in range(B)]))
-        ref = torch.empty(B, N, M)
-        _oracle_iou_fn(an, gt, 0, N, ref)
-        full = sd.sharded_box_iou(an, gt, iou_fn=_oracle_iou_fn, gather=True)
+        ref = _oracle_iou_fn(an, gt, 0, 1, T)[:, :N]
+        full = sd.sharded_box_iou(an, gt, iou_fn=_oracle_iou_fn, gather=True, tile_rows=T)
         assert torch.equal(full, ref), "all-gathered IoU differs from the single-process matrix"
-        row_max, row_arg, gt_max, (b0, e0), local = sd.sharded_assign_stats(an, gt, iou_fn=_oracle_iou_fn)
-        assert (b0, e0) == sd.shard_rows(N, rank, world)
-        assert torch.equal(local, ref[:, b0:e0])
-        assert torch.equal(row_max, ref[:, b0:e0].max(dim=2)[0]) and torch.equal(row_arg, ref[:, b0:e0].max(dim=2)[1])
+        row_max, row_arg, gt_max, rows, local = sd.sharded_assign_stats(an, gt, iou_fn=_oracle_iou_fn, tile_rows=T)
+        tiles, rows_expect = sd.shard_tiles(N, rank, world, T)
+        assert tiles == list(range(rank, 11, world)) and torch.equal(rows, rows_expect)
+        assert local.size(1) == rows.numel() and torch.equal(local, ref[:, rows])
+        assert torch.equal(row_max, ref[:, rows].max(dim=2)[0]) and torch.equal(row_arg, ref[:, rows].max(dim=2)[1])
         assert torch.equal(gt_max, ref.max(dim=1)[0]), "per-GT maxima after MAX all-reduce"
         # detections: each rank contributes its own images
         K = 5
@@ -76,6 +83,22 @@ def test_shard_rows_cover_exactly():
                 assert a1 == b0 and a0 <= a1
             assert all(b % 64 == 0 for b, _ in spans if b < n)
     assert shard_rows(21824, 7, 8) == (19264, 21824)
+
+
+def test_shard_tiles_deal_rows_cyclically_and_cover_exactly():
+    from s2anet_b200.box_iou_rotated import tile_rows_of
+    from s2anet_b200.dist import shard_tiles
+    for n in (0, 1, 255, 256, 257, 21824, 1000):
+        for world in (1, 2, 3, 8):
+            seen = torch.cat([shard_tiles(n, r, world)[1] for r in range(world)])
+            assert sorted(seen.tolist()) == list(range(n))
+            for r in range(world):
+                assert torch.equal(shard_tiles(n, r, world)[1], tile_rows_of(n, r, world))
+    # BASELINE config 4 on 8 GPUs: 86 tiles of 256 rows; every rank owns tiles of every FPN level's range it can
+    tiles, rows = shard_tiles(21824, 7, 8)
+    assert tiles == list(range(7, 86, 8)) and rows.numel() == 10 * 256
+    tiles0, rows0 = shard_tiles(21824, 5, 8)                 # the partial last tile (85) belongs to rank 5
+    assert tiles0[-1] == 85 and rows0.numel() == 10 * 256 + (21824 - 85 * 256)
 
 
 def test_two_rank_gloo():

@@ -109,6 +109,42 @@ def test_iou_full_size_properties():
     assert float((d - 1).abs().max()) <= 1e-5
 
 
+@pytest.mark.parametrize("world,tile_rows", [(1, 256), (2, 256), (8, 256), (3, 64), (5, 32)])
+def test_iou_row_tiles_dealt_cyclically(world, tile_rows):
+    """The multi-GPU form (s2a_box_iou_rotated_tiles): the union of the ranks' cyclically dealt row tiles, packed or
+    written in place, is bit-identical to the one-call matrix; slivers, a partial last tile and partial column tiles
+    included."""
+    from s2anet_b200.box_iou_rotated import box_iou_rotated_batched, box_iou_rotated_tiles, tile_rows_of
+    B = 2
+    an = synth.all_level_anchors(B, 5)[:, ::4][:, :5021].copy()           # 5,021 rows: a partial last tile
+    gt = np.stack([synth.dota_like_gt(300, 40 + i) for i in range(B)])
+    gt[:, ::9, 3] = 0.7                                                   # sub-pixel slivers
+    ta, tg = torch.from_numpy(an).to(DEV), torch.from_numpy(gt).to(DEV)
+    full = box_iou_rotated_batched(ta, tg)
+    assert torch.equal(full, box_iou_rotated_batched(ta, tg, _flags=1))   # reject tests on / off
+    inplace = torch.full_like(full, -3.0)
+    for r in range(world):
+        rows = tile_rows_of(an.shape[1], r, world, tile_rows).to(DEV)
+        packed = box_iou_rotated_tiles(ta, tg, r, world, compact=True, tile_rows=tile_rows)
+        assert packed.size(1) % tile_rows == 0 and packed.size(1) >= rows.numel()
+        assert torch.equal(packed[:, : rows.numel()], full[:, rows])
+        box_iou_rotated_tiles(ta, tg, r, world, compact=False, out=inplace, tile_rows=tile_rows)
+    assert torch.equal(inplace, full)
+
+
+def test_iou_degenerate_pairs_take_the_general_clipper(oracle):
+    """Pairs the register-resident hull refuses (more than eight candidate points, coincident candidates, collinear
+    triples: identical boxes, shared edges and corners, axis-aligned grid anchors against themselves) fall back to
+    the general 24-point routine inside the same kernel: still bit-identical to the oracle."""
+    ga = np.concatenate([synth.grid_anchors(16, 16, 8).reshape(-1, 5), synth.grid_anchors(8, 8, 16).reshape(-1, 5)])
+    assert_iou_parity(gpu_iou(ga, ga), oracle.box_iou_rotated(ga, ga))
+    adv = synth.adversarial_boxes()
+    assert_iou_parity(gpu_iou(adv, ga[::3]), oracle.box_iou_rotated(adv, ga[::3]))
+    rot = ga.copy()
+    rot[:, 4] = np.float32(np.pi / 4)
+    assert_iou_parity(gpu_iou(rot, ga), oracle.box_iou_rotated(rot, ga))
+
+
 def gpu_nms(b, s, thr, labels=None):
     from s2anet_b200.nms_rotated import ml_nms_rotated, nms_rotated_op
     tb, ts = torch.from_numpy(b).to(DEV), torch.from_numpy(s).to(DEV)

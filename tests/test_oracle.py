@@ -192,9 +192,25 @@ def test_product_iou_source_on_host(oracle, host_harness):
     col = np.repeat(base, len(shifts), 0)
     col[:, :2] += shifts
     sets.append((col, col))
+    # slivers (sides down to 1e-4 of the pair distance and far beyond the guard) near and far from fat boxes, at
+    # generic and at shared angles: the relaxed sliver guard (rbox_iou.cuh "Sliver guard") must still only ever
+    # predict an exact zero where the reference computes one
+    rng = np.random.default_rng(11)
+    n = 400
+    thin = np.stack([rng.uniform(0, 2048, n), rng.uniform(0, 2048, n), 10 ** rng.uniform(0.5, 2.7, n),
+                     10 ** rng.uniform(-4, 0.7, n), rng.uniform(-np.pi / 4, 3 * np.pi / 4, n)], 1).astype(np.float32)
+    thin[::7, 4] = 0.0
+    thin[1::7, 4] = np.float32(np.pi / 2)
+    thin[2::7, 2:4] = thin[2::7, 3:1:-1]
+    fat = synth.dota_like_gt(300, 13)
+    fat[::5, 4] = 0.0
+    sets.append((thin, fat))
+    sets.append((thin, thin))
     for b1, b2 in sets:
         ref = oracle.box_iou_rotated(b1, b2)
-        for mode in (0, 1):
+        # 0 / 1: the general clipper with / without the reject tests; 3 / 4: the IoU kernel's path (fast test -> full
+        # classify -> register-resident hull with fall-back) with / without them
+        for mode in (0, 1, 3, 4):
             np.testing.assert_array_equal(bits(host_harness(b1, b2, mode)), bits(ref))
 
 
