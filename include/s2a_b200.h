@@ -111,6 +111,18 @@ S2A_EXPORT int s2a_multiclass_nms_rotated(const float* bboxes, const float* scor
                                           float iou_thr, int64_t max_per_img, float* dets_out,
                                           float* labels_out, int32_t* num_out, int64_t max_out,
                                           void* workspace, size_t workspace_bytes, void* stream);
+/* The same NMS with the detection exchange of SURVEY.md 8e fused into its finaliser: instead of dets / labels /
+ * counts, every kept detection is stored as a 7-float row (x, y, w, h, theta, score, label) into the packed buffers
+ * dests[0 .. ndests-1], each [slots, max_out + 1, 7] fp32, at image slot slot0 + b; row max_out of a slot holds the
+ * count in column 0.  With ndests = 1 this is the "pack" of the NCCL all-gather done by the kernel that produces the
+ * detections; with ndests = world the destinations are the ranks' symmetric buffers (this rank's own and its peers'
+ * NVLink-mapped pointers, <= 8) and the stores ARE the all-gather -- the caller only adds a barrier
+ * (s2anet_b200/dist.py, DetectionExchange).  Rows past the count are unspecified. */
+S2A_EXPORT int s2a_multiclass_nms_rotated_packed(const float* bboxes, const float* scores, int64_t n,
+                                                 int64_t num_classes, int64_t batch, float score_thr,
+                                                 float iou_thr, int64_t max_per_img, float* const* dests,
+                                                 int ndests, int64_t slot0, int64_t max_out, void* workspace,
+                                                 size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * ORN: active rotating filters and rotation-invariant pooling

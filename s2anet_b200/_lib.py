@@ -28,6 +28,8 @@ PROTOTYPES = {
     "s2a_multiclass_nms_rotated_workspace_bytes": (_sz, [_i64, _i64, _i64]),
     "s2a_multiclass_nms_rotated": (_i32, [_vp, _vp, _i64, _i64, _i64, _f32, _f32, _i64, _vp, _vp, _vp, _i64, _vp,
                                           _sz, _vp]),
+    "s2a_multiclass_nms_rotated_packed": (_i32, [_vp, _vp, _i64, _i64, _i64, _f32, _f32, _i64, _vp, _i32, _i64, _i64, _vp, _sz,
+                                                 _vp]),
     "s2a_arf_forward": (_i32, [_vp, _vp, _vp] + [_i32] * 7 + [_vp]),
     "s2a_arf_backward": (_i32, [_vp, _vp, _vp] + [_i32] * 7 + [_vp]),
     "s2a_ri_pool_forward": (_i32, [_vp, _vp, _i64, _i64, _i64, _i32, _i32, _vp]),
@@ -77,7 +79,7 @@ def load():
 
 # kernels of THIS library launched by one successful C call (library sorts inside are not counted)
 KERNELS_PER_CALL = {
-    "box_iou_rotated": 1, "box_iou_rotated_batched": 1, "box_iou_rotated_tiles": 1, "nms_rotated": 4, "multiclass_nms_rotated": 6,
+    "box_iou_rotated": 1, "box_iou_rotated_batched": 1, "box_iou_rotated_tiles": 1, "nms_rotated": 4, "multiclass_nms_rotated": 6, "multiclass_nms_rotated_packed": 6,
     "arf_forward": 1, "arf_backward": 1, "ri_pool": 1, "deform_conv_forward_cuda": 1, "alignconv_forward": 1,
     "orconv_forward": 1, "conv_pack_weight": 1, "alignconv_forward_tc": 1, "orconv_forward_tc": 1, "deform_conv_forward_tc": 1,
     "alignconv_forward_tc_multi": 1, "orconv_forward_tc_multi": 1, "fam_decode": 1, "select_decode": 3, "conv2d_pack_weight": 1,

@@ -51,7 +51,7 @@ def box_iou_rotated_batched(boxes1, boxes2, row_begin=0, row_end=None, out=None,
     return out
 
 
-IOU_TILE_ROWS = 256     # kIouRowsMax in csrc/box_iou_rotated.cu: the unit the anchor rows are dealt out in
+IOU_TILE_ROWS = 64      # the unit the anchor rows are dealt out in (32, 64, 128 or 256; CTAs take up to four tiles)
 
 
 def tile_rows_of(n, tile_first, tile_step, tile_rows=IOU_TILE_ROWS):
@@ -74,6 +74,8 @@ def box_iou_rotated_tiles(boxes1, boxes2, tile_first, tile_step, compact=True, o
     m = boxes2.size(1)
     if boxes2.size(0) != B:
         raise ValueError("batch mismatch")
+    if tile_rows not in (32, 64, 128, 256):
+        raise ValueError("tile_rows must be 32, 64, 128 or 256")
     ntiles = -(-n // tile_rows)
     mine = len(range(tile_first, ntiles, tile_step))
     if out is None:

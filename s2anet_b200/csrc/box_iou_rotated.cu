@@ -30,88 +30,155 @@ namespace s2a {
 
 constexpr int kIouThreads = 256;
 constexpr int kIouWarps = kIouThreads / 32;
-constexpr int kIouCols = 256;          // columns (boxes2) per CTA tile: 32 per warp
 constexpr int kIouRowsMax = 256;       // rows (boxes1) per CTA tile (runtime: tile_rows <= this, a multiple of 32)
-constexpr int kIouQueue = 64;          // entries per warp queue: < 32 left over + <= 32 appended per step
+// CPT = columns per thread: a warp owns 32 * CPT consecutive columns (boxes2), a CTA 256 * CPT.  Two columns per thread
+// halve the per-pair share of the row-summary loads, the queue bookkeeping and the loop itself and give the
+// scheduler two independent dependency chains; one column per thread wastes fewer lanes when m is small.
+template <int CPT> __host__ __device__ constexpr int iou_cols() { return kIouThreads * CPT; }
+template <int CPT> __host__ __device__ constexpr int iou_queue() { return 32 + 16 * 32 * CPT; }   // < 32 left over + <= 16 rows x 32 * CPT appended per block
 
 struct IouArgs {
   const float* boxes1; const float* boxes2; float* out;
   int64_t n, m, ld_out, out_batch_stride, row_begin, row_end;
-  int tile_rows, tile_first, tile_step, compact, flags;
+  int tile_rows;      // rows per CTA
+  int deal_rows;      // rows per dealt tile (divides tile_rows; == tile_rows unless compact): the CTA's rows are
+                      // tile_rows / deal_rows consecutive tiles of THIS launch, i.e. every tile_step-th global tile
+  int tile_first, tile_step, compact, flags;
+  int64_t mine_rows;  // valid rows of this launch in packed order (compact) -- bounds the last CTA
 };
 
-constexpr size_t iou_smem_bytes(int tile_rows) {
-  return sizeof(RBox) * kIouCols + (sizeof(RBox) + sizeof(RFast) + sizeof(RAng)) * (size_t)tile_rows +
-         2 * sizeof(uint16_t) * kIouQueue * kIouWarps + sizeof(float) * 16 * kIouThreads;
+template <int CPT> constexpr size_t iou_smem_bytes(int tile_rows) {
+  return sizeof(RBox) * iou_cols<CPT>() + (sizeof(RBox) + sizeof(RFast) + sizeof(RAng)) * (size_t)tile_rows +
+         sizeof(uint16_t) * (iou_queue<CPT>() + 64) * kIouWarps + sizeof(float) * 16 * kIouThreads;
 }
 
 // the general 24-point clipper (thread-local arrays), out of line: reached by degenerate pairs only
 __device__ __noinline__ float iou_clip_general(const RBox& A, const RBox& B) { return rbox_iou_clip(A, B); }
 
+template <int CPT, bool NO_REJECT>
 __global__ void __launch_bounds__(kIouThreads, 3)
 box_iou_rotated_kernel(const IouArgs a) {
+  constexpr int COLS = iou_cols<CPT>(), QN = iou_queue<CPT>(), WCOLS = 32 * CPT;
+  constexpr int CBITS = CPT == 2 ? 6 : 5;                  // queue entry = row << CBITS | column inside the warp's group
   extern __shared__ __align__(16) uint8_t smem[];
   RBox* s_col = reinterpret_cast<RBox*>(smem);
-  RBox* s_row = s_col + kIouCols;
+  RBox* s_row = s_col + COLS;
   RFast* s_rowf = reinterpret_cast<RFast*>(s_row + a.tile_rows);
   RAng* s_rowa = reinterpret_cast<RAng*>(s_rowf + a.tile_rows);
   uint16_t* s_q = reinterpret_cast<uint16_t*>(s_rowa + a.tile_rows);
-  float* s_pts = reinterpret_cast<float*>(s_q + 2 * kIouQueue * kIouWarps);
+  float* s_pts = reinterpret_cast<float*>(s_q + (QN + 64) * kIouWarps);
 
   const int tid = threadIdx.x, wid = tid >> 5;
   const unsigned lane = tid & 31, lt = (1u << lane) - 1u;
   const int64_t b = blockIdx.z;
-  const int64_t tile = (int64_t)a.tile_first + (int64_t)blockIdx.x * a.tile_step;      // global row-tile index
-  const int64_t row0 = a.row_begin + tile * a.tile_rows;
-  const int64_t col0 = (int64_t)blockIdx.y * kIouCols;
-  const int nr = (int)min((int64_t)a.tile_rows, a.row_end - row0);
-  const int nc = (int)min((int64_t)kIouCols, a.m - col0);
-  // compact: the output holds only the row tiles this launch computes, packed in launch order
-  const int64_t orow0 = a.compact ? (int64_t)blockIdx.x * a.tile_rows : row0;
+  const int64_t col0 = (int64_t)blockIdx.y * COLS;
+  const int nc = (int)min((int64_t)COLS, a.m - col0);
+  // Rows of this CTA.  Dealt tiles are a.deal_rows high; CTA x takes the launch's tiles x*spt .. x*spt + spt - 1
+  // (global tile = tile_first + local tile * tile_step).  Only the matrix's last tile can be partial and it is the
+  // last tile of the launch that owns it, so the valid rows of a CTA are a prefix.
+  const int spt = a.tile_rows / a.deal_rows;
+  const int64_t lrow0 = (int64_t)blockIdx.x * a.tile_rows;                  // first row in the launch's packed order
+  const int nr = (int)min((int64_t)a.tile_rows, a.mine_rows - lrow0);
+  auto global_row = [&](int i) -> int64_t {
+    const int sub = i / a.deal_rows;
+    const int64_t gt = (int64_t)a.tile_first + ((int64_t)blockIdx.x * spt + sub) * a.tile_step;
+    return a.row_begin + gt * a.deal_rows + (i - sub * a.deal_rows);
+  };
+  // compact: the output holds only the rows this launch computes, packed in launch order
+  const int64_t orow0 = a.compact ? lrow0 : global_row(0);
   float* o = a.out + b * a.out_batch_stride + orow0 * a.ld_out + col0;
 
-  // ---- per-box work, once per tile: coalesced-ish 20-byte reads, one double-precision sin/cos per box ----
-  RFast cf; RAng ca;
-  cf.x = cf.y = cf.r = cf.mn = 0.0f; ca.s2t = ca.c2t = 0.0f;
-  const bool col_ok = tid < nc;
-  if (col_ok) {
-    const float* g = a.boxes2 + (b * a.m + col0 + tid) * 5;
-    RBox bx;
-    rbox_prep(g[0], g[1], g[2], g[3], g[4], bx);
-    s_col[tid] = bx;
-    rbox_fast_of(bx, cf, ca);
+  // ---- per-box work, once per tile: 20-byte reads, one double-precision sin/cos per box ----
+  const int cbase = wid * WCOLS;                           // first column of this warp
+  RFast cf[CPT]; RAng ca[CPT];
+  bool col_ok[CPT];
+#pragma unroll
+  for (int g = 0; g < CPT; ++g) {
+    const int c = cbase + 32 * g + (int)lane;              // this thread's g-th column
+    col_ok[g] = c < nc;
+    cf[g].x = cf[g].y = cf[g].r = cf[g].mn = 0.0f; ca[g].s2t = ca[g].c2t = 0.0f;
+    if (col_ok[g]) {
+      const float* gp = a.boxes2 + (b * a.m + col0 + c) * 5;
+      RBox bx;
+      rbox_prep(gp[0], gp[1], gp[2], gp[3], gp[4], bx);
+      s_col[c] = bx;
+      rbox_fast_of(bx, cf[g], ca[g]);
+    }
   }
   for (int i = tid; i < nr; i += kIouThreads) {
-    const float* g = a.boxes1 + (b * a.n + row0 + i) * 5;
+    const float* gp = a.boxes1 + (b * a.n + global_row(i)) * 5;
     RBox bx;
-    rbox_prep(g[0], g[1], g[2], g[3], g[4], bx);
+    rbox_prep(gp[0], gp[1], gp[2], gp[3], gp[4], bx);
     s_row[i] = bx;
     rbox_fast_of(bx, s_rowf[i], s_rowa[i]);
   }
   __syncthreads();                        // the only CTA-wide barrier
+  if (cbase >= nc) return;                // (a warp whose columns are all past m)
 
-  uint16_t* qm = s_q + wid * kIouQueue;                                  // pairs the fast test could not decide
-  uint16_t* qc = s_q + (kIouWarps + wid) * kIouQueue;                    // pairs to clip
+  uint16_t* qm = s_q + wid * QN;                                         // pairs the fast test could not decide
+  uint16_t* qc = s_q + kIouWarps * QN + wid * 64;                        // pairs to clip (< 32 left over + <= 32 per round)
   float* scratch = s_pts + tid;                                          // this thread's candidate column, stride 256
-  const int cbase = wid * 32;
-  const bool no_reject = (a.flags & S2A_IOU_NO_REJECT) != 0;
   int nm = 0, nq = 0;
 
   // One copy of every stage (instruction cache): the hot loop walks rows until the first queue holds a full round;
   // a stage runs when its queue has 32 entries -- all lanes busy -- or, once the rows are exhausted, to drain it.
   int r = 0;
+  float* orow = o + cbase + lane;                          // this thread's first column in the current row
+  const RFast* prf = s_rowf;
+  const RAng* pra = s_rowa;
   while (true) {
-    // ---- all-pairs pass: thread = column, loop over the rows (row summaries are shared-memory broadcasts) ----
-    for (; r < nr && nm < 32; ++r) {
-      bool maybe = false;
-      if (col_ok) {
-        if (!no_reject && rbox_fast_zero(s_rowf[r], s_rowa[r], cf, ca)) o[(int64_t)r * a.ld_out + tid] = 0.0f;
-        else maybe = true;
+    // ---- all-pairs pass: thread = column(s), loop over the rows (row summaries are shared-memory broadcasts).
+    // Every element gets its 0.0f here, unconditionally -- a warp writes whole 128-byte lines, no sector is ever
+    // written partially first (partial sectors cost DRAM fill reads on eviction) -- and the few pairs that turn
+    // out to intersect are overwritten by the clip stage below.
+    // Rows go in blocks of 16: the undecided pairs of a block are collected as one bit each in a per-thread register
+    // (bit 16 g + row) and appended to the queue ONCE per block -- warp prefix sum of the popcounts, then every lane
+    // writes its own few entries.  (A ballot / popc / store sequence per row ran on 96 % of the rows and took a
+    // third of this loop's instructions; per 8 rows the divergent write loop still cost 13 % of the kernel: its trip
+    // count is the MAXIMUM count over the lanes, which grows much more slowly than the block.)
+    for (; r < nr && nm < 32; r += 16, orow += 16 * a.ld_out, prf += 16, pra += 16) {
+      unsigned mk = 0u;
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        unsigned sub = 0u;                                 // bit 8 g + row of this half block
+        const int nrow = min(8, nr - r - 8 * h);
+        const RFast* hf = prf + 8 * h;
+        const RAng* ha = pra + 8 * h;
+        float* ho = orow + (int64_t)(8 * h) * a.ld_out;
+#pragma unroll
+        for (int rr = 0; rr < 8; ++rr) {
+          if (rr < nrow) {                                 // (warp-uniform; false only in the matrix's last tile)
+            const RFast rf = hf[rr];
+            const RAng ra = ha[rr];
+#pragma unroll
+            for (int g = 0; g < CPT; ++g) {
+              const bool zero = !NO_REJECT && rbox_fast_zero(rf, ra, cf[g], ca[g]);
+              if (col_ok[g]) {
+                ho[(int64_t)rr * a.ld_out + 32 * g] = 0.0f;
+                if (!zero) sub |= 1u << (g * 8 + rr);
+              }
+            }
+          }
+        }
+        mk |= ((sub & 0xffu) << (8 * h)) | ((sub >> 8) << (16 + 8 * h));
       }
-      const unsigned bal = __ballot_sync(0xffffffffu, maybe);
-      if (bal) {
-        if (maybe) qm[nm + __popc(bal & lt)] = (uint16_t)((r << 5) | lane);
-        nm += __popc(bal);
+      // append: inclusive warp scan of the per-lane counts
+      const int cntl = __popc(mk);
+      int pos = cntl;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int up = __shfl_up_sync(0xffffffffu, pos, d);
+        if ((int)lane >= d) pos += up;
+      }
+      const int total = __shfl_sync(0xffffffffu, pos, 31);
+      if (total) {
+        pos += nm - cntl;                                  // first slot of this lane
+        while (mk) {
+          const int bit = __ffs(mk) - 1;
+          mk &= mk - 1u;
+          qm[pos++] = (uint16_t)(((r + (bit & 15)) << CBITS) | ((bit >> 4) << 5) | lane);
+        }
+        nm += total;
         __syncwarp();
       }
     }
@@ -124,18 +191,17 @@ box_iou_rotated_kernel(const IouArgs a) {
       int p = 0;
       if ((int)lane < cnt) {
         p = qm[nm + lane];
-        const int pr = p >> 5, pc = cbase + (p & 31);
+        const int pr = p >> CBITS, pc = cbase + (p & (WCOLS - 1));
         const RBox& rb = s_row[pr];
         const RBox& cc = s_col[pc];
         int cls;
-        if (no_reject) {
+        if (NO_REJECT) {
           const float a1 = RB_MUL(rb.w, rb.h), a2 = RB_MUL(cc.w, cc.h);
           cls = (a1 <= RB_LO_1E14 || a2 <= RB_LO_1E14) ? RB_ZERO : RB_CLIP;
         } else {
           cls = rbox_classify(rb, cc);
         }
-        if (cls == RB_ZERO) o[(int64_t)pr * a.ld_out + pc] = 0.0f;
-        else clip = true;
+        clip = cls != RB_ZERO;                 // (zero: the element already holds its 0.0f)
       }
       const unsigned bal = __ballot_sync(0xffffffffu, clip);
       if (clip) qc[nq + __popc(bal & lt)] = (uint16_t)p;
@@ -148,7 +214,7 @@ box_iou_rotated_kernel(const IouArgs a) {
       nq -= cnt;
       if ((int)lane < cnt) {
         const int p = qc[nq + lane];
-        const int pr = p >> 5, pc = cbase + (p & 31);
+        const int pr = p >> CBITS, pc = cbase + (p & (WCOLS - 1));
         bool ok;
         float v = rbox_iou_clip_try(s_row[pr], s_col[pc], scratch, kIouThreads, ok);
         if (!ok) v = iou_clip_general(s_row[pr], s_col[pc]);
@@ -158,6 +224,16 @@ box_iou_rotated_kernel(const IouArgs a) {
     }
     if (done && nm == 0 && nq == 0) break;
   }
+}
+
+template <int CPT, bool NO_REJECT>
+static int launch_iou_kernel(const IouArgs& a, int64_t mine, int64_t batch, cudaStream_t st) {
+  auto kern = box_iou_rotated_kernel<CPT, NO_REJECT>;
+  S2A_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)iou_smem_bytes<CPT>(kIouRowsMax)));
+  dim3 grid((unsigned)mine, (unsigned)ceil_div(a.m, iou_cols<CPT>()), (unsigned)batch);
+  kern<<<grid, kIouThreads, iou_smem_bytes<CPT>(a.tile_rows), st>>>(a);
+  S2A_LAUNCH_OK("box_iou_rotated_kernel");
+  return S2A_OK;
 }
 
 static int launch_iou(const float* boxes1, int64_t n, const float* boxes2, int64_t m, int64_t batch, float* out,
@@ -173,30 +249,37 @@ static int launch_iou(const float* boxes1, int64_t n, const float* boxes2, int64
   if (tile_rows <= 0) {
     // default: 256-row tiles; smaller ones while the grid would not fill the GPU twice over
     tile_rows = kIouRowsMax;
-    const int64_t cols = ceil_div(std::max<int64_t>(m, 1), kIouCols) * std::max<int64_t>(batch, 1);
+    const int64_t cols = ceil_div(std::max<int64_t>(m, 1), iou_cols<2>()) * std::max<int64_t>(batch, 1);
     while (tile_rows > 32 && ceil_div(row_end - row_begin, tile_rows) * cols < 2 * (int64_t)sm_count() && tile_step == 1)
       tile_rows >>= 1;
   }
-  S2A_CHECK_ARG(tile_rows % 32 == 0 && tile_rows <= kIouRowsMax, "box_iou_rotated: tile_rows must be a multiple of 32 <= %d",
+  S2A_CHECK_ARG(tile_rows >= 32 && kIouRowsMax % tile_rows == 0, "box_iou_rotated: tile_rows must be 32, 64, 128 or %d",
                 kIouRowsMax);
   if (row_end == row_begin || m == 0 || batch == 0) return S2A_OK;
   S2A_CHECK_ARG(boxes1 && boxes2 && out, "box_iou_rotated: null pointer");
   S2A_CHECK_ARG(ld_out >= m, "box_iou_rotated: ld_out (%lld) < m (%lld)", (long long)ld_out, (long long)m);
-  const int64_t ntiles = ceil_div(row_end - row_begin, tile_rows);
+  const int64_t nrows = row_end - row_begin;
+  const int64_t ntiles = ceil_div(nrows, tile_rows);
   const int64_t mine = tile_first < ntiles ? ceil_div(ntiles - tile_first, tile_step) : 0;     // tiles of this launch
   if (mine == 0) return S2A_OK;
-  S2A_CHECK_ARG(batch <= 65535 && ceil_div(m, kIouCols) <= 65535 && mine < (1ll << 31),
+  // valid rows of this launch: all its tiles are full except possibly the matrix's last one
+  const int64_t last_tile = tile_first + (mine - 1) * tile_step;
+  const int64_t mine_rows = (mine - 1) * tile_rows + std::min<int64_t>(tile_rows, nrows - last_tile * tile_rows);
+  // packed output: CTAs are 256 rows high and take several dealt tiles each; in-place output: one dealt tile per CTA
+  // (its rows must be consecutive in the output)
+  const int cta_rows = (compact && tile_step > 1) ? kIouRowsMax : tile_rows;
+  const int64_t nctas = ceil_div(mine_rows, cta_rows);
+  S2A_CHECK_ARG(batch <= 65535 && ceil_div(m, iou_cols<1>()) <= 65535 && nctas < (1ll << 31),
                 "box_iou_rotated: batch and ceil(m/256) must be <= 65535");
   if (out_batch_stride <= 0) out_batch_stride = (compact ? mine * tile_rows : n) * ld_out;
-  IouArgs a{boxes1, boxes2, out, n, m, ld_out, out_batch_stride, row_begin, row_end, tile_rows, tile_first, tile_step,
-            compact ? 1 : 0, flags};
-  const size_t smem = iou_smem_bytes(tile_rows);
-  S2A_CUDA_OK(cudaFuncSetAttribute(box_iou_rotated_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)iou_smem_bytes(kIouRowsMax)));
-  dim3 grid((unsigned)mine, (unsigned)ceil_div(m, kIouCols), (unsigned)batch);
-  box_iou_rotated_kernel<<<grid, kIouThreads, smem, st>>>(a);
-  S2A_LAUNCH_OK("box_iou_rotated_kernel");
-  return S2A_OK;
+  IouArgs a{boxes1, boxes2, out, n, m, ld_out, out_batch_stride, row_begin, row_end, cta_rows, tile_rows, tile_first,
+            tile_step, compact ? 1 : 0, flags, mine_rows};
+  // two columns per thread unless one column per thread wastes fewer lanes on the last column tile
+  const int64_t waste2 = ceil_div(m, iou_cols<2>()) * iou_cols<2>() - m, waste1 = ceil_div(m, iou_cols<1>()) * iou_cols<1>() - m;
+  const bool two = waste2 <= waste1;
+  const bool nr_ = (flags & S2A_IOU_NO_REJECT) != 0;
+  if (two) return nr_ ? launch_iou_kernel<2, true>(a, nctas, batch, st) : launch_iou_kernel<2, false>(a, nctas, batch, st);
+  return nr_ ? launch_iou_kernel<1, true>(a, nctas, batch, st) : launch_iou_kernel<1, false>(a, nctas, batch, st);
 }
 
 }  // namespace s2a

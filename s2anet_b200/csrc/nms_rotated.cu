@@ -510,10 +510,20 @@ mc_sweep_kernel(const unsigned long long* __restrict__ mask, const int* __restri
 // Merge by rank: a survivor's output row is the number of survivors of the same image that precede
 // it in (score desc, box asc, class asc) order = its own position in its class + one binary search
 // per other class.
+// Destinations of the packed form: up to 8 buffers [slots, K + 1, 7] fp32 (one per rank of a node: this rank's own
+// and its peers' over NVLink), row k < K = (x, y, w, h, theta, score, label), row K = (count, 0, ...).
+constexpr int kMcMaxPeers = 8;
+struct McPush {
+  float* dst[kMcMaxPeers];
+  int npeers;          // 0: plain outputs (dets_out / labels_out / num_out)
+  int slot0;           // image b of this call goes to slot slot0 + b of every destination
+  int K;               // rows per image (max_out)
+};
+
 __global__ void mc_emit_kernel(const float* __restrict__ bboxes, const float* __restrict__ kept_score,
                                const int* __restrict__ kept_box, const int* __restrict__ kept_count, int n,
                                int C, int64_t max_per_img, int64_t max_out, float* __restrict__ dets_out,
-                               float* __restrict__ labels_out, int32_t* __restrict__ num_out) {
+                               float* __restrict__ labels_out, int32_t* __restrict__ num_out, const McPush push) {
   const int c = blockIdx.y, b = blockIdx.z;
   const size_t seg0 = (size_t)b * C;
   const int kc = kept_count[seg0 + c];
@@ -521,7 +531,12 @@ __global__ void mc_emit_kernel(const float* __restrict__ bboxes, const float* __
     long long tot = 0;
     for (int cc = 0; cc < C; ++cc) tot += kept_count[seg0 + cc];
     long long lim = max_per_img < max_out ? max_per_img : max_out;
-    num_out[b] = (int32_t)(tot < lim ? tot : lim);
+    const int32_t cnt = (int32_t)(tot < lim ? tot : lim);
+    if (num_out) num_out[b] = cnt;
+    for (int p = 0; p < push.npeers; ++p) {
+      float* o = push.dst[p] + ((size_t)(push.slot0 + b) * (push.K + 1) + push.K) * 7;
+      o[0] = (float)cnt; o[1] = 0.0f; o[2] = 0.0f; o[3] = 0.0f; o[4] = 0.0f; o[5] = 0.0f; o[6] = 0.0f;
+    }
   }
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= kc) return;
@@ -543,9 +558,18 @@ __global__ void mc_emit_kernel(const float* __restrict__ bboxes, const float* __
   const long long lim = max_per_img < max_out ? max_per_img : max_out;
   if (rank < lim) {
     const float* d = bboxes + ((size_t)b * n + box) * 5;
-    float* o = dets_out + ((size_t)b * max_out + rank) * 6;
-    o[0] = d[0]; o[1] = d[1]; o[2] = d[2]; o[3] = d[3]; o[4] = d[4]; o[5] = sv;
-    labels_out[(size_t)b * max_out + rank] = (float)c;
+    const float d0 = d[0], d1 = d[1], d2 = d[2], d3 = d[3], d4 = d[4];
+    if (dets_out) {
+      float* o = dets_out + ((size_t)b * max_out + rank) * 6;
+      o[0] = d0; o[1] = d1; o[2] = d2; o[3] = d3; o[4] = d4; o[5] = sv;
+      labels_out[(size_t)b * max_out + rank] = (float)c;
+    }
+    // the detection exchange fused into the finaliser: the row goes straight into the packed buffer of every rank
+    // (plain stores through NVLink peer mappings; a kernel boundary + the exchange's barrier publish them)
+    for (int p = 0; p < push.npeers; ++p) {
+      float* o = push.dst[p] + ((size_t)(push.slot0 + b) * (push.K + 1) + rank) * 7;
+      o[0] = d0; o[1] = d1; o[2] = d2; o[3] = d3; o[4] = d4; o[5] = sv; o[6] = (float)c;
+    }
   }
 }
 
@@ -643,21 +667,69 @@ extern "C" size_t s2a_multiclass_nms_rotated_workspace_bytes(int64_t n, int64_t 
   return s2a::carve_mc(nullptr, n, num_classes, batch).total;
 }
 
+namespace s2a {
+static int multiclass_impl(const float* bboxes, const float* scores, int64_t n, int64_t num_classes, int64_t batch,
+                           float score_thr, float iou_thr, int64_t max_per_img, float* dets_out, float* labels_out,
+                           int32_t* num_out, int64_t max_out, void* workspace, size_t workspace_bytes, void* stream,
+                           const McPush& push);
+}
+
 extern "C" int s2a_multiclass_nms_rotated(const float* bboxes, const float* scores, int64_t n,
                                           int64_t num_classes, int64_t batch, float score_thr, float iou_thr,
                                           int64_t max_per_img, float* dets_out, float* labels_out,
                                           int32_t* num_out, int64_t max_out, void* workspace,
                                           size_t workspace_bytes, void* stream) {
   using namespace s2a;
+  S2A_CHECK_ARG(num_out != nullptr || batch == 0, "multiclass_nms_rotated: num_out is null");
+  S2A_CHECK_ARG((dets_out && labels_out) || batch == 0 || n == 0 || num_classes == 0 || max_out == 0 || max_per_img <= 0,
+                "multiclass_nms_rotated: null pointer");
+  McPush push{};
+  return multiclass_impl(bboxes, scores, n, num_classes, batch, score_thr, iou_thr, max_per_img, dets_out, labels_out,
+                         num_out, max_out, workspace, workspace_bytes, stream, push);
+}
+
+extern "C" int s2a_multiclass_nms_rotated_packed(const float* bboxes, const float* scores, int64_t n, int64_t num_classes,
+                                                 int64_t batch, float score_thr, float iou_thr, int64_t max_per_img,
+                                                 float* const* dests, int ndests, int64_t slot0, int64_t max_out,
+                                                 void* workspace, size_t workspace_bytes, void* stream) {
+  using namespace s2a;
+  S2A_CHECK_ARG(dests != nullptr && ndests >= 1 && ndests <= kMcMaxPeers, "multiclass_nms_rotated_packed: 1..%d destinations",
+                kMcMaxPeers);
+  S2A_CHECK_ARG(slot0 >= 0 && max_out > 0 && max_out < (1ll << 30), "multiclass_nms_rotated_packed: bad slot / max_out");
+  McPush push{};
+  push.npeers = ndests; push.slot0 = (int)slot0; push.K = (int)max_out;
+  for (int p = 0; p < ndests; ++p) {
+    S2A_CHECK_ARG(dests[p] != nullptr, "multiclass_nms_rotated_packed: null destination");
+    push.dst[p] = dests[p];
+  }
+  return multiclass_impl(bboxes, scores, n, num_classes, batch, score_thr, iou_thr, max_per_img, nullptr, nullptr, nullptr,
+                         max_out, workspace, workspace_bytes, stream, push);
+}
+
+namespace s2a {
+__global__ void mc_zero_counts_kernel(int32_t* num_out, int batch, const McPush push) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  if (num_out) num_out[b] = 0;
+  for (int p = 0; p < push.npeers; ++p) {
+    float* o = push.dst[p] + ((size_t)(push.slot0 + b) * (push.K + 1) + push.K) * 7;
+    for (int e = 0; e < 7; ++e) o[e] = 0.0f;
+  }
+}
+
+static int multiclass_impl(const float* bboxes, const float* scores, int64_t n, int64_t num_classes, int64_t batch,
+                           float score_thr, float iou_thr, int64_t max_per_img, float* dets_out, float* labels_out,
+                           int32_t* num_out, int64_t max_out, void* workspace, size_t workspace_bytes, void* stream,
+                           const McPush& push) {
   cudaStream_t st = (cudaStream_t)stream;
   S2A_CHECK_ARG(n >= 0 && num_classes >= 0 && batch >= 0, "multiclass_nms_rotated: negative size");
-  S2A_CHECK_ARG(num_out != nullptr || batch == 0, "multiclass_nms_rotated: num_out is null");
   if (batch == 0) return S2A_OK;
   if (n == 0 || num_classes == 0 || max_out == 0 || max_per_img <= 0) {
-    S2A_CUDA_OK(cudaMemsetAsync(num_out, 0, sizeof(int32_t) * batch, st));
+    mc_zero_counts_kernel<<<(unsigned)ceil_div(batch, 128), 128, 0, st>>>(num_out, (int)batch, push);
+    S2A_LAUNCH_OK("mc_zero_counts_kernel");
     return S2A_OK;
   }
-  S2A_CHECK_ARG(bboxes && scores && dets_out && labels_out && workspace, "multiclass_nms_rotated: null pointer");
+  S2A_CHECK_ARG(bboxes && scores && workspace, "multiclass_nms_rotated: null pointer");
   S2A_CHECK_ARG(max_out > 0, "multiclass_nms_rotated: max_out must be positive");
   if (n > kMcMaxBoxes) {
     set_error("multiclass_nms_rotated: fused path supports n <= %d boxes per image (got %lld); "
@@ -697,10 +769,11 @@ extern "C" int s2a_multiclass_nms_rotated(const float* bboxes, const float* scor
   S2A_LAUNCH_OK("mc_sweep_kernel");
   dim3 gemit((unsigned)ceil_div(n, 256), C, B);
   mc_emit_kernel<<<gemit, 256, 0, st>>>(bboxes, w.kept_score, w.kept_box, w.kept_count, ni, C, max_per_img,
-                                        max_out, dets_out, labels_out, num_out);
+                                        max_out, dets_out, labels_out, num_out, push);
   S2A_LAUNCH_OK("mc_emit_kernel");
   return S2A_OK;
 }
+}  // namespace s2a
 
 // ================================================================================================
 // DOTA result-merging NMS on polygons, fp64 (second half)

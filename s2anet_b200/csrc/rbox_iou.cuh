@@ -230,39 +230,58 @@ RB_HD int rbox_candidates(const RBox& A, const RBox& B, Sink& sink) {
   rbox_vertices(RB_SUB(A.x, shx), RB_SUB(A.y, shy), A, p1x, p1y);
   rbox_vertices(RB_SUB(B.x, shx), RB_SUB(B.y, shy), B, p2x, p2y);
 
-  float e1x[4], e1y[4], e2x[4], e2y[4];
+  float e2x[4], e2y[4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    e1x[i] = RB_SUB(p1x[(i + 1) & 3], p1x[i]);
-    e1y[i] = RB_SUB(p1y[(i + 1) & 3], p1y[i]);
-    e2x[i] = RB_SUB(p2x[(i + 1) & 3], p2x[i]);
-    e2y[i] = RB_SUB(p2y[(i + 1) & 3], p2y[i]);
+  for (int j = 0; j < 4; ++j) {
+    e2x[j] = RB_SUB(p2x[(j + 1) & 3], p2x[j]);
+    e2y[j] = RB_SUB(p2y[(j + 1) & 3], p2y[j]);
   }
 
   int n = 0;
-#pragma unroll
+  // Edge i of box 1 against the four edges of box 2.  The i loop is ROLLED (one copy of the 4-edge body instead of
+  // four: the unrolled form made the clipper ~1,000 instructions long and the kernel instruction-cache bound) and
+  // box 1's vertices rotate through named registers instead of being indexed, so nothing goes to local memory.
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
   for (int i = 0; i < 4; ++i) {
+    const float ax = p1x[0], ay = p1y[0];
+    const float e1x = RB_SUB(p1x[1], ax), e1y = RB_SUB(p1y[1], ay);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      float det = rb_cross(e2x[j], e2y[j], e1x[i], e1y[i]);
-      if (fabsf(det) <= RB_LO_1E14) continue;                      // fabs(det) <= 1e-14
-      float dx = RB_SUB(p2x[j], p1x[i]), dy = RB_SUB(p2y[j], p1y[i]);
-      const float n1 = rb_cross(e2x[j], e2y[j], dx, dy), n2 = rb_cross(e1x[i], e1y[i], dx, dy);
-      // Exact pre-test: a quotient whose magnitude clearly exceeds 1, or that is clearly negative,
-      // cannot pass "0 <= t <= 1" after IEEE division either (the 1e-4 / 1e-30 margins dwarf the
-      // half-ulp of the division and exclude the underflow-to-(-0) case), so the two divisions are
-      // skipped for the ~3 of 4 edge pairs that are nowhere near crossing.  NaNs fail every
-      // comparison here and take the exact path.
+      const float det = rb_cross(e2x[j], e2y[j], e1x, e1y);
+      const float dx = RB_SUB(p2x[j], ax), dy = RB_SUB(p2y[j], ay);
+      const float n1 = rb_cross(e2x[j], e2y[j], dx, dy), n2 = rb_cross(e1x, e1y, dx, dy);
+      // Exact pre-test: parallel edges (fabs(det) <= 1e-14, :103) give no point; a quotient whose magnitude clearly
+      // exceeds 1, or that is clearly negative, cannot pass "0 <= t <= 1" after IEEE division either (the 1e-4 /
+      // 1e-30 margins dwarf the half-ulp of the division and exclude the underflow-to-(-0) case), so the two
+      // divisions are skipped for the ~3 of 4 edge pairs that are nowhere near crossing.  Every test is written
+      // as a negated comparison so that NaNs fall through to the exact path, and the tests are combined without
+      // short-circuit evaluation: ONE (rarely taken, divergent) branch per edge pair instead of four.
       const float ad = fabsf(det), lim = 1.0001f * ad, tiny = 1e-30f * ad;
-      if (fabsf(n1) > lim || fabsf(n2) > lim) continue;
-      if (((n1 < 0.0f) != (det < 0.0f) && fabsf(n1) > tiny) || ((n2 < 0.0f) != (det < 0.0f) && fabsf(n2) > tiny)) continue;
-      float t1 = RB_DIV(n1, det);
-      float t2 = RB_DIV(n2, det);
-      if (t1 >= 0.0f && t1 <= 1.0f && t2 >= 0.0f && t2 <= 1.0f) {
-        sink.put(n, RB_ADD(p1x[i], RB_MUL(e1x[i], t1)), RB_ADD(p1y[i], RB_MUL(e1y[i], t1)));
-        ++n;
+      const bool neg = det < 0.0f;
+      const bool plausible = !(ad <= RB_LO_1E14) & !(fabsf(n1) > lim) & !(fabsf(n2) > lim) &
+                             !(((n1 < 0.0f) != neg) & (fabsf(n1) > tiny)) & !(((n2 < 0.0f) != neg) & (fabsf(n2) > tiny));
+      if (plausible) {
+        const float t1 = RB_DIV(n1, det);
+        // t2 is only tested, never used: strictly inside (0.0001 |det| < |n2| < 0.9999 |det|, same sign) the rounded
+        // quotient is inside [0, 1] as well, and its division is skipped
+        bool t2_ok = ((n2 < 0.0f) == neg) & (fabsf(n2) > 1e-4f * ad) & (fabsf(n2) < 0.9999f * ad);
+        if (!t2_ok) {
+          const float t2 = RB_DIV(n2, det);
+          t2_ok = t2 >= 0.0f && t2 <= 1.0f;
+        }
+        if (t1 >= 0.0f && t1 <= 1.0f && t2_ok) {
+          sink.put(n, RB_ADD(ax, RB_MUL(e1x, t1)), RB_ADD(ay, RB_MUL(e1y, t1)));
+          ++n;
+        }
       }
     }
+    // rotate box 1's vertices: (0, 1, 2, 3) <- (1, 2, 3, 0); after four rounds they are back in place
+    p1x[0] = p1x[1]; p1y[0] = p1y[1];
+    p1x[1] = p1x[2]; p1y[1] = p1y[2];
+    p1x[2] = p1x[3]; p1y[2] = p1y[3];
+    p1x[3] = ax; p1y[3] = ay;
   }
   {
     float abab = rb_dot(e2x[0], e2y[0], e2x[0], e2y[0]);
@@ -278,13 +297,15 @@ RB_HD int rbox_candidates(const RBox& A, const RBox& B, Sink& sink) {
     }
   }
   {
-    float abab = rb_dot(e1x[0], e1y[0], e1x[0], e1y[0]);
-    float adad = rb_dot(e1x[3], e1y[3], e1x[3], e1y[3]);
+    const float e10x = RB_SUB(p1x[1], p1x[0]), e10y = RB_SUB(p1y[1], p1y[0]);      // edge 0 and edge 3 of box 1
+    const float e13x = RB_SUB(p1x[0], p1x[3]), e13y = RB_SUB(p1y[0], p1y[3]);
+    float abab = rb_dot(e10x, e10y, e10x, e10y);
+    float adad = rb_dot(e13x, e13y, e13x, e13y);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       float apx = RB_SUB(p2x[i], p1x[0]), apy = RB_SUB(p2y[i], p1y[0]);
-      float apab = rb_dot(apx, apy, e1x[0], e1y[0]);
-      float apad = -rb_dot(apx, apy, e1x[3], e1y[3]);
+      float apab = rb_dot(apx, apy, e10x, e10y);
+      float apad = -rb_dot(apx, apy, e13x, e13y);
       if (apab >= 0.0f && apad >= 0.0f && apab <= abab && apad <= adad) {
         sink.put(n, p2x[i], p2y[i]); ++n;
       }
@@ -398,31 +419,32 @@ RB_HD bool rbox_hull8(float (&qx)[8], float (&qy)[8], int n, float& inter) {
     float ax = qx[i], ay = qy[i];
 #pragma unroll
     for (int j = i + 1; j < 8; ++j) {
-      if (j < n) {
-        const float bx = qx[j], by = qy[j];
-        const float cp = rb_cross(ax, ay, bx, by);
-        bool sw = (cp <= -RB_HI_1E6);
-        if (!sw && fabsf(cp) <= RB_LO_1E6) sw = rb_dot(ax, ay, ax, ay) > rb_dot(bx, by, bx, by);
-        if (sw) { qx[j] = ax; qy[j] = ay; ax = bx; ay = by; }
-      }
+      // (selects, not branches: n differs from lane to lane)
+      const float bx = qx[j], by = qy[j];
+      const float cp = rb_cross(ax, ay, bx, by);
+      bool sw = (cp <= -RB_HI_1E6);
+      if (!sw && fabsf(cp) <= RB_LO_1E6) sw = rb_dot(ax, ay, ax, ay) > rb_dot(bx, by, bx, by);   // (rare: collinear)
+      sw = sw & (j < n);
+      qx[j] = sw ? ax : bx; qy[j] = sw ? ay : by;
+      ax = sw ? bx : ax; ay = sw ? by : ay;
     }
     qx[i] = ax; qy[i] = ay;
   }
   bool ok = rb_dot(qx[1], qy[1], qx[1], qy[1]) >= RB_HI_1E8;      // k == 1: the second point is not a copy of the first
 #pragma unroll
   for (int i = 2; i < 8; ++i) {
-    if (i < n) {
-      const float ox = qx[i - 2], oy = qy[i - 2];
-      const float cr = rb_cross(RB_SUB(qx[i], ox), RB_SUB(qy[i], oy), RB_SUB(qx[i - 1], ox), RB_SUB(qy[i - 1], oy));
-      ok = ok && !(cr >= 0.0f);                                   // the scan would not pop
-    }
+    const float ox = qx[i - 2], oy = qy[i - 2];
+    const float cr = rb_cross(RB_SUB(qx[i], ox), RB_SUB(qy[i], oy), RB_SUB(qx[i - 1], ox), RB_SUB(qy[i - 1], oy));
+    ok = ok & (!(cr >= 0.0f) | (i >= n));                         // the scan would not pop
   }
   float area = 0.0f;
   const float ox = qx[0], oy = qy[0];
 #pragma unroll
   for (int i = 1; i < 7; ++i)
-    if (i < n - 1)
-      area = RB_ADD(area, fabsf(rb_cross(RB_SUB(qx[i], ox), RB_SUB(qy[i], oy), RB_SUB(qx[i + 1], ox), RB_SUB(qy[i + 1], oy))));
+  {
+    const float tri = fabsf(rb_cross(RB_SUB(qx[i], ox), RB_SUB(qy[i], oy), RB_SUB(qx[i + 1], ox), RB_SUB(qy[i + 1], oy)));
+    area = (i < n - 1) ? RB_ADD(area, tri) : area;
+  }
   inter = RB_MUL(area, 0.5f);
   return ok;
 }

@@ -97,6 +97,33 @@ def multiclass_nms_rotated_batched(bboxes, scores, score_thr=0.05, iou_thr=0.5, 
     return dets, labels, counts
 
 
+def multiclass_nms_rotated_packed(bboxes, scores, dests, slot0=0, score_thr=0.05, iou_thr=0.5, max_per_img=2000, K=None):
+    """The batched NMS writing PACKED rows into one or several [slots, K+1, 7] buffers (see
+    s2a_multiclass_nms_rotated_packed): `dests` is a list of fp32 tensors and / or raw device pointers (ints: the
+    NVLink-mapped buffers of peer ranks, dist.DetectionExchange.targets()); image b lands in slot slot0 + b.
+    K (rows per image) defaults to dests[0].size(1) - 1.  Sync-free, graph-capturable, 6 launches."""
+    import ctypes as C
+    dev = _lib.require_cuda(bboxes, scores)
+    B, n, _ = bboxes.shape
+    nc = scores.size(2)
+    if K is None:
+        K = dests[0].size(1) - 1
+    if n > MC_FUSED_MAX_BOXES or not (iou_thr >= 0):
+        raise NotImplementedError("multiclass_nms_rotated_packed: the fused path takes n <= %d boxes and iou_thr >= 0; "
+                                  "use multiclass_nms_rotated_batched + dist.gather_detections" % MC_FUSED_MAX_BOXES)
+    bboxes = bboxes.to(torch.float32).contiguous()
+    scores = scores.to(torch.float32).contiguous()
+    ptrs = (C.c_void_p * len(dests))(*[d.data_ptr() if torch.is_tensor(d) else int(d) for d in dests])
+    lib = _lib.load()
+    ws_bytes = lib.s2a_multiclass_nms_rotated_workspace_bytes(n, nc, B)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.s2a_multiclass_nms_rotated_packed(_lib.ptr(bboxes), _lib.ptr(scores), n, nc, B, float(score_thr),
+                                                   float(iou_thr), int(max_per_img), ptrs, len(dests), int(slot0), int(K),
+                                                   _lib.ptr(ws), ws_bytes, _lib.stream_ptr(dev))
+    _lib.check(rc, "multiclass_nms_rotated_packed")
+
+
 def _multiclass_composed(bboxes, scores, score_thr, iou_thr, max_per_img):
     """Sizes the fused kernel does not take (n > 6144 boxes, negative thresholds): the reference's
     own composition (utils/bbox_nms_rotated.py:24-64) on top of the generic ml_nms_rotated kernel."""

@@ -94,11 +94,12 @@ def test_shard_tiles_deal_rows_cyclically_and_cover_exactly():
             assert sorted(seen.tolist()) == list(range(n))
             for r in range(world):
                 assert torch.equal(shard_tiles(n, r, world)[1], tile_rows_of(n, r, world))
-    # BASELINE config 4 on 8 GPUs: 86 tiles of 256 rows; every rank owns tiles of every FPN level's range it can
-    tiles, rows = shard_tiles(21824, 7, 8)
-    assert tiles == list(range(7, 86, 8)) and rows.numel() == 10 * 256
-    tiles0, rows0 = shard_tiles(21824, 5, 8)                 # the partial last tile (85) belongs to rank 5
-    assert tiles0[-1] == 85 and rows0.numel() == 10 * 256 + (21824 - 85 * 256)
+                assert torch.equal(shard_tiles(n, r, world, 256)[1], tile_rows_of(n, r, world, 256))
+    # BASELINE config 4 on 8 GPUs: 341 tiles of 64 rows; the P5-P7 anchors (rows 20,480 ...: 21 tiles) reach every rank
+    for r in range(8):
+        tiles, rows = shard_tiles(21824, r, 8)
+        assert tiles == list(range(r, 341, 8)) and sum(t >= 320 for t in tiles) in (2, 3)
+        assert rows.numel() == 64 * len(tiles)               # 21,824 = 341 x 64: no partial tile
 
 
 def test_two_rank_gloo():

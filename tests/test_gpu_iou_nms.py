@@ -109,7 +109,7 @@ def test_iou_full_size_properties():
     assert float((d - 1).abs().max()) <= 1e-5
 
 
-@pytest.mark.parametrize("world,tile_rows", [(1, 256), (2, 256), (8, 256), (3, 64), (5, 32)])
+@pytest.mark.parametrize("world,tile_rows", [(1, 256), (2, 256), (8, 64), (3, 64), (5, 32), (2, 128)])
 def test_iou_row_tiles_dealt_cyclically(world, tile_rows):
     """The multi-GPU form (s2a_box_iou_rotated_tiles): the union of the ranks' cyclically dealt row tiles, packed or
     written in place, is bit-identical to the one-call matrix; slivers, a partial last tile and partial column tiles
@@ -262,6 +262,32 @@ def _ref_gpu(name):
     if mod is None:
         pytest.skip("oracle/_ref/ext_gpu/%s not prebuilt" % name)
     return mod
+
+
+def test_multiclass_packed_form_equals_plain_outputs():
+    """The detection exchange's pack fused into the NMS finaliser (s2a_multiclass_nms_rotated_packed): rows
+    (x, y, w, h, theta, score, label) + the count row, into one or several destination buffers at a slot offset,
+    are exactly the plain outputs."""
+    from s2anet_b200.dist import packed_views
+    from s2anet_b200.nms_rotated import multiclass_nms_rotated_batched, multiclass_nms_rotated_packed
+    B, K = 3, 300
+    rng = np.random.default_rng(5)
+    bx = np.stack([synth.clustered_boxes(n_seed=150, rep=4, seed=20 + i)[0] for i in range(B)])
+    sc = (rng.uniform(0, 1, (B, bx.shape[1], 15)) ** 5).astype(np.float32)
+    sc[2] = 0.0                                                            # an image without detections
+    tb, ts = torch.from_numpy(bx).to(DEV), torch.from_numpy(sc).to(DEV)
+    d, l, c = multiclass_nms_rotated_batched(tb, ts, 0.05, 0.5, K)
+    dst0 = torch.full((5, K + 1, 7), -1.0, device=DEV)
+    dst1 = torch.full((5, K + 1, 7), -1.0, device=DEV)
+    multiclass_nms_rotated_packed(tb, ts, [dst0, dst1.data_ptr()], slot0=2, score_thr=0.05, iou_thr=0.5, max_per_img=K)
+    assert torch.equal(dst0, dst1)
+    assert bool((dst0[:2] == -1.0).all())                                  # other ranks' slots untouched
+    pd, pl, pc = packed_views(dst0[2:], K)
+    assert pc.tolist() == c.tolist() and c[2] == 0 and int(c.max()) == K
+    for i in range(B):
+        k = int(c[i])
+        assert torch.equal(pd[i, :k], d[i, :k]) and torch.equal(pl[i, :k], l[i, :k])
+    assert bool((dst0[2:, K, 1:] == 0).all())
 
 
 def test_against_reference_cuda_kernels_on_this_gpu(oracle):

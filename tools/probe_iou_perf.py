@@ -27,9 +27,11 @@ ms = t(lambda: box_iou_rotated_batched(an, gt, out=out, _flags=1), reps=2)
 print("anchor x GT, no reject (every pair clipped): %.3f ms, %.1f G pairs/s" % (ms, pairs / ms / 1e6))
 for w in (8,):
     cyc = [t(lambda r=r: box_iou_rotated_tiles(an, gt, r, w, compact=True)) for r in range(w)]
+    cyc256 = [t(lambda r=r: box_iou_rotated_tiles(an, gt, r, w, compact=True, tile_rows=256)) for r in range(w)]
     per = -(-N // w); per = -(-per // 64) * 64
     blk = [t(lambda r=r: box_iou_rotated_batched(an, gt, min(N, r * per), min(N, (r + 1) * per), out=out)) for r in range(w)]
-    print("8-way shards, ms per rank: cyclic tiles", " ".join("%.3f" % x for x in cyc), "| contiguous blocks", " ".join("%.3f" % x for x in blk))
+    print("8-way shards, ms per rank: cyclic 256-row tiles", " ".join("%.3f" % x for x in cyc256))
+    print("8-way shards, ms per rank: cyclic 64-row tiles", " ".join("%.3f" % x for x in cyc), "| contiguous blocks", " ".join("%.3f" % x for x in blk))
 bx, _, _ = synth.clustered_boxes(n_seed=1600, rep=5, seed=0)
 tb = torch.from_numpy(bx).to(dev)
 ms = t(lambda: box_iou_rotated(tb, tb))
