@@ -4,12 +4,16 @@
     python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a path
     python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's CPU path (rank 0 only)
 
-A "step" is one pass of the hot path over one batch of synthetic input: the FAM/ODM head
-(stock cuDNN conv towers + AlignConv + ORConv2d/RotationInvariantPooling from this library) over the
-five FPN levels of `--batch` 1024x1024 images per GPU, box decode, per-level top-2000 and the fused
-15-class rotated NMS.  `value` times it with the FPN features resident in HBM; `e2e` times the
-same call with the features in pinned host memory (H2D inside the timed region, double-buffered on a
-copy stream) and the detections read back to the host.  Prints ONE JSON line on rank 0.
+A "step" is one pass of the hot path over one batch of synthetic input: the FAM/ODM head (conv towers, AlignConv,
+ORConv2d + RotationInvariantPooling -- every layer a kernel of this library) over the five FPN levels of `--batch`
+1024x1024 images per GPU, box decode, per-level top-2000 and the fused 15-class rotated NMS, and -- with more than
+one GPU -- the detection exchange fused into the NMS finaliser (NVLink peer stores + one barrier).  `value` times it
+with the FPN features resident in HBM; `e2e` times the same call with the features in pinned host memory (H2D inside
+the timed region, double-buffered on a copy stream) and the rank's own detections read back to the host.
+Prints ONE JSON line on rank 0.  Extra keys next to the contract's: `iou` (BASELINE's second metric, rotated IoU
+pairs/s on configs[3], with both collective forms), `configs` (the bench legs BASELINE.md section 3 lists: config 1,
+config 2 at batch 1, config 3 at batch 1, NMS at N = 2,000 / 20,000, the step at 10 k candidates), `parity` (measured
+max-abs / rel-L2 of the 16-bit kernels against the reference CUDA ops).
 """
 import argparse
 import json
@@ -30,6 +34,18 @@ STRIDES = (8, 16, 32, 64, 128)
 NUM_CLASSES = 15
 POSITIONS = sum((IMG // s) ** 2 for s in STRIDES)            # 21,824
 ALIGN_FLOPS_PER_IMAGE = 2.0 * POSITIONS * 256 * 2304          # 25.744 GFLOP
+IOU_FLOP_PER_PAIR = 350.0                                      # SURVEY 8d counting convention
+# odm_cls_head.bias after `calibrate_scores` on the seeded bench inputs (seed 0 weights, feature seed 4): the value
+# every arm starts from, so that the CPU reference arm does not depend on a previous GPU run (round 1: it read a
+# scratch file and ran 6.6x slower when the file was missing -- more candidates, quadratic CPU NMS)
+CALIBRATED_BIAS = {3000: -6.21875}
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
 
 
 def load_peaks():
@@ -42,16 +58,40 @@ def load_peaks():
     return {"bf16_burst": 1590.0, "bf16_sustained": 1400.0, "hbm": 6650.0, "source": "fallback (B200_PROFILING.md)"}
 
 
+def load_json(rel):
+    path = os.path.join(ROOT, rel)
+    if not os.path.exists(path):
+        return None
+    with open(path) as f:
+        return json.load(f)
+
+
 def load_traffic(batch):
     """DRAM bytes per launch of the roofline kernel from the committed `ncu --set full` capture
     (profiles/roofline_traffic.json; captured at batch 8, the default): read + write, or None."""
-    path = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-    if batch != 8 or not os.path.exists(path):
+    t = (load_json("profiles/roofline_traffic.json") or {}).get("conv_tc_kernel<ALIGN,bf16>")
+    if batch != 8 or not t:
         return None
-    with open(path) as f:
-        t = json.load(f).get("conv_tc_kernel<ALIGN,bf16>")
-    return None if not t else {"dram_bytes": t["dram_bytes_read"] + t["dram_bytes_write"],
-                               "algorithmic_bytes": t["algorithmic_bytes"], "source": t["source"]}
+    return {"dram_bytes": t["dram_bytes_read"] + t["dram_bytes_write"], "algorithmic_bytes": t["algorithmic_bytes"],
+            "source": t["source"]}
+
+
+def load_parity():
+    """Measured errors of the 16-bit kernels against the reference CUDA ops (tests/test_gpu_conv_tc_vs_reference.py on
+    B200, committed as profiles/r2_parity_errors.json)."""
+    d = load_json("profiles/r2_parity_errors.json")
+    if not d:
+        return None
+    r = d["results"]
+
+    def pick(k):
+        return None if k not in r else {"max_abs_over_ref_max": r[k]["max_abs_rel"], "rel_l2": r[k]["rel_l2"]}
+    return {"source": "profiles/r2_parity_errors.json (tests/test_gpu_conv_tc_vs_reference.py, %s)" % d.get("gpu"),
+            "alignconv_bf16_P3_vs_reference_cuda_fp32": pick("alignconv_bf16_P3_vs_reference_cuda_fp32"),
+            "alignconv_fp16_P3_vs_reference_cuda_fp32": pick("alignconv_fp16_P3_vs_reference_cuda_fp32"),
+            "reference_cuda_fp16_P3_vs_its_own_fp32": pick("reference_cuda_fp16_P3_vs_reference_cuda_fp32"),
+            "deform_conv_forward_cuda_fp16_vs_reference_cuda_fp16": pick("deform_conv_forward_cuda_fp16_L0_vs_reference_cuda_fp16"),
+            "orconv_bf16_P3_vs_reference_arf_conv2d_fp32": pick("orconv_bf16_P3_vs_reference_arf_plus_conv2d_fp32")}
 
 
 class ClockSampler(threading.Thread):
@@ -167,10 +207,13 @@ class CpuReferenceHead:
         return results
 
 
-def build_head(torch, device, dtype, seed=0):
+def build_head(torch, device, dtype, seed=0, bias=None):
     from s2anet_b200.head import S2ANetHead
     head = S2ANetHead(NUM_CLASSES)
     head.init_synthetic(seed)
+    if bias is not None:
+        with torch.no_grad():
+            head.odm_cls_head.bias.fill_(bias)
     head = head.eval()
     if device is not None:
         head = head.to(device)
@@ -182,16 +225,24 @@ def build_head(torch, device, dtype, seed=0):
     return head
 
 
+def pin_cpu_threads():
+    """Same thread count whatever launched us (torchrun exports OMP_NUM_THREADS=1 to its workers, a bare `python`
+    does not): all the cores this process may run on."""
+    n = host_cores()
+    for k in ("OMP_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[k] = str(n)
+    return n
+
+
 def run_reference(args, rank, world):
-    """Reference arm: the CPU path, rank 0 only, a bounded sample (1 image per step)."""
+    """Reference arm: the CPU path, rank 0 only, a bounded sample (1 image per step).  Self-contained: the
+    classification bias is the committed calibration, the inputs are seeded, the thread count is pinned."""
     if rank != 0:
         return
+    ncores = pin_cpu_threads()
     import torch
-    torch.set_num_threads(os.cpu_count() or 1)
-    head = build_head(torch, None, torch.float32, seed=0)
-    calib = os.path.join(ROOT, "gpurun_out", "calibrated_bias.pt")
-    if os.path.exists(calib):
-        head.odm_cls_head.bias.data.copy_(torch.load(calib))
+    torch.set_num_threads(ncores)
+    head = build_head(torch, None, torch.float32, seed=0, bias=CALIBRATED_BIAS[3000])
     ref = CpuReferenceHead(head)
     feats = make_feats(torch, 1, 4, "cpu", torch.float32)
     feats = [f.contiguous() for f in feats]
@@ -207,13 +258,28 @@ def run_reference(args, rank, world):
         "ms_per_step": dt / max(1, args.steps) * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "impl": "reference",
         "config": {"workload": "S2ANet R-50-FPN head + 15-class rotated NMS, 1024x1024 (CPU reference path)",
-                   "batch_per_step": 1, "detections_img0": int(res[0][0].shape[0])},
+                   "batch_per_step": 1, "detections_img0": int(res[0][0].shape[0]),
+                   "odm_cls_bias": CALIBRATED_BIAS[3000]},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": ref.kind,
                          "sample": "1 image per step, all 5 FPN levels, torch CPU convs + torchvision deform_conv2d "
                                    "(all threads) + reference ml_nms_rotated CPU kernel (1 thread)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
+
+
+def cuda_time(torch, fn, reps, warm=3):
+    """Average ms of fn() over `reps` calls, CUDA events on the current stream."""
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps
 
 
 def main():
@@ -225,7 +291,10 @@ def main():
     ap.add_argument("--batch", type=int, default=8, help="images per GPU per step")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16", "fp32"])
     ap.add_argument("--candidates", type=int, default=3000, help="target (box, class) candidates per image")
+    ap.add_argument("--exchange", default="push", choices=["push", "nccl"],
+                    help="detection exchange at N > 1: NVLink peer stores fused into the NMS finaliser, or NCCL all-gather")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra bench legs (configs 1-3, NMS sizes, 10k candidates)")
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying CUDA graphs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -235,6 +304,9 @@ def main():
     if args.impl == "reference":
         return run_reference(args, rank, world)
 
+    if world == 1:
+        pin_cpu_threads()
+    import numpy as np
     import torch
     import torch.distributed as dist
     if not torch.cuda.is_available():
@@ -249,76 +321,131 @@ def main():
     from s2anet_b200.alignconv import alignconv_forward
     dtype = {"bf16": torch.bfloat16, "fp16": torch.float16, "fp32": torch.float32}[args.dtype]
     B = args.batch
-    head = build_head(torch, dev, dtype, seed=0)
+    head = build_head(torch, dev, dtype, seed=0, bias=CALIBRATED_BIAS.get(args.candidates))
+    K = head.max_per_img
     # two rotating input sets (> L2 together with the ~GBs of activations each step writes)
     feat_sets = [make_feats(torch, B, 4 + rank + 100 * i, dev, dtype) for i in range(2)]
     ncand = head.calibrate_scores(feat_sets[0], args.candidates)
-    if rank == 0:
-        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-        torch.save(head.odm_cls_head.bias.detach().float().cpu(), os.path.join(ROOT, "gpurun_out", "calibrated_bias.pt"))
+    calibrated_bias = float(head.odm_cls_head.bias.detach().float().mean())
+
+    # ---- detection exchange (N > 1) -------------------------------------------------------------------------
+    exch, exch_mode, exch_note = None, "none", None
+    if world > 1:
+        exch_mode = args.exchange
+        if exch_mode == "push":
+            try:
+                exch = sdist.DetectionExchange(B, K, dev, nbuf=2)
+            except Exception as e:                   # symmetric memory not available on this box: say so, use NCCL
+                exch_mode, exch_note = "nccl", "symmetric memory unavailable (%s)" % (str(e).splitlines()[0][:120],)
+        ok = torch.tensor([1 if exch_mode == "push" else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            exch_mode, exch = "nccl", None
+    send_bufs = [torch.zeros((B, K + 1, 7), dtype=torch.float32, device=dev) for _ in range(2)]
+    recv_bufs = [torch.zeros((world * B, K + 1, 7), dtype=torch.float32, device=dev) for _ in range(2)] if world > 1 else None
 
     graphs = {}
+    in_graph = {"barrier": True, "allgather": True}
 
-    def step(feats):
-        """One pass of the hot path.  The sync-free head+NMS is captured once per input buffer set into
-        a CUDA graph and replayed (the detection all-gather stays outside the graph)."""
-        key = id(feats)
+    def run_head(feats, i):
+        """The capturable part of a step for buffer set i; returns the packed buffer holding the result."""
+        if world == 1:
+            return head.detect(feats)
+        if exch_mode == "push":
+            ptrs, slot0 = exch.targets(i)
+            head.detect_packed(feats, ptrs, slot0)
+            if in_graph["barrier"]:
+                exch.handles[i].barrier(channel=0)
+            return exch.bufs[i]
+        head.detect_packed(feats, [send_bufs[i]], 0)
+        if in_graph["allgather"]:
+            dist.all_gather_into_tensor(recv_bufs[i], send_bufs[i])
+        return recv_bufs[i]
+
+    def capture(feats, i):
+        for _ in range(2):                   # warm every lazy path (weight packing, workspace allocation)
+            run_head(feats, i)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        g = torch.cuda.CUDAGraph()
+        before = _lib.launches
+        with torch.cuda.graph(g):
+            out_ = run_head(feats, i)
+        return g, out_, _lib.launches - before
+
+    def step(feats, i):
+        """One pass of the hot path.  The sync-free head + NMS (+ exchange) is captured once per buffer set into a
+        CUDA graph and replayed."""
         if args.no_graph:
-            out_ = head.detect(feats)
+            out_ = run_head(feats, i)
         else:
-            if key not in graphs:
-                for _ in range(2):                   # warm every lazy path (weight packing, cuDNN autotune)
-                    head.detect(feats)
-                torch.cuda.synchronize()
-                g = torch.cuda.CUDAGraph()
-                before = _lib.launches
-                with torch.cuda.graph(g):
-                    out_ = head.detect(feats)
-                graphs[key] = (g, out_, _lib.launches - before)     # kernels of this library inside the graph
-            g, out_, n_mine = graphs[key]
+            if i not in graphs or graphs[i][3] is not feats:
+                try:
+                    g, out_, n_mine = capture(feats, i)
+                except Exception:
+                    # the collective / barrier refused stream capture: keep it outside the graph
+                    torch.cuda.synchronize()
+                    in_graph["barrier"] = in_graph["allgather"] = False
+                    g, out_, n_mine = capture(feats, i)
+                graphs[i] = (g, out_, n_mine, feats)
+            g, out_, n_mine, _ = graphs[i]
             g.replay()
             _lib.launches += n_mine
-        dets, labels, counts = out_
         if world > 1:
-            dets, labels, counts = sdist.gather_detections(dets, labels, counts)
-        return dets, labels, counts
+            if exch_mode == "push" and not in_graph["barrier"]:
+                exch.handles[i].barrier(channel=0)
+            elif exch_mode == "nccl" and not in_graph["allgather"]:
+                dist.all_gather_into_tensor(recv_bufs[i], send_bufs[i])
+            return sdist.packed_views(out_, K)
+        return out_
 
     def sync_all():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def timed_steps(nsteps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sync_all()
+        e0.record()
+        for i in range(nsteps):
+            out_ = step(feat_sets[i % 2], i % 2)
+        e1.record()
+        sync_all()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), out_
+
     for i in range(args.warmup):
-        out = step(feat_sets[i % 2])
+        out = step(feat_sets[i % 2], i % 2)
     sync_all()
     sampler = ClockSampler(local_rank)
     sampler.start()
     l0 = _lib.launches
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sync_all()
-    e0.record()
-    for i in range(args.steps):
-        out = step(feat_sets[i % 2])
-    e1.record()
-    sync_all()
-    ms = e0.elapsed_time(e1)
+    ms, out = timed_steps(args.steps)
     launches = _lib.launches - l0
     clocks = sampler.stop()
-    t = torch.tensor([ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
     value = world * B * args.steps / (ms / 1e3)
-    ndet = int(out[2][:B].float().mean().item())
+    own = slice(rank * B, (rank + 1) * B) if world > 1 else slice(0, B)
+    ndet = int(out[2][own].float().mean().item())
+    exchange = None
+    if world > 1:
+        # every rank's images must have arrived on every rank: image counts of all slots are plausible
+        assert int((out[2] >= 0).sum().item()) == world * B
+        exchange = {"mode": exch_mode, "inside_cuda_graph": in_graph["barrier"] if exch_mode == "push" else in_graph["allgather"],
+                    "bytes_per_rank_per_step": B * (K + 1) * 7 * 4, "note": exch_note,
+                    "what": "push: mc_emit_kernel stores each kept detection into the packed buffer of every rank over NVLink "
+                            "peer pointers (torch symmetric memory) + one signal-pad barrier; nccl: the same kernel packs "
+                            "locally, then all_gather_into_tensor"}
 
-    # ---- e2e: host (pinned) features in, detections back on the host, copies inside the timed region
+    # ---- e2e: host (pinned) features in, the rank's OWN detections back on the host, copies inside the timed region
     host_sets = [make_feats(torch, B, 4 + rank + 100 * i, dev, dtype, pinned=True) for i in range(2)]
     copy_stream = torch.cuda.Stream(device=dev)
     h2d_bytes = sum(t_.numel() * t_.element_size() for t_ in host_sets[0])
-    K = head.max_per_img
-    host_out = (torch.empty((world * B if world > 1 else B, K, 6), dtype=torch.float32).pin_memory(),
-                torch.empty((world * B if world > 1 else B, K), dtype=torch.float32).pin_memory(),
-                torch.empty((world * B if world > 1 else B,), dtype=torch.int32).pin_memory())
+    host_out = (torch.empty((B, K, 6), dtype=torch.float32).pin_memory(), torch.empty((B, K), dtype=torch.float32).pin_memory(),
+                torch.empty((B,), dtype=torch.int32).pin_memory())
     d2h_bytes = sum(t_.numel() * t_.element_size() for t_ in host_out)
     dev_bufs = [[torch.empty_like(f, device=dev) for f in host_sets[0]] for _ in range(2)]
     ready = [torch.cuda.Event() for _ in range(2)]
@@ -340,11 +467,11 @@ def main():
             if i + 1 < n:
                 upload(i + 1)
             cur.wait_event(ready[i % 2])
-            dets, labels, counts = step(dev_bufs[i % 2])
+            dets, labels, counts = step(dev_bufs[i % 2], i % 2)
             freed[i % 2].record(cur)
-            host_out[0].copy_(dets, non_blocking=True)
-            host_out[1].copy_(labels, non_blocking=True)
-            host_out[2].copy_(counts, non_blocking=True)
+            host_out[0].copy_(dets[own], non_blocking=True)
+            host_out[1].copy_(labels[own], non_blocking=True)
+            host_out[2].copy_(counts[own], non_blocking=True)
         cur.synchronize()
 
     e2e_loop(min(3, args.warmup))
@@ -357,41 +484,77 @@ def main():
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * B * args.steps / float(te.item())
+    del host_sets, dev_bufs
 
-    # ---- second headline metric: rotated IoU pairs/s on BASELINE configs[3]
-    # (21,824 anchors x 500 GTs x 64 images; anchor rows sharded over the ranks, no collective needed
-    # for the assignment-aware form: every rank keeps its row block)
+    # ---- second headline metric: rotated IoU pairs/s on BASELINE configs[3] ------------------------------------
+    # 21,824 anchors x 500 GTs x 64 images; anchor rows dealt out to the ranks in 32-row tiles, cyclically; every
+    # rank allocates only its own rows.  Three forms: compute only, compute + per-GT column maxima +
+    # one [B,M] MAX all-reduce (what label assignment consumes), compute + literal all-gather of the row tiles.
     from s2anet_b200 import synth
-    from s2anet_b200.box_iou_rotated import box_iou_rotated_batched
-    import numpy as np
+    from s2anet_b200.box_iou_rotated import box_iou_rotated_tiles
     IB, IM = 64, 500
     an = torch.from_numpy(synth.all_level_anchors(IB, 3)).to(dev)
     gt = torch.from_numpy(np.stack([synth.dota_like_gt(IM, 100 + i) for i in range(IB)])).to(dev)
-    rb, re = sdist.shard_rows(an.size(1), rank, world)
-    iou_out = torch.empty((IB, an.size(1), IM), dtype=torch.float32, device=dev)      # 2.8 GB, rows [rb, re) written
-    for _ in range(3):
-        box_iou_rotated_batched(an, gt, rb, re, out=iou_out)
-    sync_all()
-    i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = 5
-    i0.record()
-    for _ in range(reps):
-        box_iou_rotated_batched(an, gt, rb, re, out=iou_out)
-    i1.record()
-    sync_all()
-    ti = torch.tensor([i0.elapsed_time(i1) / reps], device=dev, dtype=torch.float64)
+    N_an = an.size(1)
+    pairs = IB * N_an * IM
+    tiles_mine, rows_mine = sdist.shard_tiles(N_an, rank, world)
+    local_iou = torch.empty((IB, len(tiles_mine) * sdist.TILE_ROWS, IM), dtype=torch.float32, device=dev)
+
+    def iou_compute():
+        box_iou_rotated_tiles(an, gt, rank, world, compact=True, out=local_iou, tile_rows=sdist.TILE_ROWS)
+
+    def iou_max_allreduce():
+        iou_compute()
+        gmax = local_iou[:, : rows_mine.numel()].amax(dim=1)
+        if world > 1:
+            dist.all_reduce(gmax, op=dist.ReduceOp.MAX)
+        return gmax
+
+    def timed_max(fn, reps):
+        sync_all()
+        t_ = torch.tensor([cuda_time(torch, fn, reps)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+        return float(t_.item())
+
+    iou_ms = timed_max(iou_compute, 5)
+    iou_ar_ms = timed_max(iou_max_allreduce, 5)
+    iou_ag_ms = None
     if world > 1:
-        dist.all_reduce(ti, op=dist.ReduceOp.MAX)
-    iou_ms = float(ti.item())
-    pairs = IB * an.size(1) * IM
-    iou_bytes = 4.0 * pairs + 20.0 * IB * (an.size(1) + IM)
+        def iou_all_gather():
+            return sdist.sharded_box_iou(an, gt, gather=True)
+        iou_ag_ms = timed_max(iou_all_gather, 2)
+    iou_bytes = 4.0 * pairs + 20.0 * IB * (N_an + IM)
     peaks0 = load_peaks()
+    fma = None
+    if rank == 0:
+        import ctypes
+        v = ctypes.c_double(0.0)
+        with torch.cuda.device(dev):
+            rc = _lib.load().s2a_measure_fp32_fma_tflops(ctypes.byref(v), 3, _lib.stream_ptr(dev))
+        fma = float(v.value) if rc == 0 else None
     iou_metric = {"metric": "rotated IoU pairs/s", "value": pairs / (iou_ms / 1e3), "unit": "pairs/s", "ms": iou_ms,
-                  "config": "21,824 anchors x 500 GTs x 64 images (BASELINE configs[3]), anchor rows sharded over %d GPU(s)" % world,
+                  "config": "21,824 anchors x 500 GTs x 64 images (BASELINE configs[3]); anchor rows dealt to %d GPU(s) in "
+                            "%d-row tiles, cyclically; value = compute form, max over ranks" % (world, sdist.TILE_ROWS),
+                  "forms": {"compute_only_ms": iou_ms,
+                            "max_allreduce_ms": iou_ar_ms, "max_allreduce_pairs_per_s": pairs / (iou_ar_ms / 1e3),
+                            "all_gather_ms": iou_ag_ms,
+                            "all_gather_pairs_per_s": None if iou_ag_ms is None else pairs / (iou_ag_ms / 1e3),
+                            "note": "max_allreduce = kernel + per-GT column maxima of the local rows (one more read of the "
+                                    "local matrix) + one [64,500] MAX all-reduce over NCCL; all_gather = kernel + "
+                                    "all_gather_into_tensor of the packed tiles (2.8 GB on every rank) + the copy that undoes "
+                                    "the cyclic deal"},
                   "roofline": {"bound": "hbm", "achieved": iou_bytes / (iou_ms / 1e3) / 1e9 / world, "peak": peaks0["hbm"],
                                "unit": "GB/s", "frac": iou_bytes / (iou_ms / 1e3) / 1e9 / world / peaks0["hbm"],
-                               "note": "algorithmic bytes 4*N*M + 20*(N+M) per image; per-GPU figure"}}
-    del iou_out, an, gt
+                               "note": "algorithmic bytes 4*N*M + 20*(N+M) per image; per-GPU figure"},
+                  "fp32": None if not fma else {
+                      "fma_tflops_measured": fma, "flop_per_pair": IOU_FLOP_PER_PAIR,
+                      "pairs_per_s_fp32_bound": fma * 1e12 / IOU_FLOP_PER_PAIR,
+                      "frac_of_fp32_bound": pairs / (iou_ms / 1e3) / world / (fma * 1e12 / IOU_FLOP_PER_PAIR),
+                      "note": "SURVEY 8d convention: 350 FP32 flop per pair (the reference's no-intersection case) against the "
+                              "FMA throughput measured in this run (s2a_measure_fp32_fma_tflops); per-GPU figure.  The kernel "
+                              "decides ~95 % of the pairs with a ~20-flop test, so the fraction can exceed 1."}}
+    del local_iou, an, gt
 
     if rank != 0:
         if world > 1:
@@ -402,36 +565,16 @@ def main():
     # timed alone with CUDA events on its launch stream over all five levels of the batch
     peaks = load_peaks()
     roof = None
+    refines = None
     if dtype != torch.float32:
         w = head.align_conv.deform_conv.weight
         outs = head.forward_levels(feat_sets[0])
         refines = [o[5] for o in outs]
         del outs
         from s2anet_b200.conv_tc import alignconv_forward_tc_multi
-
-        def align_all():                 # what the step runs: ONE persistent launch over the five levels
-            alignconv_forward_tc_multi(feat_sets[0], refines, w, STRIDES)
-        for _ in range(3):
-            align_all()
-        torch.cuda.synchronize()
-        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = 10
-        a0.record()
-        for _ in range(reps):
-            align_all()
-        a1.record()
-        torch.cuda.synchronize()
-        t_align = a0.elapsed_time(a1) / reps / 1e3
+        t_align = cuda_time(torch, lambda: alignconv_forward_tc_multi(feat_sets[0], refines, w, STRIDES), 10) / 1e3
         p3 = feat_sets[0][0]
-        for _ in range(3):
-            alignconv_forward(p3, refines[0], w, 8)
-        torch.cuda.synchronize()
-        a0.record()
-        for _ in range(reps):
-            alignconv_forward(p3, refines[0], w, 8)
-        a1.record()
-        torch.cuda.synchronize()
-        t_p3 = a0.elapsed_time(a1) / reps / 1e3
+        t_p3 = cuda_time(torch, lambda: alignconv_forward(p3, refines[0], w, 8), 10) / 1e3
         flops_p3 = 2.0 * B * 128 * 128 * 256 * 2304
         ach = flops_p3 / t_p3 / 1e12
         roof = {"bound": "tensor", "kernel": "conv_tc_kernel<ALIGN,bf16> (AlignConv, P3 level of the batch, one launch)",
@@ -440,10 +583,14 @@ def main():
                 "all_levels_tflops": ALIGN_FLOPS_PER_IMAGE * B / t_align / 1e12,
                 "alignconv_share_of_step": t_align / (ms / 1e3 / args.steps)}
 
+    # ---- the other bench legs of BASELINE.md section 3 (rank 0, one GPU's worth of work each) ---------------------
+    extra = None
+    if not args.no_extra and world == 1:
+        extra = extra_legs(torch, np, dev, dtype, head, feat_sets, refines, peaks, args)
+
     cpu = None
-    line_iou = iou_metric
     if not args.no_cpu_baseline and world == 1:
-        torch.set_num_threads(os.cpu_count() or 1)
+        torch.set_num_threads(host_cores())
         cpu_head = build_head(torch, None, torch.float32, seed=0)
         cpu_head.odm_cls_head.bias.data.copy_(head.odm_cls_head.bias.detach().float().cpu())
         ref = CpuReferenceHead(cpu_head)
@@ -454,6 +601,8 @@ def main():
         cpu = {"value": 1.0 / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": ref.kind,
                "sample": "1 of the %d images of one step (all 5 FPN levels, %d candidates -> %d detections), fp32, "
                          "timed once: %.1f s" % (B, int(ncand), int(r[0][0].shape[0]), dt)}
+        if extra is not None:
+            extra["cpu"] = cpu_legs(torch, np, args)
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -462,15 +611,117 @@ def main():
         "config": {"workload": "S2ANet R-50-FPN head + 15-class rotated NMS at 1024x1024, batch %d per GPU "
                                "(BASELINE configs[4] per-GPU shard; configs[2] is the same at batch 1)" % B,
                    "global_batch": world * B, "positions_per_image": POSITIONS, "nms_candidates_per_image": int(ncand),
-                   "detections_per_image": ndet, "parallelism": "dp%d (image-sharded, detection all-gather)" % world,
+                   "odm_cls_bias": calibrated_bias,
+                   "detections_per_image": ndet, "parallelism": "dp%d (image-sharded, detection exchange: %s)" % (world, exch_mode),
                    "l2": "two rotating feature sets (2 x %.0f MB) plus >1 GB of activations per step: working set > 126 MB L2"
                          % (h2d_bytes / 1e6)},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes},
-        "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "iou": line_iou,
+        "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "iou": iou_metric,
+        "exchange": exchange, "configs": extra, "parity": load_parity(),
     }
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def extra_legs(torch, np, dev, dtype, head, feat_sets, refines, peaks, args):
+    """BASELINE.md section 3 legs that are not the headline: config 1 (2,000 boxes), config 2 (one AlignConv + ORConv2d
+    layer at P3, batch 1), config 3 (the head + NMS at batch 1), NMS at N = 2,000 / 20,000, the step at 10 k candidates."""
+    from s2anet_b200 import synth
+    from s2anet_b200.box_iou_rotated import box_iou_rotated
+    from s2anet_b200.nms_rotated import ml_nms_rotated, nms_rotated_op
+    out = {}
+    # config 1: IoU 2000 x 2000 and NMS on the clustered set
+    b, s, l = synth.clustered_boxes(n_seed=400, rep=5, seed=0)
+    tb, ts, tl = torch.from_numpy(b).to(dev), torch.from_numpy(s).to(dev), torch.from_numpy(l).to(dev)
+    iou_us = cuda_time(torch, lambda: box_iou_rotated(tb, tb), 20) * 1e3
+    nms_us = cuda_time(torch, lambda: nms_rotated_op(tb, ts, 0.5), 20) * 1e3
+    ml_us = cuda_time(torch, lambda: ml_nms_rotated(tb, ts, tl, 0.5), 20) * 1e3
+    out["config1_2000_boxes"] = {"box_iou_rotated_2000x2000_us": iou_us, "iou_pairs_per_s": 4e6 / (iou_us * 1e-6),
+                                 "nms_rotated_us": nms_us, "ml_nms_rotated_us": ml_us,
+                                 "kept": int(nms_rotated_op(tb, ts, 0.5).numel()),
+                                 "note": "NMS times include the 4-byte host read of the result length"}
+    # NMS at N = 20,000 (the stress point of SURVEY 8d): upper-triangle pairs per second
+    b2, s2, _ = synth.clustered_boxes(n_seed=4000, rep=5, seed=1)
+    tb2, ts2 = torch.from_numpy(b2).to(dev), torch.from_numpy(s2).to(dev)
+    n2 = b2.shape[0]
+    nms20_ms = cuda_time(torch, lambda: nms_rotated_op(tb2, ts2, 0.5), 5)
+    out["nms_rotated_20000"] = {"ms": nms20_ms, "pairs_per_s": n2 * (n2 - 1) / 2 / (nms20_ms / 1e3)}
+    if dtype != torch.float32 and refines is not None:
+        from s2anet_b200.alignconv import alignconv_forward
+        from s2anet_b200.orn import orconv_forward
+        # config 2: single AlignConv + ORConv2d layer, P3, batch 1
+        x1 = feat_sets[0][0][:1].contiguous(memory_format=torch.channels_last)
+        a1 = refines[0][:1].contiguous()
+        w = head.align_conv.deform_conv.weight
+        oc = head.or_conv
+        y1 = alignconv_forward(x1, a1, w, 8)
+        t_al = cuda_time(torch, lambda: alignconv_forward(x1, a1, w, 8), 30) / 1e3
+        t_or = cuda_time(torch, lambda: orconv_forward(y1, oc.weight, oc.indices, oc.bias, with_pool=True), 30) / 1e3
+        fl = 2.0 * 128 * 128 * 256 * 2304
+        out["config2_p3_batch1"] = {
+            "alignconv_us": t_al * 1e6, "alignconv_tflops": fl / t_al / 1e12, "alignconv_frac_of_peak": fl / t_al / 1e12 / peaks["bf16_burst"],
+            "orconv_pool_us": t_or * 1e6, "orconv_tflops": fl / t_or / 1e12, "orconv_frac_of_peak": fl / t_or / 1e12 / peaks["bf16_burst"],
+            "note": "128 tiles on 148 SMs: a batch-1 P3 launch cannot fill the GPU (86 % at best); eager calls incl. launch overhead"}
+        # config 3: head + NMS at batch 1 (CUDA graph replay latency)
+        f1 = [f[:1].contiguous(memory_format=torch.channels_last) for f in feat_sets[0]]
+        for _ in range(2):
+            head.detect(f1)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            head.detect(f1)
+        lat = cuda_time(torch, g.replay, 50)
+        out["config3_batch1"] = {"ms_per_image": lat, "images_per_s": 1e3 / lat,
+                                 "note": "head + NMS only (the ResNet-50/FPN backbone stays stock PyTorch and is not timed)"}
+        # the step at ~10 k candidates per image (SURVEY 8d: 2-10 k)
+        bias0 = head.odm_cls_head.bias.detach().clone()
+        n10 = head.calibrate_scores(feat_sets[0], 10000)
+        for _ in range(2):
+            head.detect(feat_sets[0])
+        torch.cuda.synchronize()
+        g2 = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g2):
+            head.detect(feat_sets[0])
+        ms10 = cuda_time(torch, g2.replay, 20)
+        B = feat_sets[0][0].size(0)
+        out["step_at_10k_candidates"] = {"candidates_per_image": int(n10), "ms_per_step": ms10, "images_per_s": B * 1e3 / ms10}
+        with torch.no_grad():
+            head.odm_cls_head.bias.copy_(bias0)
+    return out
+
+
+def cpu_legs(torch, np, args):
+    """The reference's CPU kernels on bounded samples of configs 1 and 4 (1 core: they are strictly serial)."""
+    from oracle import build_oracle
+    from s2anet_b200 import synth
+    out = {"cores": "1 of %d" % host_cores()}
+    iou = build_oracle.load_ref_extension("box_iou_rotated_cuda", "cpu")
+    nms = build_oracle.load_ref_extension("nms_rotated_cuda", "cpu")
+    b, s, _ = synth.clustered_boxes(n_seed=400, rep=5, seed=0)
+    tb, ts = torch.from_numpy(b), torch.from_numpy(s)
+    if iou is not None:
+        t0 = time.perf_counter()
+        iou.box_iou_rotated(tb[:250].contiguous(), tb)
+        dt = time.perf_counter() - t0
+        out["config1_box_iou_rotated_cpu"] = {"sample": "250 of the 2,000 rows (500,000 pairs)", "seconds": dt,
+                                               "pairs_per_s": 5e5 / dt, "extrapolated_2000x2000_s": dt * 8}
+        an = torch.from_numpy(synth.all_level_anchors(1, 3)[0][::22][:992].copy())
+        gt = torch.from_numpy(synth.dota_like_gt(500, 100))
+        t0 = time.perf_counter()
+        iou.box_iou_rotated(an, gt)
+        dt = time.perf_counter() - t0
+        npairs = an.size(0) * gt.size(0)
+        out["config4_box_iou_rotated_cpu"] = {"sample": "%d anchors (every 22nd) x 500 GTs of one image (%d pairs)" % (an.size(0), npairs),
+                                               "seconds": dt, "pairs_per_s": npairs / dt,
+                                               "extrapolated_698368000_pairs_s": dt * 698368000.0 / npairs}
+    if nms is not None:
+        t0 = time.perf_counter()
+        keep = nms.nms_rotated(tb[:1000].contiguous(), ts[:1000].contiguous(), 0.5)
+        dt = time.perf_counter() - t0
+        out["config1_nms_rotated_cpu"] = {"sample": "the first 1,000 of the 2,000 boxes", "seconds": dt, "kept": int(keep.numel()),
+                                           "extrapolated_2000_boxes_s": dt * 4}
+    return out
 
 
 if __name__ == "__main__":

@@ -45,6 +45,9 @@ enum {
 
 S2A_EXPORT int s2a_version(void);
 S2A_EXPORT const char* s2a_last_error(void);
+/* Measurement utility (bench.py): achieved FP32 FMA throughput of this GPU in TFLOP/s, the denominator of the
+ * "pairs/s / FP32-bound" figure SURVEY.md 8d asks for next to the rotated-IoU numbers.  Blocking. */
+S2A_EXPORT int s2a_measure_fp32_fma_tflops(double* tflops_out, int reps, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * box_iou_rotated -- replaces box_iou_rotated_cuda()

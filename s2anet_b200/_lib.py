@@ -21,6 +21,7 @@ _vp, _i64, _i32, _f32, _f64, _sz = C.c_void_p, C.c_int64, C.c_int, C.c_float, C.
 PROTOTYPES = {
     "s2a_version": (_i32, []),
     "s2a_last_error": (C.c_char_p, []),
+    "s2a_measure_fp32_fma_tflops": (_i32, [_vp, _i32, _vp]),
     "s2a_box_iou_rotated": (_i32, [_vp, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _i64, _i32, _vp]),
     "s2a_box_iou_rotated_tiles": (_i32, [_vp, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _i32, _i32, _i32, _i32, _i32, _vp]),
     "s2a_nms_rotated_workspace_bytes": (_sz, [_i64]),

@@ -51,7 +51,7 @@ def box_iou_rotated_batched(boxes1, boxes2, row_begin=0, row_end=None, out=None,
     return out
 
 
-IOU_TILE_ROWS = 64      # the unit the anchor rows are dealt out in (32, 64, 128 or 256; CTAs take up to four tiles)
+IOU_TILE_ROWS = 32      # the unit the anchor rows are dealt out in (32, 64, 128 or 256; CTAs take up to eight tiles)
 
 
 def tile_rows_of(n, tile_first, tile_step, tile_rows=IOU_TILE_ROWS):

@@ -2,6 +2,8 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace s2a {
@@ -27,7 +29,56 @@ int sm_count() {
   return cached[dev];
 }
 
+// FP32 FMA throughput probe: 8 independent FMA chains per thread, 8 CTAs of 256 threads per SM.
+__global__ void __launch_bounds__(256) fma_peak_kernel(float* out, int iters, float seed) {
+  float a0 = seed + threadIdx.x, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f, a4 = a0 + 4.f, a5 = a0 + 5.f, a6 = a0 + 6.f,
+        a7 = a0 + 7.f;
+  const float m = 0.999f, c = 1e-3f;
+#pragma unroll 1
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      a0 = fmaf(a0, m, c); a1 = fmaf(a1, m, c); a2 = fmaf(a2, m, c); a3 = fmaf(a3, m, c);
+      a4 = fmaf(a4, m, c); a5 = fmaf(a5, m, c); a6 = fmaf(a6, m, c); a7 = fmaf(a7, m, c);
+    }
+  }
+  const float r = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+  if (r == 12345.678f) out[0] = r;                     // (keeps the chains alive; never true in practice)
+}
+
 }  // namespace s2a
+
+// Measured FP32 SIMT peak ("B200 FP32 SIMT peak is not in MEASURED_PEAKS.json ... measure it with an
+// FMA loop in the same run"): best of `reps` timed launches, 2 flop per FMA.  Blocking (synchronises `stream`).
+extern "C" int s2a_measure_fp32_fma_tflops(double* tflops_out, int reps, void* stream) {
+  using namespace s2a;
+  S2A_CHECK_ARG(tflops_out != nullptr && reps >= 1, "measure_fp32_fma_tflops: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  float* scratch = nullptr;
+  S2A_CUDA_OK(cudaMalloc(&scratch, 256));
+  cudaEvent_t e0, e1;
+  S2A_CUDA_OK(cudaEventCreate(&e0));
+  S2A_CUDA_OK(cudaEventCreate(&e1));
+  const int blocks = sm_count() * 8, iters = 4096;
+  fma_peak_kernel<<<blocks, 256, 0, st>>>(scratch, iters, 1.0f);      // warm-up
+  double best = 0.0;
+  for (int r = 0; r < reps; ++r) {
+    cudaEventRecord(e0, st);
+    fma_peak_kernel<<<blocks, 256, 0, st>>>(scratch, iters, 1.0f + r);
+    cudaEventRecord(e1, st);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double flops = 2.0 * 64.0 * (double)iters * 256.0 * (double)blocks;
+    if (ms > 0.f) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(scratch);
+  S2A_LAUNCH_OK("fma_peak_kernel");
+  *tflops_out = best;
+  return S2A_OK;
+}
 
 extern "C" int s2a_version(void) { return 100; }
 extern "C" const char* s2a_last_error(void) { return s2a::g_err; }

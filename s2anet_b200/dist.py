@@ -7,7 +7,7 @@ for the plumbing (NCCL over NVLink on the box, gloo in the CPU tests).
   packed [world*B, K+1, 7] buffer of EVERY rank through NVLink peer pointers (torch symmetric memory), followed by
   one signal-pad barrier; `gather_detections` is the plain NCCL form (one all_gather_into_tensor of the same packed
   buffer, which the emit kernel also fills directly);
-* the anchor x GT IoU matrix shards by anchor rows, dealt out in 64-row tiles CYCLICALLY (rank r owns tiles r,
+* the anchor x GT IoU matrix shards by anchor rows, dealt out in 32-row tiles CYCLICALLY (rank r owns tiles r,
   r + world, ...): contiguous blocks would give the last rank every P5-P7 anchor -- large boxes whose pairs mostly
   reach the clipper -- and the first ranks only 32 px P3 anchors the reject test kills (round 1: 0.59 efficiency at 8
   GPUs with NO collective, pure imbalance).  Either the tiles are all-gathered (literal box_iou_rotated result on
@@ -19,7 +19,7 @@ No collective is invented where the path has none: NMS itself is never sharded a
 import torch
 import torch.distributed as dist
 
-TILE_ROWS = 64           # box_iou_rotated.IOU_TILE_ROWS
+TILE_ROWS = 32           # box_iou_rotated.IOU_TILE_ROWS
 
 
 def shard_rows(n, rank, world, align=64):

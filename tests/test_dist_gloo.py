@@ -95,11 +95,11 @@ def test_shard_tiles_deal_rows_cyclically_and_cover_exactly():
             for r in range(world):
                 assert torch.equal(shard_tiles(n, r, world)[1], tile_rows_of(n, r, world))
                 assert torch.equal(shard_tiles(n, r, world, 256)[1], tile_rows_of(n, r, world, 256))
-    # BASELINE config 4 on 8 GPUs: 341 tiles of 64 rows; the P5-P7 anchors (rows 20,480 ...: 21 tiles) reach every rank
+    # BASELINE config 4 on 8 GPUs: 682 tiles of 32 rows; the P5-P7 anchors (rows 20,480 ...: 42 tiles) reach every rank
     for r in range(8):
         tiles, rows = shard_tiles(21824, r, 8)
-        assert tiles == list(range(r, 341, 8)) and sum(t >= 320 for t in tiles) in (2, 3)
-        assert rows.numel() == 64 * len(tiles)               # 21,824 = 341 x 64: no partial tile
+        assert tiles == list(range(r, 682, 8)) and sum(t >= 640 for t in tiles) in (5, 6)
+        assert rows.numel() == 32 * len(tiles)               # 21,824 = 682 x 32: no partial tile
 
 
 def test_two_rank_gloo():
