@@ -341,8 +341,8 @@ def main():
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         if int(ok.item()) == 0:
             exch_mode, exch = "nccl", None
-    send_bufs = [torch.zeros((B, K + 1, 7), dtype=torch.float32, device=dev) for _ in range(2)]
-    recv_bufs = [torch.zeros((world * B, K + 1, 7), dtype=torch.float32, device=dev) for _ in range(2)] if world > 1 else None
+    send_bufs = [torch.zeros((B, K + 1, 8), dtype=torch.float32, device=dev) for _ in range(2)]
+    recv_bufs = [torch.zeros((world * B, K + 1, 8), dtype=torch.float32, device=dev) for _ in range(2)] if world > 1 else None
 
     graphs = {}
     in_graph = {"barrier": True, "allgather": True}
@@ -435,7 +435,7 @@ def main():
         # every rank's images must have arrived on every rank: image counts of all slots are plausible
         assert int((out[2] >= 0).sum().item()) == world * B
         exchange = {"mode": exch_mode, "inside_cuda_graph": in_graph["barrier"] if exch_mode == "push" else in_graph["allgather"],
-                    "bytes_per_rank_per_step": B * (K + 1) * 7 * 4, "note": exch_note,
+                    "bytes_per_rank_per_step": B * (K + 1) * 8 * 4, "note": exch_note,
                     "what": "push: mc_emit_kernel stores each kept detection into the packed buffer of every rank over NVLink "
                             "peer pointers (torch symmetric memory) + one signal-pad barrier; nccl: the same kernel packs "
                             "locally, then all_gather_into_tensor"}
@@ -557,9 +557,7 @@ def main():
     del local_iou, an, gt
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        return shutdown(torch, dist, world, graphs)
 
     # ---- roofline of the dominant kernel of this library: the AlignConv tcgen05 implicit GEMM,
     # timed alone with CUDA events on its launch stream over all five levels of the batch
@@ -619,9 +617,29 @@ def main():
         "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "iou": iou_metric,
         "exchange": exchange, "configs": extra, "parity": load_parity(),
     }
-    print(json.dumps(line))
-    if world > 1:
+    print(json.dumps(line), flush=True)
+    shutdown(torch, dist, world, graphs)
+
+
+def shutdown(torch, dist, world, graphs):
+    """Leave cleanly and in bounded time: CUDA graphs that captured collectives / peer barriers must die before the
+    communicator does (destroying the process group first hung a 2-GPU run for the whole gpurun limit), and a watchdog
+    ends the process if the teardown still stalls."""
+    if world <= 1:
+        return
+    import gc
+    wd = threading.Timer(30.0, lambda: os._exit(0))
+    wd.daemon = True
+    wd.start()
+    graphs.clear()
+    gc.collect()
+    torch.cuda.synchronize()
+    try:
         dist.destroy_process_group()
+    except Exception:
+        pass
+    sys.stdout.flush()
+    os._exit(0)
 
 
 def extra_legs(torch, np, dev, dtype, head, feat_sets, refines, peaks, args):

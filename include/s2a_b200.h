@@ -115,8 +115,8 @@ S2A_EXPORT int s2a_multiclass_nms_rotated(const float* bboxes, const float* scor
                                           float* labels_out, int32_t* num_out, int64_t max_out,
                                           void* workspace, size_t workspace_bytes, void* stream);
 /* The same NMS with the detection exchange of SURVEY.md 8e fused into its finaliser: instead of dets / labels /
- * counts, every kept detection is stored as a 7-float row (x, y, w, h, theta, score, label) into the packed buffers
- * dests[0 .. ndests-1], each [slots, max_out + 1, 7] fp32, at image slot slot0 + b; row max_out of a slot holds the
+ * counts, every kept detection is stored as an 8-float row (x, y, w, h, theta, score, label, 0: two 16-byte stores) into
+ * the packed buffers dests[0 .. ndests-1], each [slots, max_out + 1, 8] fp32 and 16-byte aligned, at image slot slot0 + b; row max_out of a slot holds the
  * count in column 0.  With ndests = 1 this is the "pack" of the NCCL all-gather done by the kernel that produces the
  * detections; with ndests = world the destinations are the ranks' symmetric buffers (this rank's own and its peers'
  * NVLink-mapped pointers, <= 8) and the stores ARE the all-gather -- the caller only adds a barrier

@@ -267,7 +267,7 @@ static int launch_iou(const float* boxes1, int64_t n, const float* boxes2, int64
   const int64_t mine_rows = (mine - 1) * tile_rows + std::min<int64_t>(tile_rows, nrows - last_tile * tile_rows);
   // packed output: CTAs are 256 rows high and take several dealt tiles each; in-place output: one dealt tile per CTA
   // (its rows must be consecutive in the output)
-  const int cta_rows = (compact && tile_step > 1) ? kIouRowsMax : tile_rows;
+  const int cta_rows = compact ? kIouRowsMax : tile_rows;
   const int64_t nctas = ceil_div(mine_rows, cta_rows);
   S2A_CHECK_ARG(batch <= 65535 && ceil_div(m, iou_cols<1>()) <= 65535 && nctas < (1ll << 31),
                 "box_iou_rotated: batch and ceil(m/256) must be <= 65535");

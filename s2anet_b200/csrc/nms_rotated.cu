@@ -510,8 +510,9 @@ mc_sweep_kernel(const unsigned long long* __restrict__ mask, const int* __restri
 // Merge by rank: a survivor's output row is the number of survivors of the same image that precede
 // it in (score desc, box asc, class asc) order = its own position in its class + one binary search
 // per other class.
-// Destinations of the packed form: up to 8 buffers [slots, K + 1, 7] fp32 (one per rank of a node: this rank's own
-// and its peers' over NVLink), row k < K = (x, y, w, h, theta, score, label), row K = (count, 0, ...).
+// Destinations of the packed form: up to 8 buffers [slots, K + 1, 8] fp32 (one per rank of a node: this rank's own
+// and its peers' over NVLink), row k < K = (x, y, w, h, theta, score, label, 0), row K = (count, 0, ...).  Rows are
+// 32 bytes so that a detection is two 16-byte stores per destination (NVLink likes wide stores).
 constexpr int kMcMaxPeers = 8;
 struct McPush {
   float* dst[kMcMaxPeers];
@@ -534,8 +535,9 @@ __global__ void mc_emit_kernel(const float* __restrict__ bboxes, const float* __
     const int32_t cnt = (int32_t)(tot < lim ? tot : lim);
     if (num_out) num_out[b] = cnt;
     for (int p = 0; p < push.npeers; ++p) {
-      float* o = push.dst[p] + ((size_t)(push.slot0 + b) * (push.K + 1) + push.K) * 7;
-      o[0] = (float)cnt; o[1] = 0.0f; o[2] = 0.0f; o[3] = 0.0f; o[4] = 0.0f; o[5] = 0.0f; o[6] = 0.0f;
+      float4* o = reinterpret_cast<float4*>(push.dst[p] + ((size_t)(push.slot0 + b) * (push.K + 1) + push.K) * 8);
+      o[0] = make_float4((float)cnt, 0.0f, 0.0f, 0.0f);
+      o[1] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     }
   }
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -566,9 +568,11 @@ __global__ void mc_emit_kernel(const float* __restrict__ bboxes, const float* __
     }
     // the detection exchange fused into the finaliser: the row goes straight into the packed buffer of every rank
     // (plain stores through NVLink peer mappings; a kernel boundary + the exchange's barrier publish them)
+    const float4 lo = make_float4(d0, d1, d2, d3), hi = make_float4(d4, sv, (float)c, 0.0f);
     for (int p = 0; p < push.npeers; ++p) {
-      float* o = push.dst[p] + ((size_t)(push.slot0 + b) * (push.K + 1) + rank) * 7;
-      o[0] = d0; o[1] = d1; o[2] = d2; o[3] = d3; o[4] = d4; o[5] = sv; o[6] = (float)c;
+      float4* o = reinterpret_cast<float4*>(push.dst[p] + ((size_t)(push.slot0 + b) * (push.K + 1) + rank) * 8);
+      o[0] = lo;
+      o[1] = hi;
     }
   }
 }
@@ -712,8 +716,8 @@ __global__ void mc_zero_counts_kernel(int32_t* num_out, int batch, const McPush 
   if (b >= batch) return;
   if (num_out) num_out[b] = 0;
   for (int p = 0; p < push.npeers; ++p) {
-    float* o = push.dst[p] + ((size_t)(push.slot0 + b) * (push.K + 1) + push.K) * 7;
-    for (int e = 0; e < 7; ++e) o[e] = 0.0f;
+    float* o = push.dst[p] + ((size_t)(push.slot0 + b) * (push.K + 1) + push.K) * 8;
+    for (int e = 0; e < 8; ++e) o[e] = 0.0f;
   }
 }
 

@@ -4,7 +4,7 @@ for the plumbing (NCCL over NVLink on the box, gloo in the CPU tests).
 * inference shards by image batch: every rank runs the head + NMS on its own images; the only exchange is the
   detections (<= max_per_img x 7 floats + a count per image).  `DetectionExchange` does it without a pack step and
   without a library collective: the NMS finaliser (mc_emit_kernel) stores every kept detection straight into the
-  packed [world*B, K+1, 7] buffer of EVERY rank through NVLink peer pointers (torch symmetric memory), followed by
+  packed [world*B, K+1, 8] buffer of EVERY rank through NVLink peer pointers (torch symmetric memory), followed by
   one signal-pad barrier; `gather_detections` is the plain NCCL form (one all_gather_into_tensor of the same packed
   buffer, which the emit kernel also fills directly);
 * the anchor x GT IoU matrix shards by anchor rows, dealt out in 32-row tiles CYCLICALLY (rank r owns tiles r,
@@ -109,21 +109,21 @@ def sharded_assign_stats(anchors, gts, iou_fn=None, group=None, tile_rows=TILE_R
 # ---- detections ---------------------------------------------------------------------------------------------
 
 def packed_views(packed, K):
-    """(dets [n,K,6], labels [n,K], counts [n] int32) views / values of a packed [n, K+1, 7] detection buffer: rows
-    < K are (x, y, w, h, theta, score, label), row K holds the count in column 0."""
+    """(dets [n,K,6], labels [n,K], counts [n] int32) views / values of a packed [n, K+1, 8] detection buffer: rows
+    < K are (x, y, w, h, theta, score, label, 0), row K holds the count in column 0."""
     return packed[:, :K, :6], packed[:, :K, 6], packed[:, K, 0].to(torch.int32)
 
 
 def gather_detections(dets, labels, counts, group=None, packed=None):
     """NCCL form of the detection exchange: dets [B,K,6], labels [B,K], counts [B] of every rank ->
     ([world*B,K,6], [world*B,K], [world*B]) on every rank.  One packed buffer, one collective.  `packed`
-    ([B,K+1,7], filled directly by multiclass_nms_rotated_batched(packed_out=...)) skips the pack."""
+    ([B,K+1,8], filled directly by multiclass_nms_rotated_packed) skips the pack."""
     rank, world = _world(group)
     if world == 1 and packed is None:
         return dets, labels, counts
     if packed is None:
         B, K, _ = dets.shape
-        packed = torch.empty((B, K + 1, 7), dtype=torch.float32, device=dets.device)
+        packed = torch.zeros((B, K + 1, 8), dtype=torch.float32, device=dets.device)
         packed[:, :K, :6] = dets
         packed[:, :K, 6] = labels
         packed[:, K, :] = 0
@@ -131,7 +131,7 @@ def gather_detections(dets, labels, counts, group=None, packed=None):
     B, K = packed.size(0), packed.size(1) - 1
     if world == 1:
         return packed_views(packed, K)
-    recv = torch.empty((world * B, K + 1, 7), dtype=torch.float32, device=packed.device)
+    recv = torch.empty((world * B, K + 1, 8), dtype=torch.float32, device=packed.device)
     dist.all_gather_into_tensor(recv, packed, group=group)
     return packed_views(recv, K)
 
@@ -139,7 +139,7 @@ def gather_detections(dets, labels, counts, group=None, packed=None):
 class DetectionExchange:
     """The detection all-gather fused into the NMS finaliser over NVLink peer memory.
 
-    Every rank owns `nbuf` symmetric buffers [world*B, K+1, 7] (torch.distributed._symmetric_memory: cudaMalloc'd
+    Every rank owns `nbuf` symmetric buffers [world*B, K+1, 8] (torch.distributed._symmetric_memory: cudaMalloc'd
     with peer access, pointers exchanged once at construction).  `targets(i)` are the peer pointers of buffer i, which
     multiclass_nms_rotated_batched(push_to=...) hands to mc_emit_kernel: each kept detection is stored into slot
     rank*B + b of EVERY rank's buffer as it is ranked -- no pack kernels, no staging copy, no collective call.
@@ -155,7 +155,7 @@ class DetectionExchange:
         self.B, self.K = B, K
         self.bufs, self.handles = [], []
         for _ in range(nbuf):
-            t = symm.empty((self.world * B, K + 1, 7), dtype=torch.float32, device=device)
+            t = symm.empty((self.world * B, K + 1, 8), dtype=torch.float32, device=device)
             t.zero_()
             h = symm.rendezvous(t, self.group.group_name)
             self.bufs.append(t)

@@ -266,7 +266,7 @@ class S2ANetHead(nn.Module):
     @torch.no_grad()
     def detect_packed(self, feats, dests, slot0=0):
         """detect() with the detection exchange fused into the NMS finaliser: rows go straight into the packed
-        [slots, max_per_img + 1, 7] buffers `dests` (tensors and / or NVLink peer pointers), image b at slot slot0 + b."""
+        [slots, max_per_img + 1, 8] buffers `dests` (tensors and / or NVLink peer pointers), image b at slot slot0 + b."""
         from .nms_rotated import multiclass_nms_rotated_packed
         bboxes, scores = self.select_and_decode(self.forward_levels(feats))
         multiclass_nms_rotated_packed(bboxes, scores, dests, slot0, self.score_thres_before_nms, self.iou_thres_nms,

@@ -98,7 +98,7 @@ def multiclass_nms_rotated_batched(bboxes, scores, score_thr=0.05, iou_thr=0.5, 
 
 
 def multiclass_nms_rotated_packed(bboxes, scores, dests, slot0=0, score_thr=0.05, iou_thr=0.5, max_per_img=2000, K=None):
-    """The batched NMS writing PACKED rows into one or several [slots, K+1, 7] buffers (see
+    """The batched NMS writing PACKED rows into one or several [slots, K+1, 8] buffers (see
     s2a_multiclass_nms_rotated_packed): `dests` is a list of fp32 tensors and / or raw device pointers (ints: the
     NVLink-mapped buffers of peer ranks, dist.DetectionExchange.targets()); image b lands in slot slot0 + b.
     K (rows per image) defaults to dests[0].size(1) - 1.  Sync-free, graph-capturable, 6 launches."""

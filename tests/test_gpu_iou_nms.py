@@ -266,7 +266,7 @@ def _ref_gpu(name):
 
 def test_multiclass_packed_form_equals_plain_outputs():
     """The detection exchange's pack fused into the NMS finaliser (s2a_multiclass_nms_rotated_packed): rows
-    (x, y, w, h, theta, score, label) + the count row, into one or several destination buffers at a slot offset,
+    (x, y, w, h, theta, score, label, 0) + the count row, into one or several destination buffers at a slot offset,
     are exactly the plain outputs."""
     from s2anet_b200.dist import packed_views
     from s2anet_b200.nms_rotated import multiclass_nms_rotated_batched, multiclass_nms_rotated_packed
@@ -277,8 +277,8 @@ def test_multiclass_packed_form_equals_plain_outputs():
     sc[2] = 0.0                                                            # an image without detections
     tb, ts = torch.from_numpy(bx).to(DEV), torch.from_numpy(sc).to(DEV)
     d, l, c = multiclass_nms_rotated_batched(tb, ts, 0.05, 0.5, K)
-    dst0 = torch.full((5, K + 1, 7), -1.0, device=DEV)
-    dst1 = torch.full((5, K + 1, 7), -1.0, device=DEV)
+    dst0 = torch.full((5, K + 1, 8), -1.0, device=DEV)
+    dst1 = torch.full((5, K + 1, 8), -1.0, device=DEV)
     multiclass_nms_rotated_packed(tb, ts, [dst0, dst1.data_ptr()], slot0=2, score_thr=0.05, iou_thr=0.5, max_per_img=K)
     assert torch.equal(dst0, dst1)
     assert bool((dst0[:2] == -1.0).all())                                  # other ranks' slots untouched
