@@ -37,8 +37,12 @@ __device__ __forceinline__ bool anchor_inside(const float* a, float img_w, float
   return a[0] >= 0.0f && a[1] >= 0.0f && a[0] <= img_w && a[1] <= img_h && a[2] < img_w && a[3] < img_h;
 }
 
+// the general 24-point clipper (thread-local arrays), out of line: reached by degenerate pairs only
+__device__ __noinline__ float asg_clip_general(const RBox& A, const RBox& B) { return rbox_iou_clip(A, B); }
+
 template <int PASS>
 __global__ void __launch_bounds__(kAsgThreads) assign_labels_kernel(const AssignParams p) {
+  extern __shared__ float s_pts[];                   // 16 x kAsgThreads floats: candidate columns of the register clipper
   __shared__ RBox s_row[kAsgR];
   __shared__ RBox s_col[kAsgC];
   __shared__ __align__(16) uint16_t s_list[kAsgR * kAsgC];
@@ -127,7 +131,9 @@ __global__ void __launch_bounds__(kAsgThreads) assign_labels_kernel(const Assign
     for (int k = tid; k < cnt; k += kAsgThreads) {
       const int pr = s_list[k];
       const int r = pr >> 8, c = pr & (kAsgC - 1);
-      const float v = rbox_iou_clip(s_row[r], s_col[c]);
+      bool ok;
+      float v = rbox_iou_clip_try(s_row[r], s_col[c], s_pts + tid, kAsgThreads, ok);
+      if (!ok) v = asg_clip_general(s_row[r], s_col[c]);
       if (!(v >= 0.0f && v <= 1.0f)) {                  // models/utils.py:89-96: out-of-range IoUs become -0.5
         if (PASS == 1) atomicAdd(&s_rbad[r], 1);
         continue;
@@ -217,9 +223,12 @@ extern "C" int s2a_assign_labels(const float* anchors, const float* gts, const i
   p.gt_max_assign_all = gt_max_assign_all; p.filter_invalid_anchors = filter_invalid_anchors;
   if (max_gts > 0) S2A_CUDA_OK(cudaMemsetAsync(p.col_best, 0, (size_t)batch * max_gts * 8, st));
   dim3 grid((unsigned)ceil_div(num_anchors, kAsgR), (unsigned)batch);
-  assign_labels_kernel<1><<<grid, kAsgThreads, 0, st>>>(p);
+  constexpr size_t kPtsBytes = sizeof(float) * 16 * kAsgThreads;     // dynamic, on top of ~45 KB of static shared memory
+  S2A_CUDA_OK(cudaFuncSetAttribute(assign_labels_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPtsBytes));
+  S2A_CUDA_OK(cudaFuncSetAttribute(assign_labels_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPtsBytes));
+  assign_labels_kernel<1><<<grid, kAsgThreads, kPtsBytes, st>>>(p);
   S2A_LAUNCH_OK("assign_labels_kernel<1>");
-  assign_labels_kernel<2><<<grid, kAsgThreads, 0, st>>>(p);
+  assign_labels_kernel<2><<<grid, kAsgThreads, kPtsBytes, st>>>(p);
   S2A_LAUNCH_OK("assign_labels_kernel<2>");
   return S2A_OK;
 }

@@ -42,8 +42,12 @@ struct MaskTileSmem {
   // one byte per (row, column) pair: "suppresses".  Plain stores -- 64-bit shared-memory atomicOr is a CAS loop, and
   // up to 64 threads setting bits of the same row word serialised on it.
   __align__(16) uint8_t flag[kBlk * kBlk];
+  float pts[16 * kMaskThreads];      // per-thread candidate column of the register-resident clipper (rbox_iou_clip_try)
   int count;
 };
+
+// the general 24-point clipper (thread-local arrays), out of line: reached by degenerate pairs only
+__device__ __noinline__ float nms_clip_general(const RBox& A, const RBox& B) { return rbox_iou_clip(A, B); }
 
 // rows/cols: pointers to the first prepared box of the row/col block; nr/nc valid counts;
 // diag: row block == col block (only c > r is evaluated); labels may be null.
@@ -112,11 +116,40 @@ __device__ __forceinline__ void mask_tile(MaskTileSmem& s, const RBox* __restric
     }
   }
   __syncthreads();
+  // full classification of the listed pairs (separating axes, collinearity guards), compacting the survivors in
+  // place: round q reads entries [256 q, 256 q + 256) and, after a barrier, appends below the entries read so far
+  const int cnt_maybe = s.count;
+  __syncthreads();
+  if (tid == 0) s.count = 0;
+  __syncthreads();
+  for (int k0 = 0; k0 < cnt_maybe; k0 += kMaskThreads) {
+    const int k = k0 + tid;
+    bool clip = false;
+    int p = 0;
+    if (k < cnt_maybe) {
+      p = s.list[k];
+      if (rbox_classify(s.row[p >> 6], s.col[p & (kBlk - 1)]) != RB_ZERO) clip = true;
+      else if (zero_suppresses) s.flag[p] = 1;                        // IoU == 0 > thr (negative thresholds only)
+    }
+    __syncthreads();
+    const unsigned bal = __ballot_sync(0xffffffffu, clip);
+    if (bal) {
+      int base = 0;
+      if (lane == 0) base = atomicAdd(&s.count, __popc(bal));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (clip) s.list[base + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)p;
+    }
+  }
+  __syncthreads();
+  // dense clipping of the survivors: candidate points in registers (rbox_hull8), general routine for degenerate pairs
   const int cnt = s.count;
   for (int k = tid; k < cnt; k += kMaskThreads) {
     const int p = s.list[k];
     const int r = p >> 6, cc = p & (kBlk - 1);
-    if (rbox_iou(s.row[r], s.col[cc]) > thr) s.flag[p] = 1;
+    bool ok;
+    float v = rbox_iou_clip_try(s.row[r], s.col[cc], s.pts + tid, kMaskThreads, ok);
+    if (!ok) v = nms_clip_general(s.row[r], s.col[cc]);
+    if (v > thr) s.flag[p] = 1;
   }
   __syncthreads();
   {
