@@ -431,11 +431,30 @@ def main():
     own = slice(rank * B, (rank + 1) * B) if world > 1 else slice(0, B)
     ndet = int(out[2][own].float().mean().item())
     exchange = None
+    rank_ms = None
+    if world > 1:
+        # the residual of the scaling curve, named: every rank's own step WITHOUT the exchange (same graph-replayed head +
+        # NMS, no peer stores, no barrier).  The exchanged step runs at the pace of the slowest GPU of the box (each step
+        # ends with all ranks' detections on every rank), so max(rank_ms) is its floor whatever the exchange costs.
+        for _ in range(2):
+            head.detect(feat_sets[0])
+        torch.cuda.synchronize()
+        g_local = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g_local):
+            head.detect(feat_sets[0])
+        sync_all()
+        mine_ms = torch.tensor([cuda_time(torch, g_local.replay, min(args.steps, 50))], device=dev, dtype=torch.float64)
+        all_ms = [torch.zeros_like(mine_ms) for _ in range(world)]
+        dist.all_gather(all_ms, mine_ms)
+        rank_ms = [float(t_.item()) for t_ in all_ms]
+        del g_local
     if world > 1:
         # every rank's images must have arrived on every rank: image counts of all slots are plausible
         assert int((out[2] >= 0).sum().item()) == world * B
         exchange = {"mode": exch_mode, "inside_cuda_graph": in_graph["barrier"] if exch_mode == "push" else in_graph["allgather"],
                     "bytes_per_rank_per_step": B * (K + 1) * 8 * 4, "note": exch_note,
+                    "ms_per_step_without_exchange_by_rank": rank_ms,
+                    "exchange_cost_ms": ms / args.steps - max(rank_ms),
                     "what": "push: mc_emit_kernel stores each kept detection into the packed buffer of every rank over NVLink "
                             "peer pointers (torch symmetric memory) + one signal-pad barrier; nccl: the same kernel packs "
                             "locally, then all_gather_into_tensor"}

@@ -247,8 +247,9 @@ static int launch_iou(const float* boxes1, int64_t n, const float* boxes2, int64
   S2A_CHECK_ARG(tile_step >= 1 && tile_first >= 0 && tile_first < tile_step,
                 "box_iou_rotated: need 0 <= tile_first < tile_step (got %d, %d)", tile_first, tile_step);
   if (tile_rows <= 0) {
-    // default: 256-row tiles; smaller ones while the grid would not fill the GPU twice over
-    tile_rows = kIouRowsMax;
+    // default: 128-row tiles (as fast as 256-row ones on config 4 and half the tail: a CTA of 128 x 512 pairs runs
+    // ~30 us); smaller ones while the grid would not fill the GPU twice over
+    tile_rows = kIouRowsMax / 2;
     const int64_t cols = ceil_div(std::max<int64_t>(m, 1), iou_cols<2>()) * std::max<int64_t>(batch, 1);
     while (tile_rows > 32 && ceil_div(row_end - row_begin, tile_rows) * cols < 2 * (int64_t)sm_count() && tile_step == 1)
       tile_rows >>= 1;
@@ -267,7 +268,7 @@ static int launch_iou(const float* boxes1, int64_t n, const float* boxes2, int64
   const int64_t mine_rows = (mine - 1) * tile_rows + std::min<int64_t>(tile_rows, nrows - last_tile * tile_rows);
   // packed output: CTAs are 256 rows high and take several dealt tiles each; in-place output: one dealt tile per CTA
   // (its rows must be consecutive in the output)
-  const int cta_rows = compact ? kIouRowsMax : tile_rows;
+  const int cta_rows = compact ? std::max(tile_rows, kIouRowsMax / 2) : tile_rows;
   const int64_t nctas = ceil_div(mine_rows, cta_rows);
   S2A_CHECK_ARG(batch <= 65535 && ceil_div(m, iou_cols<1>()) <= 65535 && nctas < (1ll << 31),
                 "box_iou_rotated: batch and ceil(m/256) must be <= 65535");

@@ -319,6 +319,8 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t sr
 }
 // all but the most recent store have finished READING their shared-memory source (two staging buffers)
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+// all but the two most recent stores have finished reading (three staging buffers used round-robin)
+__device__ __forceinline__ void tma_store_wait_read2() { asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_THREADS) : "memory"); }
 
@@ -400,6 +402,40 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "r"(taddr)
       : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// the same load without the wait: several can be in flight, tmem_ld_wait() completes all of them
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Warpgroup register reallocation (all four warps of a warpgroup execute it together).  AlignConv's 768 threads
+// start with 80 registers each; the TMA / MMA warpgroup gives registers back and the epilogue warpgroup takes them,
+// so that it can keep TWO 32-column accumulator chunks (64 fp32 registers) in flight per tensor-memory wait.
+template <int N> __device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+
+// two fp32 -> one packed 16-bit pair (lo in the low half) with the ReLU folded into the conversion
+template <typename T> __device__ __forceinline__ uint32_t pack2_relu(float lo, float hi);
+template <> __device__ __forceinline__ uint32_t pack2_relu<__nv_bfloat16>(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+template <> __device__ __forceinline__ uint32_t pack2_relu<__half>(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
 }
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
@@ -642,7 +678,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t0));
          })
 
-  if (GROUPS > 0 && warp < kProdWarps) {
+  auto role_producer = [&]() {
     // ===================== A producers (AlignConv: bilinear gather through the LSU) =====================
     // In TC_PLAIN mode (ORConv2d) the A tile is a shifted patch of the NHWC map, which TMA fetches
     // directly (zero-filled outside the map), so these warps have nothing to do.
@@ -740,7 +776,8 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       kb -= nkb;                           // first k-block of this group in the next tile
       hseq += (uint32_t)ncb;
     }
-  } else if (warp == kTmaWarp) {
+  };
+  auto role_tma = [&]() {
     // ===================== TMA: this CTA's C_out/CG weight rows (and, PLAIN, its A tile) =====================
     // (the whole warp walks the loop and waits; one elected lane arms the barrier and issues the copies)
     {
@@ -833,7 +870,8 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         warm = true;
       }
     }
-  } else if (IS_PLAIN && warp == kMmaWarp + 1) {
+  };
+  auto role_halo = [&]() {
     // ===================== plain conv: halo loads (the A operand) =====================
     // One box {64 ch, 16, 18, 1} per (tile, 64-channel block) at (tx0 - 1, ty0 - 1), zero-filled outside the map and
     // beyond C, into buffer (sequence number & 1).  A buffer is recycled when the last tap's MMAs of its channel
@@ -858,7 +896,8 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         __syncwarp();
       }
     }
-  } else if (warp == kMmaWarp) {
+  };
+  auto role_mma = [&]() {
     // ===================== MMA issuer (leader CTA only) =====================
     if (leader) {                                    // the whole warp runs the loop; one elected lane issues
       // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 (1<<4), A/B format (bf16=1, f16=0)
@@ -1023,7 +1062,8 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       }
 #endif
     }
-  } else if (warp >= kEpiWarp0 && warp < kTmaWarp) {
+  };
+  auto role_epilogue = [&]() {
     // ===================== epilogue warps (also build the sample tables) =====================
     const int et = tid - kEpiWarp0 * 32;          // 0..127
     const int quad = warp & 3;                    // TMEM lane quadrant this warp may read (warp id % 4)
@@ -1051,49 +1091,16 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
       const bool valid = (y < L.H && x < L.W) && !ghost && tc.b < p.B;       // (b == B: the padding tile before wsplit)
       const float* bias = tc.lvl >= p.wsplit ? p.bias2 : p.bias;
       const size_t pos = (size_t)(tc.b * L.H + y) * L.W + x;
-      // 32 channels at a time: TMEM -> registers -> bias / ReLU / 8-way orientation max -> 16-bit -> a 64-byte row
-      // of the staging buffer (SWIZZLE_64B, conflict-free) -> one TMA store of the 8 x 16 x 32-channel box.  The
-      // stores never touch the LSU global path the gather lives on, and partial tiles are clipped by TMA.
-      for (int c0 = 0, ci = 0; c0 < p.Co && !(p.debug & 32); c0 += TC_OUT_CH, ++ci) {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * 256 + c0), v);
-        if (c0 + TC_OUT_CH >= p.Co) {               // last columns are in registers: the accumulator is free
-          // (one arrive per warp: 128 per-thread arrives on the leader's barrier -- half of them remote -- took
-          // ~3,000 cycles to get through, on the critical path of the accumulator hand-off)
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(ld_acc_empty + 8 * as);
-        }
-        uint32_t pk[16];
-        float m[4];
-        if (MODE == TC_ALIGN) {
-          // AlignConv: ReLU only (alignconv.py:97), no bias, no pooling -- the epilogue warps share their issue
-          // slots with 16 producer warps, so every instruction here delays the hand-back of the accumulator
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            // ReLU on the packed pair after rounding (rounding is monotone and keeps 0): one HMNMX2 instead of two FMNMX
-            H2 h = from_f2<T>(__uint_as_float(v[i]), __uint_as_float(v[i + 1]));
-            if (p.relu) h = __hmax2(h, from_f2<T>(0.0f, 0.0f));       // (the generic deformable conv has no ReLU)
-            pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&h);
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            float t0 = __uint_as_float(v[i]), t1 = __uint_as_float(v[i + 1]);
-            if (bias) { t0 += __ldg(bias + c0 + i); t1 += __ldg(bias + c0 + i + 1); }
-            if (p.relu) { t0 = fmaxf(t0, 0.0f); t1 = fmaxf(t1, 0.0f); }
-            const H2 h = from_f2<T>(t0, t1);
-            pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&h);
-            const float mx = fmaxf(t0, t1);
-            m[i >> 3] = (i & 7) == 0 ? mx : fmaxf(m[i >> 3], mx);
-          }
-        }
-        // Each epilogue warp stores its own 32 tile rows (2 spatial rows x 16 pixels) -- no barrier across the four
-        // warps.  Three 2 KB staging buffers per warp: when the elected lane's wait returns, every store of this warp
-        // but the most recent one has finished reading its buffer; __syncwarp publishes that, so the chunk after this
-        // one may overwrite the buffer used two chunks before it while the store in between is still in flight.
+      // Staging + store of one packed 32-channel chunk.  Each epilogue warp stores its own 32 tile rows (2 spatial
+      // rows x 16 pixels) -- no barrier across the four warps.  Three 2 KB staging buffers per warp, used round-robin:
+      // when the elected lane's wait returns, every store of this warp but the two most recent ones has finished
+      // reading its buffer; __syncwarp publishes that.
+      // (scalars, not the struct: a by-reference capture of `tc` kept it in local memory)
+      const int tc_lvl = tc.lvl, tc_b = tc.b, tc_tx0 = tc.tx0, tc_ty0 = tc.ty0;
+      void* const pooled_ptr = L.pooled;
+      auto emit_chunk = [&](const uint32_t (&pk)[16], float m0_, float m1_, float m2_, float m3_, int c0, int ci) {
         const bool issuer = elect_one();
-        if (issuer) tma_store_wait_read();
+        if (issuer) tma_store_wait_read2();
         __syncwarp();
         uint8_t* sbuf = s_out + (ci % TC_OUT_BUFS) * TC_OUT_BYTES + quad * (32 * TC_OUT_CH * 2);
         uint8_t* row = sbuf + lane * (TC_OUT_CH * 2);
@@ -1104,13 +1111,72 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         fence_proxy_async_smem();
         __syncwarp();
         if (issuer && !ghost && !(p.debug & 64))
-          tma_store_4d(&maps.y[tc.lvl], smem_u32(sbuf), c0, tc.tx0, tc.ty0 + (32 / tc_pw<MODE>()) * quad, tc.b);
-        if (IS_PLAIN && valid && L.pooled) {
+          tma_store_4d(&maps.y[tc_lvl], smem_u32(sbuf), c0, tc_tx0, tc_ty0 + (32 / tc_pw<MODE>()) * quad, tc_b);
+        if (IS_PLAIN && valid && pooled_ptr) {
           uint2 o;
           H2* oh = reinterpret_cast<H2*>(&o);
-          oh[0] = from_f2<T>(m[0], m[1]);
-          oh[1] = from_f2<T>(m[2], m[3]);
-          *reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(L.pooled) + (pos * (p.Co / 8) + c0 / 8) * 2) = o;
+          oh[0] = from_f2<T>(m0_, m1_);
+          oh[1] = from_f2<T>(m2_, m3_);
+          *reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(pooled_ptr) + (pos * (p.Co / 8) + c0 / 8) * 2) = o;
+        }
+      };
+      const uint32_t acc_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * 256);
+      // (one arrive per warp: 128 per-thread arrives on the leader's barrier -- half of them remote -- took ~3,000
+      // cycles to get through, on the critical path of the accumulator hand-off)
+      auto release_acc = [&]() {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(ld_acc_empty + 8 * as);
+      };
+      if (MODE == TC_ALIGN) {
+        // AlignConv has ONE accumulator: the MMA warp waits for this drain between tiles, so it is organised for
+        // latency.  Two 32-column chunks are loaded per tensor-memory wait (the second load's latency hides behind the
+        // first), ReLU is folded into the conversion (cvt.rn.relu), and a pair's stores are issued without waiting for
+        // the previous pair's (three staging buffers).  No bias, no pooling (alignconv.py:97).
+        for (int c0 = 0, ci = 0; c0 < p.Co && !(p.debug & 32); c0 += 2 * TC_OUT_CH, ci += 2) {
+          const bool two = c0 + TC_OUT_CH < p.Co;
+          uint32_t va[32], vb[32];
+          tmem_ld32_nowait(acc_addr + (uint32_t)c0, va);
+          if (two) tmem_ld32_nowait(acc_addr + (uint32_t)(c0 + TC_OUT_CH), vb);
+          tmem_ld_wait();
+          if (c0 + 2 * TC_OUT_CH >= p.Co) release_acc();      // last columns are in registers: the accumulator is free
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            if (p.relu) pk[i >> 1] = pack2_relu<T>(__uint_as_float(va[i]), __uint_as_float(va[i + 1]));
+            else { const H2 h = from_f2<T>(__uint_as_float(va[i]), __uint_as_float(va[i + 1])); pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&h); }
+          }
+          emit_chunk(pk, 0.0f, 0.0f, 0.0f, 0.0f, c0, ci);
+          if (two) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              if (p.relu) pk[i >> 1] = pack2_relu<T>(__uint_as_float(vb[i]), __uint_as_float(vb[i + 1]));
+              else { const H2 h = from_f2<T>(__uint_as_float(vb[i]), __uint_as_float(vb[i + 1])); pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&h); }
+            }
+            emit_chunk(pk, 0.0f, 0.0f, 0.0f, 0.0f, c0 + TC_OUT_CH, ci + 1);
+          }
+        }
+      } else {
+        // 32 channels at a time: TMEM -> registers -> bias / ReLU / 8-way orientation max -> 16-bit -> a 64-byte row
+        // of the staging buffer (SWIZZLE_64B, conflict-free) -> one TMA store of the 8 x 16 x 32-channel box.  The
+        // stores never touch the LSU global path, and partial tiles are clipped by TMA.
+        for (int c0 = 0, ci = 0; c0 < p.Co && !(p.debug & 32); c0 += TC_OUT_CH, ++ci) {
+          uint32_t v[32];
+          tmem_ld32(acc_addr + (uint32_t)c0, v);
+          if (c0 + TC_OUT_CH >= p.Co) release_acc();          // last columns are in registers: the accumulator is free
+          uint32_t pk[16];
+          float m[4];
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            float t0 = __uint_as_float(v[i]), t1 = __uint_as_float(v[i + 1]);
+            if (bias) { t0 += __ldg(bias + c0 + i); t1 += __ldg(bias + c0 + i + 1); }
+            if (p.relu) { t0 = fmaxf(t0, 0.0f); t1 = fmaxf(t1, 0.0f); }
+            const H2 h = from_f2<T>(t0, t1);
+            pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&h);
+            const float mx = fmaxf(t0, t1);
+            m[i >> 3] = (i & 7) == 0 ? mx : fmaxf(m[i >> 3], mx);
+          }
+          emit_chunk(pk, m[0], m[1], m[2], m[3], c0, ci);
         }
       }
       if (p.debug & 32) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive_cluster(ld_acc_empty + 8 * as); }
@@ -1124,6 +1190,26 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         }
       }
     }
+  };
+  if (MODE == TC_ALIGN) {
+    // Warpgroups 0-3: producers (80 registers, the launch value), 4: epilogue, 5: TMA / MMA / two idle warps.  The
+    // last one gives registers back and the epilogue takes them (setmaxnreg is a warpgroup-wide instruction, so each
+    // role's code sits under the branch of its warpgroup and ptxas allocates per branch).
+    if (warp < kProdWarps) {
+      role_producer();
+    } else if (warp < kTmaWarp) {
+      reg_alloc<104>();
+      role_epilogue();
+    } else {
+      reg_dealloc<56>();
+      if (warp == kTmaWarp) role_tma();
+      else if (warp == kMmaWarp) role_mma();
+    }
+  } else {
+    if (warp == kTmaWarp) role_tma();
+    else if (warp == kMmaWarp + 1) role_halo();
+    else if (warp == kMmaWarp) role_mma();
+    else if (warp >= kEpiWarp0 && warp < kTmaWarp) role_epilogue();
   }
 #undef S2A_TILE_OF
 #undef S2A_IS_GHOST
