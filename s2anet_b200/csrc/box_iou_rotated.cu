@@ -70,18 +70,23 @@ box_iou_rotated_kernel(const IouArgs a) {
 
   const int tid = threadIdx.x, wid = tid >> 5;
   const unsigned lane = tid & 31, lt = (1u << lane) - 1u;
-  const int64_t b = blockIdx.z;
+  // grid = (batch, column tiles, row CTAs); CTAs are dispatched x-fastest, so all images' copies of a row CTA run
+  // together, and the row CTAs are walked from the LAST one down: in anchor x GT matrices the last rows are the
+  // large P5-P7 anchors whose pairs mostly reach the clipper (CTAs several times as long as the P3 ones), and the
+  // tail of the launch should be made of short CTAs
+  const int64_t b = blockIdx.x;
+  const int64_t bx = (int64_t)gridDim.z - 1 - blockIdx.z;
   const int64_t col0 = (int64_t)blockIdx.y * COLS;
   const int nc = (int)min((int64_t)COLS, a.m - col0);
   // Rows of this CTA.  Dealt tiles are a.deal_rows high; CTA x takes the launch's tiles x*spt .. x*spt + spt - 1
   // (global tile = tile_first + local tile * tile_step).  Only the matrix's last tile can be partial and it is the
   // last tile of the launch that owns it, so the valid rows of a CTA are a prefix.
   const int spt = a.tile_rows / a.deal_rows;
-  const int64_t lrow0 = (int64_t)blockIdx.x * a.tile_rows;                  // first row in the launch's packed order
+  const int64_t lrow0 = bx * a.tile_rows;                  // first row in the launch's packed order
   const int nr = (int)min((int64_t)a.tile_rows, a.mine_rows - lrow0);
   auto global_row = [&](int i) -> int64_t {
     const int sub = i / a.deal_rows;
-    const int64_t gt = (int64_t)a.tile_first + ((int64_t)blockIdx.x * spt + sub) * a.tile_step;
+    const int64_t gt = (int64_t)a.tile_first + (bx * spt + sub) * a.tile_step;
     return a.row_begin + gt * a.deal_rows + (i - sub * a.deal_rows);
   };
   // compact: the output holds only the rows this launch computes, packed in launch order
@@ -230,7 +235,7 @@ template <int CPT, bool NO_REJECT>
 static int launch_iou_kernel(const IouArgs& a, int64_t mine, int64_t batch, cudaStream_t st) {
   auto kern = box_iou_rotated_kernel<CPT, NO_REJECT>;
   S2A_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)iou_smem_bytes<CPT>(kIouRowsMax)));
-  dim3 grid((unsigned)mine, (unsigned)ceil_div(a.m, iou_cols<CPT>()), (unsigned)batch);
+  dim3 grid((unsigned)batch, (unsigned)ceil_div(a.m, iou_cols<CPT>()), (unsigned)mine);
   kern<<<grid, kIouThreads, iou_smem_bytes<CPT>(a.tile_rows), st>>>(a);
   S2A_LAUNCH_OK("box_iou_rotated_kernel");
   return S2A_OK;
@@ -247,11 +252,11 @@ static int launch_iou(const float* boxes1, int64_t n, const float* boxes2, int64
   S2A_CHECK_ARG(tile_step >= 1 && tile_first >= 0 && tile_first < tile_step,
                 "box_iou_rotated: need 0 <= tile_first < tile_step (got %d, %d)", tile_first, tile_step);
   if (tile_rows <= 0) {
-    // default: 128-row tiles (as fast as 256-row ones on config 4 and half the tail: a CTA of 128 x 512 pairs runs
-    // ~30 us); smaller ones while the grid would not fill the GPU twice over
-    tile_rows = kIouRowsMax / 2;
+    // default: 256-row tiles (306 G pairs/s on config 4 against 299 / 274 with 128 / 64 rows), halved while the launch
+    // would have fewer than ~8 waves of CTAs (a 256 x 512-pair CTA of large anchors runs > 100 us: the tail matters)
+    tile_rows = kIouRowsMax;
     const int64_t cols = ceil_div(std::max<int64_t>(m, 1), iou_cols<2>()) * std::max<int64_t>(batch, 1);
-    while (tile_rows > 32 && ceil_div(row_end - row_begin, tile_rows) * cols < 2 * (int64_t)sm_count() && tile_step == 1)
+    while (tile_rows > 32 && ceil_div(row_end - row_begin, tile_rows) * cols < 8ll * 3 * sm_count() && tile_step == 1)
       tile_rows >>= 1;
   }
   S2A_CHECK_ARG(tile_rows >= 32 && kIouRowsMax % tile_rows == 0, "box_iou_rotated: tile_rows must be 32, 64, 128 or %d",
@@ -268,10 +273,18 @@ static int launch_iou(const float* boxes1, int64_t n, const float* boxes2, int64
   const int64_t mine_rows = (mine - 1) * tile_rows + std::min<int64_t>(tile_rows, nrows - last_tile * tile_rows);
   // packed output: CTAs are 256 rows high and take several dealt tiles each; in-place output: one dealt tile per CTA
   // (its rows must be consecutive in the output)
-  const int cta_rows = compact ? std::max(tile_rows, kIouRowsMax / 2) : tile_rows;
+  // (64-row CTAs when 128-row ones would leave the launch with fewer than ~8 waves: the tail matters more than the
+  // ~8 % of per-tile overhead)
+  int cta_rows = tile_rows;
+  if (compact) {
+    cta_rows = kIouRowsMax;
+    const int64_t waves8 = 8ll * 3 * sm_count();
+    while (cta_rows > std::max(tile_rows, 64) && ceil_div(mine_rows, cta_rows) * ceil_div(m, iou_cols<2>()) * batch < waves8)
+      cta_rows >>= 1;
+  }
   const int64_t nctas = ceil_div(mine_rows, cta_rows);
-  S2A_CHECK_ARG(batch <= 65535 && ceil_div(m, iou_cols<1>()) <= 65535 && nctas < (1ll << 31),
-                "box_iou_rotated: batch and ceil(m/256) must be <= 65535");
+  S2A_CHECK_ARG(batch < (1ll << 31) && ceil_div(m, iou_cols<1>()) <= 65535 && nctas <= 65535,
+                "box_iou_rotated: ceil(m/256) and the number of row CTAs must be <= 65535");
   if (out_batch_stride <= 0) out_batch_stride = (compact ? mine * tile_rows : n) * ld_out;
   IouArgs a{boxes1, boxes2, out, n, m, ld_out, out_batch_stride, row_begin, row_end, cta_rows, tile_rows, tile_first,
             tile_step, compact ? 1 : 0, flags, mine_rows};
