@@ -12,9 +12,11 @@ The reference imports six pybind11 extension modules by name (SURVEY.md section 
     utils.ml_nms_rotated.ml_nms_rotated_cuda        ml_nms_rotated
 
 `install()` registers Python modules with exactly those names and function signatures in
-sys.modules, each forwarding to libs2a_b200.so through the ctypes binding.  Functions outside the
-hot path (backward of deform conv, modulated DCN, PS-RoI pooling, RIE) exist so imports succeed and
-raise NotImplementedError when called.  `accelerate(model)` additionally swaps the *fused* forward
+sys.modules, each forwarding to libs2a_b200.so through the ctypes binding.  `deform_conv_forward_cuda`
+takes fp32, fp16 (the reference's `AT_DISPATCH_FLOATING_TYPES_AND_HALF`, what val.py's `model.half()`
+reaches) and bf16 tensors; the two deform-conv backward entries and `arf_backward` are implemented
+(fp32 accumulate).  Functions outside the hot path (modulated DCN, PS-RoI pooling, RIE) exist so imports
+succeed and raise NotImplementedError when called.  `accelerate(model)` additionally swaps the *fused* forward
 paths in (AlignConv without an offset tensor, ORConv2d with the ARF folded into the weight load and
 the orientation pooling into the epilogue) while keeping every parameter / buffer name.
 """

@@ -9,6 +9,14 @@ DOTA_devkit/polyiou (csrc/polyiou.cpp:110-126, iou_poly).
   iou_poly(p, q)                         polyiou.iou_poly for one pair of 8-number polygons (sequence or VectorDouble)
   VectorDouble                           stand-in for polyiou.VectorDouble (a list of floats)
   iou_poly_pairs(p, q)                   [n, 8] x [n, 8] float64 CUDA tensors -> [n] IoUs (parity probe)
+
+Tie rule (stated, because the reference's is not): the reference orders with `scores.argsort()[::-1]`
+(ResultMerge_multi_process.py:81) -- numpy's default introsort is not stable, so which of two EQUAL scores comes
+first is unspecified there (for short arrays the insertion-sort path happens to put the higher index first).  Here
+the order is a stable descending sort: among equal scores the LOWER row index is visited first, as in nms_rotated.
+With distinct scores (the goldens, and every test of this repo) the keep lists are identical; with duplicated scores
+-- possible after merging patches -- the kept SET can differ from one particular numpy build's by which duplicate
+survives.  NaN IoUs (0/0 of two zero-area polygons) suppress, as `np.where(hbb_ovr <= thresh)` makes them do.
 """
 import numpy as np
 import torch
