@@ -684,6 +684,27 @@ def extra_legs(torch, np, dev, dtype, head, feat_sets, refines, peaks, args):
     n2 = b2.shape[0]
     nms20_ms = cuda_time(torch, lambda: nms_rotated_op(tb2, ts2, 0.5), 5)
     out["nms_rotated_20000"] = {"ms": nms20_ms, "pairs_per_s": n2 * (n2 - 1) / 2 / (nms20_ms / 1e3)}
+    # per-call host cost of the eager drop-in path (ctypes binding + argument checks + launch), on inputs so small that
+    # the kernels are empty: wall clock per call over 200 back-to-back calls, one synchronize at the end
+    def call_us(fn, n=200):
+        for _ in range(10):
+            fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(n):
+            fn()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / n * 1e6
+    tiny = tb[:4].contiguous()
+    xs_ = torch.randn(1, 64, 8, 8, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    an_ = torch.from_numpy(synth.refined_anchors(1, 8, 8, 8, seed=1)).to(dev)
+    w_ = (torch.randn(64, 64, 3, 3, device=dev) * 0.05).to(torch.bfloat16)
+    from s2anet_b200.alignconv import alignconv_forward as _af
+    out["dropin_call_overhead_us"] = {
+        "box_iou_rotated_4x4": call_us(lambda: box_iou_rotated(tiny, tiny)),
+        "alignconv_forward_bf16_8x8": call_us(lambda: _af(xs_, an_, w_, 8)),
+        "nms_rotated_4_boxes_incl_4_byte_readback": call_us(lambda: nms_rotated_op(tiny, ts[:4].contiguous(), 0.5), 50),
+        "note": "Python wrapper + ctypes + kernel launch per call; the bench step itself replays a CUDA graph and pays none of it"}
     if dtype != torch.float32 and refines is not None:
         from s2anet_b200.alignconv import alignconv_forward
         from s2anet_b200.orn import orconv_forward
