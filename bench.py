@@ -381,10 +381,18 @@ def main():
             out_ = run_head(feats, i)
         else:
             if i not in graphs or graphs[i][3] is not feats:
+                ok = 1
                 try:
                     g, out_, n_mine = capture(feats, i)
                 except Exception:
-                    # the collective / barrier refused stream capture: keep it outside the graph
+                    ok = 0
+                if world > 1:                        # every rank takes the same decision
+                    flag = torch.tensor([ok], device=dev)
+                    torch.cuda.synchronize()
+                    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+                    ok = int(flag.item())
+                if not ok:
+                    # the collective / barrier refused stream capture somewhere: keep it outside the graph everywhere
                     torch.cuda.synchronize()
                     in_graph["barrier"] = in_graph["allgather"] = False
                     g, out_, n_mine = capture(feats, i)

@@ -66,6 +66,13 @@ def _worker(rank, world, port, q):
             assert torch.equal(gd[r * B:(r + 1) * B], torch.full((B, K, 6), float(r)) + torch.arange(B).view(B, 1, 1))
             assert torch.equal(gl[r * B:(r + 1) * B], torch.full((B, K), float(10 + r)))
             assert gc[r * B:(r + 1) * B].tolist() == [r + 1, r + 2]
+        # the packed form (what the NMS finaliser writes): one collective, no pack step
+        packed = torch.zeros((B, K + 1, 8))
+        packed[:, :K, :6] = dets
+        packed[:, :K, 6] = labels
+        packed[:, K, 0] = counts.float()
+        pd, pl, pc = sd.gather_detections(None, None, None, packed=packed)
+        assert torch.equal(pd, gd) and torch.equal(pl, gl) and torch.equal(pc, gc)
         q.put((rank, "ok"))
     except Exception as e:      # surface the failure to the parent
         q.put((rank, repr(e)))

@@ -184,3 +184,29 @@ def test_orconv_tc_vs_reference_arf_binary_and_cudnn():
         amax, arel = TOL[dtype]
         assert e["max_abs_rel"] <= amax and e["rel_l2"] <= arel, e
         assert torch.equal(yp, y.view(1, 32, 8, 128, 128).max(dim=2)[0])
+
+
+def test_generic_entry_3d_input_and_weight_cache_after_half(ref_dc):
+    """The reference entry also takes an unbatched [C,H,W] input (deform_conv_cuda.cpp:172-180); and a module moved
+    with `.half()` (param.data reassigned, `_version` unchanged -- ADVICE r1) must not reuse the packed fp32-sourced
+    weights of its previous life."""
+    from s2anet_b200 import dcn
+    from s2anet_b200.alignconv import AlignConv
+    g = torch.Generator().manual_seed(12)
+    x = torch.randn(64, 10, 14, generator=g).to(DEV).half()
+    w = (torch.randn(64, 64, 3, 3, generator=g) * 0.05).to(DEV).half()
+    off = (torch.randn(18, 10, 14, generator=g)).to(DEV).half()
+    out = x.new_empty((64, 10, 14))
+    assert dcn.deform_conv_forward_cuda(x, w, off, out, x.new_empty(0), x.new_empty(0), 3, 3, 1, 1, 1, 1, 1, 1, 1, 1, 1) == 1
+    ref = ref_deform(ref_dc, x[None], w, off[None])[0]
+    e = errs(out, ref)
+    assert e["rel_l2"] <= 2e-3, e
+    m = AlignConv(64, 64).to(DEV)
+    m.init_weights()
+    xb = torch.randn(1, 64, 12, 12, generator=g).to(DEV)
+    anc = torch.from_numpy(synth.refined_anchors(1, 12, 12, 8, seed=2)).to(DEV)
+    with torch.no_grad():
+        y_bf = m.to(torch.bfloat16)(xb.bfloat16(), anc, 8)                 # packs bf16 weights
+        m.deform_conv.weight.data = (m.deform_conv.weight.data.float() * 2.0).to(torch.bfloat16)   # new storage, same Parameter
+        y2 = m(xb.bfloat16(), anc, 8)
+    assert float((y2.float() - 2.0 * y_bf.float()).abs().max()) <= 2e-2 * float(y2.float().abs().max()) + 1e-3

@@ -366,3 +366,24 @@ def test_duplicate_boxes_are_the_only_keep_list_difference_to_the_reference_bina
     # and the common part is in the same (descending score) order
     common = [i for i in ref.tolist() if i in mine_set]
     assert common == mine.tolist()
+
+
+def test_multiclass_batched_takes_more_than_6144_boxes(oracle):
+    """the fused kernel stops at 6,144 candidate boxes per image (5 levels x top-2000 on inputs
+    above ~1,100 px exceed it); the batched entry then composes the generic ml_nms_rotated kernel per image instead of
+    raising, with the same fixed-shape outputs."""
+    from s2anet_b200.nms_rotated import MC_FUSED_MAX_BOXES, multiclass_nms_rotated, multiclass_nms_rotated_batched
+    n = MC_FUSED_MAX_BOXES + 200
+    b, _, _ = synth.clustered_boxes(n_seed=n // 4 + 1, rep=4, seed=31)
+    b = b[:n]
+    rng = np.random.default_rng(8)
+    sc = (rng.uniform(0, 1, (n, 3)) ** 6).astype(np.float32)
+    tb, ts = torch.from_numpy(b).to(DEV), torch.from_numpy(sc).to(DEV)
+    d, l, c = multiclass_nms_rotated_batched(torch.stack([tb, tb]), torch.stack([ts, ts * 0.0]), 0.05, 0.5, 500)
+    rd, rl = oracle.multiclass_nms_rotated(b, sc, 0.05, 0.5, 500)
+    k = int(c[0])
+    assert k == rd.shape[0] and int(c[1]) == 0
+    np.testing.assert_array_equal(d[0, :k].cpu().numpy(), rd)
+    np.testing.assert_array_equal(l[0, :k].cpu().numpy(), rl)
+    d1, l1 = multiclass_nms_rotated(tb, ts, 0.05, 0.5, 500)                # the single-image wrapper takes the same route
+    np.testing.assert_array_equal(d1.cpu().numpy(), rd)
