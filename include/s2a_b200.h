@@ -212,6 +212,18 @@ S2A_EXPORT int s2a_alignconv_forward_tc(const void* x, const float* anchors,
 S2A_EXPORT int s2a_deform_conv_forward_tc(const void* x, const void* offsets, int offsets_dtype,
                                           const void* packed_weight, void* out, int B, int C, int H, int W,
                                           int Co, int relu, int round_positions, int dtype, void* stream);
+/* Deformable-conv backward w.r.t. the input (and, optionally, the offsets) on the tcgen05 kernel, 16-bit tensors:
+ * replaces deform_conv_backward_input_cuda (models/dcn/src/deform_conv_cuda.cpp:262-373; kernels
+ * deformable_col2im(_coord)_gpu_kernel, deform_conv_cuda_kernel.cu:278-435) for S2ANet's geometry (3x3, stride / pad /
+ * dilation 1, one group).  Per tap: col_grad = grad_out x W_t^T as a 1x1 implicit GEMM (grad_out NHWC [B,H,W,Co],
+ * wd [9][C][Co]: wd[t][c][co] = weight[co][c][t]) whose accumulator tile is scattered from tensor memory with the
+ * bilinear weights of (pixel, tap) into grad_input (fp32 NHWC [B,H,W,C], ACCUMULATED -- zero it first, as the
+ * reference's caller does, deform_conv.py:88-89) -- no column buffer, no library GEMM.  grad_offset (fp32
+ * [B,18,H,W], accumulated; needs x NHWC 16-bit) may be NULL.  Nine launches. */
+S2A_EXPORT int s2a_deform_conv_dgrad_tc(const void* grad_out, const void* offsets, int offsets_dtype,
+                                        const void* wd, const void* x, float* grad_input,
+                                        float* grad_offset, int B, int C, int H, int W, int Co, int dtype,
+                                        void* stream);
 S2A_EXPORT int s2a_orconv_forward_tc(const void* x, const void* packed_weight, const float* bias,
                                      void* out, void* pooled, int B, int C, int H, int W, int Co,
                                      int dtype, void* stream);

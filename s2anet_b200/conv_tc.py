@@ -132,6 +132,43 @@ def deform_conv_forward_tc(x, offset, weight, out=None, relu=False, round_positi
     return out
 
 
+def deform_conv_dgrad_tc(grad_out, offset, weight, x=None, need_offset_grad=False):
+    """Deformable-conv backward w.r.t. the input (3x3, stride / pad / dilation 1, one group) on the tcgen05 kernel:
+    nine 1x1 implicit GEMMs grad_out x W_t^T whose accumulator tiles are scattered from tensor memory into grad_input
+    with the bilinear weights -- no column buffer, no library GEMM.  grad_out [B,Co,H,W] bf16/fp16, offset [B,18,H,W]
+    (fp32 or grad_out's dtype), weight [Co,C,3,3]; x [B,C,H,W] is only needed for the offset gradient.
+    Returns (grad_input [B,C,H,W] fp32, channels_last; grad_offset [B,18,H,W] fp32 or None)."""
+    dev = _lib.require_cuda(grad_out, offset, weight, x)
+    B, Co, H, W = grad_out.shape
+    C = weight.size(1)
+    if tuple(weight.shape) != (Co, C, 3, 3) or tuple(offset.shape) != (B, 18, H, W):
+        raise ValueError("deform_conv_dgrad_tc: shapes do not match a 3x3 deformable conv")
+    dt = grad_out.dtype
+    go = _nhwc(grad_out)
+    off = offset if offset.dtype in (torch.float32, dt) else offset.to(dt)
+    off = off.contiguous()
+    # wd[t][c][co] = weight[co][c][t]: for a 1x1 conv with C_in = Co (a multiple of 64) this IS the packed layout
+    wd = weight.detach().to(dt).permute(2, 3, 1, 0).reshape(9, C, Co).contiguous()
+    gi = torch.zeros((B, H, W, C), dtype=torch.float32, device=dev)
+    goff, xc = None, None
+    if need_offset_grad:
+        if x is None:
+            raise ValueError("deform_conv_dgrad_tc: the offset gradient needs x")
+        goff = torch.zeros((B, 18, H, W), dtype=torch.float32, device=dev)
+        xc = _nhwc(x.to(dt))
+    with torch.cuda.device(dev):
+        rc = _lib.load().s2a_deform_conv_dgrad_tc(_lib.ptr(go), _lib.ptr(off), _lib.dtype_code(off), _lib.ptr(wd), _lib.ptr(xc),
+                                                  _lib.ptr(gi), _lib.ptr(goff), B, C, H, W, Co, _lib.dtype_code(go),
+                                                  _lib.stream_ptr(dev))
+    _lib.check(rc, "deform_conv_dgrad_tc")
+    return gi.permute(0, 3, 1, 2), goff
+
+
+def deform_conv_dgrad_tc_supported(C, Co, kH, kW, dH, dW, padH, padW, dilH, dilW, group, deformable_group):
+    return (kH == 3 and kW == 3 and dH == 1 and dW == 1 and padH == 1 and padW == 1 and dilH == 1 and dilW == 1 and
+            group == 1 and deformable_group == 1 and C % 32 == 0 and C <= 256 and Co % 64 == 0)
+
+
 def orconv_forward_tc(x, weight, indices, bias, with_pool=False):
     dev = _lib.require_cuda(x, weight, indices, bias)
     B, C, H, W = x.shape

@@ -150,6 +150,16 @@ struct TcParams {
   int off_f32;            // generic deformable conv: the offsets are fp32 (else the activations' 16-bit type)
   int pos_round;          // ... and sampling positions / bilinear weights are rounded like the reference's scalar_t = half path
   int debug;              // timing experiments only (S2A_TC_DEBUG): 1 = no weight TMA after warm-up, 2 = no gather loads
+  // TC_PLAIN, 1 x 1, "dgrad" epilogue (sc_tap >= 0): the accumulator tile is the column gradient of ONE tap,
+  // col_grad[pixel, c] = sum_co grad_out[pixel, co] * W[co, c, tap]; instead of being stored it is scattered with the
+  // bilinear weights of (pixel, tap) into grad_input (fp32 NHWC, red.global.add.v4.f32) and, optionally, contracted with
+  // the corner differences of x into the offset gradient (deform_conv_cuda_kernel.cu:278-435).  Level 0 only.
+  float* sc_gi;           // [B, H, W, Co] fp32, accumulated
+  float* sc_goff;         // [B, 18, H, W] fp32, accumulated (+=), or null
+  const void* sc_x;       // [B, H, W, Co] 16-bit (needed for sc_goff)
+  const void* sc_off;     // [B, 18, H, W] offsets, fp32 or the 16-bit type
+  int sc_off_f32;
+  int sc_tap;             // -1: ordinary epilogue
 };
 
 struct TileCoord { int lvl, b, ty0, tx0; };
@@ -436,6 +446,10 @@ template <> __device__ __forceinline__ uint32_t pack2_relu<__half>(float lo, flo
   uint32_t d;
   asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
   return d;
+}
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
@@ -1156,6 +1170,89 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
             emit_chunk(pk, 0.0f, 0.0f, 0.0f, 0.0f, c0 + TC_OUT_CH, ci + 1);
           }
         }
+      } else if (IS_PLAIN && p.sc_tap >= 0) {
+        // ---- dgrad: scatter the column gradient of tap sc_tap (this thread: one pixel, 32 channels at a time) ----
+        const int H = L.H, W = L.W, t = p.sc_tap;
+        const int ti = t / 3, tj = t - 3 * ti;
+        bool inb = false, c_t = false, c_b = false, c_l = false, c_r = false;
+        float hy = 0.f, hx = 0.f, ly = 0.f, lx = 0.f;
+        int yt = 0, xl = 0;
+        if (valid) {
+          const size_t oi = (((size_t)tc.b * 18 + 2 * t) * H + y) * W + x, plane = (size_t)H * W;
+          float offy, offx;
+          if (p.sc_off_f32) {
+            offy = reinterpret_cast<const float*>(p.sc_off)[oi];
+            offx = reinterpret_cast<const float*>(p.sc_off)[oi + plane];
+          } else {
+            offy = (float)reinterpret_cast<const T*>(p.sc_off)[oi];
+            offx = (float)reinterpret_cast<const T*>(p.sc_off)[oi + plane];
+          }
+          const float h = (float)(y - 1 + ti) + offy, w = (float)(x - 1 + tj) + offx;
+          if (h > -1.0f && w > -1.0f && h < (float)H && w < (float)W) {
+            inb = true;
+            const float hf = floorf(h), wf = floorf(w);
+            const int y0 = (int)hf, x0 = (int)wf;
+            ly = h - hf; lx = w - wf; hy = 1.0f - ly; hx = 1.0f - lx;
+            c_t = y0 >= 0; c_b = y0 + 1 <= H - 1; c_l = x0 >= 0; c_r = x0 + 1 <= W - 1;
+            yt = y0; xl = x0;
+          }
+        }
+        const float w1 = (c_t && c_l) ? hy * hx : 0.f, w2 = (c_t && c_r) ? hy * lx : 0.f;
+        const float w3 = (c_b && c_l) ? ly * hx : 0.f, w4 = (c_b && c_r) ? ly * lx : 0.f;
+        const int Cg = p.Co;                                   // channels of x / grad_input (the GEMM's N)
+        // clamped corner addresses (a corner outside the map has weight 0 and is never touched)
+        const size_t rowp = (size_t)W * Cg;
+        // per-corner element offsets: top-left (yt, xl), top-right (yt, xl + 1), bottom-left (yt + 1, xl), bottom-right
+        const size_t a_tl = ((size_t)tc.b * H + max(yt, 0)) * rowp + (size_t)max(xl, 0) * Cg;
+        const size_t a_tr = ((size_t)tc.b * H + max(yt, 0)) * rowp + (size_t)min(xl + 1, W - 1) * Cg;
+        const size_t a_bl = ((size_t)tc.b * H + min(yt + 1, H - 1)) * rowp + (size_t)max(xl, 0) * Cg;
+        const size_t a_br = ((size_t)tc.b * H + min(yt + 1, H - 1)) * rowp + (size_t)min(xl + 1, W - 1) * Cg;
+        float gy = 0.f, gx = 0.f;
+        for (int c0 = 0; c0 < p.Co; c0 += TC_OUT_CH) {
+          uint32_t v[32];
+          tmem_ld32(acc_addr + (uint32_t)c0, v);
+          if (c0 + TC_OUT_CH >= p.Co) release_acc();
+          if (inb) {
+            float* gi = p.sc_gi + c0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float v0 = __uint_as_float(v[j]), v1 = __uint_as_float(v[j + 1]), v2 = __uint_as_float(v[j + 2]),
+                          v3 = __uint_as_float(v[j + 3]);
+              if (w1 != 0.f) red_add_v4(gi + a_tl + j, w1 * v0, w1 * v1, w1 * v2, w1 * v3);
+              if (w2 != 0.f) red_add_v4(gi + a_tr + j, w2 * v0, w2 * v1, w2 * v2, w2 * v3);
+              if (w3 != 0.f) red_add_v4(gi + a_bl + j, w3 * v0, w3 * v1, w3 * v2, w3 * v3);
+              if (w4 != 0.f) red_add_v4(gi + a_br + j, w4 * v0, w4 * v1, w4 * v2, w4 * v3);
+            }
+            if (p.sc_goff) {
+              // get_coordinate_weight (:147-187): d(sample)/d(offset_h), d(sample)/d(offset_w), corners outside the
+              // map count as zeros
+              const T* xp = reinterpret_cast<const T*>(p.sc_x) + c0;
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                const uint4 q1 = (c_t && c_l) ? ldg_nc_v4(xp + a_tl + j) : make_uint4(0u, 0u, 0u, 0u);
+                const uint4 q2 = (c_t && c_r) ? ldg_nc_v4(xp + a_tr + j) : make_uint4(0u, 0u, 0u, 0u);
+                const uint4 q3 = (c_b && c_l) ? ldg_nc_v4(xp + a_bl + j) : make_uint4(0u, 0u, 0u, 0u);
+                const uint4 q4 = (c_b && c_r) ? ldg_nc_v4(xp + a_br + j) : make_uint4(0u, 0u, 0u, 0u);
+                const H2* h1 = reinterpret_cast<const H2*>(&q1);
+                const H2* h2 = reinterpret_cast<const H2*>(&q2);
+                const H2* h3 = reinterpret_cast<const H2*>(&q3);
+                const H2* h4 = reinterpret_cast<const H2*>(&q4);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 x1 = to_f2(h1[e]), x2 = to_f2(h2[e]), x3 = to_f2(h3[e]), x4 = to_f2(h4[e]);
+                  const float ga = __uint_as_float(v[j + 2 * e]), gb = __uint_as_float(v[j + 2 * e + 1]);
+                  gy += ga * (hx * (x3.x - x1.x) + lx * (x4.x - x2.x)) + gb * (hx * (x3.y - x1.y) + lx * (x4.y - x2.y));
+                  gx += ga * (hy * (x2.x - x1.x) + ly * (x4.x - x3.x)) + gb * (hy * (x2.y - x1.y) + ly * (x4.y - x3.y));
+                }
+              }
+            }
+          }
+        }
+        if (p.sc_goff && valid) {       // one thread per (pixel, tap) and one tap per launch: plain read-modify-write
+          float* go = p.sc_goff + (((size_t)tc.b * 18 + 2 * t) * H + y) * W + x;
+          go[0] += gy;
+          go[(size_t)H * W] += gx;
+        }
       } else {
         // 32 channels at a time: TMEM -> registers -> bias / ReLU / 8-way orientation max -> 16-bit -> a 64-byte row
         // of the staging buffer (SWIZZLE_64B, conflict-free) -> one TMA store of the 8 x 16 x 32-channel box.  The
@@ -1353,11 +1450,14 @@ static int launch_tc(const TcMaps& tmap, const TcParams& p, cudaStream_t st) {
   return S2A_OK;
 }
 
+struct TcScatter { float* gi; float* goff; const void* x; const void* off; int off_f32; int tap; };
+
 static int conv_tc_common(int mode, int nlevels, const void* const* xs, const float* const* anchors, const void* wp,
                           const float* bias, void* const* outs, void* const* pooleds, const int* Hs, const int* Ws,
                           const float* strides, int B, int C, int Co, int relu, int dtype, cudaStream_t st, int ks = 3,
                           int wsplit = -1, const void* wp2 = nullptr, const float* bias2 = nullptr,
-                          const void* const* offsets = nullptr, int off_f32 = 0, int pos_round = 0) {
+                          const void* const* offsets = nullptr, int off_f32 = 0, int pos_round = 0,
+                          const TcScatter* sc = nullptr) {
   if (wsplit < 0) wsplit = nlevels;              // one problem: every level uses the first weights
   S2A_CHECK_ARG(nlevels >= 1 && nlevels <= TC_MAX_LEVELS, "conv_tc: 1..%d levels per launch", TC_MAX_LEVELS);
   S2A_CHECK_ARG(B >= 0 && C > 0 && Co > 0, "conv_tc: bad tensor sizes");
@@ -1435,6 +1535,12 @@ static int conv_tc_common(int mode, int nlevels, const void* const* xs, const fl
   }
   p.bias = bias; p.bias2 = bias2; p.wsplit = wsplit; p.nlevels = nlevels; p.total_tiles = (int)tiles;
   p.B = B; p.C = C; p.Co = Co; p.relu = relu; p.ks = ks; p.off_f32 = off_f32; p.pos_round = pos_round;
+  p.sc_tap = -1;
+  if (sc) {
+    S2A_CHECK_ARG(mode == TC_PLAIN && ks == 1 && nlevels == 1 && sc->tap >= 0 && sc->tap < 9 && sc->gi && sc->off &&
+                  (!sc->goff || sc->x), "conv_tc: bad dgrad (scatter) arguments");
+    p.sc_gi = sc->gi; p.sc_goff = sc->goff; p.sc_x = sc->x; p.sc_off = sc->off; p.sc_off_f32 = sc->off_f32; p.sc_tap = sc->tap;
+  }
   { const char* e = getenv("S2A_TC_DEBUG"); p.debug = e ? atoi(e) : 0; }
   if (mode == TC_ALIGN) {
     return dtype == S2A_BF16 ? launch_tc<TC_ALIGN, __nv_bfloat16>(tmap, p, st) : launch_tc<TC_ALIGN, __half>(tmap, p, st);
@@ -1500,6 +1606,30 @@ extern "C" int s2a_deform_conv_forward_tc(const void* x, const void* offsets, in
   return conv_tc_common(TC_ALIGN, 1, &x, nullptr, packed_weight, nullptr, &out, nullptr, &H, &W, &one, B, C, Co, relu ? 1 : 0,
                         dtype, (cudaStream_t)stream, 3, -1, nullptr, nullptr, &offsets, offsets_dtype == S2A_F32 ? 1 : 0,
                         round_positions ? 1 : 0);
+}
+
+extern "C" int s2a_deform_conv_dgrad_tc(const void* grad_out, const void* offsets, int offsets_dtype, const void* wd,
+                                        const void* x, float* grad_input, float* grad_offset, int B, int C, int H, int W,
+                                        int Co, int dtype, void* stream) {
+  using namespace s2a;
+  S2A_CHECK_ARG(H > 0 && W > 0 && B >= 0, "deform_conv_dgrad_tc: bad sizes");
+  S2A_CHECK_ARG(C % 32 == 0 && C <= 256 && Co % 64 == 0,
+                "deform_conv_dgrad_tc: needs C %% 32 == 0 <= 256 and C_out %% 64 == 0 (got C=%d, C_out=%d)", C, Co);
+  S2A_CHECK_ARG(offsets_dtype == S2A_F32 || offsets_dtype == dtype, "deform_conv_dgrad_tc: offsets must be fp32 or the tensors' dtype");
+  if (B == 0) return S2A_OK;
+  S2A_CHECK_ARG(grad_out && offsets && wd && grad_input && (!grad_offset || x), "deform_conv_dgrad_tc: null pointer");
+  // nine 1 x 1 convolutions grad_out [pixels, Co] x W_t^T [C, Co] on the plain-conv mainloop, each with the scatter
+  // epilogue of its tap; wd = [9][C][Co] 16-bit is already the packed layout of a 1 x 1 weight (Co %% 64 == 0)
+  void* fake_out = grad_input;             // (only to build an output tensor map the scatter epilogue never uses)
+  for (int t = 0; t < 9; ++t) {
+    TcScatter sc{grad_input, grad_offset, x, offsets, offsets_dtype == S2A_F32 ? 1 : 0, t};
+    const void* wt = reinterpret_cast<const uint8_t*>(wd) + (size_t)t * C * Co * 2;
+    const int rc = conv_tc_common(TC_PLAIN, 1, &grad_out, nullptr, wt, nullptr, &fake_out, nullptr, &H, &W, nullptr, B,
+                                  /*C_in=*/Co, /*C_out=*/C, 0, dtype, (cudaStream_t)stream, 1, -1, nullptr, nullptr, nullptr, 0, 0,
+                                  &sc);
+    if (rc != S2A_OK) return rc;
+  }
+  return S2A_OK;
 }
 
 extern "C" int s2a_orconv_forward_tc(const void* x, const void* packed_weight, const float* bias, void* out, void* pooled,

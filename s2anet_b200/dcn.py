@@ -103,6 +103,15 @@ def deform_conv_backward_input_cuda(input, offset, gradOutput, gradInput, gradOf
     _lib.require_cuda(gradOutput, gradInput, gradOffset)
     B, C, H, W = input.shape
     Co = weight.size(0)
+    if gradOutput.dtype in (torch.float16, torch.bfloat16) and gradOutput.dtype == input.dtype:
+        from . import conv_tc
+        if conv_tc.deform_conv_dgrad_tc_supported(C, Co, kH, kW, dH, dW, padH, padW, dilationH, dilationW, group, deformable_group):
+            # 16-bit training (the reference's half route): tcgen05 implicit GEMMs with a scatter epilogue, no columns
+            gi, goff = conv_tc.deform_conv_dgrad_tc(gradOutput.detach(), offset.detach(), weight, x=input.detach(),
+                                                    need_offset_grad=True)
+            gradInput.add_(gi.to(gradInput.dtype))
+            gradOffset.add_(goff.to(gradOffset.dtype))
+            return 1
     x = input.detach().float().contiguous()
     off = offset.detach().float().contiguous()
     go = gradOutput.detach().float().contiguous()
@@ -196,7 +205,19 @@ class DeformConvFunction(Function):
             raise NotImplementedError
         cur_im2col_step = min(ctx.im2col_step, input.shape[0])
         assert (input.shape[0] % cur_im2col_step) == 0, 'im2col step must divide batchsize'
-        if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
+        from . import conv_tc
+        tc_dgrad = (grad_output.dtype in (torch.float16, torch.bfloat16) and grad_output.dtype == input.dtype and
+                    conv_tc.deform_conv_dgrad_tc_supported(input.size(1), weight.size(0), weight.size(2), weight.size(3),
+                                                           ctx.stride[0], ctx.stride[1], ctx.padding[0], ctx.padding[1],
+                                                           ctx.dilation[0], ctx.dilation[1], ctx.groups, ctx.deformable_groups))
+        if tc_dgrad and (ctx.needs_input_grad[0] or ctx.needs_input_grad[1]):
+            # 16-bit training: tcgen05 dgrad with the scatter epilogue; the offset gradient only when somebody wants it
+            # (S2ANet detaches the anchors, models/head.py:333-335, so normally nobody does)
+            gi, goff = conv_tc.deform_conv_dgrad_tc(grad_output, offset, weight, x=input,
+                                                    need_offset_grad=bool(ctx.needs_input_grad[1]))
+            grad_input = gi.to(input.dtype)
+            grad_offset = goff.to(offset.dtype) if goff is not None else None
+        elif ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
             grad_input = torch.zeros_like(input)
             grad_offset = torch.zeros_like(offset)
             deform_conv_backward_input_cuda(input, offset, grad_output, grad_input, grad_offset, weight, ctx.bufs_[0],

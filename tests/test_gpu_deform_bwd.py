@@ -118,3 +118,93 @@ def test_extension_entries_accumulate_and_check_arguments():
     with pytest.raises(NotImplementedError):
         dcn.deform_conv_backward_input_cuda(x.cpu(), off.cpu(), gy.cpu(), gi.cpu(), gof.cpu(), w.cpu(), e.cpu(), 3, 3, 1, 1, 1,
                                             1, 1, 1, 1, 1, 1)
+
+
+# ---- 16-bit backward on tcgen05 (round 2): dgrad = nine 1x1 implicit GEMMs with a scatter epilogue ----------------------
+
+def errs16(a, b):
+    a, b = a.float(), b.float()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-12)), float((a - b).norm() / (b.norm() + 1e-12))
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=["bf16", "fp16"])
+@pytest.mark.parametrize("B,C,H,W,Co", [(1, 64, 9, 13, 64), (2, 256, 24, 40, 256), (3, 32, 5, 3, 128)])
+def test_dgrad_tc_vs_fp32_kernels(dtype, B, C, H, W, Co):
+    """grad_input and grad_offset of the tcgen05 dgrad against this repo's fp32 backward (itself checked against
+    torchvision autograd and the reference binary above) fed with the SAME 16-bit-rounded operands.  Differences:
+    the column gradient's fp32 accumulation order, and x / grad_out / W enter the GEMM as 16-bit values (they ARE
+    16-bit values here).  Stated tolerance: bf16 / fp16 max-abs <= 2e-3 of max, rel-L2 <= 2e-3 (fp32 accumulation on
+    both sides; only the atomics' order differs)."""
+    from s2anet_b200 import dcn
+    from s2anet_b200.conv_tc import deform_conv_dgrad_tc
+    g = torch.Generator().manual_seed(C + H + B)
+    x = torch.randn(B, C, H, W, generator=g).to(DEV).to(dtype)
+    w = (torch.randn(Co, C, 3, 3, generator=g) * 0.05).to(DEV).to(dtype)
+    off = (torch.randn(B, 18, H, W, generator=g) * 1.5).to(DEV)
+    off[0, :, 0, 0] = 50.0                                   # a pixel whose samples all fall outside the map
+    gy = torch.randn(B, Co, H, W, generator=g).to(DEV).to(dtype)
+    gi, goff = deform_conv_dgrad_tc(gy, off, w, x=x, need_offset_grad=True)
+    assert gi.dtype == torch.float32 and tuple(gi.shape) == (B, C, H, W) and tuple(goff.shape) == (B, 18, H, W)
+    gi_r, goff_r = torch.zeros(B, C, H, W, device=DEV), torch.zeros_like(off)
+    e = gi_r.new_empty(0)
+    dcn.deform_conv_backward_input_cuda(x.float(), off, gy.float(), gi_r, goff_r, w.float(), e, 3, 3, 1, 1, 1, 1, 1, 1, 1, 1, B)
+    for name, a, b in (("grad_input", gi, gi_r), ("grad_offset", goff, goff_r)):
+        mx, l2 = errs16(a, b)
+        assert mx <= 2e-3 and l2 <= 2e-3, (name, mx, l2)
+    gi2, none = deform_conv_dgrad_tc(gy, off.to(dtype), w)       # 16-bit offsets, no offset gradient
+    assert none is None
+    gi_r2, goff_r2 = torch.zeros_like(gi_r), torch.zeros_like(off)
+    dcn.deform_conv_backward_input_cuda(x.float(), off.to(dtype).float(), gy.float(), gi_r2, goff_r2, w.float(), e, 3, 3, 1, 1, 1,
+                                        1, 1, 1, 1, 1, B)
+    mx, l2 = errs16(gi2, gi_r2)
+    assert mx <= 2e-3 and l2 <= 2e-3, (mx, l2)
+
+
+def test_half_precision_training_step_uses_tc_dgrad_and_matches_reference_binary():
+    """The reference's fp16 route end to end: DeformConvFunction (this repo's) forward + backward on half tensors at
+    P4 size -- forward and dgrad on tcgen05 -- against the reference's deform_conv_cuda binary run in half, and the
+    extension-level `deform_conv_backward_input_cuda` shim with half tensors against the same binary."""
+    from oracle import build_oracle
+    from s2anet_b200 import _lib, dcn
+    ref = build_oracle.load_ref_extension("deform_conv_cuda", "gpu")
+    if ref is None:
+        pytest.skip("oracle/_ref/ext_gpu/deform_conv_cuda not prebuilt")
+    g = torch.Generator().manual_seed(6)
+    B, C, H = 2, 256, 64
+    # smooth features: the half kernels round sampling positions to 1/32 - 1/16 px (see DESIGN.md section 3)
+    x = torch.nn.functional.interpolate(torch.randn(B, C, H // 4, H // 4, generator=g), size=(H, H), mode="bilinear").to(DEV).half()
+    w = (torch.randn(C, C, 3, 3, generator=g) * 0.02).to(DEV).half()
+    off = (torch.randn(B, 18, H, H, generator=g) * 1.2).to(DEV).half()
+    gy = torch.randn(B, C, H, H, generator=g).to(DEV).half()
+    xr = x.clone().requires_grad_()
+    wr = w.clone().requires_grad_()
+    before = _lib.launches
+    y = dcn.deform_conv(xr, off, wr, 1, 1, 1, 1, 1)
+    y.backward(gy)
+    assert _lib.launches - before >= 10                       # 1 forward + 9 dgrad launches of this library (+ wgrad path)
+    e = x.new_empty(0)
+    gi_ref, gof_ref, gw_ref = torch.zeros_like(x), torch.zeros_like(off), torch.zeros_like(w)
+    ref.deform_conv_backward_input_cuda(x, off, gy, gi_ref, gof_ref, w, e, 3, 3, 1, 1, 1, 1, 1, 1, 1, 1, B)
+    ref.deform_conv_backward_parameters_cuda(x, off, gy, gw_ref, e, e, 3, 3, 1, 1, 1, 1, 1, 1, 1, 1, 1.0, B)
+    # ... and the same binary in fp32 on the same half-valued operands: the yardstick.  (Its half run accumulates
+    # grad_input with half-precision atomics and rounds the sampling positions to half; it is itself ~1e-2 away.)
+    x32, off32, gy32, w32 = x.float(), off.float(), gy.float(), w.float()
+    e32 = x32.new_empty(0)
+    gi_r32, gof_r32, gw_r32 = torch.zeros_like(x32), torch.zeros_like(off32), torch.zeros_like(w32)
+    ref.deform_conv_backward_input_cuda(x32, off32, gy32, gi_r32, gof_r32, w32, e32, 3, 3, 1, 1, 1, 1, 1, 1, 1, 1, B)
+    ref.deform_conv_backward_parameters_cuda(x32, off32, gy32, gw_r32, e32, e32, 3, 3, 1, 1, 1, 1, 1, 1, 1, 1, 1.0, B)
+    torch.cuda.synchronize()
+    ref_half_err = errs16(gi_ref, gi_r32)[1]
+    mx, l2 = errs16(xr.grad, gi_r32)
+    assert xr.grad.dtype == torch.float16 and l2 <= 2e-3, ("grad_input vs the reference binary in fp32", mx, l2)
+    assert l2 <= ref_half_err + 1e-4                          # at least as close to fp32 as the reference's own half run
+    assert errs16(xr.grad, gi_ref)[1] <= 5e-2
+    mx, l2 = errs16(wr.grad, gw_r32)
+    assert l2 <= 2e-3, ("grad_weight vs the reference binary in fp32", mx, l2)
+    gi_s, gof_s = torch.zeros_like(x), torch.zeros_like(off)
+    assert dcn.deform_conv_backward_input_cuda(x, off, gy, gi_s, gof_s, w, e, 3, 3, 1, 1, 1, 1, 1, 1, 1, 1, B) == 1
+    mx, l2 = errs16(gi_s, gi_r32)
+    assert l2 <= 2e-3, ("shim grad_input", mx, l2)
+    mx, l2 = errs16(gof_s, gof_r32)
+    assert l2 <= 5e-3, ("shim grad_offset", mx, l2)
+    print("reference half backward vs its own fp32 run: rel-L2 %.2e; tcgen05 dgrad vs that fp32 run: %.2e" % (ref_half_err, errs16(xr.grad, gi_r32)[1]))
