@@ -224,6 +224,16 @@ S2A_EXPORT int s2a_deform_conv_dgrad_tc(const void* grad_out, const void* offset
                                         const void* wd, const void* x, float* grad_input,
                                         float* grad_offset, int B, int C, int H, int W, int Co, int dtype,
                                         void* stream);
+/* Deformable-conv backward w.r.t. the weight on tcgen05, 16-bit tensors: replaces deform_conv_backward_parameters_cuda
+ * (models/dcn/src/deform_conv_cuda.cpp:376-489: deformable_im2col into a column buffer + addmm_) for S2ANet's geometry
+ * (3x3, stride / pad / dilation 1, one group; C and C_out in {128, 256}).  dW[co, c, tap] = sum over pixels of
+ * grad_out[pixel, co] * sample[pixel, tap, c]: the contraction runs over pixels, both operands are MN-major
+ * shared-memory tiles (grad_out NHWC via TMA; the bilinear samples built by the producer warps), the C_out x C fp32
+ * accumulator of a tap lives in tensor memory across all pixel tiles of a CTA.  grad_weight_t is fp32 [9][C_out][C]
+ * (tap-major; the caller permutes it to [C_out, C, 3, 3]) and is ACCUMULATED.  x, grad_out NHWC 16-bit. */
+S2A_EXPORT int s2a_deform_conv_wgrad_tc(const void* x, const void* offsets, int offsets_dtype,
+                                        const void* grad_out, float* grad_weight_t, int B, int C, int H, int W,
+                                        int Co, int dtype, void* stream);
 S2A_EXPORT int s2a_orconv_forward_tc(const void* x, const void* packed_weight, const float* bias,
                                      void* out, void* pooled, int B, int C, int H, int W, int Co,
                                      int dtype, void* stream);

@@ -164,6 +164,33 @@ def deform_conv_dgrad_tc(grad_out, offset, weight, x=None, need_offset_grad=Fals
     return gi.permute(0, 3, 1, 2), goff
 
 
+def deform_conv_wgrad_tc(x, offset, grad_out):
+    """Deformable-conv backward w.r.t. the weight (3x3, stride / pad / dilation 1, one group; C, C_out in {128, 256})
+    on tcgen05: dW[co,c,tap] = sum_pixels grad_out[pixel,co] * sample[pixel,tap,c] with both operands as MN-major
+    shared-memory tiles and the accumulator in tensor memory -- no column buffer, no library GEMM.
+    x [B,C,H,W], grad_out [B,Co,H,W] bf16/fp16; offset [B,18,H,W] fp32 or that dtype.  Returns fp32 [Co,C,3,3]."""
+    dev = _lib.require_cuda(x, offset, grad_out)
+    B, C, H, W = x.shape
+    Co = grad_out.size(1)
+    if tuple(offset.shape) != (B, 18, H, W) or tuple(grad_out.shape) != (B, Co, H, W):
+        raise ValueError("deform_conv_wgrad_tc: shapes do not match a 3x3 deformable conv")
+    dt = x.dtype
+    xc, go = _nhwc(x), _nhwc(grad_out.to(dt))
+    off = offset if offset.dtype in (torch.float32, dt) else offset.to(dt)
+    off = off.contiguous()
+    dwt = torch.zeros((9, Co, C), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        rc = _lib.load().s2a_deform_conv_wgrad_tc(_lib.ptr(xc), _lib.ptr(off), _lib.dtype_code(off), _lib.ptr(go), _lib.ptr(dwt),
+                                                  B, C, H, W, Co, _lib.dtype_code(xc), _lib.stream_ptr(dev))
+    _lib.check(rc, "deform_conv_wgrad_tc")
+    return dwt.permute(1, 2, 0).reshape(Co, C, 3, 3)
+
+
+def deform_conv_wgrad_tc_supported(C, Co, kH, kW, dH, dW, padH, padW, dilH, dilW, group, deformable_group):
+    return (kH == 3 and kW == 3 and dH == 1 and dW == 1 and padH == 1 and padW == 1 and dilH == 1 and dilW == 1 and
+            group == 1 and deformable_group == 1 and C in (128, 256) and Co in (128, 256))
+
+
 def deform_conv_dgrad_tc_supported(C, Co, kH, kW, dH, dW, padH, padW, dilH, dilW, group, deformable_group):
     return (kH == 3 and kW == 3 and dH == 1 and dW == 1 and padH == 1 and padW == 1 and dilH == 1 and dilW == 1 and
             group == 1 and deformable_group == 1 and C % 32 == 0 and C <= 256 and Co % 64 == 0)

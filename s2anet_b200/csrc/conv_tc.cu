@@ -1550,6 +1550,246 @@ static int conv_tc_common(int mode, int nlevels, const void* const* xs, const fl
   return dtype == S2A_BF16 ? launch_tc<TC_PLAIN, __nv_bfloat16>(tmap, p, st) : launch_tc<TC_PLAIN, __half>(tmap, p, st);
 }
 
+// =================================================================================================
+// wgrad: dW[co, c, tap] = sum_pixels grad_out[pixel, co] * S[pixel, tap, c]   (S = the bilinear samples of the forward)
+//
+// Replaces deform_conv_backward_parameters_cuda for S2ANet's geometry (models/dcn/src/deform_conv_cuda.cpp:376-489:
+// deformable_im2col into a [C*9, H*W] column buffer + addmm_).  The contraction runs over PIXELS, so both operands
+// arrive "MN-major" for the tensor core: grad_out is NHWC ([pixel][co], co contiguous) and a tile of samples is
+// [pixel][channel].  Both are 128-byte rows in SWIZZLE_128B shared memory -- exactly the tiles the forward kernels
+// already build -- read through MN-major descriptors (canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units:
+// 64 M/N elements per 128-byte row, K rows 128 B apart, 8-row groups SBO = 1024 B apart, the next 64 M/N elements LBO
+// away; instruction-descriptor bits 15 / 16 select MN-major A / B).  No column buffer, no library GEMM.
+//
+// One CTA (no pairs) owns ONE TAP and every `ngroups`-th 8 x 16-pixel tile: its accumulator dW[:, :, tap] -- Co x C fp32 =
+// 2 x 128 lanes x 256 columns -- stays in tensor memory (all 512 columns) across its tiles and is added to global memory
+// once at the end (red.global.add.v4.f32 into a [9][Co][C] buffer).  Per tile: a TMA warp loads the grad_out tile
+// (Co/64 boxes {64 co, 16, 8, 1}, two buffers); 16 producer warps compute their pixel's sampling position from the
+// offsets, gather the four corners straight from global memory (L2), blend in packed 16-bit math like the forward and
+// store 128-byte sample rows, swizzled, into the two 32 KB stages (128 channels each); the MMA warp issues, per stage,
+// Co/128 x 8 tcgen05.mma (M = 128 co, N = 128 channels, K = 16 pixels).
+// =================================================================================================
+constexpr int WG_PROD_WARPS = 16;
+constexpr int WG_THREADS = (WG_PROD_WARPS + 2) * 32;          // + TMA warp + MMA warp
+constexpr int WG_BLOCK_BYTES = TC_M * 128;                    // one [128 pixels x 64 channels] sub-tile: 16 KB
+constexpr int WG_STAGE_BYTES = 2 * WG_BLOCK_BYTES;            // a stage: 128 channels
+constexpr int WG_G_BYTES = 4 * WG_BLOCK_BYTES;                // a grad_out tile: up to 256 co
+constexpr size_t WG_SMEM = 1024 + 2 * WG_STAGE_BYTES + 2 * WG_G_BYTES + 16 * 8 + 16;
+
+struct WgParams {
+  const void* x;          // [B, H, W, C] 16-bit
+  const void* off;        // [B, 18, H, W]
+  float* dwt;             // [9, Co, C] fp32, accumulated
+  int off_f32;
+  int B, C, Co, H, W, tiles_x, tiles_y, total_tiles;
+};
+
+// MN-major, SWIZZLE_128B shared-memory matrix descriptor (see the header comment)
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes = 1024) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(WG_THREADS, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap gmap, const WgParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sS = smem;                                   // 2 stages x 32 KB
+  uint8_t* sG = sS + 2 * WG_STAGE_BYTES;                // 2 grad_out tiles x 64 KB
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(sG + 2 * WG_G_BYTES);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 16);
+  const uint32_t bar_s_full = smem_u32(s_bar), bar_s_empty = bar_s_full + 16, bar_g_full = bar_s_full + 32,
+                 bar_g_empty = bar_s_full + 48, bar_acc = bar_s_full + 64;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tap = blockIdx.x % 9, grp = blockIdx.x / 9, ngrp = gridDim.x / 9;
+  const int nh = p.Co / 128;                            // output-channel halves (MMA M = 128)
+  const int nf = p.C / 128;                             // stage fills per tile (128 channels each)
+
+  if (tid == 0) {
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar_s_full + 8 * s, WG_PROD_WARPS / 2);  // one elected arrive per producer warp of the stage
+      mbar_init(bar_s_empty + 8 * s, 1);                 // tcgen05.commit
+      mbar_init(bar_g_full + 8 * s, 1);                  // expect_tx arrive (+ bytes)
+      mbar_init(bar_g_empty + 8 * s, 1);                 // tcgen05.commit
+    }
+    mbar_init(bar_acc, 1);
+    fence_barrier_init();
+  }
+  if (warp == WG_PROD_WARPS + 1) tmem_alloc<1>(smem_u32(s_tmem), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+  const int my_tiles = grp < p.total_tiles ? (p.total_tiles - grp + ngrp - 1) / ngrp : 0;
+
+  if (warp < WG_PROD_WARPS) {
+    // ===================== producers: sample rows into the stages =====================
+    // group = 4 warps = the 128 pixels of a tile for ONE 64-channel block; groups 2f, 2f + 1 fill stage f
+    const int group = warp >> 2, f = group >> 1, sub = group & 1;
+    const int r = (warp & 3) * 32 + lane;               // tile row = pixel (y = r / 16, x = r % 16)
+    const int ti = tap / 3, tj = tap - 3 * ti;
+    uint8_t* dst_row = sS + f * WG_STAGE_BYTES + sub * WG_BLOCK_BYTES + r * 128;
+    const int cb = 2 * f + sub;                         // 64-channel block of x this thread samples
+    for (int it = 0; it < my_tiles && f < nf; ++it) {
+      int tile = grp + it * ngrp;
+      const int tpi = p.tiles_x * p.tiles_y;
+      const int b = tile / tpi;
+      tile -= b * tpi;
+      const int ty0 = (tile / p.tiles_x) * TC_PH, tx0 = (tile % p.tiles_x) * TC_PW;
+      const int y = ty0 + r / TC_PW, x = tx0 + r % TC_PW;
+      // this pixel's sampling position for the CTA's tap (deform_conv_cuda_kernel.cu:218-227) -> corners + weights
+      uint32_t w01 = 0u, w23 = 0u;
+      size_t a_tl = 0, a_tr = 0, a_bl = 0, a_br = 0;    // element offsets of the (clamped) corners inside x
+      if (y < p.H && x < p.W) {
+        const size_t oi = (((size_t)b * 18 + 2 * tap) * p.H + y) * p.W + x, plane = (size_t)p.H * p.W;
+        float offy, offx;
+        if (p.off_f32) {
+          offy = reinterpret_cast<const float*>(p.off)[oi];
+          offx = reinterpret_cast<const float*>(p.off)[oi + plane];
+        } else {
+          offy = (float)reinterpret_cast<const T*>(p.off)[oi];
+          offx = (float)reinterpret_cast<const T*>(p.off)[oi + plane];
+        }
+        const float h = (float)(y - 1 + ti) + offy, w = (float)(x - 1 + tj) + offx;
+        if (h > -1.0f && w > -1.0f && h < (float)p.H && w < (float)p.W) {
+          const float hf = floorf(h), wf = floorf(w);
+          const int y0 = (int)hf, x0 = (int)wf;
+          const float ly = h - hf, lx = w - wf, hy = 1.0f - ly, hx = 1.0f - lx;
+          const bool t_ok = y0 >= 0, b_ok = y0 + 1 <= p.H - 1, l_ok = x0 >= 0, r_ok = x0 + 1 <= p.W - 1;
+          using H2 = typename Half2Of<T>::type;
+          const H2 p01 = from_f2<T>((t_ok && l_ok) ? hy * hx : 0.0f, (t_ok && r_ok) ? hy * lx : 0.0f);
+          const H2 p23 = from_f2<T>((b_ok && l_ok) ? ly * hx : 0.0f, (b_ok && r_ok) ? ly * lx : 0.0f);
+          w01 = *reinterpret_cast<const uint32_t*>(&p01);
+          w23 = *reinterpret_cast<const uint32_t*>(&p23);
+          const size_t rowp = (size_t)p.W * p.C, img = (size_t)b * p.H * rowp;
+          const int yt = max(y0, 0), yb = min(y0 + 1, p.H - 1), xl = max(x0, 0), xr = min(x0 + 1, p.W - 1);
+          a_tl = img + yt * rowp + (size_t)xl * p.C; a_tr = img + yt * rowp + (size_t)xr * p.C;
+          a_bl = img + yb * rowp + (size_t)xl * p.C; a_br = img + yb * rowp + (size_t)xr * p.C;
+        }
+      }
+      mbar_wait(bar_s_empty + 8 * f, (uint32_t)(it & 1) ^ 1u);
+      const T* xp = reinterpret_cast<const T*>(p.x) + cb * 64;
+#pragma unroll 2
+      for (int j = 0; j < 8; ++j) {                     // the eight 16-byte chunks (8 channels) of this pixel's row
+        uint4 o = make_uint4(0u, 0u, 0u, 0u);
+        if ((w01 | w23) != 0u) {
+          const uint4 v0 = ldg_nc_v4(xp + a_tl + 8 * j), v1 = ldg_nc_v4(xp + a_tr + 8 * j);
+          const uint4 v2 = ldg_nc_v4(xp + a_bl + 8 * j), v3 = ldg_nc_v4(xp + a_br + 8 * j);
+          o = blend4<T>(v0, v1, v2, v3, w01, w23);
+        }
+        *reinterpret_cast<uint4*>(dst_row + ((j ^ (r & 7)) << 4)) = o;          // SWIZZLE_128B
+      }
+      fence_proxy_async_smem();                          // generic-proxy stores -> visible to the tensor core
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_s_full + 8 * f);
+    }
+  } else if (warp == WG_PROD_WARPS) {
+    // ===================== TMA: grad_out tiles =====================
+    for (int it = 0; it < my_tiles; ++it) {
+      int tile = grp + it * ngrp;
+      const int tpi = p.tiles_x * p.tiles_y;
+      const int b = tile / tpi;
+      tile -= b * tpi;
+      const int ty0 = (tile / p.tiles_x) * TC_PH, tx0 = (tile % p.tiles_x) * TC_PW;
+      const int buf = it & 1;
+      mbar_wait(bar_g_empty + 8 * buf, ((uint32_t)(it >> 1) & 1u) ^ 1u);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(bar_g_full + 8 * buf, (uint32_t)(p.Co / 64) * WG_BLOCK_BYTES);
+        for (int j = 0; j < p.Co / 64; ++j)
+          tma_load_4d<1>(smem_u32(sG + buf * WG_G_BYTES + j * WG_BLOCK_BYTES), &gmap, j * 64, tx0, ty0, b, bar_g_full + 8 * buf);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===================== MMA issuer =====================
+    const uint32_t fmt = std::is_same<T, __nv_bfloat16>::value ? 1u : 0u;
+    // D = f32, A / B format, A and B MN-major (bits 15, 16), N = 128, M = 128
+    const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(128 >> 3) << 17) |
+                           ((uint32_t)(128 >> 4) << 24);
+    for (int it = 0; it < my_tiles; ++it) {
+      const int buf = it & 1;
+      mbar_wait(bar_g_full + 8 * buf, (uint32_t)(it >> 1) & 1u);
+      for (int f = 0; f < nf; ++f) {
+        mbar_wait(bar_s_full + 8 * f, (uint32_t)(it & 1));
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t sbase = smem_u32(sS + f * WG_STAGE_BYTES);
+          for (int h = 0; h < nh; ++h) {
+            const uint32_t gbase = smem_u32(sG + buf * WG_G_BYTES + 2 * h * WG_BLOCK_BYTES);
+            const uint32_t d_tmem = tmem_base + (uint32_t)(h * 256 + f * 128);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {               // K = 16 pixels per MMA: two 8-row groups = 2048 bytes
+              const uint64_t adesc = umma_desc_mn_sw128(gbase + k * 2048, WG_BLOCK_BYTES);
+              const uint64_t bdesc = umma_desc_mn_sw128(sbase + k * 2048, WG_BLOCK_BYTES);
+              umma_f16<1>(d_tmem, adesc, bdesc, idesc, (it | k) != 0 ? 1u : 0u);
+            }
+          }
+          umma_commit<1>(bar_s_empty + 8 * f);           // the stage may be refilled once these MMAs have read it
+          if (f == nf - 1) umma_commit<1>(bar_g_empty + 8 * buf);
+          if (f == nf - 1 && it == my_tiles - 1) umma_commit<1>(bar_acc);
+        }
+        __syncwarp();
+      }
+    }
+  }
+
+  // ===================== epilogue: tensor memory -> dWt[tap] (fp32, atomics; once per CTA) =====================
+  if (my_tiles > 0 && warp < 4) {
+    mbar_wait(bar_acc, 0u);
+    tc_fence_after();
+    for (int h = 0; h < nh; ++h) {
+      float* orow = p.dwt + ((size_t)tap * p.Co + h * 128 + warp * 32 + lane) * p.C;
+      for (int c0 = 0; c0 < p.C; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(h * 256 + c0), v);
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          red_add_v4(orow + c0 + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                     __uint_as_float(v[j + 3]));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == WG_PROD_WARPS + 1) {
+    tc_fence_after();
+    tmem_dealloc<1>(tmem_base, 512);
+  }
+}
+
+static int launch_wgrad(const void* x, const void* off, int off_f32, const void* grad_out, float* dwt, int B, int C, int H,
+                        int W, int Co, int dtype, cudaStream_t st) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) { set_error("wgrad_tc: cuTensorMapEncodeTiled is not available from the driver"); return S2A_ERR_CUDA; }
+  CUtensorMap gmap;
+  memset(&gmap, 0, sizeof(gmap));
+  const CUtensorMapDataType tdt = dtype == S2A_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  const cuuint64_t gd[4] = {(cuuint64_t)Co, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  const cuuint64_t gs[3] = {(cuuint64_t)Co * 2, (cuuint64_t)W * Co * 2, (cuuint64_t)H * W * Co * 2};
+  const cuuint32_t gb[4] = {64, (cuuint32_t)TC_PW, (cuuint32_t)TC_PH, 1};
+  const cuuint32_t ge[4] = {1, 1, 1, 1};
+  CUresult cr = enc(&gmap, tdt, 4, const_cast<void*>(grad_out), gd, gs, gb, ge, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) { set_error("wgrad_tc: cuTensorMapEncodeTiled failed (%d)", (int)cr); return S2A_ERR_CUDA; }
+  WgParams p{};
+  p.x = x; p.off = off; p.dwt = dwt; p.off_f32 = off_f32; p.B = B; p.C = C; p.Co = Co; p.H = H; p.W = W;
+  p.tiles_x = (W + TC_PW - 1) / TC_PW; p.tiles_y = (H + TC_PH - 1) / TC_PH;
+  const long long tiles = (long long)B * p.tiles_x * p.tiles_y;
+  S2A_CHECK_ARG(tiles < (1ll << 31), "wgrad_tc: too many tiles");
+  p.total_tiles = (int)tiles;
+  const int groups = std::max(1, std::min((int)std::min<long long>(tiles, 1 << 20), sm_count() / 9));
+  if (dtype == S2A_BF16) {
+    S2A_CUDA_OK(cudaFuncSetAttribute(wgrad_tc_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WG_SMEM));
+    wgrad_tc_kernel<__nv_bfloat16><<<9 * groups, WG_THREADS, WG_SMEM, st>>>(gmap, p);
+  } else {
+    S2A_CUDA_OK(cudaFuncSetAttribute(wgrad_tc_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WG_SMEM));
+    wgrad_tc_kernel<__half><<<9 * groups, WG_THREADS, WG_SMEM, st>>>(gmap, p);
+  }
+  S2A_LAUNCH_OK("wgrad_tc_kernel");
+  return S2A_OK;
+}
+
 template <typename TIn>
 static int pack_dispatch(const void* w, const uint8_t* idx, void* wp, int Co, int C, int nOri, int nRot, int arfI,
                          int out_dtype, cudaStream_t st) {
@@ -1630,6 +1870,22 @@ extern "C" int s2a_deform_conv_dgrad_tc(const void* grad_out, const void* offset
     if (rc != S2A_OK) return rc;
   }
   return S2A_OK;
+}
+
+extern "C" int s2a_deform_conv_wgrad_tc(const void* x, const void* offsets, int offsets_dtype, const void* grad_out,
+                                        float* grad_weight_t, int B, int C, int H, int W, int Co, int dtype, void* stream) {
+  using namespace s2a;
+  S2A_CHECK_ARG(H > 0 && W > 0 && B >= 0, "deform_conv_wgrad_tc: bad sizes");
+  S2A_CHECK_ARG(dtype == S2A_BF16 || dtype == S2A_F16, "deform_conv_wgrad_tc: dtype must be bf16 or f16");
+  if ((C != 128 && C != 256) || (Co != 128 && Co != 256)) {
+    set_error("deform_conv_wgrad_tc: needs C and C_out in {128, 256} (the accumulator is C_out x C fp32 in tensor memory; got C=%d, C_out=%d)", C, Co);
+    return S2A_ERR_UNSUPPORTED;
+  }
+  S2A_CHECK_ARG(offsets_dtype == S2A_F32 || offsets_dtype == dtype, "deform_conv_wgrad_tc: offsets must be fp32 or the tensors' dtype");
+  if (B == 0) return S2A_OK;
+  S2A_CHECK_ARG(x && offsets && grad_out && grad_weight_t, "deform_conv_wgrad_tc: null pointer");
+  return launch_wgrad(x, offsets, offsets_dtype == S2A_F32 ? 1 : 0, grad_out, grad_weight_t, B, C, H, W, Co, dtype,
+                      (cudaStream_t)stream);
 }
 
 extern "C" int s2a_orconv_forward_tc(const void* x, const void* packed_weight, const float* bias, void* out, void* pooled,

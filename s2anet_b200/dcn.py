@@ -146,6 +146,13 @@ def deform_conv_backward_parameters_cuda(input, offset, gradOutput, gradWeight, 
     _lib.require_cuda(gradOutput)
     B, C, H, W = input.shape
     Co = gradWeight.size(0)
+    if input.dtype in (torch.float16, torch.bfloat16) and gradOutput.dtype == input.dtype:
+        from . import conv_tc
+        if conv_tc.deform_conv_wgrad_tc_supported(C, Co, kH, kW, dH, dW, padH, padW, dilationH, dilationW, group, deformable_group):
+            # 16-bit training: tcgen05 wgrad (MN-major operands, accumulator in tensor memory), no columns
+            dw = conv_tc.deform_conv_wgrad_tc(input.detach(), offset.detach(), gradOutput.detach())
+            gradWeight.add_(dw.to(gradWeight.dtype), alpha=float(scale))
+            return 1
     x = input.detach().float().contiguous()
     off = offset.detach().float().contiguous()
     go = gradOutput.detach().float().contiguous()

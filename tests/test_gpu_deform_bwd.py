@@ -208,3 +208,36 @@ def test_half_precision_training_step_uses_tc_dgrad_and_matches_reference_binary
     mx, l2 = errs16(gof_s, gof_r32)
     assert l2 <= 5e-3, ("shim grad_offset", mx, l2)
     print("reference half backward vs its own fp32 run: rel-L2 %.2e; tcgen05 dgrad vs that fp32 run: %.2e" % (ref_half_err, errs16(xr.grad, gi_r32)[1]))
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=["bf16", "fp16"])
+@pytest.mark.parametrize("B,C,H,W,Co", [(1, 128, 8, 16, 128), (2, 256, 24, 40, 256), (3, 128, 13, 7, 256), (1, 256, 64, 64, 256)])
+def test_wgrad_tc_vs_fp32_kernels(dtype, B, C, H, W, Co):
+    """grad_weight of the tcgen05 wgrad (MN-major operands, accumulator in tensor memory across all pixel tiles of a
+    CTA, one tap per CTA) against this repo's fp32 path (im2col + GEMM, checked against torchvision autograd and the
+    reference binary above) on the SAME 16-bit-rounded operands.  Difference: the bilinear samples are rounded to 16
+    bits before the MMA (as in the forward) and the summation order.  Stated tolerance: bf16 max-abs <= 2e-2 of max,
+    rel-L2 <= 5e-3; fp16 4e-3 / 1e-3."""
+    from s2anet_b200 import dcn
+    from s2anet_b200.conv_tc import deform_conv_wgrad_tc
+    g = torch.Generator().manual_seed(C + H + B + Co)
+    x = torch.randn(B, C, H, W, generator=g).to(DEV).to(dtype)
+    off = (torch.randn(B, 18, H, W, generator=g) * 1.5).to(DEV)
+    off[0, :, 0, 0] = -40.0
+    gy = torch.randn(B, Co, H, W, generator=g).to(DEV).to(dtype)
+    dw = deform_conv_wgrad_tc(x, off, gy)
+    assert dw.dtype == torch.float32 and tuple(dw.shape) == (Co, C, 3, 3)
+    ref = torch.zeros(Co, C, 3, 3, device=DEV)
+    e = ref.new_empty(0)
+    dcn.deform_conv_backward_parameters_cuda(x.float(), off, gy.float(), ref, e, e, 3, 3, 1, 1, 1, 1, 1, 1, 1, 1, 1.0, B)
+    mx, l2 = errs16(dw, ref)
+    amax, arel = (2e-2, 5e-3) if dtype == torch.bfloat16 else (4e-3, 1e-3)
+    assert mx <= amax and l2 <= arel, (mx, l2)
+    # accumulation + scale through the reference-shaped entry with 16-bit tensors
+    gw = torch.ones(Co, C, 3, 3, device=DEV, dtype=dtype)
+    e16 = x.new_empty(0)
+    assert dcn.deform_conv_backward_parameters_cuda(x, off.to(dtype), gy, gw, e16, e16, 3, 3, 1, 1, 1, 1, 1, 1, 1, 1, 0.5, B) == 1
+    ref2 = torch.zeros(Co, C, 3, 3, device=DEV)
+    dcn.deform_conv_backward_parameters_cuda(x.float(), off.to(dtype).float(), gy.float(), ref2, e, e, 3, 3, 1, 1, 1, 1, 1, 1, 1, 1, 0.5, B)
+    mx, l2 = errs16(gw.float() - 1.0, ref2)
+    assert l2 <= 2e-2, (mx, l2)                       # (the 16-bit gradWeight tensor itself rounds the sum)
