@@ -740,6 +740,19 @@ def extra_legs(torch, np, dev, dtype, head, feat_sets, refines, peaks, args):
         lat = cuda_time(torch, g.replay, 50)
         out["config3_batch1"] = {"ms_per_image": lat, "images_per_s": 1e3 / lat,
                                  "note": "head + NMS only (the ResNet-50/FPN backbone stays stock PyTorch and is not timed)"}
+        # the deformable-conv backward of AlignConv at P3, batch 8, on tcgen05 (16-bit training route)
+        from s2anet_b200.conv_tc import deform_conv_dgrad_tc, deform_conv_wgrad_tc
+        xb = feat_sets[0][0]
+        gyb = torch.randn_like(xb)
+        offb = torch.randn(xb.size(0), 18, xb.size(2), xb.size(3), device=dev) * 1.2
+        t_dg = cuda_time(torch, lambda: deform_conv_dgrad_tc(gyb, offb, w), 3, warm=1)
+        t_wg = cuda_time(torch, lambda: deform_conv_wgrad_tc(xb, offb, gyb), 3, warm=1)
+        flb = 2.0 * xb.size(0) * 128 * 128 * 256 * 2304
+        out["backward_p3_batch%d" % xb.size(0)] = {
+            "dgrad_ms": t_dg, "dgrad_tflops": flb / t_dg / 1e9, "wgrad_ms": t_wg, "wgrad_tflops": flb / t_wg / 1e9,
+            "note": "dgrad = nine 1x1 implicit GEMMs with a bilinear scatter epilogue (bound by 302 M 16-byte L2 atomics); wgrad = "
+                    "MN-major operands, accumulator in tensor memory (bound by the nine-fold re-gather from L2); no column buffer"}
+        del gyb, offb
         # the step at ~10 k candidates per image (2-10 k)
         bias0 = head.odm_cls_head.bias.detach().clone()
         n10 = head.calibrate_scores(feat_sets[0], 10000)
