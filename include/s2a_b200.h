@@ -234,6 +234,18 @@ S2A_EXPORT int s2a_deform_conv_dgrad_tc(const void* grad_out, const void* offset
 S2A_EXPORT int s2a_deform_conv_wgrad_tc(const void* x, const void* offsets, int offsets_dtype,
                                         const void* grad_out, float* grad_weight_t, int B, int C, int H, int W,
                                         int Co, int dtype, void* stream);
+/* fp32 tensors on the tensor cores (3 x TF32 split, ~21 mantissa bits per product: inside the fp32 parity bar): the fast
+ * route of the fp32 entries above for 3x3 / stride 1 / pad 1 / one group, C %% 32 == 0, C_out %% 32 == 0 <= 256.
+ * s2a_conv_pack_weight_tf32: weight [Co][C][3][3] fp32 (or the ORConv bank through the ARF map, as
+ * s2a_conv_pack_weight) -> two fp32 planes [Co][9*C], K order (tap, channel).  s2a_conv_forward_tf32x3: x NHWC fp32
+ * [B,H,W,C]; mode 0: aux = anchors [B,H,W,5] (AlignConv, alignconv.py:29-98), mode 1: aux = offsets [B,18,H,W]
+ * (deform_conv_forward_cuda), mode 2: regular grid (ORConv2d / conv2d, aux ignored); out NCHW fp32 [B,Co,H,W] (the
+ * reference's layout), pooled [B,Co/8,H,W] or NULL; bias [Co] or NULL; relu != 0 fuses the ReLU. */
+S2A_EXPORT int s2a_conv_pack_weight_tf32(const float* weight, const uint8_t* arf_indices, float* packed_hi,
+                                         float* packed_lo, int Co, int C, int nOri, int nRot, void* stream);
+S2A_EXPORT int s2a_conv_forward_tf32x3(const float* x, const float* aux, int mode, const float* packed_hi,
+                                       const float* packed_lo, const float* bias, float* out, float* pooled,
+                                       int B, int C, int H, int W, int Co, float stride, int relu, void* stream);
 S2A_EXPORT int s2a_orconv_forward_tc(const void* x, const void* packed_weight, const float* bias,
                                      void* out, void* pooled, int B, int C, int H, int W, int Co,
                                      int dtype, void* stream);

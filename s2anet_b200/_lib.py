@@ -42,6 +42,8 @@ PROTOTYPES = {
     "s2a_deform_conv_forward_tc": (_i32, [_vp, _vp, _i32, _vp, _vp] + [_i32] * 8 + [_vp]),
     "s2a_deform_conv_dgrad_tc": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp, _vp] + [_i32] * 6 + [_vp]),
     "s2a_deform_conv_wgrad_tc": (_i32, [_vp, _vp, _i32, _vp, _vp] + [_i32] * 6 + [_vp]),
+    "s2a_conv_pack_weight_tf32": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
+    "s2a_conv_forward_tf32x3": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp] + [_i32] * 5 + [_f32, _i32, _vp]),
     "s2a_orconv_forward_tc": (_i32, [_vp, _vp, _vp, _vp, _vp] + [_i32] * 6 + [_vp]),
     "s2a_alignconv_forward_tc_multi": (_i32, [_i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp] + [_i32] * 4 + [_vp]),
     "s2a_orconv_forward_tc_multi": (_i32, [_i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp] + [_i32] * 4 + [_vp]),
@@ -84,7 +86,7 @@ def load():
 KERNELS_PER_CALL = {
     "box_iou_rotated": 1, "box_iou_rotated_batched": 1, "box_iou_rotated_tiles": 1, "nms_rotated": 4, "multiclass_nms_rotated": 6, "multiclass_nms_rotated_packed": 6,
     "arf_forward": 1, "arf_backward": 1, "ri_pool": 1, "deform_conv_forward_cuda": 1, "alignconv_forward": 1,
-    "orconv_forward": 1, "conv_pack_weight": 1, "alignconv_forward_tc": 1, "orconv_forward_tc": 1, "deform_conv_forward_tc": 1, "deform_conv_dgrad_tc": 9, "deform_conv_wgrad_tc": 1,
+    "orconv_forward": 1, "conv_pack_weight": 1, "alignconv_forward_tc": 1, "orconv_forward_tc": 1, "deform_conv_forward_tc": 1, "deform_conv_dgrad_tc": 9, "deform_conv_wgrad_tc": 1, "conv_pack_weight_tf32": 1, "conv_forward_tf32x3": 1,
     "alignconv_forward_tc_multi": 1, "orconv_forward_tc_multi": 1, "fam_decode": 1, "select_decode": 3, "conv2d_pack_weight": 1,
     "conv2d_forward_tc_multi": 1, "conv2d_forward_tc_multi2": 1, "assign_labels": 2, "deform_im2col": 1, "deform_col2im": 1,
     "poly_nms": 4, "poly_iou_pairs": 1,

@@ -13,6 +13,9 @@ from . import _lib
 from .dcn import DeformConv
 
 
+_FORCE_SIMT_F32 = False      # tests / probes: keep fp32 tensors on the SIMT kernel (conv_f32.cu) whatever the shape
+
+
 def alignconv_forward(x, anchors, weight, stride):
     """relu(deform_conv(x, offsets(anchors), weight)); x [B,C,H,W], anchors [B,H,W,5], weight [Co,C,3,3]."""
     dev = _lib.require_cuda(x, anchors, weight)
@@ -25,6 +28,11 @@ def alignconv_forward(x, anchors, weight, stride):
     if x.dtype != torch.float32:
         from . import conv_tc
         return conv_tc.alignconv_forward_tc(x, anchors, weight, stride)
+    from . import conv_tc
+    if conv_tc.tf32x3_supported(C, Co) and not _FORCE_SIMT_F32:
+        # fp32 on the tensor cores (3 x TF32 split, ~21 mantissa bits per product): conv_tf32x3_kernel
+        return conv_tc.conv_forward_tf32x3(x, anchors.reshape(B, H, W, 5), 0, conv_tc.pack_weight_tf32(weight), relu=True,
+                                           stride=stride)
     xc = x.contiguous()
     a = anchors.to(torch.float32).contiguous()
     w = weight.to(torch.float32).contiguous()

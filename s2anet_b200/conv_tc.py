@@ -97,6 +97,60 @@ def alignconv_forward_tc(x, anchors, weight, stride):
     return out
 
 
+def tf32x3_supported(C, Co):
+    """Shapes the fp32-on-tensor-cores kernel takes (3x3, stride / pad / dilation 1, one group assumed by the caller)."""
+    return C > 0 and C % 32 == 0 and Co % 32 == 0 and 0 < Co <= 256
+
+
+def pack_weight_tf32(weight, indices=None):
+    """fp32 weights -> (hi, lo) TF32 planes [Co][9*C] for conv_forward_tf32x3 (cached); ORConv banks through the ARF map."""
+    sources = (weight,) if indices is None else (weight, indices)
+    key = (tuple(id(t) for t in sources), torch.float32, "tf32x3")
+    hit = _cache_get(key, sources)
+    if hit is not None:
+        return hit
+    dev = weight.device
+    w = weight.detach().to(torch.float32).contiguous()
+    if indices is None:
+        Co, C = w.size(0), w.size(1)
+        nOri = nRot = 1
+        idx = None
+    else:
+        O, I, nOri = w.size(0), w.size(1), w.size(2)
+        nRot = indices.size(3)
+        Co, C = O * nRot, I * nOri
+        idx = indices.to(torch.uint8).contiguous()
+    hi = torch.empty((Co, 9 * C), dtype=torch.float32, device=dev)
+    lo = torch.empty_like(hi)
+    with torch.cuda.device(dev):
+        rc = _lib.load().s2a_conv_pack_weight_tf32(_lib.ptr(w), _lib.ptr(idx), _lib.ptr(hi), _lib.ptr(lo), Co, C, nOri, nRot,
+                                                   _lib.stream_ptr(dev))
+    _lib.check(rc, "conv_pack_weight_tf32")
+    return _cache_put(key, sources, (hi, lo))
+
+
+def conv_forward_tf32x3(x, aux, mode, packed, bias=None, relu=False, stride=1.0, with_pool=False, out=None):
+    """fp32 3x3 conv on tcgen05 with the 3 x TF32 split: mode 0 AlignConv (aux = anchors [B,H,W,5]), 1 generic
+    deformable conv (aux = offsets [B,18,H,W]), 2 regular grid (ORConv2d).  x fp32 [B,C,H,W] (converted to
+    channels_last once if it is not); returns NCHW-contiguous fp32 [B,Co,H,W] (+ pooled [B,Co/8,H,W])."""
+    dev = _lib.require_cuda(x, aux, bias)
+    hi, lo = packed
+    B, C, H, W = x.shape
+    Co = hi.size(0)
+    xc = _nhwc(x.to(torch.float32))
+    a = None if aux is None else aux.to(torch.float32).contiguous()
+    b = None if bias is None else bias.detach().to(torch.float32).contiguous()
+    if out is None or out.dtype != torch.float32 or not out.is_contiguous() or tuple(out.shape) != (B, Co, H, W):
+        out = torch.empty((B, Co, H, W), dtype=torch.float32, device=dev)
+    pooled = torch.empty((B, Co // 8, H, W), dtype=torch.float32, device=dev) if with_pool else None
+    with torch.cuda.device(dev):
+        rc = _lib.load().s2a_conv_forward_tf32x3(_lib.ptr(xc), _lib.ptr(a), int(mode), _lib.ptr(hi), _lib.ptr(lo), _lib.ptr(b),
+                                                 _lib.ptr(out), _lib.ptr(pooled), B, C, H, W, Co, float(stride),
+                                                 1 if relu else 0, _lib.stream_ptr(dev))
+    _lib.check(rc, "conv_forward_tf32x3")
+    return (out, pooled) if with_pool else out
+
+
 def deform_conv_tc_supported(C, Co, kH, kW, dH, dW, padH, padW, dilH, dilW, group, deformable_group):
     """Shapes the tcgen05 deformable conv takes (everything S2ANet's AlignConv uses)."""
     return (kH == 3 and kW == 3 and dH == 1 and dW == 1 and padH == 1 and padW == 1 and dilH == 1 and dilW == 1 and

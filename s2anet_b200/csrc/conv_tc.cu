@@ -1790,6 +1790,338 @@ static int launch_wgrad(const void* x, const void* off, int off_f32, const void*
   return S2A_OK;
 }
 
+// =================================================================================================
+// fp32 AlignConv / DeformConv / ORConv2d on the tensor cores: 3 x TF32 split (round 2)
+//
+// The exact-arithmetic fp32 path of round 1 (conv_f32.cu, SIMT FMAs fed by a scalar NCHW gather) ran AlignConv at P3
+// in 0.98 ms where the reference's im2col + cuBLAS SGEMM takes 0.59 ms.  Here the same contraction runs on
+// tcgen05.mma.kind::tf32 with both operands split into two TF32 terms, a = a_hi + a_lo (a_hi = a with the low 13
+// mantissa bits cleared, a_lo = a - a_hi, exact in fp32), and three MMAs per K step: a_hi*w_hi + a_lo*w_hi + a_hi*w_lo
+// (the dropped a_lo*w_lo term is 2^-20 relative).  Products of TF32 values are exact in the fp32 accumulator, so the
+// result carries ~21 mantissa bits per product: inside the fp32 bar of the parity tests (1e-4 + 1e-4 |ref|) by two
+// orders of magnitude.
+//
+// One CTA (no pairs) per 8 x 16-pixel tile, persistent.  12 producer warps (3 groups of 128 threads, one pixel each)
+// compute the sampling position of (pixel, tap) -- from the anchors (AlignConv, alignconv.py:29-86), an explicit offset
+// tensor (deform_conv_cuda_kernel.cu:218-227) or the regular grid (ORConv2d) --, gather the four corners from the NHWC
+// fp32 map with 16-byte loads, blend in fp32, split and store 128-byte rows (32 channels) of the hi and lo tiles; a TMA
+// warp streams the hi / lo halves of the packed weights (32 KB each per 32-channel k-block); the MMA warp issues 12
+// tcgen05.mma (M = 128, N = C_out, K = 8) per k-block into one of two tensor-memory accumulators; 4 epilogue warps add
+// the bias, apply ReLU / the 8-way orientation max and store NCHW fp32 (a warp writes 2 x 64 contiguous bytes per channel).
+// =================================================================================================
+constexpr int TF_KB = 32;                                   // channels per k-block: 128 bytes of fp32
+constexpr int TF_PROD_GROUPS = 3, TF_PROD_WARPS = 4 * TF_PROD_GROUPS;
+constexpr int TF_THREADS = (TF_PROD_WARPS + 4 + 2) * 32;    // + 4 epilogue warps + TMA warp + MMA warp
+constexpr int TF_A_BYTES = TC_M * 128;                      // one [128 pixels x 32 channels] fp32 tile: 16 KB
+constexpr int TF_B_BYTES = 256 * 128;                       // one [256 co x 32 channels] fp32 tile: 32 KB
+constexpr int TF_STAGE_BYTES = 2 * TF_A_BYTES + 2 * TF_B_BYTES;     // hi + lo of both operands: 96 KB
+constexpr size_t TF_SMEM = 1024 + 2 * TF_STAGE_BYTES + 16 * 8 + 16;
+enum { TF_ANCHORS = 0, TF_OFFSETS = 1, TF_GRID = 2 };
+
+struct TfParams {
+  const float* x;         // [B, H, W, C] fp32 (channels_last)
+  const float* aux;       // anchors [B, H, W, 5] (TF_ANCHORS) or offsets [B, 18, H, W] (TF_OFFSETS)
+  const float* bias;      // [Co] or null
+  float* out;             // [B, Co, H, W] fp32 (NCHW, the reference's layout)
+  float* pooled;          // [B, Co/8, H, W] or null
+  int mode, relu;
+  float stride;
+  int B, C, Co, H, W, tiles_x, tiles_y, total_tiles;
+};
+
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ float tf32_hi(float v) { return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
+__device__ __forceinline__ uint4 ldg_nc_f4(const float* p) { return ldg_nc_v4(p); }
+
+__global__ void __launch_bounds__(TF_THREADS, 1)
+conv_tf32x3_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo, const TfParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + 2 * TF_STAGE_BYTES);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 16);
+  const uint32_t bar_full = smem_u32(s_bar), bar_empty = bar_full + 16, bar_acc_full = bar_full + 32, bar_acc_empty = bar_full + 48;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr int kEpi0 = TF_PROD_WARPS, kTma = TF_PROD_WARPS + 4, kMma = TF_PROD_WARPS + 5;
+  const int ncb = p.C / TF_KB, nkb = 9 * ncb;
+  const int my_tiles = (int)blockIdx.x < p.total_tiles ? (p.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const uint32_t b_bytes = (uint32_t)p.Co * 128u;
+
+  if (tid == 0) {
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar_full + 8 * s, 4 + 1);               // four producer warps of the owning group + the TMA thread's expect_tx
+      mbar_init(bar_empty + 8 * s, 1);                  // tcgen05.commit
+      mbar_init(bar_acc_full + 8 * s, 1);               // tcgen05.commit after the last k-block of a tile
+      mbar_init(bar_acc_empty + 8 * s, 4);              // one elected arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == kMma) tmem_alloc<1>(smem_u32(s_tmem), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+
+  auto tile_coords = [&](int it, int& b, int& ty0, int& tx0) {
+    int tile = (int)blockIdx.x + it * (int)gridDim.x;
+    const int tpi = p.tiles_x * p.tiles_y;
+    b = tile / tpi;
+    tile -= b * tpi;
+    ty0 = (tile / p.tiles_x) * TC_PH;
+    tx0 = (tile % p.tiles_x) * TC_PW;
+  };
+
+  if (warp < TF_PROD_WARPS) {
+    // ===================== producers: fp32 samples, split into TF32 hi / lo rows =====================
+    const int group = warp >> 2;
+    const int r = (warp & 3) * 32 + lane;               // tile row = pixel
+    for (int it = 0; it < my_tiles; ++it) {
+      int b, ty0, tx0;
+      tile_coords(it, b, ty0, tx0);
+      const int y = ty0 + r / TC_PW, x = tx0 + r % TC_PW;
+      const bool inside = y < p.H && x < p.W;
+      float ax = 0.f, ay = 0.f, dw = 0.f, dh = 0.f, cs = 1.f, sn = 0.f;
+      if (p.mode == TF_ANCHORS && inside) {
+        const float* a = p.aux + ((size_t)(b * p.H + y) * p.W + x) * 5;
+        ax = a[0] / p.stride; ay = a[1] / p.stride;
+        dw = (a[2] / p.stride) / 3.0f; dh = (a[3] / p.stride) / 3.0f;
+        cs = cosf(a[4]); sn = sinf(a[4]);
+      }
+      const size_t rowp = (size_t)p.W * p.C, img = (size_t)b * p.H * rowp;
+      int last_tap = -1;
+      float w1 = 0.f, w2 = 0.f, w3 = 0.f, w4 = 0.f;
+      size_t a_tl = 0, a_tr = 0, a_bl = 0, a_br = 0;
+      for (int kb = group; kb < nkb; kb += TF_PROD_GROUPS) {
+        const int n = it * nkb + kb, s = n & 1;
+        const int tap = kb / ncb, cb = kb - tap * ncb;
+        if (tap != last_tap) {
+          // sampling position of (pixel, tap) and its bilinear corners / weights (deform_conv_cuda_kernel.cu:83-114, :228)
+          last_tap = tap;
+          w1 = w2 = w3 = w4 = 0.f;
+          if (inside) {
+            const int ti = tap / 3, tj = tap - 3 * ti;
+            float h, w;
+            if (p.mode == TF_ANCHORS) {               // models/alignconv.py:29-86, operation order preserved
+              const float fi = (float)(ti - 1), fj = (float)(tj - 1);
+              const float txx = __fmul_rn(dw, fj), tyy = __fmul_rn(dh, fi);
+              const float xr = __fsub_rn(__fmul_rn(cs, txx), __fmul_rn(sn, tyy));
+              const float yr = __fadd_rn(__fmul_rn(sn, txx), __fmul_rn(cs, tyy));
+              const float xa = __fadd_rn(xr, ax), ya = __fadd_rn(yr, ay);
+              const float offx = __fsub_rn(xa, __fadd_rn((float)x, fj));
+              const float offy = __fsub_rn(ya, __fadd_rn((float)y, fi));
+              h = __fadd_rn((float)(y - 1 + ti), offy);
+              w = __fadd_rn((float)(x - 1 + tj), offx);
+            } else if (p.mode == TF_OFFSETS) {
+              const size_t oi = (((size_t)b * 18 + 2 * tap) * p.H + y) * p.W + x;
+              h = (float)(y - 1 + ti) + p.aux[oi];
+              w = (float)(x - 1 + tj) + p.aux[oi + (size_t)p.H * p.W];
+            } else {
+              h = (float)(y - 1 + ti);
+              w = (float)(x - 1 + tj);
+            }
+            if (h > -1.0f && w > -1.0f && h < (float)p.H && w < (float)p.W) {
+              const float hf = floorf(h), wf = floorf(w);
+              const int y0 = (int)hf, x0 = (int)wf;
+              const float ly = h - hf, lx = w - wf, hy = 1.0f - ly, hx = 1.0f - lx;
+              const bool t_ok = y0 >= 0, b_ok = y0 + 1 <= p.H - 1, l_ok = x0 >= 0, r_ok = x0 + 1 <= p.W - 1;
+              w1 = (t_ok && l_ok) ? hy * hx : 0.f; w2 = (t_ok && r_ok) ? hy * lx : 0.f;
+              w3 = (b_ok && l_ok) ? ly * hx : 0.f; w4 = (b_ok && r_ok) ? ly * lx : 0.f;
+              const int yt = max(y0, 0), yb = min(y0 + 1, p.H - 1), xl = max(x0, 0), xrr = min(x0 + 1, p.W - 1);
+              a_tl = img + yt * rowp + (size_t)xl * p.C; a_tr = img + yt * rowp + (size_t)xrr * p.C;
+              a_bl = img + yb * rowp + (size_t)xl * p.C; a_br = img + yb * rowp + (size_t)xrr * p.C;
+            }
+          }
+        }
+        mbar_wait(bar_empty + 8 * s, ((uint32_t)(n >> 1) & 1u) ^ 1u);
+        uint8_t* row_hi = smem + s * TF_STAGE_BYTES + r * 128;
+        uint8_t* row_lo = row_hi + TF_A_BYTES;
+        const float* xp = p.x + cb * TF_KB;
+        const bool any = (w1 != 0.f) | (w2 != 0.f) | (w3 != 0.f) | (w4 != 0.f);
+#pragma unroll 2
+        for (int j = 0; j < 8; ++j) {                   // eight 16-byte chunks = 4 channels each
+          float v[4] = {0.f, 0.f, 0.f, 0.f};
+          if (any) {
+            const uint4 q1 = ldg_nc_f4(xp + a_tl + 4 * j), q2 = ldg_nc_f4(xp + a_tr + 4 * j);
+            const uint4 q3 = ldg_nc_f4(xp + a_bl + 4 * j), q4 = ldg_nc_f4(xp + a_br + 4 * j);
+            const uint32_t u1[4] = {q1.x, q1.y, q1.z, q1.w}, u2[4] = {q2.x, q2.y, q2.z, q2.w};
+            const uint32_t u3[4] = {q3.x, q3.y, q3.z, q3.w}, u4[4] = {q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              v[e] = w1 * __uint_as_float(u1[e]) + w2 * __uint_as_float(u2[e]) + w3 * __uint_as_float(u3[e]) +
+                     w4 * __uint_as_float(u4[e]);
+          }
+          float hi[4], lo[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) { hi[e] = tf32_hi(v[e]); lo[e] = tf32_hi(v[e] - hi[e]); }
+          const int sw = (j ^ (r & 7)) << 4;            // SWIZZLE_128B
+          *reinterpret_cast<float4*>(row_hi + sw) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<float4*>(row_lo + sw) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_full + 8 * s);
+      }
+    }
+  } else if (warp == kTma) {
+    // ===================== TMA: hi / lo halves of the packed weights, one k-block per stage =====================
+    for (int it = 0; it < my_tiles; ++it) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int n = it * nkb + kb, s = n & 1;
+        mbar_wait(bar_empty + 8 * s, ((uint32_t)(n >> 1) & 1u) ^ 1u);
+        if (elect_one()) {
+          uint8_t* sb = smem + s * TF_STAGE_BYTES + 2 * TF_A_BYTES;
+          mbar_arrive_expect_tx(bar_full + 8 * s, 2u * b_bytes);
+          tma_load_2d<1>(smem_u32(sb), &map_hi, kb * TF_KB, 0, bar_full + 8 * s);
+          tma_load_2d<1>(smem_u32(sb + TF_B_BYTES), &map_lo, kb * TF_KB, 0, bar_full + 8 * s);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == kMma) {
+    // ===================== MMA issuer =====================
+    // D = f32, A / B = TF32 (format 2), K-major, N = C_out, M = 128
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.Co >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+    for (int it = 0; it < my_tiles; ++it) {
+      const int as = it & 1;
+      mbar_wait(bar_acc_empty + 8 * as, ((uint32_t)(it >> 1) & 1u) ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(as * 256);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int n = it * nkb + kb, s = n & 1;
+        mbar_wait(bar_full + 8 * s, (uint32_t)(n >> 1) & 1u);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t sa = smem_u32(smem + s * TF_STAGE_BYTES);
+          const uint64_t a_hi = umma_desc_sw128(sa), a_lo = umma_desc_sw128(sa + TF_A_BYTES);
+          const uint64_t b_hi = umma_desc_sw128(sa + 2 * TF_A_BYTES), b_lo = umma_desc_sw128(sa + 2 * TF_A_BYTES + TF_B_BYTES);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {                 // K = 8 fp32 = 32 bytes per step inside the 128-byte swizzle atom
+            umma_tf32(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_tf32(d_tmem, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);
+            umma_tf32(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
+          }
+          umma_commit<1>(bar_empty + 8 * s);
+          if (kb == nkb - 1) umma_commit<1>(bar_acc_full + 8 * as);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===================== epilogue: bias / ReLU / orientation max, NCHW fp32 stores =====================
+    const int quad = warp & 3;                          // warps 12..15: warp % 4 = the TMEM lane quadrant
+    const int r = quad * 32 + lane;
+    for (int it = 0; it < my_tiles; ++it) {
+      int b, ty0, tx0;
+      tile_coords(it, b, ty0, tx0);
+      const int as = it & 1;
+      const int y = ty0 + r / TC_PW, x = tx0 + r % TC_PW;
+      const bool valid = y < p.H && x < p.W;
+      mbar_wait(bar_acc_full + 8 * as, (uint32_t)(it >> 1) & 1u);
+      tc_fence_after();
+      const size_t plane = (size_t)p.H * p.W, pix = (size_t)y * p.W + x;
+      for (int c0 = 0; c0 < p.Co; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * 256 + c0), v);
+        if (c0 + 32 >= p.Co) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_acc_empty + 8 * as);
+        }
+        if (valid) {
+          float* o = p.out + ((size_t)b * p.Co + c0) * plane + pix;
+          float m[4];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float t = __uint_as_float(v[j]);
+            if (p.bias) t += __ldg(p.bias + c0 + j);
+            if (p.relu) t = fmaxf(t, 0.0f);
+            o[(size_t)j * plane] = t;
+            m[j >> 3] = (j & 7) == 0 ? t : fmaxf(m[j >> 3], t);
+          }
+          if (p.pooled) {
+            float* po = p.pooled + ((size_t)b * (p.Co / 8) + c0 / 8) * plane + pix;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) po[(size_t)g * plane] = m[g];
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMma) {
+    tc_fence_after();
+    tmem_dealloc<1>(tmem_base, 512);
+  }
+}
+
+// weights [Co][C][3][3] fp32 (optionally through the ARF map: w [O, I, nOri, 3, 3], indices [nOri*9, nRot]) ->
+// hi / lo TF32 planes [Co][(tap, c)] (K' = 9 C, k-block = 32 channels of one tap)
+__global__ void pack_weight_tf32_kernel(const float* __restrict__ w, const uint8_t* __restrict__ arf_idx, float* __restrict__ hi,
+                                        float* __restrict__ lo, int Co, int C, int nOri, int nRot, int arfI) {
+  __shared__ uint8_t s_inv[8 * 72];
+  const int nEntry = nOri * 9;
+  if (arf_idx) {
+    for (int i = threadIdx.x; i < nEntry * nRot; i += blockDim.x) {
+      const int l = i / nRot, k = i % nRot;
+      s_inv[k * nEntry + ((int)arf_idx[i] - 1)] = (uint8_t)l;
+    }
+    __syncthreads();
+  }
+  const int64_t total = (int64_t)Co * C * 9;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int cin = (int)(e % C);
+    int64_t rr = e / C;
+    const int tap = (int)(rr % 9);
+    const int n = (int)(rr / 9);
+    float v;
+    if (arf_idx) {
+      const int o = n / nRot, k = n % nRot;
+      const int ii = cin / nOri, lay = cin % nOri;
+      const int l = s_inv[k * nEntry + lay * 9 + tap];
+      v = w[((int64_t)o * arfI + ii) * nEntry + l];
+    } else {
+      v = w[((int64_t)n * C + cin) * 9 + tap];
+    }
+    const float h = tf32_hi(v);
+    hi[e] = h;
+    lo[e] = tf32_hi(v - h);
+  }
+}
+
+static int launch_tf32x3(const TfParams& p0, const float* w_hi, const float* w_lo, cudaStream_t st) {
+  TfParams p = p0;
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) { set_error("conv_tf32x3: cuTensorMapEncodeTiled is not available from the driver"); return S2A_ERR_CUDA; }
+  CUtensorMap maps[2];
+  memset(maps, 0, sizeof(maps));
+  const int Kp = 9 * p.C;
+  const cuuint64_t gd[2] = {(cuuint64_t)Kp, (cuuint64_t)p.Co};
+  const cuuint64_t gs[1] = {(cuuint64_t)Kp * 4};
+  const cuuint32_t box[2] = {(cuuint32_t)TF_KB, (cuuint32_t)p.Co};
+  const cuuint32_t es[2] = {1, 1};
+  for (int i = 0; i < 2; ++i) {
+    CUresult cr = enc(&maps[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(i == 0 ? w_hi : w_lo), gd, gs, box, es,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) { set_error("conv_tf32x3: cuTensorMapEncodeTiled failed (%d)", (int)cr); return S2A_ERR_CUDA; }
+  }
+  p.tiles_x = (p.W + TC_PW - 1) / TC_PW; p.tiles_y = (p.H + TC_PH - 1) / TC_PH;
+  const long long tiles = (long long)p.B * p.tiles_x * p.tiles_y;
+  S2A_CHECK_ARG(tiles < (1ll << 31), "conv_tf32x3: too many tiles");
+  p.total_tiles = (int)tiles;
+  S2A_CUDA_OK(cudaFuncSetAttribute(conv_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TF_SMEM));
+  const int grid = (int)std::max<long long>(1, std::min<long long>(tiles, sm_count()));
+  conv_tf32x3_kernel<<<grid, TF_THREADS, TF_SMEM, st>>>(maps[0], maps[1], p);
+  S2A_LAUNCH_OK("conv_tf32x3_kernel");
+  return S2A_OK;
+}
+
 template <typename TIn>
 static int pack_dispatch(const void* w, const uint8_t* idx, void* wp, int Co, int C, int nOri, int nRot, int arfI,
                          int out_dtype, cudaStream_t st) {
@@ -1886,6 +2218,43 @@ extern "C" int s2a_deform_conv_wgrad_tc(const void* x, const void* offsets, int 
   S2A_CHECK_ARG(x && offsets && grad_out && grad_weight_t, "deform_conv_wgrad_tc: null pointer");
   return launch_wgrad(x, offsets, offsets_dtype == S2A_F32 ? 1 : 0, grad_out, grad_weight_t, B, C, H, W, Co, dtype,
                       (cudaStream_t)stream);
+}
+
+extern "C" int s2a_conv_pack_weight_tf32(const float* weight, const uint8_t* arf_indices, float* packed_hi, float* packed_lo,
+                                         int Co, int C, int nOri, int nRot, void* stream) {
+  using namespace s2a;
+  S2A_CHECK_ARG(Co > 0 && C > 0 && weight && packed_hi && packed_lo, "conv_pack_weight_tf32: bad arguments");
+  int arfI = 0;
+  if (arf_indices) {
+    S2A_CHECK_ARG(nOri >= 1 && nOri <= 8 && nRot >= 1 && nRot <= 8 && C % nOri == 0 && Co % nRot == 0,
+                  "conv_pack_weight_tf32: bad ARF configuration");
+    arfI = C / nOri;
+  }
+  const int64_t total = (int64_t)Co * C * 9;
+  const int blocks = (int)std::min<int64_t>(ceil_div(total, 256), (int64_t)sm_count() * 8);
+  pack_weight_tf32_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(weight, arf_indices, packed_hi, packed_lo, Co, C, nOri, nRot, arfI);
+  S2A_LAUNCH_OK("pack_weight_tf32_kernel");
+  return S2A_OK;
+}
+
+extern "C" int s2a_conv_forward_tf32x3(const float* x, const float* aux, int mode, const float* packed_hi, const float* packed_lo,
+                                       const float* bias, float* out, float* pooled, int B, int C, int H, int W, int Co,
+                                       float stride, int relu, void* stream) {
+  using namespace s2a;
+  S2A_CHECK_ARG(B >= 0 && H > 0 && W > 0, "conv_forward_tf32x3: bad tensor sizes");
+  S2A_CHECK_ARG(mode == TF_ANCHORS || mode == TF_OFFSETS || mode == TF_GRID, "conv_forward_tf32x3: mode must be 0, 1 or 2");
+  if (C % 32 != 0 || Co % 32 != 0 || Co > 256 || C <= 0) {
+    set_error("conv_forward_tf32x3: needs C %% 32 == 0 and C_out a multiple of 32 up to 256 (got C=%d, C_out=%d)", C, Co);
+    return S2A_ERR_UNSUPPORTED;
+  }
+  S2A_CHECK_ARG(mode != TF_ANCHORS || stride > 0.0f, "conv_forward_tf32x3: stride must be positive");
+  S2A_CHECK_ARG(!pooled || Co % 8 == 0, "conv_forward_tf32x3: pooling needs C_out %% 8 == 0");
+  if (B == 0) return S2A_OK;
+  S2A_CHECK_ARG(x && packed_hi && packed_lo && out && (mode == TF_GRID || aux), "conv_forward_tf32x3: null pointer");
+  TfParams p{};
+  p.x = x; p.aux = aux; p.bias = bias; p.out = out; p.pooled = pooled; p.mode = mode; p.relu = relu; p.stride = stride;
+  p.B = B; p.C = C; p.Co = Co; p.H = H; p.W = W;
+  return launch_tf32x3(p, packed_hi, packed_lo, (cudaStream_t)stream);
 }
 
 extern "C" int s2a_orconv_forward_tc(const void* x, const void* packed_weight, const float* bias, void* out, void* pooled,

@@ -63,6 +63,15 @@ def deform_conv_forward_cuda(input, weight, offset, output, columns, ones, kW, k
         return 1
     if input.dtype != torch.float32:
         raise TypeError("deform_conv_forward_cuda: unsupported dtype %s (float32, float16, bfloat16)" % input.dtype)
+    from . import alignconv, conv_tc
+    s2a_geometry = (kH == 3 and kW == 3 and dH == 1 and dW == 1 and padH == 1 and padW == 1 and dilationH == 1 and
+                    dilationW == 1 and group == 1 and deformable_group == 1)
+    if s2a_geometry and conv_tc.tf32x3_supported(C, Co) and not alignconv._FORCE_SIMT_F32:
+        # fp32 on the tensor cores (3 x TF32 split): explicit offsets -> sampling positions inside the kernel
+        y = conv_tc.conv_forward_tf32x3(input, offset, 1, conv_tc.pack_weight_tf32(weight), out=output)
+        if y is not output:
+            output.copy_(y.view_as(output))
+        return 1
     x = input.contiguous()
     off = offset.to(torch.float32).contiguous()
     w = weight.to(torch.float32).contiguous()

@@ -119,6 +119,12 @@ def orconv_forward(x, weight, indices, bias, with_pool=False):
     if x.dtype != torch.float32:
         from . import conv_tc
         return conv_tc.orconv_forward_tc(x, weight, indices, bias, with_pool)
+    from . import alignconv, conv_tc
+    if conv_tc.tf32x3_supported(C, O * nRot) and C == I * nOri and not alignconv._FORCE_SIMT_F32 and \
+            (not with_pool or (O * nRot) % 8 == 0):
+        # fp32 on the tensor cores (3 x TF32 split); the ARF rotation is folded into the weight packing
+        return conv_tc.conv_forward_tf32x3(x, None, 2, conv_tc.pack_weight_tf32(weight, indices), bias=bias, relu=False,
+                                           with_pool=with_pool)
     xc = x.contiguous()
     w = weight.to(torch.float32).contiguous()
     idx = indices.to(torch.uint8).contiguous()

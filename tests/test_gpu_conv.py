@@ -231,3 +231,62 @@ def test_orconv2d_and_pooling_keep_the_autograd_graph(oracle):
         yi = m(x.detach())
     assert getattr(yi, "_s2a_pooled", None) is not None
     np.testing.assert_allclose(yi.cpu().numpy(), y.detach().cpu().numpy(), rtol=RTOL, atol=ATOL)
+
+
+# ---- fp32 tensors on the tensor cores: 3 x TF32 split (round 2) ---------------------------------------------------------
+
+@pytest.mark.parametrize("B,C,H,W,Co,stride", [(1, 32, 8, 16, 32, 8), (2, 64, 13, 21, 96, 16), (1, 256, 20, 20, 256, 32),
+                                               (3, 96, 5, 3, 64, 64)])
+def test_tf32x3_alignconv_matches_the_simt_fp32_kernel_and_the_oracle(oracle, B, C, H, W, Co, stride):
+    """conv_tf32x3_kernel (tcgen05.mma.kind::tf32, three MMAs per K step on hi / lo splits) against the exact SIMT
+    kernel of conv_f32.cu and, at the smallest shape, the scalar oracle: the fp32 bar 1e-4 + 1e-4 |ref|; measured
+    differences are ~1e-6 relative (21 mantissa bits per product, fp32 accumulation)."""
+    from s2anet_b200 import alignconv
+    rng = np.random.default_rng(C + H + Co)
+    x = rng.normal(size=(B, C, H, W)).astype(np.float32)
+    anc = synth.refined_anchors(B, H, W, stride, seed=H)
+    w = (rng.normal(size=(Co, C, 3, 3)) * 0.1).astype(np.float32)
+    y = alignconv.alignconv_forward(t(x), t(anc), t(w), stride)
+    assert y.is_contiguous() and y.dtype == torch.float32
+    alignconv._FORCE_SIMT_F32 = True
+    try:
+        ref = alignconv.alignconv_forward(t(x), t(anc), t(w), stride)
+    finally:
+        alignconv._FORCE_SIMT_F32 = False
+    err = float((y - ref).abs().max())
+    assert err <= 1e-5 + 2e-5 * float(ref.abs().max()), err
+    if C <= 32:
+        np.testing.assert_allclose(y.cpu().numpy(), oracle.alignconv_forward(x, anc, w, stride), rtol=RTOL, atol=ATOL)
+
+
+def test_tf32x3_orconv_pool_and_generic_offsets(oracle):
+    """The regular-grid mode (ORConv2d: ARF folded into the packed hi / lo planes, bias, fused orientation max) and
+    the explicit-offset mode (`deform_conv_forward_cuda` with fp32 tensors) of the same kernel."""
+    import torchvision
+    from s2anet_b200 import alignconv, dcn
+    from s2anet_b200.orn import ORConv2d, orconv_forward
+    torch.backends.cudnn.allow_tf32 = False
+    g = torch.Generator().manual_seed(2)
+    m = ORConv2d(64, 8, 3, padding=1, arf_config=(1, 8)).to(DEV)
+    with torch.no_grad():
+        m.weight.copy_(torch.randn(m.weight.shape, generator=g) * 0.05)
+        m.bias.copy_(torch.randn(64, generator=g) * 0.1)
+    x = torch.randn(2, 64, 19, 27, generator=g).to(DEV)
+    y, yp = orconv_forward(x, m.weight, m.indices, m.bias, with_pool=True)
+    ref = torch.nn.functional.conv2d(x, m.rotate_arf(), m.bias, padding=1)
+    assert float((y - ref).abs().max()) <= 1e-5 + 2e-5 * float(ref.abs().max())
+    assert torch.equal(yp, y.view(2, 8, 8, 19, 27).max(dim=2)[0])
+    w = (torch.randn(96, 64, 3, 3, generator=g) * 0.05).to(DEV)
+    off = (torch.randn(2, 18, 19, 27, generator=g) * 2.0).to(DEV)
+    out = torch.empty(2, 96, 19, 27, device=DEV)
+    e = x.new_empty(0)
+    assert dcn.deform_conv_forward_cuda(x, w, off, out, e, e, 3, 3, 1, 1, 1, 1, 1, 1, 1, 1, 2) == 1
+    ref = torchvision.ops.deform_conv2d(x, off, w, padding=1)
+    assert float((out - ref).abs().max()) <= ATOL + RTOL * float(ref.abs().max())
+    alignconv._FORCE_SIMT_F32 = True
+    try:
+        out2 = torch.empty_like(out)
+        dcn.deform_conv_forward_cuda(x, w, off, out2, e, e, 3, 3, 1, 1, 1, 1, 1, 1, 1, 1, 2)
+    finally:
+        alignconv._FORCE_SIMT_F32 = False
+    assert float((out - out2).abs().max()) <= 1e-5 + 2e-5 * float(out2.abs().max())
