@@ -1814,8 +1814,14 @@ constexpr int TF_PROD_GROUPS = 3, TF_PROD_WARPS = 4 * TF_PROD_GROUPS;
 constexpr int TF_THREADS = (TF_PROD_WARPS + 4 + 2) * 32;    // + 4 epilogue warps + TMA warp + MMA warp
 constexpr int TF_A_BYTES = TC_M * 128;                      // one [128 pixels x 32 channels] fp32 tile: 16 KB
 constexpr int TF_B_BYTES = 256 * 128;                       // one [256 co x 32 channels] fp32 tile: 32 KB
-constexpr int TF_STAGE_BYTES = 2 * TF_A_BYTES + 2 * TF_B_BYTES;     // hi + lo of both operands: 96 KB
-constexpr size_t TF_SMEM = 1024 + 2 * TF_STAGE_BYTES + 16 * 8 + 16;
+// Stages: one A stage (hi + lo, 32 KB) PER PRODUCER GROUP -- k-block n is always produced by group n % 3 into A stage
+// n % 3 (9 * C/32 is a multiple of 3), so a group only ever waits on the next phase of its own barrier (with two shared
+// stages a group could run two phases ahead of the barrier it polls, which a parity wait cannot tell apart) -- and two B
+// stages (hi + lo, 64 KB) filled in order by the TMA warp.
+constexpr int TF_A_STAGE = 2 * TF_A_BYTES, TF_B_STAGE = 2 * TF_B_BYTES;
+constexpr int TF_A_STAGES = TF_PROD_GROUPS, TF_B_STAGES = 2;
+constexpr int TF_B_OFF = TF_A_STAGES * TF_A_STAGE;
+constexpr size_t TF_SMEM = 1024 + TF_A_STAGES * TF_A_STAGE + TF_B_STAGES * TF_B_STAGE + 16 * 8 + 16;
 enum { TF_ANCHORS = 0, TF_OFFSETS = 1, TF_GRID = 2 };
 
 struct TfParams {
@@ -1843,9 +1849,10 @@ __global__ void __launch_bounds__(TF_THREADS, 1)
 conv_tf32x3_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo, const TfParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + 2 * TF_STAGE_BYTES);
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + TF_B_OFF + TF_B_STAGES * TF_B_STAGE);
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 16);
-  const uint32_t bar_full = smem_u32(s_bar), bar_empty = bar_full + 16, bar_acc_full = bar_full + 32, bar_acc_empty = bar_full + 48;
+  const uint32_t bar_a_full = smem_u32(s_bar), bar_a_empty = bar_a_full + 24, bar_b_full = bar_a_full + 48,
+                 bar_b_empty = bar_a_full + 64, bar_acc_full = bar_a_full + 80, bar_acc_empty = bar_a_full + 96;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   constexpr int kEpi0 = TF_PROD_WARPS, kTma = TF_PROD_WARPS + 4, kMma = TF_PROD_WARPS + 5;
   const int ncb = p.C / TF_KB, nkb = 9 * ncb;
@@ -1853,9 +1860,13 @@ conv_tf32x3_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
   const uint32_t b_bytes = (uint32_t)p.Co * 128u;
 
   if (tid == 0) {
+    for (int s = 0; s < TF_A_STAGES; ++s) {
+      mbar_init(bar_a_full + 8 * s, 4);                 // the four producer warps of the owning group
+      mbar_init(bar_a_empty + 8 * s, 1);                // tcgen05.commit
+    }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(bar_full + 8 * s, 4 + 1);               // four producer warps of the owning group + the TMA thread's expect_tx
-      mbar_init(bar_empty + 8 * s, 1);                  // tcgen05.commit
+      mbar_init(bar_b_full + 8 * s, 1);                 // the TMA thread's expect_tx
+      mbar_init(bar_b_empty + 8 * s, 1);                // tcgen05.commit
       mbar_init(bar_acc_full + 8 * s, 1);               // tcgen05.commit after the last k-block of a tile
       mbar_init(bar_acc_empty + 8 * s, 4);              // one elected arrive per epilogue warp
     }
@@ -1897,7 +1908,7 @@ conv_tf32x3_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
       float w1 = 0.f, w2 = 0.f, w3 = 0.f, w4 = 0.f;
       size_t a_tl = 0, a_tr = 0, a_bl = 0, a_br = 0;
       for (int kb = group; kb < nkb; kb += TF_PROD_GROUPS) {
-        const int n = it * nkb + kb, s = n & 1;
+        const int use = it * (nkb / TF_PROD_GROUPS) + kb / TF_PROD_GROUPS;     // how often this group's stage was filled
         const int tap = kb / ncb, cb = kb - tap * ncb;
         if (tap != last_tap) {
           // sampling position of (pixel, tap) and its bilinear corners / weights (deform_conv_cuda_kernel.cu:83-114, :228)
@@ -1937,8 +1948,8 @@ conv_tf32x3_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
             }
           }
         }
-        mbar_wait(bar_empty + 8 * s, ((uint32_t)(n >> 1) & 1u) ^ 1u);
-        uint8_t* row_hi = smem + s * TF_STAGE_BYTES + r * 128;
+        mbar_wait(bar_a_empty + 8 * group, ((uint32_t)use & 1u) ^ 1u);
+        uint8_t* row_hi = smem + group * TF_A_STAGE + r * 128;
         uint8_t* row_lo = row_hi + TF_A_BYTES;
         const float* xp = p.x + cb * TF_KB;
         const bool any = (w1 != 0.f) | (w2 != 0.f) | (w3 != 0.f) | (w4 != 0.f);
@@ -1964,7 +1975,7 @@ conv_tf32x3_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
         }
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar_full + 8 * s);
+        if (lane == 0) mbar_arrive(bar_a_full + 8 * group);
       }
     }
   } else if (warp == kTma) {
@@ -1972,12 +1983,12 @@ conv_tf32x3_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
     for (int it = 0; it < my_tiles; ++it) {
       for (int kb = 0; kb < nkb; ++kb) {
         const int n = it * nkb + kb, s = n & 1;
-        mbar_wait(bar_empty + 8 * s, ((uint32_t)(n >> 1) & 1u) ^ 1u);
+        mbar_wait(bar_b_empty + 8 * s, ((uint32_t)(n >> 1) & 1u) ^ 1u);
         if (elect_one()) {
-          uint8_t* sb = smem + s * TF_STAGE_BYTES + 2 * TF_A_BYTES;
-          mbar_arrive_expect_tx(bar_full + 8 * s, 2u * b_bytes);
-          tma_load_2d<1>(smem_u32(sb), &map_hi, kb * TF_KB, 0, bar_full + 8 * s);
-          tma_load_2d<1>(smem_u32(sb + TF_B_BYTES), &map_lo, kb * TF_KB, 0, bar_full + 8 * s);
+          uint8_t* sb = smem + TF_B_OFF + s * TF_B_STAGE;
+          mbar_arrive_expect_tx(bar_b_full + 8 * s, 2u * b_bytes);
+          tma_load_2d<1>(smem_u32(sb), &map_hi, kb * TF_KB, 0, bar_b_full + 8 * s);
+          tma_load_2d<1>(smem_u32(sb + TF_B_BYTES), &map_lo, kb * TF_KB, 0, bar_b_full + 8 * s);
         }
         __syncwarp();
       }
@@ -1992,20 +2003,23 @@ conv_tf32x3_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(as * 256);
       for (int kb = 0; kb < nkb; ++kb) {
-        const int n = it * nkb + kb, s = n & 1;
-        mbar_wait(bar_full + 8 * s, (uint32_t)(n >> 1) & 1u);
+        const int n = it * nkb + kb, s = n & 1, g = kb % TF_PROD_GROUPS;
+        const int use = it * (nkb / TF_PROD_GROUPS) + kb / TF_PROD_GROUPS;
+        mbar_wait(bar_a_full + 8 * g, (uint32_t)use & 1u);
+        mbar_wait(bar_b_full + 8 * s, (uint32_t)(n >> 1) & 1u);
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t sa = smem_u32(smem + s * TF_STAGE_BYTES);
+          const uint32_t sa = smem_u32(smem + g * TF_A_STAGE), sb = smem_u32(smem + TF_B_OFF + s * TF_B_STAGE);
           const uint64_t a_hi = umma_desc_sw128(sa), a_lo = umma_desc_sw128(sa + TF_A_BYTES);
-          const uint64_t b_hi = umma_desc_sw128(sa + 2 * TF_A_BYTES), b_lo = umma_desc_sw128(sa + 2 * TF_A_BYTES + TF_B_BYTES);
+          const uint64_t b_hi = umma_desc_sw128(sb), b_lo = umma_desc_sw128(sb + TF_B_BYTES);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {                 // K = 8 fp32 = 32 bytes per step inside the 128-byte swizzle atom
             umma_tf32(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
             umma_tf32(d_tmem, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);
             umma_tf32(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
           }
-          umma_commit<1>(bar_empty + 8 * s);
+          umma_commit<1>(bar_a_empty + 8 * g);
+          umma_commit<1>(bar_b_empty + 8 * s);
           if (kb == nkb - 1) umma_commit<1>(bar_acc_full + 8 * as);
         }
         __syncwarp();
