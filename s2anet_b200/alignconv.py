@@ -13,7 +13,19 @@ from . import _lib
 from .dcn import DeformConv
 
 
-_FORCE_SIMT_F32 = False      # tests / probes: keep fp32 tensors on the SIMT kernel (conv_f32.cu) whatever the shape
+_FORCE_SIMT_F32 = False      # set through set_fp32_path(); read by alignconv / orn / dcn when they route fp32 tensors
+
+
+def set_fp32_path(path):
+    """Which kernel fp32 tensors take in AlignConv / DeformConv / ORConv2d forward (C % 32 == 0, C_out % 16 == 0, <= 256):
+    "tf32x3" (default) -- conv_tf32x3_kernel on tcgen05, three TF32 MMAs per K step on hi / lo splits: rel-L2 ~5e-6 of an
+    fp64 evaluation (profiles/r2_parity_errors.json), 0.25 ms at P3 batch 1 where the reference takes 0.59 ms;
+    "simt" -- the FMA kernel of conv_f32.cu: individually rounded fp32 operations in the reference's order, rel-L2 ~1e-6
+    like the reference's own SGEMM path, 0.98 ms.  Other shapes always take the SIMT kernel."""
+    global _FORCE_SIMT_F32
+    if path not in ("tf32x3", "simt"):
+        raise ValueError("set_fp32_path: expected 'tf32x3' or 'simt', got %r" % (path,))
+    _FORCE_SIMT_F32 = path == "simt"
 
 
 def alignconv_forward(x, anchors, weight, stride):
@@ -30,7 +42,7 @@ def alignconv_forward(x, anchors, weight, stride):
         return conv_tc.alignconv_forward_tc(x, anchors, weight, stride)
     from . import conv_tc
     if conv_tc.tf32x3_supported(C, Co) and not _FORCE_SIMT_F32:
-        # fp32 on the tensor cores (3 x TF32 split, ~21 mantissa bits per product): conv_tf32x3_kernel
+        # fp32 on the tensor cores (3 x TF32 split): conv_tf32x3_kernel
         return conv_tc.conv_forward_tf32x3(x, anchors.reshape(B, H, W, 5), 0, conv_tc.pack_weight_tf32(weight), relu=True,
                                            stride=stride)
     xc = x.contiguous()

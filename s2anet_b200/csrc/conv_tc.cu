@@ -1795,8 +1795,8 @@ static int launch_wgrad(const void* x, const void* off, int off_f32, const void*
 //
 // The exact-arithmetic fp32 path of round 1 (conv_f32.cu, SIMT FMAs fed by a scalar NCHW gather) ran AlignConv at P3
 // in 0.98 ms where the reference's im2col + cuBLAS SGEMM takes 0.59 ms.  Here the same contraction runs on
-// tcgen05.mma.kind::tf32 with both operands split into two TF32 terms, a = a_hi + a_lo (a_hi = a with the low 13
-// mantissa bits cleared, a_lo = a - a_hi, exact in fp32), and three MMAs per K step: a_hi*w_hi + a_lo*w_hi + a_hi*w_lo
+// tcgen05.mma.kind::tf32 with both operands split into two TF32 terms, a = a_hi + a_lo (a_hi = a rounded to the
+// nearest TF32 value, a_lo = a - a_hi, exact in fp32, rounded likewise), and three MMAs per K step: a_hi*w_hi + a_lo*w_hi + a_hi*w_lo
 // (the dropped a_lo*w_lo term is 2^-20 relative).  Products of TF32 values are exact in the fp32 accumulator, so the
 // result carries ~21 mantissa bits per product: inside the fp32 bar of the parity tests (1e-4 + 1e-4 |ref|) by two
 // orders of magnitude.
@@ -1806,7 +1806,7 @@ static int launch_wgrad(const void* x, const void* off, int off_f32, const void*
 // tensor (deform_conv_cuda_kernel.cu:218-227) or the regular grid (ORConv2d) --, gather the four corners from the NHWC
 // fp32 map with 16-byte loads, blend in fp32, split and store 128-byte rows (32 channels) of the hi and lo tiles; a TMA
 // warp streams the hi / lo halves of the packed weights (32 KB each per 32-channel k-block); the MMA warp issues 12
-// tcgen05.mma (M = 128, N = C_out, K = 8) per k-block into one of two tensor-memory accumulators; 4 epilogue warps add
+// tcgen05.mma (M = 128, N = C_out, K = 8) per k-block into two tensor-memory accumulators (main / correction terms); 4 epilogue warps add
 // the bias, apply ReLU / the 8-way orientation max and store NCHW fp32 (a warp writes 2 x 64 contiguous bytes per channel).
 // =================================================================================================
 constexpr int TF_KB = 32;                                   // channels per k-block: 128 bytes of fp32
@@ -1842,7 +1842,13 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
       : "memory");
 }
-__device__ __forceinline__ float tf32_hi(float v) { return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
+// nearest TF32 value (ties away from zero), low 13 mantissa bits zero: with hi = rna(v), lo = rna(v - hi) the residual
+// v - hi - lo is below 2^-24 |v| and unbiased (a mask would truncate: twice the residual, and always towards zero)
+__device__ __forceinline__ float tf32_hi(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
+}
 __device__ __forceinline__ uint4 ldg_nc_f4(const float* p) { return ldg_nc_v4(p); }
 
 __global__ void __launch_bounds__(TF_THREADS, 1)
@@ -1867,9 +1873,9 @@ conv_tf32x3_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar_b_full + 8 * s, 1);                 // the TMA thread's expect_tx
       mbar_init(bar_b_empty + 8 * s, 1);                // tcgen05.commit
-      mbar_init(bar_acc_full + 8 * s, 1);               // tcgen05.commit after the last k-block of a tile
-      mbar_init(bar_acc_empty + 8 * s, 4);              // one elected arrive per epilogue warp
     }
+    mbar_init(bar_acc_full, 1);                         // tcgen05.commit after the last k-block of a tile
+    mbar_init(bar_acc_empty, 4);                        // one elected arrive per epilogue warp
     fence_barrier_init();
   }
   if (warp == kMma) tmem_alloc<1>(smem_u32(s_tmem), 512);
@@ -1997,11 +2003,14 @@ conv_tf32x3_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
     // ===================== MMA issuer =====================
     // D = f32, A / B = TF32 (format 2), K-major, N = C_out, M = 128
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.Co >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+    // Two accumulators per tile: the hi*hi products in columns [0, 256), the two correction products (2^-11 of the
+    // former) in [256, 512).  The tensor core TRUNCATES when it adds into the fp32 accumulator (measured: all 864 MMAs of
+    // an output into one accumulator leave rel-L2 1.6e-5 against fp64, the SIMT kernel 1.4e-6); keeping the small terms
+    // apart takes two thirds of the additions out of the large sum, and the epilogue adds the two in round-to-nearest.
     for (int it = 0; it < my_tiles; ++it) {
-      const int as = it & 1;
-      mbar_wait(bar_acc_empty + 8 * as, ((uint32_t)(it >> 1) & 1u) ^ 1u);
+      mbar_wait(bar_acc_empty, ((uint32_t)it & 1u) ^ 1u);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + (uint32_t)(as * 256);
+      const uint32_t d_main = tmem_base, d_corr = tmem_base + 256u;
       for (int kb = 0; kb < nkb; ++kb) {
         const int n = it * nkb + kb, s = n & 1, g = kb % TF_PROD_GROUPS;
         const int use = it * (nkb / TF_PROD_GROUPS) + kb / TF_PROD_GROUPS;
@@ -2014,13 +2023,13 @@ conv_tf32x3_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
           const uint64_t b_hi = umma_desc_sw128(sb), b_lo = umma_desc_sw128(sb + TF_B_BYTES);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {                 // K = 8 fp32 = 32 bytes per step inside the 128-byte swizzle atom
-            umma_tf32(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-            umma_tf32(d_tmem, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);
-            umma_tf32(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
+            umma_tf32(d_main, a_hi + 2 * k, b_hi + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_tf32(d_corr, a_lo + 2 * k, b_hi + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_tf32(d_corr, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
           }
           umma_commit<1>(bar_a_empty + 8 * g);
           umma_commit<1>(bar_b_empty + 8 * s);
-          if (kb == nkb - 1) umma_commit<1>(bar_acc_full + 8 * as);
+          if (kb == nkb - 1) umma_commit<1>(bar_acc_full);
         }
         __syncwarp();
       }
@@ -2032,26 +2041,27 @@ conv_tf32x3_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
     for (int it = 0; it < my_tiles; ++it) {
       int b, ty0, tx0;
       tile_coords(it, b, ty0, tx0);
-      const int as = it & 1;
       const int y = ty0 + r / TC_PW, x = tx0 + r % TC_PW;
       const bool valid = y < p.H && x < p.W;
-      mbar_wait(bar_acc_full + 8 * as, (uint32_t)(it >> 1) & 1u);
+      mbar_wait(bar_acc_full, (uint32_t)it & 1u);
       tc_fence_after();
       const size_t plane = (size_t)p.H * p.W, pix = (size_t)y * p.W + x;
       for (int c0 = 0; c0 < p.Co; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * 256 + c0), v);
+        uint32_t v[32], vc[32];
+        tmem_ld32_nowait(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, v);
+        tmem_ld32_nowait(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(256 + c0), vc);
+        tmem_ld_wait();
         if (c0 + 32 >= p.Co) {
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(bar_acc_empty + 8 * as);
+          if (lane == 0) mbar_arrive(bar_acc_empty);
         }
         if (valid) {
           float* o = p.out + ((size_t)b * p.Co + c0) * plane + pix;
           float m[4];
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            float t = __uint_as_float(v[j]);
+            float t = __uint_as_float(v[j]) + __uint_as_float(vc[j]);
             if (p.bias) t += __ldg(p.bias + c0 + j);
             if (p.relu) t = fmaxf(t, 0.0f);
             o[(size_t)j * plane] = t;

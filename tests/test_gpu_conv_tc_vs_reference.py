@@ -210,3 +210,36 @@ def test_generic_entry_3d_input_and_weight_cache_after_half(ref_dc):
         m.deform_conv.weight.data = (m.deform_conv.weight.data.float() * 2.0).to(torch.bfloat16)   # new storage, same Parameter
         y2 = m(xb.bfloat16(), anc, 8)
     assert float((y2.float() - 2.0 * y_bf.float()).abs().max()) <= 2e-2 * float(y2.float().abs().max()) + 1e-3
+
+
+def test_fp32_tf32x3_alignconv_vs_reference_binary_and_fp64(ref_dc):
+    """fp32 tensors: conv_tf32x3_kernel (tcgen05 kind::tf32, hi / lo split, three MMAs per K step) against the
+    reference binary in fp32 and against an fp64 evaluation of the same op (torchvision on doubles), next to how far the
+    reference binary itself and this repo's SIMT fp32 kernel are from fp64.  Stated tolerance of the fp32 path:
+    max-abs <= 2e-5 * max|ref| and rel-L2 <= 1e-5 against fp64 (the tensor core adds into its fp32 accumulator with
+    truncation, which leaves a few 1e-6; plain TF32 would be ~5e-4)."""
+    import torchvision
+    from s2anet_b200 import alignconv
+    torch.backends.cuda.matmul.allow_tf32 = False
+    xs, ancs, offs, w = level_inputs(1, torch.float32, seed=33)
+    for l, s in enumerate(STRIDES):
+        y = alignconv.alignconv_forward(xs[l], ancs[l], w, s)
+        alignconv._FORCE_SIMT_F32 = True
+        try:
+            y_simt = alignconv.alignconv_forward(xs[l], ancs[l], w, s)
+        finally:
+            alignconv._FORCE_SIMT_F32 = False
+        ref32 = torch.relu(ref_deform(ref_dc, xs[l], w, offs[l]))
+        ref64 = torch.relu(torchvision.ops.deform_conv2d(xs[l].double(), offs[l].double(), w.double(), padding=1))
+
+        def e64(t):
+            d = (t.double() - ref64)
+            return {"max_abs": float(d.abs().max()), "ref_max": float(ref64.abs().max()),
+                    "max_abs_rel": float(d.abs().max() / ref64.abs().max()), "rel_l2": float(d.norm() / ref64.norm())}
+        e = e64(y)
+        record("alignconv_fp32_tf32x3_P%d_vs_fp64" % (l + 3), e)
+        record("alignconv_fp32_simt_P%d_vs_fp64" % (l + 3), e64(y_simt))
+        record("reference_cuda_fp32_P%d_vs_fp64" % (l + 3), e64(ref32))
+        record("alignconv_fp32_tf32x3_P%d_vs_reference_cuda_fp32" % (l + 3), errs(y, ref32))
+        assert e["max_abs_rel"] <= 2e-5 and e["rel_l2"] <= 1e-5, (l, e)
+        assert errs(y, ref32)["max_abs_rel"] <= 2e-5

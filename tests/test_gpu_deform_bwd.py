@@ -73,7 +73,14 @@ def test_alignconv_training_step_p4_vs_torchvision_and_reference_cuda():
     off = torch.stack([ac.get_offset(anc[i].reshape(-1, 5), (H, H), 16) for i in range(B)])
     x2 = x.detach().clone().requires_grad_()
     w2 = ac.deform_conv.weight.detach().clone().requires_grad_()
-    y2 = torch.relu(torchvision.ops.deform_conv2d(x2, off, w2, padding=1))
+    pre2 = torchvision.ops.deform_conv2d(x2, off, w2, padding=1)
+    # the ReLU mask is taken from OUR forward: an output within rounding of zero (the two forwards differ by ~1e-6
+    # relative -- summation order, 3 x TF32 split) may land on either side of it, and one flipped element moves
+    # grad_input by a whole |gy * w| term.  Flips are allowed only where the pre-activation is that small.
+    mask = y.detach() > 0
+    flips = mask != (pre2.detach() > 0)
+    assert int(flips.sum()) <= 8 and float(pre2.detach()[flips].abs().max() if flips.any() else 0.0) <= 1e-5
+    y2 = pre2 * mask
     y2.backward(gy)
     close(y.detach(), y2.detach(), "forward")
     close(x.grad, x2.grad, "grad_input")

@@ -1,4 +1,5 @@
-"""Time the fp32 exact-arithmetic conv path (AlignConv / ORConv2d at P3) -- csrc/conv_f32.cu."""
+"""Time the fp32 conv paths (AlignConv / ORConv2d at P3): conv_tf32x3_kernel (tcgen05, 3 x TF32) against the SIMT kernel
+of csrc/conv_f32.cu (alignconv._FORCE_SIMT_F32)."""
 import os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -23,6 +24,13 @@ for B in (1, 8):
     w = torch.randn(256, 256, 3, 3, device=dev) * 0.01
     wo = torch.randn(32, 256, 1, 3, 3, device=dev) * 0.01
     fl = 2.0 * B * H * H * 256 * 2304
-    ms = t(lambda: alignconv_forward(x, anc, w, 8))
-    ms2 = t(lambda: orconv_forward(x, wo, idx, None, with_pool=True))
-    print("fp32 P3 B=%d: alignconv %.3f ms %.1f TF/s | orconv %.3f ms %.1f TF/s" % (B, ms, fl / ms / 1e9, ms2, fl / ms2 / 1e9))
+    from s2anet_b200 import alignconv
+    xcl = x.contiguous(memory_format=torch.channels_last)
+    for simt in (False, True):
+        alignconv._FORCE_SIMT_F32 = simt
+        ms = t(lambda: alignconv_forward(x, anc, w, 8))
+        ms1 = t(lambda: alignconv_forward(xcl, anc, w, 8))
+        ms2 = t(lambda: orconv_forward(x, wo, idx, None, with_pool=True))
+        print("fp32 P3 B=%d %s: alignconv %.3f ms %.1f TF/s (channels_last input %.3f ms) | orconv %.3f ms %.1f TF/s" % (
+            B, "simt  " if simt else "tf32x3", ms, fl / ms / 1e9, ms1, ms2, fl / ms2 / 1e9))
+    alignconv._FORCE_SIMT_F32 = False
