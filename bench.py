@@ -729,6 +729,21 @@ def extra_legs(torch, np, dev, dtype, head, feat_sets, refines, peaks, args):
             "alignconv_us": t_al * 1e6, "alignconv_tflops": fl / t_al / 1e12, "alignconv_frac_of_peak": fl / t_al / 1e12 / peaks["bf16_burst"],
             "orconv_pool_us": t_or * 1e6, "orconv_tflops": fl / t_or / 1e12, "orconv_frac_of_peak": fl / t_or / 1e12 / peaks["bf16_burst"],
             "note": "128 tiles on 148 SMs: a batch-1 P3 launch cannot fill the GPU (86 % at best); eager calls incl. launch overhead"}
+        # config 2 with fp32 tensors (the dtype the reference's training runs the op in): 3 x TF32 on tcgen05, the SIMT
+        # kernel beside it; BASELINE.md quotes the reference binary at 0.59 ms for this layer on this GPU
+        from s2anet_b200 import alignconv as _ac
+        x32, w32 = x1.float(), w.float()
+        t_tf = cuda_time(torch, lambda: alignconv_forward(x32, a1, w32, 8), 20) / 1e3
+        _ac.set_fp32_path("simt")
+        try:
+            t_simt = cuda_time(torch, lambda: alignconv_forward(x32, a1, w32, 8), 5) / 1e3
+        finally:
+            _ac.set_fp32_path("tf32x3")
+        out["config2_p3_batch1_fp32"] = {
+            "alignconv_tf32x3_us": t_tf * 1e6, "alignconv_tf32x3_tflops": fl / t_tf / 1e12, "alignconv_simt_us": t_simt * 1e6,
+            "note": "fp32 in / fp32 NCHW out; tf32x3 = three tcgen05.mma.kind::tf32 per K step on hi / lo splits (rel-L2 5.5e-6 "
+                    "of fp64, profiles/r2_parity_errors.json); simt = individually rounded FMAs (set_fp32_path('simt'))"}
+        del x32, w32
         # config 3: head + NMS at batch 1 (CUDA graph replay latency)
         f1 = [f[:1].contiguous(memory_format=torch.channels_last) for f in feat_sets[0]]
         for _ in range(2):
