@@ -765,7 +765,7 @@ def extra_legs(torch, np, dev, dtype, head, feat_sets, refines, peaks, args):
         flb = 2.0 * xb.size(0) * 128 * 128 * 256 * 2304
         out["backward_p3_batch%d" % xb.size(0)] = {
             "dgrad_ms": t_dg, "dgrad_tflops": flb / t_dg / 1e9, "wgrad_ms": t_wg, "wgrad_tflops": flb / t_wg / 1e9,
-            "note": "dgrad = nine 1x1 implicit GEMMs with a bilinear scatter epilogue (bound by 302 M 16-byte L2 atomics); wgrad = "
+            "note": "dgrad = nine 1x1 implicit GEMMs with a bilinear scatter epilogue (bound by 4.8 GB of L2 reductions, issued as full 128-byte segments); wgrad = "
                     "MN-major operands, accumulator in tensor memory (bound by the nine-fold re-gather from L2); no column buffer"}
         del gyb, offb
         # the step at ~10 k candidates per image (2-10 k)

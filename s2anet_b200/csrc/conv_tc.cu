@@ -1208,21 +1208,41 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         const size_t a_bl = ((size_t)tc.b * H + min(yt + 1, H - 1)) * rowp + (size_t)max(xl, 0) * Cg;
         const size_t a_br = ((size_t)tc.b * H + min(yt + 1, H - 1)) * rowp + (size_t)min(xl + 1, W - 1) * Cg;
         float gy = 0.f, gx = 0.f;
+        // The reductions are issued COALESCED: a warp's 32 x 32-channel chunk goes through a 4 KB shared-memory
+        // transpose (16-byte chunks XOR-swizzled by the pixel), then for every pixel of the warp lanes 8c .. 8c+7 add
+        // the 128 contiguous bytes of corner c -- one instruction = four full 128-byte segments of grad_input.  (Round-2
+        // first version: every lane reduced into its own pixel's row, 32 half-used sectors per instruction; the L2
+        // reduction rate, not the tensor core, is what bounds this kernel.)
+        float* s_tile = reinterpret_cast<float*>(s_out) + quad * 1024;                  // [32 px][32 ch] fp32
+        uint32_t* s_corner = reinterpret_cast<uint32_t*>(s_out + 16384) + quad * 256;   // [32 px][4 weights | 4 offsets / 4]
+        __syncwarp();
+        s_corner[lane * 8 + 0] = __float_as_uint(w1); s_corner[lane * 8 + 1] = __float_as_uint(w2);
+        s_corner[lane * 8 + 2] = __float_as_uint(w3); s_corner[lane * 8 + 3] = __float_as_uint(w4);
+        s_corner[lane * 8 + 4] = (uint32_t)(a_tl >> 2); s_corner[lane * 8 + 5] = (uint32_t)(a_tr >> 2);
+        s_corner[lane * 8 + 6] = (uint32_t)(a_bl >> 2); s_corner[lane * 8 + 7] = (uint32_t)(a_br >> 2);
+        const int cn = lane >> 3, sub = lane & 7;
         for (int c0 = 0; c0 < p.Co; c0 += TC_OUT_CH) {
           uint32_t v[32];
           tmem_ld32(acc_addr + (uint32_t)c0, v);
           if (c0 + TC_OUT_CH >= p.Co) release_acc();
-          if (inb) {
-            float* gi = p.sc_gi + c0;
+          __syncwarp();                                   // the previous chunk has been read by every lane
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float v0 = __uint_as_float(v[j]), v1 = __uint_as_float(v[j + 1]), v2 = __uint_as_float(v[j + 2]),
-                          v3 = __uint_as_float(v[j + 3]);
-              if (w1 != 0.f) red_add_v4(gi + a_tl + j, w1 * v0, w1 * v1, w1 * v2, w1 * v3);
-              if (w2 != 0.f) red_add_v4(gi + a_tr + j, w2 * v0, w2 * v1, w2 * v2, w2 * v3);
-              if (w3 != 0.f) red_add_v4(gi + a_bl + j, w3 * v0, w3 * v1, w3 * v2, w3 * v3);
-              if (w4 != 0.f) red_add_v4(gi + a_br + j, w4 * v0, w4 * v1, w4 * v2, w4 * v3);
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<uint4*>(s_tile + lane * 32 + ((j ^ (lane & 7)) << 2)) =
+                make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          __syncwarp();
+          {
+            float* gi = p.sc_gi + c0 + 4 * sub;
+#pragma unroll 4
+            for (int r = 0; r < 32; ++r) {
+              const float wq = __uint_as_float(s_corner[r * 8 + cn]);
+              if (wq != 0.f) {
+                const float4 q = *reinterpret_cast<const float4*>(s_tile + r * 32 + ((sub ^ (r & 7)) << 2));
+                red_add_v4(gi + ((size_t)s_corner[r * 8 + 4 + cn] << 2), wq * q.x, wq * q.y, wq * q.z, wq * q.w);
+              }
             }
+          }
+          if (inb) {
             if (p.sc_goff) {
               // get_coordinate_weight (:147-187): d(sample)/d(offset_h), d(sample)/d(offset_w), corners outside the
               // map count as zeros
