@@ -1649,8 +1649,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap gmap, const WgParams p) {
     const int group = warp >> 2, f = group >> 1, sub = group & 1;
     const int r = (warp & 3) * 32 + lane;               // tile row = pixel (y = r / 16, x = r % 16)
     const int ti = tap / 3, tj = tap - 3 * ti;
-    uint8_t* dst_row = sS + f * WG_STAGE_BYTES + sub * WG_BLOCK_BYTES + r * 128;
+    uint8_t* dst_tile = sS + f * WG_STAGE_BYTES + sub * WG_BLOCK_BYTES + (warp & 3) * (32 * 128);    // this warp's 32 rows
     const int cb = 2 * f + sub;                         // 64-channel block of x this thread samples
+    // lane = the pixel whose parameters it computes; the loads are issued with eight lanes per pixel (four full 128-byte
+    // lines per warp instruction, parameters by shuffle) -- see conv_tf32x3_kernel
+    const int src0 = lane >> 3, jch = lane & 7;
     for (int it = 0; it < my_tiles && f < nf; ++it) {
       int tile = grp + it * ngrp;
       const int tpi = p.tiles_x * p.tiles_y;
@@ -1660,7 +1663,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap gmap, const WgParams p) {
       const int y = ty0 + r / TC_PW, x = tx0 + r % TC_PW;
       // this pixel's sampling position for the CTA's tap (deform_conv_cuda_kernel.cu:218-227) -> corners + weights
       uint32_t w01 = 0u, w23 = 0u;
-      size_t a_tl = 0, a_tr = 0, a_bl = 0, a_br = 0;    // element offsets of the (clamped) corners inside x
+      uint32_t base = 0;      // (element offset of the clamped top-left corner) / 8, bit 0: right neighbour, bit 1: lower one
+      const size_t rowp = (size_t)p.W * p.C;
       if (y < p.H && x < p.W) {
         const size_t oi = (((size_t)b * 18 + 2 * tap) * p.H + y) * p.W + x, plane = (size_t)p.H * p.W;
         float offy, offx;
@@ -1682,23 +1686,29 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap gmap, const WgParams p) {
           const H2 p23 = from_f2<T>((b_ok && l_ok) ? ly * hx : 0.0f, (b_ok && r_ok) ? ly * lx : 0.0f);
           w01 = *reinterpret_cast<const uint32_t*>(&p01);
           w23 = *reinterpret_cast<const uint32_t*>(&p23);
-          const size_t rowp = (size_t)p.W * p.C, img = (size_t)b * p.H * rowp;
-          const int yt = max(y0, 0), yb = min(y0 + 1, p.H - 1), xl = max(x0, 0), xr = min(x0 + 1, p.W - 1);
-          a_tl = img + yt * rowp + (size_t)xl * p.C; a_tr = img + yt * rowp + (size_t)xr * p.C;
-          a_bl = img + yb * rowp + (size_t)xl * p.C; a_br = img + yb * rowp + (size_t)xr * p.C;
+          const size_t img = (size_t)b * p.H * rowp;
+          const int yt = max(y0, 0), xl = max(x0, 0);
+          const bool has_r = min(x0 + 1, p.W - 1) > xl, has_b = min(y0 + 1, p.H - 1) > yt;
+          // (C is a multiple of 64: the offset / 8 has its low three bits free)
+          base = (uint32_t)((img + yt * rowp + (size_t)xl * p.C) >> 3) | (has_r ? 1u : 0u) | (has_b ? 2u : 0u);
         }
       }
       mbar_wait(bar_s_empty + 8 * f, (uint32_t)(it & 1) ^ 1u);
-      const T* xp = reinterpret_cast<const T*>(p.x) + cb * 64;
+      const T* xp = reinterpret_cast<const T*>(p.x) + cb * 64 + 8 * jch;
 #pragma unroll 2
-      for (int j = 0; j < 8; ++j) {                     // the eight 16-byte chunks (8 channels) of this pixel's row
+      for (int i = 0; i < 8; ++i) {                     // four pixels x eight 16-byte chunks (8 channels) per instruction
+        const int src = 4 * i + src0;
+        const uint32_t s01 = __shfl_sync(0xffffffffu, w01, src), s23 = __shfl_sync(0xffffffffu, w23, src);
+        const uint32_t sb = __shfl_sync(0xffffffffu, base, src);
         uint4 o = make_uint4(0u, 0u, 0u, 0u);
-        if ((w01 | w23) != 0u) {
-          const uint4 v0 = ldg_nc_v4(xp + a_tl + 8 * j), v1 = ldg_nc_v4(xp + a_tr + 8 * j);
-          const uint4 v2 = ldg_nc_v4(xp + a_bl + 8 * j), v3 = ldg_nc_v4(xp + a_br + 8 * j);
-          o = blend4<T>(v0, v1, v2, v3, w01, w23);
+        if ((s01 | s23) != 0u) {
+          const T* q0 = xp + ((size_t)(sb & ~7u) << 3);
+          const size_t dx = (sb & 1u) ? (size_t)p.C : 0, dy = (sb & 2u) ? rowp : 0;
+          const uint4 v0 = ldg_nc_v4(q0), v1 = ldg_nc_v4(q0 + dx);
+          const uint4 v2 = ldg_nc_v4(q0 + dy), v3 = ldg_nc_v4(q0 + dy + dx);
+          o = blend4<T>(v0, v1, v2, v3, s01, s23);
         }
-        *reinterpret_cast<uint4*>(dst_row + ((j ^ (r & 7)) << 4)) = o;          // SWIZZLE_128B
+        *reinterpret_cast<uint4*>(dst_tile + src * 128 + ((jch ^ (src & 7)) << 4)) = o;          // SWIZZLE_128B
       }
       fence_proxy_async_smem();                          // generic-proxy stores -> visible to the tensor core
       __syncwarp();
@@ -1916,7 +1926,13 @@ conv_tf32x3_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
   if (warp < TF_PROD_WARPS) {
     // ===================== producers: fp32 samples, split into TF32 hi / lo rows =====================
     const int group = warp >> 2;
-    const int r = (warp & 3) * 32 + lane;               // tile row = pixel
+    const int wq = warp & 3;
+    const int r = wq * 32 + lane;                       // the tile row (pixel) whose sampling parameters this lane computes
+    // The gather itself is issued with eight lanes per (pixel, corner): a warp instruction reads four full 128-byte lines
+    // (pixels 4 i .. 4 i + 3 of the warp's 32, i = 0..7) instead of 32 sectors in 32 lines -- ncu of the first version
+    // (a lane = a pixel, looping over the eight chunks): L1TEX at 83 %, everything else below 31 %.  The parameters of
+    // a pixel travel from the lane that computed them by shuffle.
+    const int src0 = lane >> 3, jch = lane & 7;
     for (int it = 0; it < my_tiles; ++it) {
       int b, ty0, tx0;
       tile_coords(it, b, ty0, tx0);
@@ -1932,7 +1948,7 @@ conv_tf32x3_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
       const size_t rowp = (size_t)p.W * p.C, img = (size_t)b * p.H * rowp;
       int last_tap = -1;
       float w1 = 0.f, w2 = 0.f, w3 = 0.f, w4 = 0.f;
-      size_t a_tl = 0, a_tr = 0, a_bl = 0, a_br = 0;
+      uint32_t base = 0;      // (element offset of the clamped top-left corner) / 4, bit 0: a right neighbour exists, bit 1: a lower one
       for (int kb = group; kb < nkb; kb += TF_PROD_GROUPS) {
         const int use = it * (nkb / TF_PROD_GROUPS) + kb / TF_PROD_GROUPS;     // how often this group's stage was filled
         const int tap = kb / ncb, cb = kb - tap * ncb;
@@ -1940,6 +1956,7 @@ conv_tf32x3_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
           // sampling position of (pixel, tap) and its bilinear corners / weights (deform_conv_cuda_kernel.cu:83-114, :228)
           last_tap = tap;
           w1 = w2 = w3 = w4 = 0.f;
+          base = 0;
           if (inside) {
             const int ti = tap / 3, tj = tap - 3 * ti;
             float h, w;
@@ -1968,36 +1985,41 @@ conv_tf32x3_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
               const bool t_ok = y0 >= 0, b_ok = y0 + 1 <= p.H - 1, l_ok = x0 >= 0, r_ok = x0 + 1 <= p.W - 1;
               w1 = (t_ok && l_ok) ? hy * hx : 0.f; w2 = (t_ok && r_ok) ? hy * lx : 0.f;
               w3 = (b_ok && l_ok) ? ly * hx : 0.f; w4 = (b_ok && r_ok) ? ly * lx : 0.f;
-              const int yt = max(y0, 0), yb = min(y0 + 1, p.H - 1), xl = max(x0, 0), xrr = min(x0 + 1, p.W - 1);
-              a_tl = img + yt * rowp + (size_t)xl * p.C; a_tr = img + yt * rowp + (size_t)xrr * p.C;
-              a_bl = img + yb * rowp + (size_t)xl * p.C; a_br = img + yb * rowp + (size_t)xrr * p.C;
+              // clamped corners (a corner outside the map has weight 0): top-left (yt, xl); the right / lower neighbours
+              // are one pixel / one row further unless the clamp folds them onto the same pixel
+              const int yt = max(y0, 0), xl = max(x0, 0);
+              const bool has_r = min(x0 + 1, p.W - 1) > xl, has_b = min(y0 + 1, p.H - 1) > yt;
+              base = (uint32_t)((img + yt * rowp + (size_t)xl * p.C) >> 2) | (has_r ? 1u : 0u) | (has_b ? 2u : 0u);
             }
           }
         }
         mbar_wait(bar_a_empty + 8 * group, ((uint32_t)use & 1u) ^ 1u);
-        uint8_t* row_hi = smem + group * TF_A_STAGE + r * 128;
-        uint8_t* row_lo = row_hi + TF_A_BYTES;
-        const float* xp = p.x + cb * TF_KB;
-        const bool any = (w1 != 0.f) | (w2 != 0.f) | (w3 != 0.f) | (w4 != 0.f);
+        uint8_t* tile_hi = smem + group * TF_A_STAGE + wq * (32 * 128);
+        const float* xp = p.x + cb * TF_KB + 4 * jch;
 #pragma unroll 2
-        for (int j = 0; j < 8; ++j) {                   // eight 16-byte chunks = 4 channels each
+        for (int i = 0; i < 8; ++i) {                   // four pixels x eight 16-byte chunks per warp instruction
+          const int src = 4 * i + src0;
+          const float s1 = __shfl_sync(0xffffffffu, w1, src), s2 = __shfl_sync(0xffffffffu, w2, src);
+          const float s3 = __shfl_sync(0xffffffffu, w3, src), s4 = __shfl_sync(0xffffffffu, w4, src);
+          const uint32_t sb = __shfl_sync(0xffffffffu, base, src);
           float v[4] = {0.f, 0.f, 0.f, 0.f};
-          if (any) {
-            const uint4 q1 = ldg_nc_f4(xp + a_tl + 4 * j), q2 = ldg_nc_f4(xp + a_tr + 4 * j);
-            const uint4 q3 = ldg_nc_f4(xp + a_bl + 4 * j), q4 = ldg_nc_f4(xp + a_br + 4 * j);
+          if ((s1 != 0.f) | (s2 != 0.f) | (s3 != 0.f) | (s4 != 0.f)) {
+            const float* q0 = xp + ((size_t)(sb & ~7u) << 2);
+            const size_t dx = (sb & 1u) ? (size_t)p.C : 0, dy = (sb & 2u) ? rowp : 0;
+            const uint4 q1 = ldg_nc_f4(q0), q2 = ldg_nc_f4(q0 + dx), q3 = ldg_nc_f4(q0 + dy), q4 = ldg_nc_f4(q0 + dy + dx);
             const uint32_t u1[4] = {q1.x, q1.y, q1.z, q1.w}, u2[4] = {q2.x, q2.y, q2.z, q2.w};
             const uint32_t u3[4] = {q3.x, q3.y, q3.z, q3.w}, u4[4] = {q4.x, q4.y, q4.z, q4.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e)
-              v[e] = w1 * __uint_as_float(u1[e]) + w2 * __uint_as_float(u2[e]) + w3 * __uint_as_float(u3[e]) +
-                     w4 * __uint_as_float(u4[e]);
+              v[e] = s1 * __uint_as_float(u1[e]) + s2 * __uint_as_float(u2[e]) + s3 * __uint_as_float(u3[e]) +
+                     s4 * __uint_as_float(u4[e]);
           }
           float hi[4], lo[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) { hi[e] = tf32_hi(v[e]); lo[e] = tf32_hi(v[e] - hi[e]); }
-          const int sw = (j ^ (r & 7)) << 4;            // SWIZZLE_128B
-          *reinterpret_cast<float4*>(row_hi + sw) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-          *reinterpret_cast<float4*>(row_lo + sw) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+          uint8_t* row_hi = tile_hi + src * 128 + ((jch ^ (src & 7)) << 4);           // SWIZZLE_128B
+          *reinterpret_cast<float4*>(row_hi) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<float4*>(row_hi + TF_A_BYTES) = make_float4(lo[0], lo[1], lo[2], lo[3]);
         }
         fence_proxy_async_smem();
         __syncwarp();
