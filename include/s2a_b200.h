@@ -48,6 +48,11 @@ S2A_EXPORT const char* s2a_last_error(void);
 /* Measurement utility (bench.py): achieved FP32 FMA throughput of this GPU in TFLOP/s, the denominator of the
  * "pairs/s / FP32-bound" figure SURVEY.md 8d asks for next to the rotated-IoU numbers.  Blocking. */
 S2A_EXPORT int s2a_measure_fp32_fma_tflops(double* tflops_out, int reps, void* stream);
+/* Layout conversion between the reference's NCHW tensors (models/dcn/src/deform_conv_cuda.cpp:168-170 makes them
+ * contiguous NCHW) and the NHWC operands of the tensor-core kernels: src [batch][rows][cols] -> dst [batch][cols][rows],
+ * elements of 2 or 4 bytes.  NCHW -> NHWC: rows = C, cols = H*W; NHWC -> NCHW: rows = H*W, cols = C. */
+S2A_EXPORT int s2a_transpose_planes(const void* src, void* dst, int64_t batch, int64_t rows, int64_t cols,
+                                    int elem_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * box_iou_rotated -- replaces box_iou_rotated_cuda()

@@ -22,6 +22,7 @@ PROTOTYPES = {
     "s2a_version": (_i32, []),
     "s2a_last_error": (C.c_char_p, []),
     "s2a_measure_fp32_fma_tflops": (_i32, [_vp, _i32, _vp]),
+    "s2a_transpose_planes": (_i32, [_vp, _vp, _i64, _i64, _i64, _i32, _vp]),
     "s2a_box_iou_rotated": (_i32, [_vp, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _i64, _i32, _vp]),
     "s2a_box_iou_rotated_tiles": (_i32, [_vp, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _i32, _i32, _i32, _i32, _i32, _vp]),
     "s2a_nms_rotated_workspace_bytes": (_sz, [_i64]),
@@ -84,7 +85,7 @@ def load():
 
 # kernels of THIS library launched by one successful C call (library sorts inside are not counted)
 KERNELS_PER_CALL = {
-    "box_iou_rotated": 1, "box_iou_rotated_batched": 1, "box_iou_rotated_tiles": 1, "nms_rotated": 4, "multiclass_nms_rotated": 6, "multiclass_nms_rotated_packed": 6,
+    "transpose_planes": 1, "box_iou_rotated": 1, "box_iou_rotated_batched": 1, "box_iou_rotated_tiles": 1, "nms_rotated": 4, "multiclass_nms_rotated": 6, "multiclass_nms_rotated_packed": 6,
     "arf_forward": 1, "arf_backward": 1, "ri_pool": 1, "deform_conv_forward_cuda": 1, "alignconv_forward": 1,
     "orconv_forward": 1, "conv_pack_weight": 1, "alignconv_forward_tc": 1, "orconv_forward_tc": 1, "deform_conv_forward_tc": 1, "deform_conv_dgrad_tc": 9, "deform_conv_wgrad_tc": 1, "conv_pack_weight_tf32": 1, "conv_forward_tf32x3": 1,
     "alignconv_forward_tc_multi": 1, "orconv_forward_tc_multi": 1, "fam_decode": 1, "select_decode": 3, "conv2d_pack_weight": 1,

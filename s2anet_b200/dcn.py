@@ -54,7 +54,7 @@ def deform_conv_forward_cuda(input, weight, offset, output, columns, ones, kW, k
             # (the packer rounds an fp32 weight to the 16-bit type once, which is what `weight.type_as(input)` does)
             y = conv_tc.deform_conv_forward_tc(input, offset, weight, out=output)
             if y is not output:
-                output.copy_(y if y.shape == output.shape else y.reshape(output.shape))
+                conv_tc.nchw_from_nhwc(y, output)
             return 1
         out32 = torch.empty((B, Co, Ho, Wo), dtype=torch.float32, device=dev)
         deform_conv_forward_cuda(input.float(), weight.float(), offset.float(), out32, columns, ones, kW, kH, dW, dH, padW,

@@ -290,3 +290,20 @@ def test_tf32x3_orconv_pool_and_generic_offsets(oracle):
     finally:
         alignconv._FORCE_SIMT_F32 = False
     assert float((out - out2).abs().max()) <= 1e-5 + 2e-5 * float(out2.abs().max())
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("shape", [(2, 256, 16, 16), (1, 24, 5, 3), (3, 33, 7, 9), (1, 64, 128, 128)])
+def test_native_layout_conversion_is_a_bit_exact_copy(dtype, shape):
+    """s2a_transpose_planes (NCHW <-> NHWC around the tensor-core kernels) against torch's own conversion."""
+    from s2anet_b200 import conv_tc
+    g = torch.Generator().manual_seed(sum(shape))
+    x = torch.randn(*shape, generator=g).to(dtype).to(DEV)
+    y = conv_tc._nhwc(x)
+    assert y.is_contiguous(memory_format=torch.channels_last) and y.shape == x.shape
+    assert torch.equal(y, x)
+    assert y.data_ptr() != x.data_ptr() or shape[1] == 1
+    back = torch.empty_like(x)
+    conv_tc.nchw_from_nhwc(y, back)
+    assert back.is_contiguous() and torch.equal(back, x)
+    assert conv_tc._nhwc(y) is y                         # already NHWC: no copy
