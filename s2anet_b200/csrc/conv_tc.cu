@@ -1218,9 +1218,20 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
         __syncwarp();
         s_corner[lane * 8 + 0] = __float_as_uint(w1); s_corner[lane * 8 + 1] = __float_as_uint(w2);
         s_corner[lane * 8 + 2] = __float_as_uint(w3); s_corner[lane * 8 + 3] = __float_as_uint(w4);
-        s_corner[lane * 8 + 4] = (uint32_t)(a_tl >> 2); s_corner[lane * 8 + 5] = (uint32_t)(a_tr >> 2);
-        s_corner[lane * 8 + 6] = (uint32_t)(a_bl >> 2); s_corner[lane * 8 + 7] = (uint32_t)(a_br >> 2);
+        // (offsets are multiples of C / 4 >= 8: bit 0 carries "this corner lies inside the map")
+        s_corner[lane * 8 + 4] = (uint32_t)(a_tl >> 2) | ((inb && c_t && c_l) ? 1u : 0u);
+        s_corner[lane * 8 + 5] = (uint32_t)(a_tr >> 2) | ((inb && c_t && c_r) ? 1u : 0u);
+        s_corner[lane * 8 + 6] = (uint32_t)(a_bl >> 2) | ((inb && c_b && c_l) ? 1u : 0u);
+        s_corner[lane * 8 + 7] = (uint32_t)(a_br >> 2) | ((inb && c_b && c_r) ? 1u : 0u);
         const int cn = lane >> 3, sub = lane & 7;
+        // offset gradient (get_coordinate_weight, deform_conv_cuda_kernel.cu:147-187): needs D_c = <column gradient of
+        // the pixel, x at corner c> for the four corners (a corner outside the map counts as zeros).  The lanes that
+        // reduce corner c of pixel r into grad_input also load the matching 4 channels of x there (8 bytes each, 64
+        // contiguous bytes per corner) and keep a partial D_c per pixel; the partials are combined after the channel loop.
+        const bool want_goff = p.sc_goff != nullptr;
+        float dacc[32];
+#pragma unroll
+        for (int r = 0; r < 32; ++r) dacc[r] = 0.f;
         for (int c0 = 0; c0 < p.Co; c0 += TC_OUT_CH) {
           uint32_t v[32];
           tmem_ld32(acc_addr + (uint32_t)c0, v);
@@ -1231,40 +1242,47 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcPa
             *reinterpret_cast<uint4*>(s_tile + lane * 32 + ((j ^ (lane & 7)) << 2)) =
                 make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
           __syncwarp();
-          {
-            float* gi = p.sc_gi + c0 + 4 * sub;
-#pragma unroll 4
+          // the x loads of the offset gradient are issued first: their latency hides behind the reduction loop (the
+          // reductions are volatile asm statements no load can be scheduled across)
+          uint2 xv[32];
+          if (want_goff) {
+            const T* xs = reinterpret_cast<const T*>(p.sc_x) + c0 + 4 * sub;
+#pragma unroll
             for (int r = 0; r < 32; ++r) {
-              const float wq = __uint_as_float(s_corner[r * 8 + cn]);
-              if (wq != 0.f) {
-                const float4 q = *reinterpret_cast<const float4*>(s_tile + r * 32 + ((sub ^ (r & 7)) << 2));
-                red_add_v4(gi + ((size_t)s_corner[r * 8 + 4 + cn] << 2), wq * q.x, wq * q.y, wq * q.z, wq * q.w);
-              }
+              const uint32_t ow = s_corner[r * 8 + 4 + cn];
+              xv[r] = (ow & 1u) ? __ldg(reinterpret_cast<const uint2*>(xs + ((size_t)(ow & ~7u) << 2))) : make_uint2(0u, 0u);
             }
           }
-          if (inb) {
-            if (p.sc_goff) {
-              // get_coordinate_weight (:147-187): d(sample)/d(offset_h), d(sample)/d(offset_w), corners outside the
-              // map count as zeros
-              const T* xp = reinterpret_cast<const T*>(p.sc_x) + c0;
+          float* gi = p.sc_gi + c0 + 4 * sub;
+#pragma unroll 4
+          for (int r = 0; r < 32; ++r) {
+            const float wq = __uint_as_float(s_corner[r * 8 + cn]);
+            if (wq != 0.f) {
+              const float4 q = *reinterpret_cast<const float4*>(s_tile + r * 32 + ((sub ^ (r & 7)) << 2));
+              red_add_v4(gi + ((size_t)(s_corner[r * 8 + 4 + cn] & ~7u) << 2), wq * q.x, wq * q.y, wq * q.z, wq * q.w);
+            }
+          }
+          if (want_goff) {
 #pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                const uint4 q1 = (c_t && c_l) ? ldg_nc_v4(xp + a_tl + j) : make_uint4(0u, 0u, 0u, 0u);
-                const uint4 q2 = (c_t && c_r) ? ldg_nc_v4(xp + a_tr + j) : make_uint4(0u, 0u, 0u, 0u);
-                const uint4 q3 = (c_b && c_l) ? ldg_nc_v4(xp + a_bl + j) : make_uint4(0u, 0u, 0u, 0u);
-                const uint4 q4 = (c_b && c_r) ? ldg_nc_v4(xp + a_br + j) : make_uint4(0u, 0u, 0u, 0u);
-                const H2* h1 = reinterpret_cast<const H2*>(&q1);
-                const H2* h2 = reinterpret_cast<const H2*>(&q2);
-                const H2* h3 = reinterpret_cast<const H2*>(&q3);
-                const H2* h4 = reinterpret_cast<const H2*>(&q4);
+            for (int r = 0; r < 32; ++r) {
+              const float4 q = *reinterpret_cast<const float4*>(s_tile + r * 32 + ((sub ^ (r & 7)) << 2));
+              const float2 xa = to_f2(*reinterpret_cast<const H2*>(&xv[r].x)), xb = to_f2(*reinterpret_cast<const H2*>(&xv[r].y));
+              dacc[r] += q.x * xa.x + q.y * xa.y + q.z * xb.x + q.w * xb.y;
+            }
+          }
+        }
+        if (want_goff) {
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const float2 x1 = to_f2(h1[e]), x2 = to_f2(h2[e]), x3 = to_f2(h3[e]), x4 = to_f2(h4[e]);
-                  const float ga = __uint_as_float(v[j + 2 * e]), gb = __uint_as_float(v[j + 2 * e + 1]);
-                  gy += ga * (hx * (x3.x - x1.x) + lx * (x4.x - x2.x)) + gb * (hx * (x3.y - x1.y) + lx * (x4.y - x2.y));
-                  gx += ga * (hy * (x2.x - x1.x) + ly * (x4.x - x3.x)) + gb * (hy * (x2.y - x1.y) + ly * (x4.y - x3.y));
-                }
-              }
+          for (int r = 0; r < 32; ++r) {
+            float d = dacc[r];
+            d += __shfl_xor_sync(0xffffffffu, d, 1);
+            d += __shfl_xor_sync(0xffffffffu, d, 2);
+            d += __shfl_xor_sync(0xffffffffu, d, 4);
+            const float D1 = __shfl_sync(0xffffffffu, d, 0), D2 = __shfl_sync(0xffffffffu, d, 8);
+            const float D3 = __shfl_sync(0xffffffffu, d, 16), D4 = __shfl_sync(0xffffffffu, d, 24);
+            if (lane == r) {
+              gy = hx * (D3 - D1) + lx * (D4 - D2);
+              gx = hy * (D2 - D1) + ly * (D4 - D3);
             }
           }
         }
