@@ -19,7 +19,7 @@ _FORCE_SIMT_F32 = False      # set through set_fp32_path(); read by alignconv / 
 def set_fp32_path(path):
     """Which kernel fp32 tensors take in AlignConv / DeformConv / ORConv2d forward (C % 32 == 0, C_out % 32 == 0, <= 256):
     "tf32x3" (default) -- conv_tf32x3_kernel on tcgen05, three TF32 MMAs per K step on hi / lo splits: rel-L2 ~5e-6 of an
-    fp64 evaluation (profiles/r2_parity_errors.json), 0.14 ms at P3 batch 1 where the reference takes 0.59 ms;
+    fp64 evaluation (profiles/r2_parity_errors.json), 0.11 ms at P3 batch 1 where the reference takes 0.59 ms;
     "simt" -- the FMA kernel of conv_f32.cu: individually rounded fp32 operations in the reference's order, rel-L2 ~1e-6
     like the reference's own SGEMM path, 0.98 ms.  Other shapes always take the SIMT kernel."""
     global _FORCE_SIMT_F32

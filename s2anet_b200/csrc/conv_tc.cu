@@ -478,6 +478,12 @@ __device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
   asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
   return r;
 }
+// 16-byte store through a 32-bit shared-space address.  A store through a generic pointer into dynamic shared memory
+// makes the compiler rebuild the shared window from SR_CgaCtaId (an S2R -- XU pipe) next to EVERY store of a loop: ncu
+// showed the XU pipe 98 % busy in conv_tf32x3_kernel's producers before its stores went through this.
+__device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
 __device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
   uint4 r;
   asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
@@ -1667,7 +1673,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap gmap, const WgParams p) {
     const int group = warp >> 2, f = group >> 1, sub = group & 1;
     const int r = (warp & 3) * 32 + lane;               // tile row = pixel (y = r / 16, x = r % 16)
     const int ti = tap / 3, tj = tap - 3 * ti;
-    uint8_t* dst_tile = sS + f * WG_STAGE_BYTES + sub * WG_BLOCK_BYTES + (warp & 3) * (32 * 128);    // this warp's 32 rows
+    const uint32_t dst_tile = smem_u32(sS) + (uint32_t)(f * WG_STAGE_BYTES + sub * WG_BLOCK_BYTES + (warp & 3) * (32 * 128));   // this warp's 32 rows
     const int cb = 2 * f + sub;                         // 64-channel block of x this thread samples
     // lane = the pixel whose parameters it computes; the loads are issued with eight lanes per pixel (four full 128-byte
     // lines per warp instruction, parameters by shuffle) -- see conv_tf32x3_kernel
@@ -1711,22 +1717,33 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap gmap, const WgParams p) {
           base = (uint32_t)((img + yt * rowp + (size_t)xl * p.C) >> 3) | (has_r ? 1u : 0u) | (has_b ? 2u : 0u);
         }
       }
-      mbar_wait(bar_s_empty + 8 * f, (uint32_t)(it & 1) ^ 1u);
       const T* xp = reinterpret_cast<const T*>(p.x) + cb * 64 + 8 * jch;
-#pragma unroll 2
-      for (int i = 0; i < 8; ++i) {                     // four pixels x eight 16-byte chunks (8 channels) per instruction
-        const int src = 4 * i + src0;
-        const uint32_t s01 = __shfl_sync(0xffffffffu, w01, src), s23 = __shfl_sync(0xffffffffu, w23, src);
-        const uint32_t sb = __shfl_sync(0xffffffffu, base, src);
-        uint4 o = make_uint4(0u, 0u, 0u, 0u);
-        if ((s01 | s23) != 0u) {
+      // batches of two iterations: shuffles + eight corner loads first, then the blends and stores (volatile asm keeps
+      // loads and stores in program order: interleaved, every iteration paid its own L2 round trip); no branch around
+      // the loads (base 0 is a valid address, zero weights give a zero row); the first batch flies while the stage drains
+#pragma unroll 1
+      for (int i0 = 0; i0 < 8; i0 += 2) {               // four pixels x eight 16-byte chunks (8 channels) per instruction
+        uint4 q[2][4];
+        uint32_t s01[2], s23[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int src = 4 * (i0 + u) + src0;
+          s01[u] = __shfl_sync(0xffffffffu, w01, src);
+          s23[u] = __shfl_sync(0xffffffffu, w23, src);
+          const uint32_t sb = __shfl_sync(0xffffffffu, base, src);
           const T* q0 = xp + ((size_t)(sb & ~7u) << 3);
           const size_t dx = (sb & 1u) ? (size_t)p.C : 0, dy = (sb & 2u) ? rowp : 0;
-          const uint4 v0 = ldg_nc_v4(q0), v1 = ldg_nc_v4(q0 + dx);
-          const uint4 v2 = ldg_nc_v4(q0 + dy), v3 = ldg_nc_v4(q0 + dy + dx);
-          o = blend4<T>(v0, v1, v2, v3, s01, s23);
+          q[u][0] = ldg_nc_v4(q0); q[u][1] = ldg_nc_v4(q0 + dx);
+          q[u][2] = ldg_nc_v4(q0 + dy); q[u][3] = ldg_nc_v4(q0 + dy + dx);
         }
-        *reinterpret_cast<uint4*>(dst_tile + src * 128 + ((jch ^ (src & 7)) << 4)) = o;          // SWIZZLE_128B
+        if (i0 == 0) mbar_wait(bar_s_empty + 8 * f, (uint32_t)(it & 1) ^ 1u);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int src = 4 * (i0 + u) + src0;
+          uint4 o = blend4<T>(q[u][0], q[u][1], q[u][2], q[u][3], s01[u], s23[u]);
+          if ((s01[u] | s23[u]) == 0u) o = make_uint4(0u, 0u, 0u, 0u);          // (0 x NaN of an unrelated pixel)
+          sts_v4(dst_tile + (uint32_t)(src * 128 + ((jch ^ (src & 7)) << 4)), o.x, o.y, o.z, o.w);          // SWIZZLE_128B
+        }
       }
       fence_proxy_async_smem();                          // generic-proxy stores -> visible to the tensor core
       __syncwarp();
@@ -1859,6 +1876,7 @@ static int launch_wgrad(const void* x, const void* off, int off_f32, const void*
 // =================================================================================================
 constexpr int TF_KB = 32;                                   // channels per k-block: 128 bytes of fp32
 constexpr int TF_PROD_GROUPS = 3, TF_PROD_WARPS = 4 * TF_PROD_GROUPS;
+constexpr int TF_NB = 2;                                    // gather iterations whose loads are in flight together
 constexpr int TF_THREADS = (TF_PROD_WARPS + 4 + 2) * 32;    // + 4 epilogue warps + TMA warp + MMA warp
 constexpr int TF_A_BYTES = TC_M * 128;                      // one [128 pixels x 32 channels] fp32 tile: 16 KB
 constexpr int TF_B_BYTES = 256 * 128;                       // one [256 co x 32 channels] fp32 tile: 32 KB
@@ -1951,6 +1969,7 @@ conv_tf32x3_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
     // (a lane = a pixel, looping over the eight chunks): L1TEX at 83 %, everything else below 31 %.  The parameters of
     // a pixel travel from the lane that computed them by shuffle.
     const int src0 = lane >> 3, jch = lane & 7;
+    const uint32_t tile_hi = smem_u32(smem) + (uint32_t)(group * TF_A_STAGE + wq * (32 * 128));   // this warp's 32 rows
     for (int it = 0; it < my_tiles; ++it) {
       int b, ty0, tx0;
       tile_coords(it, b, ty0, tx0);
@@ -2011,40 +2030,57 @@ conv_tf32x3_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
             }
           }
         }
-        mbar_wait(bar_a_empty + 8 * group, ((uint32_t)use & 1u) ^ 1u);
-        uint8_t* tile_hi = smem + group * TF_A_STAGE + wq * (32 * 128);
         const float* xp = p.x + cb * TF_KB + 4 * jch;
-#pragma unroll 2
-        for (int i = 0; i < 8; ++i) {                   // four pixels x eight 16-byte chunks per warp instruction
-          const int src = 4 * i + src0;
-          const float s1 = __shfl_sync(0xffffffffu, w1, src), s2 = __shfl_sync(0xffffffffu, w2, src);
-          const float s3 = __shfl_sync(0xffffffffu, w3, src), s4 = __shfl_sync(0xffffffffu, w4, src);
-          const uint32_t sb = __shfl_sync(0xffffffffu, base, src);
-          float v[4] = {0.f, 0.f, 0.f, 0.f};
-          if ((s1 != 0.f) | (s2 != 0.f) | (s3 != 0.f) | (s4 != 0.f)) {
+        // Batches of TF_NB iterations (four pixels x eight 16-byte chunks per warp instruction each): all shuffles and
+        // corner loads of a batch are issued before any of its stores -- the loads and stores are volatile asm
+        // statements the compiler keeps in program order, so interleaving them (first version) meant one L2 round trip
+        // per iteration.  There is no branch around the loads either: a pixel without a sample has base 0, a valid
+        // address, and its row is zeroed by a select.  The first batch is in flight while the stage drains.
+#pragma unroll 1
+        for (int i0 = 0; i0 < 8; i0 += TF_NB) {
+          uint4 q[TF_NB][4];
+          float sw[TF_NB][4];
+#pragma unroll
+          for (int u = 0; u < TF_NB; ++u) {
+            const int src = 4 * (i0 + u) + src0;
+            sw[u][0] = __shfl_sync(0xffffffffu, w1, src); sw[u][1] = __shfl_sync(0xffffffffu, w2, src);
+            sw[u][2] = __shfl_sync(0xffffffffu, w3, src); sw[u][3] = __shfl_sync(0xffffffffu, w4, src);
+            const uint32_t sb = __shfl_sync(0xffffffffu, base, src);
             const float* q0 = xp + ((size_t)(sb & ~7u) << 2);
             const size_t dx = (sb & 1u) ? (size_t)p.C : 0, dy = (sb & 2u) ? rowp : 0;
-            const uint4 q1 = ldg_nc_f4(q0), q2 = ldg_nc_f4(q0 + dx), q3 = ldg_nc_f4(q0 + dy), q4 = ldg_nc_f4(q0 + dy + dx);
-            const uint32_t u1[4] = {q1.x, q1.y, q1.z, q1.w}, u2[4] = {q2.x, q2.y, q2.z, q2.w};
-            const uint32_t u3[4] = {q3.x, q3.y, q3.z, q3.w}, u4[4] = {q4.x, q4.y, q4.z, q4.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-              v[e] = s1 * __uint_as_float(u1[e]) + s2 * __uint_as_float(u2[e]) + s3 * __uint_as_float(u3[e]) +
-                     s4 * __uint_as_float(u4[e]);
+            q[u][0] = ldg_nc_f4(q0); q[u][1] = ldg_nc_f4(q0 + dx);
+            q[u][2] = ldg_nc_f4(q0 + dy); q[u][3] = ldg_nc_f4(q0 + dy + dx);
           }
-          float hi[4], lo[4];
+          if (i0 == 0) mbar_wait(bar_a_empty + 8 * group, ((uint32_t)use & 1u) ^ 1u);
 #pragma unroll
-          for (int e = 0; e < 4; ++e) { hi[e] = tf32_hi(v[e]); lo[e] = tf32_hi(v[e] - hi[e]); }
-          uint8_t* row_hi = tile_hi + src * 128 + ((jch ^ (src & 7)) << 4);           // SWIZZLE_128B
-          *reinterpret_cast<float4*>(row_hi) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-          *reinterpret_cast<float4*>(row_hi + TF_A_BYTES) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+          for (int u = 0; u < TF_NB; ++u) {
+            const int src = 4 * (i0 + u) + src0;
+            const float s1 = sw[u][0], s2 = sw[u][1], s3 = sw[u][2], s4 = sw[u][3];
+            const bool any = (s1 != 0.f) | (s2 != 0.f) | (s3 != 0.f) | (s4 != 0.f);
+            const uint32_t u1[4] = {q[u][0].x, q[u][0].y, q[u][0].z, q[u][0].w}, u2[4] = {q[u][1].x, q[u][1].y, q[u][1].z, q[u][1].w};
+            const uint32_t u3[4] = {q[u][2].x, q[u][2].y, q[u][2].z, q[u][2].w}, u4[4] = {q[u][3].x, q[u][3].y, q[u][3].z, q[u][3].w};
+            float hi[4], lo[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float t = s1 * __uint_as_float(u1[e]) + s2 * __uint_as_float(u2[e]) + s3 * __uint_as_float(u3[e]) +
+                              s4 * __uint_as_float(u4[e]);
+              const float v = any ? t : 0.f;
+              hi[e] = tf32_hi(v);
+              lo[e] = tf32_hi(v - hi[e]);
+            }
+            const uint32_t row_hi = tile_hi + (uint32_t)(src * 128 + ((jch ^ (src & 7)) << 4));           // SWIZZLE_128B
+            sts_v4(row_hi, __float_as_uint(hi[0]), __float_as_uint(hi[1]), __float_as_uint(hi[2]), __float_as_uint(hi[3]));
+            sts_v4(row_hi + TF_A_BYTES, __float_as_uint(lo[0]), __float_as_uint(lo[1]), __float_as_uint(lo[2]),
+                   __float_as_uint(lo[3]));
+          }
         }
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_a_full + 8 * group);
       }
     }
-  } else if (warp == kTma) {
+  } else if (warp >= kTma) {
+   if (warp == kTma) {
     // ===================== TMA: hi / lo halves of the packed weights, one k-block per stage =====================
     for (int it = 0; it < my_tiles; ++it) {
       for (int kb = 0; kb < nkb; ++kb) {
@@ -2059,7 +2095,7 @@ conv_tf32x3_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
         __syncwarp();
       }
     }
-  } else if (warp == kMma) {
+   } else {
     // ===================== MMA issuer =====================
     // D = f32, A / B = TF32 (format 2), K-major, N = C_out, M = 128
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.Co >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
@@ -2094,6 +2130,7 @@ conv_tf32x3_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_cons
         __syncwarp();
       }
     }
+   }
   } else {
     // ===================== epilogue: bias / ReLU / orientation max, NCHW fp32 stores =====================
     const int quad = warp & 3;                          // warps 12..15: warp % 4 = the TMEM lane quadrant
