@@ -9,7 +9,7 @@ import subprocess
 import sys
 
 KEEP = ("conv_tc_kernel", "box_iou_rotated_kernel", "mc_mask_kernel", "nms_mask_kernel", "assign_labels_kernel", "mc_emit_kernel",
-        "select_decode_kernel", "pack_weight_kernel", "wgrad_tc_kernel")
+        "select_decode_kernel", "pack_weight_kernel", "wgrad_tc_kernel", "conv_tf32x3_kernel", "transpose_planes_kernel")
 BLACKWELL = re.compile(r"^(UTCHMMA|UTMALDG|UTMASTG|UTMAPF|LDTM|STTM|UTCBAR|UTCATOMSWS|USETMAXREG|UCGABAR|SYNCS|ELECT|FENCE\.VIEW\.ASYNC)")
 
 
