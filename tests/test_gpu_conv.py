@@ -307,3 +307,26 @@ def test_native_layout_conversion_is_a_bit_exact_copy(dtype, shape):
     conv_tc.nchw_from_nhwc(y, back)
     assert back.is_contiguous() and torch.equal(back, x)
     assert conv_tc._nhwc(y) is y                         # already NHWC: no copy
+
+
+def test_tf32x3_edge_cases_tiny_maps_and_samples_outside(oracle):
+    """1 x 1 and 2 x 3 maps (a single partial tile), offsets that throw every sample out of the map (all-zero output,
+    deform_conv_cuda_kernel.cu:228) and an empty batch, through the fp32 tensor-core route of deform_conv_forward_cuda."""
+    import torchvision
+    from s2anet_b200 import dcn
+    g = torch.Generator().manual_seed(11)
+    e = torch.empty(0, device=DEV)
+    for (B, H, W) in ((1, 1, 1), (2, 2, 3)):
+        x = torch.randn(B, 32, H, W, generator=g).to(DEV)
+        w = (torch.randn(32, 32, 3, 3, generator=g) * 0.1).to(DEV)
+        off = (torch.randn(B, 18, H, W, generator=g) * 0.7).to(DEV)
+        out = torch.full((B, 32, H, W), 7.0, device=DEV)
+        assert dcn.deform_conv_forward_cuda(x, w, off, out, e, e, 3, 3, 1, 1, 1, 1, 1, 1, 1, 1, B) == 1
+        ref = torchvision.ops.deform_conv2d(x, off, w, padding=1)
+        assert float((out - ref).abs().max()) <= ATOL + RTOL * float(ref.abs().max())
+        far = torch.full_like(off, 1000.0)
+        dcn.deform_conv_forward_cuda(x, w, far, out, e, e, 3, 3, 1, 1, 1, 1, 1, 1, 1, 1, B)
+        assert float(out.abs().max()) == 0.0
+    x0 = torch.empty(0, 32, 4, 4, device=DEV)
+    out0 = torch.empty(0, 32, 4, 4, device=DEV)
+    assert dcn.deform_conv_forward_cuda(x0, w, torch.empty(0, 18, 4, 4, device=DEV), out0, e, e, 3, 3, 1, 1, 1, 1, 1, 1, 1, 1, 1) == 1
