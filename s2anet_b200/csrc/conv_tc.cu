@@ -1858,20 +1858,23 @@ static int launch_wgrad(const void* x, const void* off, int off_f32, const void*
 // =================================================================================================
 // fp32 AlignConv / DeformConv / ORConv2d on the tensor cores: 3 x TF32 split (round 2)
 //
-// The exact-arithmetic fp32 path of round 1 (conv_f32.cu, SIMT FMAs fed by a scalar NCHW gather) ran AlignConv at P3
-// in 0.98 ms where the reference's im2col + cuBLAS SGEMM takes 0.59 ms.  Here the same contraction runs on
-// tcgen05.mma.kind::tf32 with both operands split into two TF32 terms, a = a_hi + a_lo (a_hi = a rounded to the
-// nearest TF32 value, a_lo = a - a_hi, exact in fp32, rounded likewise), and three MMAs per K step: a_hi*w_hi + a_lo*w_hi + a_hi*w_lo
-// (the dropped a_lo*w_lo term is 2^-20 relative).  Products of TF32 values are exact in the fp32 accumulator, so the
-// result carries ~21 mantissa bits per product: inside the fp32 bar of the parity tests (1e-4 + 1e-4 |ref|) by two
-// orders of magnitude.
+// The exact-order fp32 path of round 1 (conv_f32.cu, SIMT FMAs fed by a scalar NCHW gather) ran AlignConv at P3 in
+// 0.98 ms where the reference's im2col + cuBLAS SGEMM takes 0.59 ms.  Here the same contraction runs on
+// tcgen05.mma.kind::tf32 with both operands split into two TF32 terms, a = a_hi + a_lo (a_hi = a rounded to the nearest
+// TF32 value, a_lo = a - a_hi, exact in fp32, rounded likewise: the residual is below 2^-24 |a|), and three MMAs per K
+// step: a_hi*w_hi + a_lo*w_hi + a_hi*w_lo (the dropped a_lo*w_lo term is 2^-22 relative).  Products of TF32 values are
+// exact in fp32; what is left is the accumulation, which the tensor core does with truncation -- hence the second
+// accumulator below.  Measured against fp64: rel-L2 5.5e-6 (the SIMT kernel 1.4e-6, the reference binary 8.6e-7).
 //
-// One CTA (no pairs) per 8 x 16-pixel tile, persistent.  12 producer warps (3 groups of 128 threads, one pixel each)
-// compute the sampling position of (pixel, tap) -- from the anchors (AlignConv, alignconv.py:29-86), an explicit offset
-// tensor (deform_conv_cuda_kernel.cu:218-227) or the regular grid (ORConv2d) --, gather the four corners from the NHWC
-// fp32 map with 16-byte loads, blend in fp32, split and store 128-byte rows (32 channels) of the hi and lo tiles; a TMA
-// warp streams the hi / lo halves of the packed weights (32 KB each per 32-channel k-block); the MMA warp issues 12
-// tcgen05.mma (M = 128, N = C_out, K = 8) per k-block into two tensor-memory accumulators (main / correction terms); 4 epilogue warps add
+// One CTA (no pairs) per 8 x 16-pixel tile, persistent, 18 warps.  12 producer warps in 3 groups of 128 threads; a group
+// fills one A stage (the hi and lo [128 pixels x 32 channels] tiles of one k-block = 32 channels of one tap).  A lane
+// computes the sampling position of ITS pixel for the tap -- from the anchors (AlignConv, alignconv.py:29-86), an explicit
+// offset tensor (deform_conv_cuda_kernel.cu:218-227) or the regular grid (ORConv2d) -- but the gather is issued with
+// eight lanes per (pixel, corner): a warp instruction reads four full 128-byte lines of the NHWC fp32 map, the pixel's
+// weights and packed corner offset arrive by shuffle, the loads of two such iterations are in flight before either is
+// blended (fp32), split and stored (swizzled 16-byte chunks).  A TMA warp streams the hi / lo planes of the packed
+// weights (32 KB each per k-block, two stages); the MMA warp issues 12 tcgen05.mma (M = 128, N = C_out, K = 8) per
+// k-block into two tensor-memory accumulators (a_hi*w_hi | the two correction products); 4 epilogue warps add the two,
 // the bias, apply ReLU / the 8-way orientation max and store NCHW fp32 (a warp writes 2 x 64 contiguous bytes per channel).
 // =================================================================================================
 constexpr int TF_KB = 32;                                   // channels per k-block: 128 bytes of fp32
