@@ -49,3 +49,27 @@ def test_cache_sees_data_reassignment_and_dtype_or_device_moves():
     assert conv_tc._cache_get(key2, (m.weight,)) is None
     conv_tc.invalidate_pack_cache()
     assert not conv_tc._PACK_CACHE
+
+
+def test_fp32_path_switch_and_layout_helpers_on_the_host():
+    """Host-side logic of the fp32 route selection and the layout helpers (no GPU): bad names are refused, the shape
+    rule of the tensor-core fp32 kernel, and the CPU fall-backs of the NHWC helpers are plain torch copies."""
+    import pytest
+    import torch
+    from s2anet_b200 import alignconv, conv_tc
+    assert alignconv._FORCE_SIMT_F32 is False
+    alignconv.set_fp32_path("simt")
+    assert alignconv._FORCE_SIMT_F32 is True
+    alignconv.set_fp32_path("tf32x3")
+    assert alignconv._FORCE_SIMT_F32 is False
+    with pytest.raises(ValueError):
+        alignconv.set_fp32_path("fp64")
+    assert conv_tc.tf32x3_supported(256, 256) and conv_tc.tf32x3_supported(32, 32) and conv_tc.tf32x3_supported(96, 64)
+    assert not conv_tc.tf32x3_supported(24, 32) and not conv_tc.tf32x3_supported(32, 48) and not conv_tc.tf32x3_supported(32, 288)
+    x = torch.randn(2, 8, 3, 5)
+    y = conv_tc._nhwc(x)                                  # CPU tensor: torch's own conversion
+    assert y.is_contiguous(memory_format=torch.channels_last) and torch.equal(x, y)
+    back = torch.empty_like(x)
+    assert conv_tc.nchw_from_nhwc(y, back) is back and back.is_contiguous() and torch.equal(back, x)
+    with pytest.raises(ValueError):
+        conv_tc._nhwc(torch.zeros(3, 4))
