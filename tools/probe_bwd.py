@@ -48,5 +48,12 @@ for B in (1, 8):
             gw = torch.zeros_like(wh)
             ref.deform_conv_backward_parameters_cuda(xh, offh, gyh, gw, eh, eh, 3, 3, 1, 1, 1, 1, 1, 1, 1, 1, 1.0, B)
         print("B=%d reference binary (fp16): backward_input %.3f ms, backward_parameters %.3f ms" % (B, t(ref_in, 2), t(ref_w, 2)))
+        def ref_in32():
+            gi, gof = torch.zeros_like(x32), torch.zeros_like(off)
+            ref.deform_conv_backward_input_cuda(x32, off, gy32, gi, gof, w32, e, 3, 3, 1, 1, 1, 1, 1, 1, 1, 1, B)
+        def ref_w32():
+            gw = torch.zeros_like(w32)
+            ref.deform_conv_backward_parameters_cuda(x32, off, gy32, gw, e, e, 3, 3, 1, 1, 1, 1, 1, 1, 1, 1, 1.0, B)
+        print("B=%d reference binary (fp32): backward_input %.3f ms, backward_parameters %.3f ms" % (B, t(ref_in32, 2), t(ref_w32, 2)))
     except Exception as ex:
         print("reference binary not available:", ex)
