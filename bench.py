@@ -708,11 +708,24 @@ def extra_legs(torch, np, dev, dtype, head, feat_sets, refines, peaks, args):
     an_ = torch.from_numpy(synth.refined_anchors(1, 8, 8, 8, seed=1)).to(dev)
     w_ = (torch.randn(64, 64, 3, 3, device=dev) * 0.05).to(torch.bfloat16)
     from s2anet_b200.alignconv import alignconv_forward as _af
-    out["dropin_call_overhead_us"] = {
+    from s2anet_b200 import _torch_ext
+    ext_on = _torch_ext.module() is not None
+    over = {
+        "binding": "torch extension (_s2a_torch.so: at::Tensor in, one C-ABI call, at::Tensor out)" if ext_on else "ctypes",
         "box_iou_rotated_4x4": call_us(lambda: box_iou_rotated(tiny, tiny)),
         "alignconv_forward_bf16_8x8": call_us(lambda: _af(xs_, an_, w_, 8)),
         "nms_rotated_4_boxes_incl_4_byte_readback": call_us(lambda: nms_rotated_op(tiny, ts[:4].contiguous(), 0.5), 50),
-        "note": "Python wrapper + ctypes + kernel launch per call; the bench step itself replays a CUDA graph and pays none of it"}
+        "note": "wrapper + binding + kernel launch per call (alignconv always goes through ctypes: its packed-weight cache lives "
+                "in Python); the bench step itself replays a CUDA graph and pays none of it"}
+    if ext_on:                                            # the same two calls through the ctypes wrappers, for comparison
+        saved = (_torch_ext._MOD, _torch_ext._TRIED)
+        _torch_ext._MOD, _torch_ext._TRIED = None, True
+        try:
+            over["ctypes_box_iou_rotated_4x4"] = call_us(lambda: box_iou_rotated(tiny, tiny))
+            over["ctypes_nms_rotated_4_boxes_incl_4_byte_readback"] = call_us(lambda: nms_rotated_op(tiny, ts[:4].contiguous(), 0.5), 50)
+        finally:
+            _torch_ext._MOD, _torch_ext._TRIED = saved
+    out["dropin_call_overhead_us"] = over
     if dtype != torch.float32 and refines is not None:
         from s2anet_b200.alignconv import alignconv_forward
         from s2anet_b200.orn import orconv_forward

@@ -55,12 +55,49 @@ def build(force=False, verbose=False):
                     print(out)
     objs = [os.path.join(OBJ, os.path.basename(s)[:-3] + ".o") for s in srcs]
     if jobs or _newer(LIB, objs):
-        cmd = ["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs
+        cmd = ["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-Xlinker", "-soname=libs2a_b200.so", "-o", LIB] + objs
         r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         if r.returncode != 0:
             raise RuntimeError("link failed:\n%s" % r.stdout)
     return LIB
 
 
+TORCH_EXT = os.path.join(HERE, "_s2a_torch.so")
+TORCH_EXT_SRC = os.path.join(CSRC, "torch_binding.cpp")
+
+
+def build_torch_ext(force=False):
+    """g++ the thin torch-extension binding (csrc/torch_binding.cpp: at::Tensor in, one C-ABI call, at::Tensor out) into
+    s2anet_b200/_s2a_torch.so, linked against csrc/libs2a_b200.so (rpath $ORIGIN/csrc) and torch's own libraries.  In-tree
+    like the CUDA library, so it travels with the gpurun snapshot.  No CUDA sources: builds without a GPU."""
+    hdrs = glob.glob(os.path.join(ROOT, "include", "*.h"))
+    if not (force or _newer(TORCH_EXT, [TORCH_EXT_SRC, LIB] + hdrs)):
+        return TORCH_EXT
+    import sysconfig
+    import torch
+    from torch.utils import cpp_extension as ce
+    cuda_home = ce.CUDA_HOME or "/usr/local/cuda"
+    try:                                                   # (the argument is a device-type string in recent torch, a flag before)
+        incs, libdirs = ce.include_paths("cuda"), ce.library_paths("cuda")
+    except TypeError:
+        incs, libdirs = ce.include_paths(True), ce.library_paths(True)
+    incs = [os.path.join(ROOT, "include")] + incs + [os.path.join(cuda_home, "include"), sysconfig.get_paths()["include"]]
+    libdirs = libdirs + [os.path.join(cuda_home, "lib64")]
+    cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-DTORCH_EXTENSION_NAME=_s2a_torch",
+           "-DTORCH_API_INCLUDE_EXTENSION_H", "-D_GLIBCXX_USE_CXX11_ABI=%d" % int(torch._C._GLIBCXX_USE_CXX11_ABI),
+           "-Wno-deprecated-declarations"]
+    for i in incs:
+        cmd += ["-isystem" if "site-packages" in i or "cuda" in i else "-I", i]
+    cmd += [TORCH_EXT_SRC, "-o", TORCH_EXT, "-L", CSRC, "-l:libs2a_b200.so", "-Wl,-rpath,$ORIGIN/csrc"]
+    for d in libdirs:
+        cmd += ["-L", d, "-Wl,-rpath," + d]
+    cmd += ["-lc10", "-lc10_cuda", "-ltorch_cpu", "-ltorch_cuda", "-ltorch", "-ltorch_python", "-lcudart"]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("g++ failed for %s:\n%s" % (TORCH_EXT_SRC, r.stdout))
+    return TORCH_EXT
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    print(build_torch_ext(force="--force" in sys.argv))

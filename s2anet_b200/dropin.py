@@ -12,7 +12,9 @@ The reference imports six pybind11 extension modules by name (SURVEY.md section 
     utils.ml_nms_rotated.ml_nms_rotated_cuda        ml_nms_rotated
 
 `install()` registers Python modules with exactly those names and function signatures in
-sys.modules, each forwarding to libs2a_b200.so through the ctypes binding.  `deform_conv_forward_cuda`
+sys.modules.  `box_iou_rotated`, `nms_rotated`, `ml_nms_rotated` and `arf_forward` go through the thin torch
+extension (`_s2a_torch.so`, csrc/torch_binding.cpp: at::Tensor in, one C-ABI call, at::Tensor out) when it has been
+built, everything else -- and everything when it has not -- through the ctypes binding of libs2a_b200.so.  `deform_conv_forward_cuda`
 takes fp32, fp16 (the reference's `AT_DISPATCH_FLOATING_TYPES_AND_HALF`, what val.py's `model.half()`
 reaches) and bf16 tensors; the two deform-conv backward entries and `arf_backward` are implemented
 (fp32 accumulate).  Functions outside the hot path (modulated DCN, PS-RoI pooling, RIE) exist so imports

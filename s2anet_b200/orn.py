@@ -13,7 +13,7 @@ from torch.nn.modules import Conv2d
 from torch.nn.modules.utils import _pair
 from torch.nn.parameter import Parameter
 
-from . import _lib
+from . import _lib, _torch_ext
 
 
 def arf_forward(weight, indices):
@@ -22,6 +22,11 @@ def arf_forward(weight, indices):
     dev = _lib.require_cuda(weight, indices)
     if weight.dim() != 5:
         raise RuntimeError("only supports a batch of ARFs.")
+    ext = _torch_ext.module()
+    if ext is not None and indices.dtype == torch.uint8:
+        out = ext.arf_forward(weight, indices)
+        _lib.check(0, "arf_forward")
+        return out
     O, I, nOri, kH, kW = weight.shape
     nRot = indices.size(3)
     w = weight.contiguous()

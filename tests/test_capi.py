@@ -117,3 +117,21 @@ def test_module_surface_matches_reference_checkpoint_contract():
     assert tuple(sd["weight"].shape) == (32, 256, 1, 3, 3)
     assert tuple(sd["bias"].shape) == (256,)
     assert tuple(sd["indices"].shape) == (1, 3, 3, 8) and sd["indices"].dtype == torch.uint8
+
+
+def test_torch_extension_binding_loads_and_exports_the_reference_names():
+    """The thin torch extension over the C ABI (s2anet_b200/_s2a_torch.so, built by __graft_entry__.build()): loads
+    without a GPU, reports the library's ABI version and exports the reference's extension-level function names
+    (utils/*/src/*.h, models/orn/src/vision.cpp:7-12)."""
+    from s2anet_b200 import _lib, _torch_ext, build
+    build.build()
+    build.build_torch_ext()
+    m = _torch_ext.module()
+    assert m is not None
+    assert m.abi_version() == _lib.load().s2a_version()
+    for name in ("box_iou_rotated", "nms_rotated", "ml_nms_rotated", "arf_forward", "arf_backward"):
+        assert callable(getattr(m, name))
+    import pytest
+    import torch
+    with pytest.raises(RuntimeError):                   # CPU tensors: refused loudly, like every other entry of the library
+        m.box_iou_rotated(torch.zeros(2, 5), torch.zeros(3, 5))

@@ -387,3 +387,45 @@ def test_multiclass_batched_takes_more_than_6144_boxes(oracle):
     np.testing.assert_array_equal(l[0, :k].cpu().numpy(), rl)
     d1, l1 = multiclass_nms_rotated(tb, ts, 0.05, 0.5, 500)                # the single-image wrapper takes the same route
     np.testing.assert_array_equal(d1.cpu().numpy(), rd)
+
+
+def test_torch_extension_binding_matches_the_ctypes_path_bit_for_bit(oracle):
+    """csrc/torch_binding.cpp (pybind11, at::Tensor in / out) and the ctypes wrappers call the same C-ABI entries: same
+    bits for the IoU matrix, same keep lists for nms / ml_nms (strided dets[:, :5] views and fp16 scores included), same
+    ARF scatter; and the reference's error type for bad arguments."""
+    import os
+    from s2anet_b200 import _torch_ext, box_iou_rotated as biou, nms_rotated as nmsr, orn
+    ext = _torch_ext.module()
+    assert ext is not None, "s2anet_b200/_s2a_torch.so is not built"
+    b, s, l = synth.clustered_boxes(n_seed=120, rep=5, seed=4)
+    tb, ts, tl = torch.from_numpy(b).to(DEV), torch.from_numpy(s).to(DEV), torch.from_numpy(l).to(DEV)
+    iou_ext = ext.box_iou_rotated(tb, tb[:77])
+    os.environ["S2A_NO_TORCH_EXT"] = "1"
+    saved = (_torch_ext._MOD, _torch_ext._TRIED)
+    _torch_ext._MOD, _torch_ext._TRIED = None, False
+    try:
+        assert _torch_ext.module() is None
+        iou_ct = biou.box_iou_rotated(tb, tb[:77])
+        keep_ct = nmsr.nms_rotated_op(tb, ts, 0.5)
+        ml_ct = nmsr.ml_nms_rotated(tb, ts, tl, 0.5)
+        dets6 = torch.cat([tb, ts[:, None]], dim=1)
+        strided_ct = nmsr.nms_rotated_op(dets6[:, :5], dets6[:, 5].half(), 0.3)
+    finally:
+        del os.environ["S2A_NO_TORCH_EXT"]
+        _torch_ext._MOD, _torch_ext._TRIED = saved
+    assert torch.equal(iou_ext, iou_ct)
+    np.testing.assert_array_equal(iou_ext.cpu().numpy(), oracle.box_iou_rotated(b, b[:77]))
+    assert torch.equal(ext.nms_rotated(tb, ts, 0.5), keep_ct)
+    assert torch.equal(ext.ml_nms_rotated(tb, ts, tl, 0.5), ml_ct)
+    assert torch.equal(ext.nms_rotated(dets6[:, :5], dets6[:, 5].half(), 0.3), strided_ct)
+    assert ext.nms_rotated(tb[:0], ts[:0], 0.5).shape == (0,) and ext.box_iou_rotated(tb[:0], tb).shape == (0, b.shape[0])
+    idx = torch.from_numpy(oracle.arf_indices(1, 8, 3)).to(DEV)
+    w = torch.randn(4, 6, 1, 3, 3, device=DEV)
+    rot = ext.arf_forward(w, idx)
+    assert torch.equal(rot, torch.from_numpy(oracle.arf_forward(w.cpu().numpy(), oracle.arf_indices(1, 8, 3))).to(DEV))
+    g = torch.randn_like(rot)
+    assert torch.allclose(ext.arf_backward(idx, g), orn.arf_backward(idx, g))
+    with pytest.raises(RuntimeError):
+        ext.box_iou_rotated(tb[:, :4], tb)
+    with pytest.raises(RuntimeError):
+        ext.nms_rotated(tb, ts[:5], 0.5)
