@@ -273,7 +273,7 @@ static int launch_iou(const float* boxes1, int64_t n, const float* boxes2, int64
   const int64_t mine_rows = (mine - 1) * tile_rows + std::min<int64_t>(tile_rows, nrows - last_tile * tile_rows);
   // packed output: CTAs are 256 rows high and take several dealt tiles each; in-place output: one dealt tile per CTA
   // (its rows must be consecutive in the output)
-  // (64-row CTAs when 128-row ones would leave the launch with fewer than ~8 waves: the tail matters more than the
+  // (64-row CTAs when 128-row ones would leave the launch with fewer than ~6 waves: the tail matters more than the
   // ~8 % of per-tile overhead)
   int cta_rows = tile_rows;
   if (compact) {
